@@ -1,0 +1,216 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/*.py) on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (where /root/reference is mounted); the
+fixtures it writes are committed so they travel to the GPU box, which has no /root/reference.
+
+    python oracle/make_golden.py            # rewrites tests/golden/{lightgcn,igcn,igcn_fr,imf,mf}_tiny.npz
+
+The three third-party leaves the reference imports but this image lacks (dgl, info_nce,
+torchmetrics) are satisfied by oracle/stubs (contract: SURVEY.md Appendix B).  Everything recorded
+here is an output of the reference's own classes:
+  * graph: LightGCN.generate_graph (model.py:89-98) -> norm_adj COO (row-major, coalesced)
+  * get_rep (model.py:100-110 / :4188-4200), bpr_forward (:112-120 / :4046-4052)
+  * BPRTrainer / IGCNTrainer loss + backward + Adam step (trainer.py:412-429 / :531-561)
+  * BasicTrainer.eval top-K ids + metrics (trainer.py:146-210, :115-144)
+  * IGCN feat_mat / row_sum / anneal (model.py:4127-4175), dropout mask draw (:4016-4028)
+"""
+import contextlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(REPO, "inductive-recommendation_b200"))
+from b200rec import synth  # noqa: E402  (graph generator only; no kernels)
+
+sys.path.remove(os.path.join(REPO, "inductive-recommendation_b200"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "stubs"))
+
+import torch  # noqa: E402
+
+with contextlib.redirect_stdout(io.StringIO()):
+    import dataset as ref_dataset  # noqa: E402
+    import model as ref_model  # noqa: E402
+    import trainer as ref_trainer  # noqa: E402
+    import utils as ref_utils  # noqa: E402
+
+TOPKS = [1, 5, 10, 15, 20]
+CPU = torch.device("cpu")
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def coo_of(sp):
+    sp = sp.coalesce()
+    return sp.indices().numpy().copy(), sp.values().detach().numpy().copy()
+
+
+def run_case(tag, graph, model_cfg, trainer_cfg, out_dir, seed=2021, batch=256):
+    tmp = tempfile.mkdtemp()
+    synth.write_processed(graph, tmp)
+    ds = quiet(ref_dataset.get_dataset, {"name": "ProcessedDataset", "path": tmp, "device": CPU})
+    ref_utils.set_seed(seed)
+    model = quiet(ref_model.get_model, dict(model_cfg, device=CPU), ds)
+    tr = quiet(ref_trainer.get_trainer,
+               dict(trainer_cfg, device=CPU, dataloader_num_workers=0, topks=TOPKS, n_epochs=1,
+                    batch_size=batch, test_batch_size=128), ds, model)
+    out = {}
+    out["n_users"], out["n_items"] = ds.n_users, ds.n_items
+    out["train_indptr"] = graph.train_indptr.numpy()
+    out["train_items"] = graph.train_items.numpy()
+    out["val_indptr"], out["val_items"] = graph.val_indptr.numpy(), graph.val_items.numpy()
+    out["test_indptr"], out["test_items"] = graph.test_indptr.numpy(), graph.test_items.numpy()
+    name = model_cfg["name"]
+    if hasattr(model, "norm_adj"):
+        out["adj_idx"], out["adj_val"] = coo_of(model.norm_adj)
+    if name == "MF":
+        out["user_emb0"] = model.user_embedding.weight.detach().numpy().copy()
+        out["item_emb0"] = model.item_embedding.weight.detach().numpy().copy()
+    else:
+        out["emb0"] = model.embedding.weight.detach().numpy().copy()
+    is_igcn = name in ("IGCN", "IMF")
+    if is_igcn:
+        out["feat_idx"], out["feat_val_a1"] = coo_of(model.feat_mat)
+        out["row_sum"] = model.row_sum.numpy().copy()
+        out["user_map_keys"] = np.array(list(model.user_map.keys()), dtype=np.int64)
+        out["user_map_vals"] = np.array(list(model.user_map.values()), dtype=np.int64)
+        out["item_map_keys"] = np.array(list(model.item_map.keys()), dtype=np.int64)
+        out["item_map_vals"] = np.array(list(model.item_map.values()), dtype=np.int64)
+        out["w0"] = model.w.detach().numpy().copy()
+
+    # ---- eval-mode representation + full-rank evaluation (no dropout) ----
+    model.eval()
+    if name != "MF":
+        with torch.no_grad():
+            out["rep_eval"] = model.get_rep().numpy().copy()
+    users_all = torch.arange(ds.n_users, dtype=torch.int64)
+    with torch.no_grad():
+        out["scores_head"] = model.predict(users_all[:8]).numpy().copy()
+    for split in ("train", "val", "test"):
+        _, metrics, _ = tr.eval(split)
+        # the reference does not keep rec_items; recompute exactly as trainer.py:146-170 does
+        rec = []
+        with torch.no_grad():
+            for (users,) in tr.test_user_loader:
+                scores = model.predict(users)
+                if split != "train":
+                    ex_u, ex_i = [], []
+                    for ui, u in enumerate(users.tolist()):
+                        items = ds.train_data[u]
+                        if split == "test":
+                            items = items + ds.val_data[u]
+                        ex_u.extend([ui] * len(items))
+                        ex_i.extend(items)
+                    scores[ex_u, ex_i] = -np.inf
+                v, it = torch.topk(scores, k=max(TOPKS))
+                rec.append((v.numpy(), it.numpy()))
+        out["topk_ids_" + split] = np.concatenate([r[1] for r in rec], 0)
+        out["topk_val_" + split] = np.concatenate([r[0] for r in rec], 0)
+        for m in ("Precision", "Recall", "NDCG"):
+            out["metric_%s_%s" % (m, split)] = np.array([metrics[m][k] for k in TOPKS], dtype=np.float64)
+    # banned-item pass used by inductive_eval (trainer.py:236-238)
+    n_old_items = int(ds.n_items * 0.8)
+    _, metrics, _ = tr.eval("test", banned_items=np.arange(n_old_items, ds.n_items))
+    out["banned_lo"], out["banned_hi"] = n_old_items, ds.n_items
+    for m in ("Precision", "Recall", "NDCG"):
+        out["metric_%s_test_banned" % m] = np.array([metrics[m][k] for k in TOPKS], dtype=np.float64)
+
+    # ---- one training step on a recorded batch (training mode) ----
+    model.train()
+    ref_utils.set_seed(seed + 1)
+    rows = [ds[0] for _ in range(batch)]  # BasicDataset.__getitem__ (dataset.py:119-131)
+    b = torch.tensor(np.stack(rows)[:, 0, :], dtype=torch.int64)
+    out["batch"] = b.numpy().copy()
+    users, pos, neg = b[:, 0], b[:, 1], b[:, 2]
+    if is_igcn:
+        # record the dropout draw NGCF.dropout_sp_mat makes (model.py:4019-4021): CPU generator
+        torch.manual_seed(seed + 2)
+        nnz = model.feat_mat._nnz()
+        rnd = torch.rand(nnz)
+        keep = torch.floor((1 - model.dropout) + rnd).type(torch.bool)
+        out["drop_keep"] = np.packbits(keep.numpy())
+        out["drop_nnz"] = nnz
+        out["dropout"] = model.dropout
+        torch.manual_seed(seed + 2)
+    ur, pr, nr, l2 = model.bpr_forward(users, pos, neg)
+    out["users_r"], out["pos_r"], out["neg_r"], out["l2_norm_sq"] = (
+        ur.detach().numpy().copy(), pr.detach().numpy().copy(), nr.detach().numpy().copy(), l2.detach().numpy().copy())
+    F = torch.nn.functional
+    bpr = F.softplus((ur * nr).sum(1) - (ur * pr).sum(1)).mean()
+    l2_reg = trainer_cfg["l2_reg"]
+    loss = bpr + l2_reg * l2.mean()
+    if name in ("IGCN", "IMF") and trainer_cfg["name"] == "IGCNTrainer":
+        aux_ds = tr.aux_dataloader.dataset
+        ref_utils.set_seed(seed + 3)
+        arows = [aux_ds[0] for _ in range(batch)]
+        ab = torch.tensor(np.stack(arows)[:, 0, :], dtype=torch.int64)
+        out["aux_batch"] = ab.numpy().copy()
+        au, ap, an = ab[:, 0], ab[:, 1], ab[:, 2]
+        tu = len(model.user_map)
+        e_u, e_p, e_n = model.embedding(au), model.embedding(ap + tu), model.embedding(an + tu)
+        ps = (e_u * e_p * model.w[None, :]).sum(1)
+        ns = (e_u * e_n * model.w[None, :]).sum(1)
+        aux = F.softplus(ns - ps).mean()
+        out["aux_loss"] = float(aux)
+        loss = loss + trainer_cfg["aux_reg"] * aux
+    out["bpr_loss"] = float(bpr)
+    out["loss"] = float(loss)
+    tr.opt.zero_grad()
+    loss.backward()
+    if name == "MF":
+        out["grad_user"] = model.user_embedding.weight.grad.numpy().copy()
+        out["grad_item"] = model.item_embedding.weight.grad.numpy().copy()
+    else:
+        out["grad_emb"] = model.embedding.weight.grad.numpy().copy()
+    if is_igcn:
+        out["grad_w"] = model.w.grad.numpy().copy()
+    tr.opt.step()
+    if name == "MF":
+        out["user_emb1"] = model.user_embedding.weight.detach().numpy().copy()
+        out["item_emb1"] = model.item_embedding.weight.detach().numpy().copy()
+    else:
+        out["emb1"] = model.embedding.weight.detach().numpy().copy()
+    if is_igcn:
+        out["w1"] = model.w.detach().numpy().copy()
+        model.feat_mat_anneal()
+        out["alpha_after"] = model.alpha
+        out["feat_val_anneal"] = coo_of(model.feat_mat)[1]
+    out["lr"] = trainer_cfg["lr"]
+    out["l2_reg"] = l2_reg
+    out["aux_reg"] = trainer_cfg.get("aux_reg", 0.0)
+    out["n_layers"] = model_cfg.get("n_layers", 0)
+    out["topks"] = np.array(TOPKS)
+    path = os.path.join(out_dir, tag + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+def main():
+    out_dir = os.path.join(REPO, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    g = synth.generate(300, 500, 6000, seed=7)
+    bpr = {"name": "BPRTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 1e-4}
+    igcn = {"name": "IGCNTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 0.0, "aux_reg": 0.01}
+    run_case("lightgcn_tiny", g, {"name": "LightGCN", "embedding_size": 64, "n_layers": 3}, bpr, out_dir)
+    run_case("mf_tiny", g, {"name": "MF", "embedding_size": 64}, dict(bpr, l2_reg=1e-3), out_dir)
+    run_case("igcn_tiny", g, {"name": "IGCN", "embedding_size": 64, "n_layers": 3, "dropout": 0.3,
+                              "feature_ratio": 1.0}, igcn, out_dir)
+    run_case("igcn_fr_tiny", g, {"name": "IGCN", "embedding_size": 64, "n_layers": 2, "dropout": 0.3,
+                                 "feature_ratio": 0.5}, dict(igcn, l2_reg=1e-5), out_dir)
+    run_case("imf_tiny", g, {"name": "IMF", "embedding_size": 64, "n_layers": 0, "dropout": 0.3,
+                             "feature_ratio": 1.0}, igcn, out_dir)
+    # a D=128 / L=4 case (the C4 kernel configuration) on a graph with hub rows
+    g2 = synth.generate(400, 300, 9000, seed=11, a_item=1.1)
+    run_case("lightgcn_d128", g2, {"name": "LightGCN", "embedding_size": 128, "n_layers": 4}, bpr, out_dir)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+"""Pin the CPU oracle (oracle/ref_port.py) against the fixtures the UNMODIFIED reference produced
+(tests/golden/*.npz, written by oracle/make_golden.py).  CPU-only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import lists_from_csr
+from oracle import ref_port as rp
+
+TOPKS = [1, 5, 10, 15, 20]
+
+
+def _pairs(g):
+    return rp.pairs_from_csr(g["train_indptr"], g["train_items"])
+
+
+def _maps(g):
+    return (dict(zip(g["user_map_keys"].tolist(), g["user_map_vals"].tolist())),
+            dict(zip(g["item_map_keys"].tolist(), g["item_map_vals"].tolist())))
+
+
+def _build(g, name):
+    nu, ni = int(g["n_users"]), int(g["n_items"])
+    users, items = _pairs(g)
+    if name.startswith("lightgcn"):
+        return rp.LightGCNPort(nu, ni, users, items, g["emb0"], int(g["n_layers"]))
+    if name.startswith("mf"):
+        return rp.MFPort(g["user_emb0"], g["item_emb0"])
+    um, im = _maps(g)
+    return rp.IGCNPort(nu, ni, users, items, g["emb0"], int(g["n_layers"]), float(g["dropout"]), um, im, g["w0"])
+
+
+@pytest.mark.parametrize("name", ["lightgcn_tiny", "lightgcn_d128", "igcn_tiny"])
+def test_norm_adj_bit_exact(golden, name):
+    g = golden(name)
+    users, items = _pairs(g)
+    a = rp.norm_adjacency(int(g["n_users"]), int(g["n_items"]), users, items).tocoo()
+    assert np.array_equal(np.stack([a.row, a.col]), g["adj_idx"])
+    assert np.array_equal(a.data, g["adj_val"])  # same numpy calls -> bit-exact values
+    # symmetric: backward may reuse the forward CSR
+    at = a.T.tocsr()
+    at.sort_indices()
+    assert np.array_equal(at.tocoo().data, g["adj_val"])
+
+
+@pytest.mark.parametrize("name", ["igcn_tiny", "igcn_fr_tiny", "imf_tiny"])
+def test_feat_structure_and_values(golden, name):
+    g = golden(name)
+    users, items = _pairs(g)
+    um, im = _maps(g)
+    feat, row_sum = rp.build_feat(int(g["n_users"]), int(g["n_items"]), users, items, um, im)
+    coo = feat.tocoo()
+    assert np.array_equal(np.stack([coo.row, coo.col]), g["feat_idx"])
+    assert np.array_equal(row_sum, g["row_sum"])
+    assert np.array_equal(rp.feat_values(row_sum, coo.row, 1.0), g["feat_val_a1"])
+    assert np.array_equal(rp.feat_values(row_sum, coo.row, float(g["alpha_after"])), g["feat_val_anneal"])
+
+
+def test_template_ranking(golden):
+    g = golden("igcn_fr_tiny")
+    users, items = _pairs(g)
+    um, im = rp.template_maps(int(g["n_users"]), int(g["n_items"]), users, items, 0.5)
+    gum, gim = _maps(g)
+    assert um == gum and im == gim
+
+
+@pytest.mark.parametrize("name", ["lightgcn_tiny", "lightgcn_d128", "igcn_tiny", "igcn_fr_tiny", "imf_tiny"])
+def test_get_rep_eval(golden, name):
+    g = golden(name)
+    m = _build(g, name).eval()
+    with torch.no_grad():
+        rep = m.get_rep().numpy()
+    np.testing.assert_allclose(rep, g["rep_eval"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["lightgcn_tiny", "lightgcn_d128", "mf_tiny", "igcn_tiny", "igcn_fr_tiny", "imf_tiny"])
+def test_train_step(golden, name):
+    g = golden(name)
+    m = _build(g, name).train()
+    if "drop_keep" in g:
+        m.forced_keep = np.unpackbits(g["drop_keep"])[: int(g["drop_nnz"])].astype(bool)
+    batch = torch.from_numpy(g["batch"])
+    bpr, loss, (ur, pr, nr, l2) = rp.bpr_loss(m, batch, float(g["l2_reg"]))
+    np.testing.assert_allclose(ur.detach().numpy(), g["users_r"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(nr.detach().numpy(), g["neg_r"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(l2.detach().numpy(), g["l2_norm_sq"], rtol=1e-5)
+    assert abs(float(bpr) - float(g["bpr_loss"])) < 1e-6
+    if "aux_batch" in g:
+        aux = rp.aux_loss(m, torch.from_numpy(g["aux_batch"]))
+        assert abs(float(aux) - float(g["aux_loss"])) < 1e-6
+        loss = loss + float(g["aux_reg"]) * aux
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    opt = torch.optim.Adam(m.parameters(), lr=float(g["lr"]))
+    opt.zero_grad()
+    loss.backward()
+    if name.startswith("mf"):
+        np.testing.assert_allclose(m.user_embedding.weight.grad.numpy(), g["grad_user"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(m.item_embedding.weight.grad.numpy(), g["grad_item"], rtol=1e-5, atol=1e-9)
+    else:
+        np.testing.assert_allclose(m.embedding.weight.grad.numpy(), g["grad_emb"], rtol=1e-4, atol=1e-9)
+    if "grad_w" in g:
+        np.testing.assert_allclose(m.w.grad.numpy(), g["grad_w"], rtol=1e-4, atol=1e-9)
+    opt.step()
+    if name.startswith("mf"):
+        np.testing.assert_allclose(m.user_embedding.weight.detach().numpy(), g["user_emb1"], rtol=1e-5, atol=2e-6)
+    else:
+        np.testing.assert_allclose(m.embedding.weight.detach().numpy(), g["emb1"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["lightgcn_tiny", "mf_tiny", "igcn_tiny"])
+def test_eval_topk_and_metrics(golden, name):
+    g = golden(name)
+    m = _build(g, name)
+    tr = lists_from_csr(g["train_indptr"], g["train_items"])
+    va = lists_from_csr(g["val_indptr"], g["val_items"])
+    te = lists_from_csr(g["test_indptr"], g["test_items"])
+    for split, ev in (("train", tr), ("val", va), ("test", te)):
+        rec, metrics = rp.evaluate(m, tr, va, ev, split, TOPKS, test_batch_size=128)
+        ref_ids, ref_val = g["topk_ids_" + split], g["topk_val_" + split]
+        # ids agree wherever the reference's own adjacent scores are separated (tie order is
+        # unspecified for torch.topk, trainer.py:169)
+        gap_ok = np.ones_like(ref_ids, dtype=bool)
+        d = np.abs(np.diff(ref_val, axis=1)) > 1e-6
+        gap_ok[:, 1:] &= d
+        gap_ok[:, :-1] &= d
+        assert gap_ok.mean() > 0.99
+        assert np.array_equal(rec[gap_ok], ref_ids[gap_ok])
+        for mname in ("Precision", "Recall", "NDCG"):
+            ours = np.array([metrics[mname][k] for k in TOPKS])
+            np.testing.assert_allclose(ours, g["metric_%s_%s" % (mname, split)], rtol=1e-5, atol=1e-7)
+    rec, metrics = rp.evaluate(m, tr, va, te, "test", TOPKS, 128, banned=(int(g["banned_lo"]), int(g["banned_hi"])))
+    for mname in ("Precision", "Recall", "NDCG"):
+        ours = np.array([metrics[mname][k] for k in TOPKS])
+        np.testing.assert_allclose(ours, g["metric_%s_test_banned" % mname], rtol=1e-5, atol=1e-7)
