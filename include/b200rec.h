@@ -1,0 +1,192 @@
+/*
+ * b200rec.h -- C ABI of libb200rec.so: the B200 (sm_100a) hot path of the inductive graph-convolution
+ * recommender (LightGCN / IGCN / IMF / MF of umaDosey/Inductive-Recommendation).
+ *
+ * The reference has no FFI; its replaceable boundary is the DGL / ATen leaf calls made from model.py and
+ * trainer.py.  Every entry point below cites the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types.  Unless a parameter is marked HOST, every pointer is a
+ *     DEVICE pointer into caller-owned memory (the Python host passes tensor.data_ptr()).
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it; nothing allocates,
+ *     synchronises or keeps global state, so calls can be captured into a CUDA graph.
+ *   - return 0 on success, negative b200rec_status otherwise; b200rec_last_error() gives the text
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every compute call fails.
+ *   - indices are int32 (all BASELINE shapes have nnz < 2^31), embeddings fp32 row-major [rows, D],
+ *     D in {16, 32, 64, 128, 256}.
+ */
+#ifndef B200REC_H
+#define B200REC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200REC_OK = 0,
+  B200REC_ERR_ARG = -1,      /* bad argument (null pointer, unsupported D, K too large ...) */
+  B200REC_ERR_CUDA = -2,     /* a CUDA runtime call or launch failed */
+  B200REC_ERR_UNSUPPORTED = -3
+} b200rec_status;
+
+const char* b200rec_last_error(void);
+int b200rec_version(void);
+/* number of kernels this library has launched from the calling process (bench.py "gpu_launches") */
+uint64_t b200rec_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sparse operand: CSR + a load-balanced work decomposition ("work items").
+ *
+ * A work item is a slice [item_start, item_end) of the nnz arrays that belongs to one row.  Rows with
+ * at most `chunk` entries are one item whose item_dst is the row id; longer rows (hubs of the
+ * power-law graph, IGCN's two shared template columns) are split into chunk-sized items whose item_dst
+ * is ~slot (negative) -- they write a partial row into `partial[slot]`, and a second deterministic
+ * kernel adds the slots of each long row in slot order.  Items are sorted by length, longest first.
+ * The decomposition is built once per graph by b200rec_plan_build().
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_rows;            /* output rows */
+  int32_t n_cols;            /* rows of the gathered table */
+  int32_t nnz;
+  const int32_t* rowptr;     /* [n_rows+1] */
+  const int32_t* colidx;     /* [nnz] ascending inside a row */
+  const float* vals;         /* [nnz] per-edge value, or NULL (all ones) */
+  const float* nbr_scale;    /* [n_cols] multiplies each gathered row, or NULL */
+  const float* row_scale;    /* [n_rows] multiplies the finished row sum, or NULL */
+  const int32_t* eid;        /* [nnz] edge id used to look up keep_bits (transposed operand), or NULL = position */
+  /* work decomposition */
+  int32_t n_items;
+  const int32_t* item_start; /* [n_items] */
+  const int32_t* item_end;   /* [n_items] */
+  const int32_t* item_dst;   /* [n_items] row id, or ~slot for a piece of a long row */
+  int32_t n_long;            /* rows that were split */
+  const int32_t* long_row;   /* [n_long] */
+  const int32_t* long_slot0; /* [n_long] first slot */
+  const int32_t* long_nslot; /* [n_long] */
+  int32_t n_slots;
+  float* partial;            /* [n_slots, D] scratch for split rows (caller-owned, D = largest D used) */
+} b200rec_csr;
+
+/* Build the decomposition on the HOST (one-time, per graph).  All pointers here are HOST pointers.
+ * Call once with the output arrays NULL to get the sizes, allocate, call again to fill. */
+int b200rec_plan_build_host(const int32_t* rowptr /*HOST [n_rows+1]*/, int32_t n_rows, int32_t chunk,
+                            int32_t* n_items, int32_t* n_long, int32_t* n_slots,
+                            int32_t* item_start, int32_t* item_end, int32_t* item_dst,
+                            int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot);
+
+/* Symmetric-normalised adjacency values (model.py:89-98 LightGCN.generate_graph; utils.py:42-50).
+ * deg[r] = max(1, sum of multiplicities in row r); dinv = deg^-1/2 (fp32, correctly rounded);
+ * vals[e] = fl(fl(dinv[r] * mult[e]) * dinv[col[e]]).  mult may be NULL (= 1). */
+int b200rec_adj_normalize(const int32_t* rowptr, const int32_t* colidx, const float* mult, int32_t n_rows,
+                          float* dinv /*out [n_rows]*/, float* vals /*out [nnz]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SpMM with fused epilogue -- replaces dgl.ops.gspmm(g,'mul','sum',X,vals) (model.py:106, :4184, :4196).
+ *   s[r]  = row_scale[r] * post_scale * sum_e keep(e) * vals[e] * nbr_scale[col[e]] * X[col[e], :]
+ *   y[r]   = s[r]                                   (if y   != NULL)
+ *   out[r] = (addend[r] + s[r]) * out_scale         (if out != NULL; addend may be NULL = 0)
+ * keep_bits: optional edge-dropout bitmask (bit e of word e>>5; NGCF.dropout_sp_mat model.py:4016-4028),
+ * post_scale carries its 1/(1-p).  `out` may alias `addend`.  Row-sum order is CSR order (deterministic).
+ * ------------------------------------------------------------------------------------------------ */
+int b200rec_spmm_f32(const b200rec_csr* a /*HOST struct of device pointers*/, const float* x, int32_t d,
+                     const uint32_t* keep_bits, float post_scale,
+                     float* y, const float* addend, float* out, float out_scale, void* stream);
+
+/* L-layer propagation + layer mean (model.py:100-110 LightGCN.get_rep; :4193-4199 IGCN.get_rep):
+ *   X_{k+1} = A X_k,  mean_out = (X_0 + ... + X_L) / (L+1).  buf0/buf1: [n_rows, D] scratch (L >= 2 needs both).
+ * The running sum lives in mean_out; the last layer writes only the mean (no (L+1) x N x D stack). */
+int b200rec_propagate_fwd(const b200rec_csr* a, const float* x0, int32_t d, int32_t n_layers,
+                          float* buf0, float* buf1, float* mean_out, void* stream);
+/* Backward of the above w.r.t. X_0 given G = dLoss/d(mean_out) (the autograd of model.py:100-110):
+ *   dX0 = (1/(L+1)) sum_k A^k G, evaluated as H <- G + A H (A is bit-wise symmetric, so the forward CSR serves). */
+int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32_t d, int32_t n_layers,
+                          float* buf0, float* buf1, float* dx0_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BPR sampling -- the distribution of BasicDataset.__getitem__ (dataset.py:119-131): user uniform over
+ * users with a non-empty train row; positive uniform over that row; negative uniform over items,
+ * rejected while it is in the (sorted) row.  The reference's MT19937 / NumPy streams cannot be matched
+ * on device; the stated stream is Philox4x32-10, key = (seed_lo, seed_hi), counter = (slot, step, draw, purpose),
+ * restated bit-exactly in oracle/oracle_c.c.  `step` is read from device memory so a captured graph advances.
+ * out_batch: int64 [B,3] = (user, pos, neg), the layout trainer.py:414-415 slices.
+ * ------------------------------------------------------------------------------------------------ */
+int b200rec_bpr_sample(const int32_t* user_ptr, const int32_t* user_items, int32_t n_users, int32_t n_items,
+                       uint64_t seed, const int64_t* step /*device scalar*/, int32_t batch,
+                       int64_t* out_batch, void* stream);
+
+/* Row gather / scatter-add used by the autograd-compatible bpr_forward (model.py:118-119 rep[idx,:] and its
+ * index_put_(accumulate) backward).  idx int64 [n]; offset is added to every index (n_users for items). */
+int b200rec_gather_rows(const float* table, int32_t d, const int64_t* idx, int64_t offset, int32_t n,
+                        float* out /*[n,D]*/, float* sqnorm /*[n] or NULL*/, void* stream);
+int b200rec_scatter_add_rows(float* table, int32_t d, const int64_t* idx, int64_t offset, int32_t n,
+                             const float* src /*[n,D]*/, void* stream);
+
+/* Fused BPR forward + backward (trainer.py:414-424 with model.py:112-120 / :4046-4052 / :66-71):
+ *   pos = <u,p>, neg = <u,n>;  *loss_out += loss_scale * (mean softplus(neg-pos) + [reg_mode 1] l2_reg * mean l2);
+ *   the gradient w.r.t. the gathered rows is scatter-added into g_rep (pre-zeroed [rows, D]) with
+ *   red.global.add.v4.f32 (one 128-bit reduction per lane).
+ * reg_mode 0: no L2 here (LightGCN regularises layer-0 rows: b200rec_bpr_l2_emb0);
+ *          1: L2 on the gathered `rep` rows (NGCF.bpr_forward used by IGCN/IMF, and MF), gradient into g_rep.
+ * w (optional, [D]): elementwise score weight of the IGCN auxiliary loss (trainer.py:542-549); g_w [D] is
+ *   OVERWRITTEN with dLoss/dw (deterministic block-ordered sum).
+ * loss_scale multiplies the loss term and all gradients (aux_reg for the auxiliary term, else 1).
+ * item_offset: added to pos / neg ids (n_users for the joint table, template-user count for the aux loss).
+ * block_scratch: b200rec_bpr_scratch_floats(B, D) floats, zero-initialised once by the caller (the ticket
+ *   counter in it resets itself); the loss sum is taken in block order, so it is run-to-run deterministic. */
+int64_t b200rec_bpr_scratch_floats(int32_t n_batch, int32_t d);
+int b200rec_bpr_fwd_bwd(const float* rep, int32_t d, const int64_t* batch /*[B,3]*/, int32_t n_batch,
+                        int64_t item_offset, float l2_reg, int32_t reg_mode, const float* w,
+                        float loss_scale, float* g_rep, float* g_w, float* loss_out,
+                        float* block_scratch, void* stream);
+/* LightGCN's layer-0 regulariser (model.py:114-117): g_emb0 += l2_reg * d(mean ||e_u||^2+||e_p||^2+||e_n||^2)/de,
+ * *loss_out += l2_reg * mean(l2). */
+int b200rec_bpr_l2_emb0(const float* emb0, int32_t d, const int64_t* batch, int32_t n_batch, int64_t item_offset,
+                        float l2_reg, float* g_emb0, float* loss_out, float* block_scratch, void* stream);
+
+/* Dense Adam, the arithmetic of torch.optim.Adam defaults (trainer.py:44-46): no weight decay / amsgrad.
+ * step (device int64 scalar) is the count BEFORE this update; the kernel uses step+1 for the bias corrections. */
+int b200rec_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, const int64_t* step, void* stream);
+/* End of an optimiser step: *step += 1, *step_b += 1 (each if non-NULL; e.g. the Adam count and the sampler count),
+ * and AverageMeter.update(loss, B) (utils.py:286-289) on device: loss_accum[0] += *loss * n_batch,
+ * loss_accum[1] += n_batch (if both given). */
+int b200rec_step_advance(int64_t* step, int64_t* step_b, const float* loss, double* loss_accum /*[2]*/,
+                         int32_t n_batch, void* stream);
+
+/* Edge-dropout keep mask of NGCF.dropout_sp_mat (model.py:4016-4021) drawn on device: bit e = floor((1-p) + r[e]),
+ * r uniform [0,1) at 24-bit resolution from Philox4x32-10 (key = seed, counter = (e>>2, step_lo, step_hi, 0xD0),
+ * lane e&3); restated in oracle/oracle_c.c.  keep_bits: uint32 [ceil(nnz/32)], edge order = CSR position. */
+int b200rec_dropout_mask(int32_t nnz, float p, uint64_t seed, const int64_t* step /*device scalar*/,
+                         uint32_t* keep_bits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Full-rank evaluation (model.py:122-127 predict; trainer.py:146-170 eval).
+ * ------------------------------------------------------------------------------------------------ */
+/* Dense scores[b, n_items] = U[b,:] . I[j,:]  in fp32, accumulated with fmaf in d = 0..D-1 order (the order the
+ * oracle restates), for API parity with predict().  users: int64 [b] row ids into rep_users. */
+int b200rec_score_dense_f32(const float* rep_users, const int64_t* users, int32_t n_batch_users,
+                            const float* rep_items, int32_t n_items, int32_t d, float* scores, void* stream);
+/* Fused score + mask + top-K (never materialises the score matrix):
+ *   for each listed user: score all items, drop items in its exclusion rows (train, and val when testing:
+ *   excl_ptr_a/excl_idx_a and optional excl_ptr_b/excl_idx_b, sorted CSR by user, trainer.py:155-165) and items in
+ *   [banned_lo, banned_hi) (trainer.py:166-167), return the K best as (score desc, item id asc).
+ * precision 0: exact fp32 CUDA-core path;  1: tcgen05 bf16 candidate pass + exact fp32 re-score (same ids and
+ *   scores as precision 0 by construction: the candidate margin bounds the bf16 error).
+ * workspace: device scratch, size from b200rec_score_topk_workspace(). */
+int64_t b200rec_score_topk_workspace(int32_t n_batch_users, int32_t n_items, int32_t d, int32_t k, int32_t precision);
+int b200rec_score_topk(const float* rep_users, const int64_t* users, int32_t n_batch_users,
+                       const float* rep_items, int32_t n_items, int32_t d,
+                       const int32_t* excl_ptr_a, const int32_t* excl_idx_a,
+                       const int32_t* excl_ptr_b, const int32_t* excl_idx_b,
+                       int32_t banned_lo, int32_t banned_hi, int32_t k, int32_t precision,
+                       int32_t* out_ids /*[b,K]*/, float* out_scores /*[b,K]*/, void* workspace, void* stream);
+/* hit[u,j] = rec[u,j] in eval row u (trainer.py:117-121), eval rows sorted CSR. */
+int b200rec_hit_matrix(const int32_t* rec_ids, int32_t n_rows, int32_t k, int64_t user0,
+                       const int32_t* eval_ptr, const int32_t* eval_idx, float* hit, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REC_H */

@@ -1,0 +1,232 @@
+"""Fused BPR training step, captured once as a CUDA graph and replayed per batch.
+
+One replay = one iteration of BPRTrainer / IGCNTrainer.train_one_epoch (trainer.py:412-429, :531-558):
+  device sampling (or a host batch copied in) -> [edge dropout + inductive layer] -> L x SpMM + layer mean
+  -> fused BPR loss/grad -> L x SpMM backward (Horner) -> [transposed inductive layer, auxiliary BPR] -> Adam
+  -> AverageMeter update + step counters -- all libb200rec kernels on one stream, no host round trip.
+On the C1-C3 shapes one SpMM layer is ~10 us of memory work, so per-kernel launch latency would dominate an eager
+loop; the graph removes it.  The Adam moments are the tensors inside the trainer's torch.optim.Adam state, so
+optimiser state_dicts stay interchangeable with the eager path.
+"""
+import torch
+
+from . import ops
+
+
+def _adam_state(opt, p):
+    """create (or fetch) torch.optim.Adam's per-parameter state in its own layout"""
+    st = opt.state[p]
+    if len(st) == 0:
+        st['step'] = torch.tensor(0.0, dtype=torch.float32)
+        st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+    return st
+
+
+class BprEngine:
+    def __init__(self, model, dataset, opt, batch_size, l2_reg, aux_reg=0.0, aux_dataset=None, seed=2021,
+                 use_graph=True, partition=None):
+        self.model, self.dataset, self.opt = model, dataset, opt
+        self.kind = type(model).__name__
+        if self.kind not in ('LightGCN', 'IGCN', 'IMF', 'MF'):
+            raise ValueError('BprEngine supports LightGCN / IGCN / IMF / MF, got ' + self.kind)
+        if type(opt).__name__ != 'Adam':
+            raise ValueError('the fused step implements Adam; use the autograd path for other optimisers')
+        g = opt.param_groups[0]
+        if g.get('weight_decay', 0) != 0 or g.get('amsgrad', False) or g.get('maximize', False):
+            raise ValueError('fused Adam supports the default torch.optim.Adam options only')
+        self.lr, (self.b1, self.b2), self.eps = g['lr'], g['betas'], g['eps']
+        self.B, self.l2_reg, self.aux_reg, self.seed = batch_size, float(l2_reg), float(aux_reg), seed
+        self.partition = partition
+        dev = model.device
+        self.dev = dev
+        D = model.embedding_size
+        self.D = D
+        i64 = dict(dtype=torch.int64, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.batch = torch.zeros((batch_size, 3), **i64)
+        self.sample_step = torch.zeros(1, **i64)
+        self.adam_step = torch.zeros(1, **i64)
+        self.loss = torch.zeros(1, **f32)
+        self.loss_accum = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.scratch = ops.bpr_scratch(batch_size, D, dev)
+        self.user_ptr, self.user_items = dataset.csr('train', device=dev)
+        n = model.n_users + model.n_items
+        self.n = n
+        if self.kind == 'MF':
+            self.table = model._joint
+            self.params = [(model.user_embedding.weight, slice(0, model.n_users)),
+                           (model.item_embedding.weight, slice(model.n_users, n))]
+            self.grad = torch.zeros_like(self.table)
+            self.m, self.v = torch.zeros_like(self.table), torch.zeros_like(self.table)
+            for p, sl in self.params:
+                st = _adam_state(opt, p)
+                self.m[sl].copy_(st['exp_avg'])
+                self.v[sl].copy_(st['exp_avg_sq'])
+                st['exp_avg'], st['exp_avg_sq'] = self.m[sl], self.v[sl]
+                p.grad = self.grad[sl]
+                self.adam_step.fill_(int(st['step']))
+        else:
+            emb = model.embedding.weight
+            self.table = emb.data
+            self.grad = torch.zeros_like(self.table)
+            emb.grad = self.grad
+            st = _adam_state(opt, emb)
+            st['exp_avg'], st['exp_avg_sq'] = st['exp_avg'].to(dev), st['exp_avg_sq'].to(dev)
+            self.m, self.v = st['exp_avg'], st['exp_avg_sq']
+            self.adam_step.fill_(int(st['step']))
+            self.g_rep = torch.zeros((n, D), **f32)
+            self.rep = torch.empty((n, D), **f32)
+            L = model.n_layers
+            self.bufs = [torch.empty((n, D), **f32) if L >= 2 + i else None for i in range(2)]
+            if self.kind in ('IGCN', 'IMF'):
+                self.x0 = torch.empty((n, D), **f32)
+                self.dx0 = torch.empty((n, D), **f32)
+                self.keep_bits = torch.zeros((model.feat_mat.nnz + 31) // 32, dtype=torch.int32, device=dev)
+                self.row_scale = model.row_scale.clone()
+                self.feat_fwd = model.feat_mat.fwd.with_scales(row_scale=self.row_scale)
+                self.feat_bwd = model.feat_mat.bwd.with_scales(nbr_scale=self.row_scale)
+                self.aux_batch = torch.zeros((batch_size, 3), **i64)
+                self.g_w = torch.zeros(D, **f32)
+                model.w.grad = self.g_w
+                stw = _adam_state(opt, model.w)
+                stw['exp_avg'], stw['exp_avg_sq'] = stw['exp_avg'].to(dev), stw['exp_avg_sq'].to(dev)
+                self.m_w, self.v_w = stw['exp_avg'], stw['exp_avg_sq']
+                self.aux = aux_dataset
+                if aux_dataset is not None:
+                    self.aux_ptr, self.aux_items = aux_dataset.csr('train', device=dev)
+        self.use_graph = use_graph
+        self._graphs = {}
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------------------------------------ one step
+    def _propagate_fwd(self, x0):
+        m = self.model
+        if self.partition is not None:
+            self.partition.propagate_fwd(m.norm_adj, x0, m.n_layers, self.bufs, self.rep)
+        else:
+            ops.propagate_fwd(m.norm_adj, x0, m.n_layers, self.bufs, self.rep)
+
+    def _propagate_bwd(self, out):
+        m = self.model
+        if self.partition is not None:
+            self.partition.propagate_bwd(m.norm_adj, self.g_rep, m.n_layers, self.bufs, out)
+        else:
+            ops.propagate_bwd(m.norm_adj, self.g_rep, m.n_layers, self.bufs, out)
+
+    def _body(self, sample, draw_mask=True):
+        m, B = self.model, self.B
+        nu = m.n_users
+        if sample:
+            ops.bpr_sample(self.user_ptr, self.user_items, self.dataset.n_users, self.dataset.n_items, self.seed,
+                           self.sample_step, B, out=self.batch)
+        self.loss.zero_()
+        if self.kind == 'MF':
+            self.grad.zero_()
+            ops.bpr_fwd_bwd(self.table, self.batch, nu, self.l2_reg, 1, self.grad, self.loss, self.scratch)
+            ops.adam_step(self.table, self.grad, self.m, self.v, self.adam_step, self.lr, self.b1, self.b2, self.eps)
+        elif self.kind == 'LightGCN':
+            self.g_rep.zero_()
+            self._propagate_fwd(self.table)
+            ops.bpr_fwd_bwd(self.rep, self.batch, nu, 0.0, 0, self.g_rep, self.loss, self.scratch)
+            self._propagate_bwd(self.grad)
+            if self.l2_reg != 0.0:
+                ops.bpr_l2_emb0(self.table, self.batch, nu, self.l2_reg, self.grad, self.loss, self.scratch)
+            ops.adam_step(self.table, self.grad, self.m, self.v, self.adam_step, self.lr, self.b1, self.b2, self.eps)
+        else:  # IGCN / IMF
+            p = float(m.dropout)
+            keep, inv_keep = None, 1.0
+            if p > 0.0:
+                if draw_mask:
+                    ops.dropout_bits(m.feat_mat.nnz, p, m.dropout_seed, self.sample_step, out=self.keep_bits)
+                keep, inv_keep = self.keep_bits, 1.0 / (1.0 - p)
+            if self.aux is not None and sample:
+                ops.bpr_sample(self.aux_ptr, self.aux_items, self.aux.n_users, self.aux.n_items, self.seed + 1,
+                               self.sample_step, B, out=self.aux_batch)
+            self.g_rep.zero_()
+            ops.spmm(self.feat_fwd, self.table, keep_bits=keep, post_scale=inv_keep, y=self.x0)
+            self._propagate_fwd(self.x0)
+            ops.bpr_fwd_bwd(self.rep, self.batch, nu, self.l2_reg, 1 if self.l2_reg != 0.0 else 0, self.g_rep, self.loss,
+                            self.scratch)
+            self._propagate_bwd(self.dx0)
+            ops.spmm(self.feat_bwd, self.dx0, keep_bits=keep, post_scale=inv_keep, y=self.grad)
+            if self.aux is not None:
+                ops.bpr_fwd_bwd(self.table, self.aux_batch, len(m.user_map), 0.0, 0, self.grad, self.loss, self.scratch,
+                                w=m.w.data, g_w=self.g_w, loss_scale=self.aux_reg)
+                ops.adam_step(m.w.data, self.g_w, self.m_w, self.v_w, self.adam_step, self.lr, self.b1, self.b2, self.eps)
+            ops.adam_step(self.table, self.grad, self.m, self.v, self.adam_step, self.lr, self.b1, self.b2, self.eps)
+        ops.step_advance(self.adam_step, self.sample_step, self.loss, self.loss_accum, B)
+
+    def _run(self, sample, draw_mask=True):
+        if not self.use_graph:
+            self._body(sample, draw_mask)
+            return
+        g = self._graphs.get((sample, draw_mask))
+        if g is None:
+            # warm-up on a side stream (lazy module loading, cudaFuncSetAttribute) with state restored afterwards
+            snap = [t.clone() for t in self._state_tensors()]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body(sample, draw_mask)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            for t, c in zip(self._state_tensors(), snap):
+                t.copy_(c)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body(sample, draw_mask)
+            for t, c in zip(self._state_tensors(), snap):  # capture does not execute, but keep state exact anyway
+                t.copy_(c)
+            self._graphs[(sample, draw_mask)] = g
+        g.replay()
+
+    def _state_tensors(self):
+        ts = [self.table, self.m, self.v, self.adam_step, self.sample_step, self.loss_accum, self.loss]
+        if self.kind in ('IGCN', 'IMF'):
+            ts += [self.model.w.data, self.m_w, self.v_w]
+        return ts
+
+    # ------------------------------------------------------------------------------------------------ public
+    def step(self, host_batch=None, host_aux_batch=None, host_keep_bits=None):
+        """One optimiser step.  host_batch: optional pinned int64 [B,3] (the reference's DataLoader batch,
+        trainer.py:414); without it the triples are drawn on device."""
+        if host_batch is not None:
+            self.batch.copy_(host_batch.reshape(self.B, 3), non_blocking=True)
+            if host_aux_batch is not None:
+                self.aux_batch.copy_(host_aux_batch.reshape(self.B, 3), non_blocking=True)
+            draw_mask = True
+            if host_keep_bits is not None:
+                self.keep_bits.copy_(host_keep_bits, non_blocking=True)
+                draw_mask = False
+            elif self.kind in ('IGCN', 'IMF') and self.model.dropout > 0 and self.model.dropout_rng == 'host':
+                self.keep_bits.copy_(self.model._keep_bits())  # the reference's CPU torch.rand draw (model.py:4020)
+                draw_mask = False
+            self._run(False, draw_mask)
+        else:
+            self._run(True)
+        self.model._rep_cache = None  # kernels update parameters in place, behind autograd's version counter
+        self.steps_done += 1
+
+    def refresh_row_scale(self):
+        """after IGCN.feat_mat_anneal(): the graph reads the scale vector in place"""
+        if self.kind in ('IGCN', 'IMF'):
+            self.row_scale.copy_(self.model.row_scale)
+
+    def reset_meter(self):
+        self.loss_accum.zero_()
+
+    def meter_avg(self):
+        a = self.loss_accum.cpu()
+        return float(a[0] / a[1]) if float(a[1]) > 0 else 0.0
+
+    def last_loss(self):
+        return float(self.loss.item())
+
+    def sync_optimizer_state(self):
+        """write the step count back into torch.optim.Adam's state (it keeps `step` as a CPU scalar tensor)"""
+        t = float(self.adam_step.item())
+        for p in [q for grp in self.opt.param_groups for q in grp['params']]:
+            if p in self.opt.state and 'step' in self.opt.state[p]:
+                self.opt.state[p]['step'] = torch.tensor(t, dtype=torch.float32)
+        self.model._rep_cache = None

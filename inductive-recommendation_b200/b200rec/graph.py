@@ -1,0 +1,229 @@
+"""Device-resident sparse operands of the hot path and their construction.
+
+  * `CsrOperand`       -- int32 CSR + the load-balanced work decomposition libb200rec's SpMM consumes.
+  * `build_norm_adj`   -- D^-1/2 A D^-1/2 of the user-item graph (utils.py:42-50 generate_daj_mat +
+                          model.py:89-98 LightGCN.generate_graph): rows [users | items], nnz = 2E, bit-wise symmetric.
+  * `build_feat`       -- IGCN's template feature matrix F and its transpose (model.py:4139-4175 generate_feat).
+
+HBM layout: rowptr int32[N+1], colidx int32[nnz] ascending inside a row (the order of the reference's coalesced COO,
+utils.py:33-39), vals fp32[nnz]; 8 B/edge instead of the reference's 20 B/edge int64 COO.  Index sorting uses torch
+device ops (one-time setup plumbing); the edge values come from the library (b200rec_adj_normalize).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+
+CHUNK = 1024  # rows longer than this are split into chunk-sized work items (deterministic two-pass reduce)
+
+
+class CsrOperand:
+    def __init__(self, rowptr, colidx, n_cols, vals=None, nbr_scale=None, row_scale=None, eid=None, chunk=CHUNK,
+                 max_d=256):
+        _abi.require_cuda(rowptr, colidx, vals, nbr_scale, row_scale, eid)
+        assert rowptr.dtype == torch.int32 and colidx.dtype == torch.int32
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.nbr_scale, self.row_scale, self.eid = nbr_scale, row_scale, eid
+        self.n_rows = rowptr.numel() - 1
+        self.n_cols = int(n_cols)
+        self.nnz = colidx.numel()
+        self.device = rowptr.device
+        self.chunk = chunk
+        self._build_plan(max_d)
+        self._struct = None
+
+    def _build_plan(self, max_d):
+        lib = _abi.load()
+        rp = self.rowptr.cpu().numpy()
+        n_items, n_long, n_slots = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        null = C.c_void_p(0)
+        _abi.check(lib.b200rec_plan_build_host(rp.ctypes.data, self.n_rows, self.chunk, C.addressof(n_items),
+                                               C.addressof(n_long), C.addressof(n_slots), null, null, null, null, null,
+                                               null), "plan_build_host(size)")
+        ni, nl, ns = n_items.value, n_long.value, n_slots.value
+        a = [np.empty(max(ni, 1), dtype=np.int32) for _ in range(3)]
+        b = [np.empty(max(nl, 1), dtype=np.int32) for _ in range(3)]
+        _abi.check(lib.b200rec_plan_build_host(rp.ctypes.data, self.n_rows, self.chunk, C.addressof(n_items),
+                                               C.addressof(n_long), C.addressof(n_slots),
+                                               a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+                                               b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data), "plan_build_host")
+        dev = self.device
+        self.n_items, self.n_long, self.n_slots = ni, nl, ns
+        self.item_start, self.item_end, self.item_dst = (torch.from_numpy(x[:max(ni, 1)]).to(dev) for x in a)
+        self.long_row, self.long_slot0, self.long_nslot = (torch.from_numpy(x[:max(nl, 1)]).to(dev) for x in b)
+        self.partial = torch.empty((max(ns, 1), max_d), dtype=torch.float32, device=dev) if ns else None
+        self.max_d = max_d
+
+    def struct(self):
+        if self._struct is None:
+            s = _abi.CsrStruct()
+            s.n_rows, s.n_cols, s.nnz = self.n_rows, self.n_cols, self.nnz
+            p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+            s.rowptr, s.colidx, s.vals = p(self.rowptr), p(self.colidx), p(self.vals)
+            s.nbr_scale, s.row_scale, s.eid = p(self.nbr_scale), p(self.row_scale), p(self.eid)
+            s.n_items = self.n_items
+            s.item_start, s.item_end, s.item_dst = p(self.item_start), p(self.item_end), p(self.item_dst)
+            s.n_long = self.n_long
+            s.long_row, s.long_slot0, s.long_nslot = p(self.long_row), p(self.long_slot0), p(self.long_nslot)
+            s.n_slots = self.n_slots
+            s.partial = p(self.partial)
+            self._struct = s
+        return self._struct
+
+    def with_scales(self, nbr_scale=None, row_scale=None):
+        """same structure/plan, different per-node scale vectors (IGCN anneal: F's values change every epoch)"""
+        o = object.__new__(CsrOperand)
+        o.__dict__.update(self.__dict__)
+        o.nbr_scale, o.row_scale, o._struct = nbr_scale, row_scale, None
+        return o
+
+    def row_slice(self, lo, hi):
+        """rows [lo, hi) as an operand that writes into the FULL output table at global row ids
+        (multi-GPU row partition: per-row sums are unchanged, so P-rank results equal 1-rank bit for bit)."""
+        o = object.__new__(CsrOperand)
+        o.__dict__.update(self.__dict__)
+        o._struct = None
+        keep_long = (self.long_row[:self.n_long] >= lo) & (self.long_row[:self.n_long] < hi) if self.n_long else None
+        dst = self.item_dst[:self.n_items]
+        is_row = dst >= 0
+        keep = is_row & (dst >= lo) & (dst < hi)
+        if self.n_long:
+            # pieces of split rows: slot -> owning long row
+            slot_owner = torch.repeat_interleave(self.long_row[:self.n_long].long(), self.long_nslot[:self.n_long].long())
+            piece = ~is_row
+            owner = torch.zeros_like(dst, dtype=torch.int64)
+            owner[piece] = slot_owner[(~dst[piece]).long()]
+            keep |= piece & (owner >= lo) & (owner < hi)
+        o.item_start = self.item_start[:self.n_items][keep].contiguous()
+        o.item_end = self.item_end[:self.n_items][keep].contiguous()
+        o.item_dst = self.item_dst[:self.n_items][keep].contiguous()
+        o.n_items = int(o.item_start.numel())
+        if self.n_long:
+            o.long_row = self.long_row[:self.n_long][keep_long].contiguous()
+            o.long_slot0 = self.long_slot0[:self.n_long][keep_long].contiguous()
+            o.long_nslot = self.long_nslot[:self.n_long][keep_long].contiguous()
+            o.n_long = int(o.long_row.numel())
+            for name in ("long_row", "long_slot0", "long_nslot"):
+                if getattr(o, name).numel() == 0:
+                    setattr(o, name, torch.zeros(1, dtype=torch.int32, device=self.device))
+        if o.n_items == 0:
+            for name in ("item_start", "item_end", "item_dst"):
+                setattr(o, name, torch.zeros(1, dtype=torch.int32, device=self.device))
+        return o
+
+    # ---- views for API compatibility / tests (the reference's norm_adj is a coalesced sparse COO tensor) ----
+    @property
+    def shape(self):
+        return torch.Size([self.n_rows, self.n_cols])
+
+    def _nnz(self):
+        return self.nnz
+
+    def coalesce(self):
+        return self
+
+    def indices(self):
+        r, c, _ = self.to_coo()
+        return torch.stack([r, c])
+
+    def values(self):
+        return self.vals
+
+    def to_coo(self):
+        rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.device),
+                                       (self.rowptr[1:] - self.rowptr[:-1]).long())
+        return rows, self.colidx.long(), self.vals
+
+
+def _rowptr_from_sorted_rows(rows, n_rows):
+    counts = torch.bincount(rows, minlength=n_rows)
+    rp = torch.zeros(n_rows + 1, dtype=torch.int64, device=rows.device)
+    torch.cumsum(counts, 0, out=rp[1:])
+    return rp
+
+
+def _coalesce(rows, cols, n_rows, n_cols):
+    """sort by (row, col), merge duplicates -> (rowptr int32, colidx int32, mult fp32 or None)"""
+    key = rows * n_cols + cols
+    key, _ = torch.sort(key)
+    uniq, counts = torch.unique_consecutive(key, return_counts=True)
+    r = torch.div(uniq, n_cols, rounding_mode="floor")
+    c = uniq - r * n_cols
+    mult = None
+    if uniq.numel() != key.numel():
+        mult = counts.to(torch.float32)
+    rp = _rowptr_from_sorted_rows(r, n_rows)
+    assert int(rp[-1]) < 2 ** 31, "nnz must fit int32"
+    return rp.to(torch.int32), c.to(torch.int32), mult
+
+
+def build_norm_adj(n_users, n_items, users, items, device=None):
+    """users/items: int64 tensors of the E train pairs (train_array, dataset.py:149-151), any order, duplicates allowed
+    (they are summed, like scipy's COO->CSR in utils.py:47-49).  Returns (CsrOperand with .vals/.dinv, mult)."""
+    device = torch.device(device) if device is not None else users.device
+    users, items = users.to(device, torch.int64), items.to(device, torch.int64)
+    n = n_users + n_items
+    rows = torch.cat([users, items + n_users])
+    cols = torch.cat([items + n_users, users])
+    rowptr, colidx, mult = _coalesce(rows, cols, n, n)
+    dinv = torch.empty(n, dtype=torch.float32, device=device)
+    vals = torch.empty(colidx.numel(), dtype=torch.float32, device=device)
+    lib = _abi.load()
+    _abi.require_cuda(rowptr)
+    _abi.check(lib.b200rec_adj_normalize(_abi.ptr(rowptr), _abi.ptr(colidx), _abi.ptr(mult), n, _abi.ptr(dinv),
+                                         _abi.ptr(vals), _abi.stream_ptr()), "adj_normalize")
+    op = CsrOperand(rowptr, colidx, n, vals=vals)
+    op.dinv = dinv
+    op.mult = mult
+    return op
+
+
+class FeatOperand:
+    """IGCN's F [N, T] (T = template users + template items + 2) and F^T, structure only: every value of row r is
+    row_sum[r] ** ((alpha-1)/2 - 0.5) (model.py:4127-4130), so the kernels take a per-row scale vector instead of
+    per-edge values; F^T stores the forward edge position (`eid`) so both directions share one dropout bitmask."""
+
+    def __init__(self, fwd, bwd, row_sum):
+        self.fwd, self.bwd, self.row_sum = fwd, bwd, row_sum
+        self.n_rows, self.n_cols, self.nnz = fwd.n_rows, fwd.n_cols, fwd.nnz
+
+    def row_scale(self, alpha):
+        return torch.pow(self.row_sum, (alpha - 1.) / 2. - 0.5)
+
+
+def build_feat(n_users, n_items, users, items, user_tmpl, item_tmpl, device=None):
+    """user_tmpl / item_tmpl: int64 [n_users] / [n_items], template column of each node or -1 (the reference's
+    user_map / item_map dicts).  Entry list follows model.py:4160-4169."""
+    device = torch.device(device) if device is not None else users.device
+    users, items = users.to(device, torch.int64), items.to(device, torch.int64)
+    user_tmpl, item_tmpl = user_tmpl.to(device), item_tmpl.to(device)
+    tu, ti = int((user_tmpl >= 0).sum()), int((item_tmpl >= 0).sum())
+    t = tu + ti + 2
+    n = n_users + n_items
+    mi = item_tmpl[items] >= 0
+    mu = user_tmpl[users] >= 0
+    ar_u = torch.arange(n_users, device=device)
+    ar_i = torch.arange(n_items, device=device)
+    rows = torch.cat([users[mi], n_users + items[mu], ar_u, n_users + ar_i])
+    cols = torch.cat([tu + item_tmpl[items[mi]], user_tmpl[users[mu]],
+                      torch.full_like(ar_u, tu + ti), torch.full_like(ar_i, tu + ti + 1)])
+    rowptr, colidx, mult = _coalesce(rows, cols, n, t)
+    if mult is None:
+        row_sum = (rowptr[1:] - rowptr[:-1]).to(torch.float32)
+    else:  # np.sum(feat, axis=1) counts duplicates
+        r = torch.repeat_interleave(torch.arange(n, device=device), (rowptr[1:] - rowptr[:-1]).long())
+        row_sum = torch.zeros(n, dtype=torch.float32, device=device).index_add_(0, r, mult)
+    fwd = CsrOperand(rowptr, colidx, t)
+    # transpose: sort edges by (col, row); remember the forward position of every edge
+    nnz = colidx.numel()
+    r = torch.repeat_interleave(torch.arange(n, device=device), (rowptr[1:] - rowptr[:-1]).long())
+    key = colidx.long() * n + r
+    key, eid = torch.sort(key)
+    tc = torch.div(key, n, rounding_mode="floor")
+    tr = key - tc * n
+    trp = _rowptr_from_sorted_rows(tc, t).to(torch.int32)
+    bwd = CsrOperand(trp, tr.to(torch.int32), n, eid=eid.to(torch.int32))
+    assert nnz == bwd.nnz
+    return FeatOperand(fwd, bwd, row_sum), tu, ti

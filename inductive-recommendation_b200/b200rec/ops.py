@@ -1,0 +1,209 @@
+"""Python wrappers + torch.autograd.Functions over the C ABI (include/b200rec.h).
+
+These are what the drop-in model.py calls where the reference calls dgl.ops.gspmm / advanced indexing:
+  propagate(A, X0, L)        == stack([X0, A X0, ..., A^L X0]).mean(0)     (model.py:100-110)
+  inductive_layer(F, E, ...) == dropout(F) @ E                             (model.py:4177-4190)
+  gather_rows(table, idx)    == table[idx + offset, :]  (+ squared norms)  (model.py:116-119)
+Everything runs on the current CUDA stream; nothing here falls back to torch math.
+"""
+import ctypes as C
+
+import torch
+
+from . import _abi
+from ._abi import check, ptr, stream_ptr
+
+
+def _lib():
+    return _abi.load()
+
+
+# ------------------------------------------------------------------------------------------------ raw calls
+def spmm(op, x, keep_bits=None, post_scale=1.0, y=None, addend=None, out=None, out_scale=1.0):
+    _abi.require_cuda(x, keep_bits, y, addend, out)
+    d = x.shape[1]
+    assert x.dtype == torch.float32 and x.shape[0] >= op.n_cols
+    assert op.partial is None or d <= op.max_d
+    check(_lib().b200rec_spmm_f32(C.byref(op.struct()), ptr(x), d, ptr(keep_bits), post_scale, ptr(y), ptr(addend),
+                                  ptr(out), out_scale, stream_ptr()), "spmm_f32")
+
+
+def propagate_fwd(op, x0, n_layers, bufs, mean_out):
+    _abi.require_cuda(x0, mean_out)
+    check(_lib().b200rec_propagate_fwd(C.byref(op.struct()), ptr(x0), x0.shape[1], n_layers, ptr(bufs[0]), ptr(bufs[1]),
+                                       ptr(mean_out), stream_ptr()), "propagate_fwd")
+
+
+def propagate_bwd(op, g, n_layers, bufs, dx0):
+    _abi.require_cuda(g, dx0)
+    check(_lib().b200rec_propagate_bwd(C.byref(op.struct()), ptr(g), g.shape[1], n_layers, ptr(bufs[0]), ptr(bufs[1]),
+                                       ptr(dx0), stream_ptr()), "propagate_bwd")
+
+
+def bpr_sample(user_ptr, user_items, n_users, n_items, seed, step, batch_size, out=None):
+    if out is None:
+        out = torch.empty((batch_size, 3), dtype=torch.int64, device=user_ptr.device)
+    _abi.require_cuda(user_ptr, user_items, step, out)
+    check(_lib().b200rec_bpr_sample(ptr(user_ptr), ptr(user_items), n_users, n_items, C.c_uint64(seed), ptr(step),
+                                    batch_size, ptr(out), stream_ptr()), "bpr_sample")
+    return out
+
+
+def bpr_scratch(batch_size, d, device):
+    n = int(_lib().b200rec_bpr_scratch_floats(batch_size, d))
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+def bpr_fwd_bwd(rep, batch, item_offset, l2_reg, reg_mode, g_rep, loss_out, scratch, w=None, g_w=None, loss_scale=1.0):
+    _abi.require_cuda(rep, batch, g_rep, loss_out, scratch, w, g_w)
+    assert batch.dtype == torch.int64 and batch.shape[1] == 3
+    check(_lib().b200rec_bpr_fwd_bwd(ptr(rep), rep.shape[1], ptr(batch), batch.shape[0], item_offset, l2_reg, reg_mode,
+                                     ptr(w), loss_scale, ptr(g_rep), ptr(g_w), ptr(loss_out), ptr(scratch),
+                                     stream_ptr()), "bpr_fwd_bwd")
+
+
+def bpr_l2_emb0(emb0, batch, item_offset, l2_reg, g_emb0, loss_out, scratch):
+    _abi.require_cuda(emb0, batch, g_emb0, loss_out, scratch)
+    check(_lib().b200rec_bpr_l2_emb0(ptr(emb0), emb0.shape[1], ptr(batch), batch.shape[0], item_offset, l2_reg,
+                                     ptr(g_emb0), ptr(loss_out), ptr(scratch), stream_ptr()), "bpr_l2_emb0")
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    _abi.require_cuda(param, grad, exp_avg, exp_avg_sq, step)
+    check(_lib().b200rec_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
+                                   eps, ptr(step), stream_ptr()), "adam_step")
+
+
+def step_advance(step, step_b=None, loss=None, loss_accum=None, n_batch=0):
+    check(_lib().b200rec_step_advance(ptr(step), ptr(step_b), ptr(loss), ptr(loss_accum), n_batch, stream_ptr()),
+          "step_advance")
+
+
+def dropout_bits(nnz, p, seed, step, out=None):
+    """device-drawn edge-dropout keep mask (uint32 words viewed as int32), step: device int64 scalar"""
+    if out is None:
+        out = torch.empty((nnz + 31) // 32, dtype=torch.int32, device=step.device)
+    _abi.require_cuda(step, out)
+    check(_lib().b200rec_dropout_mask(nnz, p, C.c_uint64(seed), ptr(step), ptr(out), stream_ptr()), "dropout_mask")
+    return out
+
+
+def score_dense(rep_users, users, rep_items):
+    _abi.require_cuda(rep_users, users, rep_items)
+    out = torch.empty((users.numel(), rep_items.shape[0]), dtype=torch.float32, device=rep_users.device)
+    check(_lib().b200rec_score_dense_f32(ptr(rep_users), ptr(users), users.numel(), ptr(rep_items), rep_items.shape[0],
+                                         rep_items.shape[1], ptr(out), stream_ptr()), "score_dense_f32")
+    return out
+
+
+def score_topk(rep_users, users, rep_items, k, excl_a=None, excl_b=None, banned=None, precision=0):
+    """excl_a / excl_b: (ptr int32 [n_all_users+1], idx int32) sorted CSR by ABSOLUTE user id; banned: (lo, hi)."""
+    _abi.require_cuda(rep_users, users, rep_items)
+    nb, ni, d = users.numel(), rep_items.shape[0], rep_items.shape[1]
+    ws_bytes = int(_lib().b200rec_score_topk_workspace(nb, ni, d, k, precision))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=rep_users.device)
+    ids = torch.empty((nb, k), dtype=torch.int32, device=rep_users.device)
+    sc = torch.empty((nb, k), dtype=torch.float32, device=rep_users.device)
+    ea = excl_a if excl_a is not None else (None, None)
+    eb = excl_b if excl_b is not None else (None, None)
+    lo, hi = banned if banned is not None else (0, 0)
+    check(_lib().b200rec_score_topk(ptr(rep_users), ptr(users), nb, ptr(rep_items), ni, d, ptr(ea[0]), ptr(ea[1]),
+                                    ptr(eb[0]), ptr(eb[1]), lo, hi, k, precision, ptr(ids), ptr(sc), ptr(ws),
+                                    stream_ptr()), "score_topk")
+    return ids, sc
+
+
+def hit_matrix(rec_ids, user0, eval_ptr, eval_idx):
+    _abi.require_cuda(rec_ids, eval_ptr, eval_idx)
+    hit = torch.empty(rec_ids.shape, dtype=torch.float32, device=rec_ids.device)
+    check(_lib().b200rec_hit_matrix(ptr(rec_ids), rec_ids.shape[0], rec_ids.shape[1], user0, ptr(eval_ptr), ptr(eval_idx),
+                                    ptr(hit), stream_ptr()), "hit_matrix")
+    return hit
+
+
+def pack_keep_bits(keep_bool):
+    """bool [nnz] (CSR edge order) -> uint32 words, bit e&31 of word e>>5"""
+    nnz = keep_bool.numel()
+    pad = (-nnz) % 32
+    k = torch.cat([keep_bool.to(torch.int64), torch.zeros(pad, dtype=torch.int64, device=keep_bool.device)])
+    w = (k.view(-1, 32) << torch.arange(32, device=k.device)).sum(1)
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)  # two's-complement view of the 32-bit word
+    return w.to(torch.int32)
+
+
+# ------------------------------------------------------------------------------------------------ autograd
+class _Propagate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, op, n_layers):
+        x0 = x0.contiguous()
+        n, d = x0.shape
+        bufs = [torch.empty_like(x0) if n_layers >= 2 + i else None for i in range(2)]
+        out = torch.empty_like(x0)
+        propagate_fwd(op, x0, n_layers, bufs, out)
+        ctx.op, ctx.n_layers = op, n_layers
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        n_layers = ctx.n_layers
+        bufs = [torch.empty_like(g) if n_layers >= 2 + i else None for i in range(2)]
+        dx0 = torch.empty_like(g)
+        propagate_bwd(ctx.op, g, n_layers, bufs, dx0)
+        return dx0, None, None
+
+
+def propagate(op, x0, n_layers):
+    """mean over layers of A^k X0, k = 0..L (differentiable w.r.t. x0)"""
+    return _Propagate.apply(x0, op, n_layers)
+
+
+class _InductiveLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, feat, row_scale, keep_bits, inv_keep):
+        emb = emb.contiguous()
+        out = torch.empty((feat.n_rows, emb.shape[1]), dtype=torch.float32, device=emb.device)
+        spmm(feat.fwd.with_scales(row_scale=row_scale), emb, keep_bits=keep_bits, post_scale=inv_keep, y=out)
+        ctx.feat, ctx.row_scale, ctx.keep_bits, ctx.inv_keep = feat, row_scale, keep_bits, inv_keep
+        ctx.t = emb.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        demb = torch.empty((ctx.t, g.shape[1]), dtype=torch.float32, device=g.device)
+        spmm(ctx.feat.bwd.with_scales(nbr_scale=ctx.row_scale), g, keep_bits=ctx.keep_bits, post_scale=ctx.inv_keep, y=demb)
+        return demb, None, None, None, None
+
+
+def inductive_layer(feat, emb, row_scale, keep_bits=None, inv_keep=1.0):
+    """X0 = dropout(F) @ E_T with F[r, c] = row_scale[r] (model.py:4177-4190)"""
+    return _InductiveLayer.apply(emb, feat, row_scale, keep_bits, inv_keep)
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, idx, offset):
+        table = table.contiguous()
+        idx = idx.contiguous()
+        n, d = idx.numel(), table.shape[1]
+        out = torch.empty((n, d), dtype=torch.float32, device=table.device)
+        _abi.require_cuda(table, idx)
+        check(_lib().b200rec_gather_rows(ptr(table), d, ptr(idx), offset, n, ptr(out), None, stream_ptr()), "gather_rows")
+        ctx.save_for_backward(idx)
+        ctx.offset, ctx.shape = offset, table.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = g.contiguous()
+        dt = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        check(_lib().b200rec_scatter_add_rows(ptr(dt), g.shape[1], ptr(idx), ctx.offset, idx.numel(), ptr(g),
+                                              stream_ptr()), "scatter_add_rows")
+        return dt, None, None
+
+
+def gather_rows(table, idx, offset=0):
+    """table[idx + offset, :] with a scatter-add backward (the index_put_(accumulate) of autograd)"""
+    return _GatherRows.apply(table, idx, offset)

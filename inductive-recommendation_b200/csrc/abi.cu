@@ -1,0 +1,11 @@
+// Library-wide state of libb200rec.so: error text, launch counter, version.
+#include "common.cuh"
+
+namespace b200rec {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+}  // namespace b200rec
+
+extern "C" const char* b200rec_last_error(void) { return b200rec::g_err; }
+extern "C" int b200rec_version(void) { return 100; }
+extern "C" uint64_t b200rec_launch_count(void) { return b200rec::g_launches.load(); }

@@ -1,0 +1,447 @@
+// BPR step kernels: device sampler, row gather / scatter-add, fused BPR forward+backward, layer-0 L2, Adam.
+// Reference: dataset.py:119-131 (sampler), model.py:112-120 / :4046-4052 / :66-71 (bpr_forward),
+// trainer.py:414-428 / :542-553 (loss, backward, optimiser step).
+#include "common.cuh"
+
+namespace b200rec {
+
+// ---------------------------------------------------------------------------------------------- sampler
+__device__ __forceinline__ void philox_pair(uint64_t seed, uint32_t slot, uint64_t step, uint32_t draw, uint64_t& a,
+                                            uint64_t& b) {
+  uint32_t c[4] = {slot, (uint32_t)step, draw, (uint32_t)(step >> 32)};
+  Philox::gen(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  a = (uint64_t)c[0] | ((uint64_t)c[1] << 32);
+  b = (uint64_t)c[2] | ((uint64_t)c[3] << 32);
+}
+__device__ __forceinline__ bool row_contains(const int32_t* row, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int v = __ldg(row + mid);
+    if (v < key) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && __ldg(row + lo) == key;
+}
+__global__ void bpr_sample_kernel(const int32_t* __restrict__ user_ptr, const int32_t* __restrict__ user_items,
+                                  int n_users, int n_items, uint64_t seed, const int64_t* __restrict__ step_ptr,
+                                  int batch, int64_t* __restrict__ out) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= batch) return;
+  const uint64_t step = (uint64_t)(*step_ptr);
+  uint32_t draw = 0;
+  uint64_t a, b;
+  int user = 0, s = 0, deg = 0;
+  for (;; ++draw) {  // user uniform, redrawn while its train row is empty (dataset.py:120-122)
+    philox_pair(seed, (uint32_t)slot, step, draw, a, b);
+    user = (int)__umul64hi(a, (uint64_t)n_users);
+    s = __ldg(user_ptr + user);
+    deg = __ldg(user_ptr + user + 1) - s;
+    if (deg > 0 || draw > (1u << 20)) break;
+  }
+  const int32_t* row = user_items + s;
+  const int pos = deg > 0 ? __ldg(row + (int)__umul64hi(b, (uint64_t)deg)) : 0;  // np.random.choice(train_data[user])
+  int neg = 0;
+  for (++draw;; ++draw) {  // negative uniform over items, rejected while in the row (dataset.py:126-128)
+    philox_pair(seed, (uint32_t)slot, step, draw, a, b);
+    neg = (int)__umul64hi(a, (uint64_t)n_items);
+    if (!row_contains(row, deg, neg)) break;
+    neg = (int)__umul64hi(b, (uint64_t)n_items);
+    if (!row_contains(row, deg, neg) || draw > (1u << 20)) break;
+  }
+  out[3 * (size_t)slot + 0] = user;
+  out[3 * (size_t)slot + 1] = pos;
+  out[3 * (size_t)slot + 2] = neg;
+}
+
+// Edge-dropout keep mask of NGCF.dropout_sp_mat (model.py:4016-4021): keep[e] = floor((1-p) + r[e]) with r uniform in
+// [0,1) at 24-bit resolution (torch.rand fp32).  The reference draws r on the CPU generator; the device stream is
+// Philox4x32-10, key = seed, counter = (e >> 2, step_lo, step_hi, 0xD0), lane e & 3.  One thread fills one 32-bit word.
+__global__ void dropout_mask_kernel(int nnz, float keep_base, uint64_t seed, const int64_t* __restrict__ step_ptr,
+                                    uint32_t* __restrict__ bits) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_words = (nnz + 31) >> 5;
+  if (w >= n_words) return;
+  const uint64_t step = (uint64_t)(*step_ptr);
+  uint32_t word = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t c[4] = {(uint32_t)(w * 8 + j), (uint32_t)step, (uint32_t)(step >> 32), 0xD0u};
+    Philox::gen(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float r = (float)(c[q] >> 8) * (1.0f / 16777216.0f);
+      if (floorf(keep_base + r) >= 1.f) word |= 1u << (j * 4 + q);
+    }
+  }
+  const int rem = nnz - w * 32;
+  if (rem < 32) word &= (1u << rem) - 1u;
+  bits[w] = word;
+}
+
+// ---------------------------------------------------------------------------------------------- gather / scatter
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
+                                                          int64_t offset, int n, float* __restrict__ out,
+                                                          float* __restrict__ sqnorm) {
+  constexpr int D = G * VPL * 4;
+  const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G), gl = threadIdx.x & (G - 1);
+  const bool active = g < n;
+  const int64_t row = active ? idx[g] + offset : 0;
+  float ss = 0.f;
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    const int c = (gl + t * G) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+      v = ldg_f4(table + (size_t)row * D + c);
+      st_f4(out + (size_t)g * D + c, v);
+    }
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = group_sum<G>(ss);
+  if (active && sqnorm && gl == 0) sqnorm[g] = ss;
+}
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(float* __restrict__ table, const int64_t* __restrict__ idx,
+                                                               int64_t offset, int n, const float* __restrict__ src) {
+  constexpr int D = G * VPL * 4;
+  const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G), gl = threadIdx.x & (G - 1);
+  if (g >= n) return;
+  const int64_t row = idx[g] + offset;
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    const int c = (gl + t * G) * 4;
+    red_add_f4(table + (size_t)row * D + c, ldg_f4(src + (size_t)g * D + c));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fused BPR
+// Deterministic cross-block reduction: every block stores its partial, the last block to finish (ticket counter in
+// scratch[0], self-resetting) adds the partials in block order.
+__device__ __forceinline__ bool last_block_ticket(float* scratch) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* counter = reinterpret_cast<unsigned*>(scratch);
+    const unsigned t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // F.softplus defaults
+// derivative torch uses for softplus: z/(z+1) with z = exp(x) (x <= threshold), else 1
+__device__ __forceinline__ float sigmoid_t(float x) {
+  if (x > 20.f) return 1.f;
+  const float z = expf(x);
+  return z / (z + 1.f);
+}
+
+template <int G, int VPL, bool HAS_W>
+__global__ void __launch_bounds__(256) bpr_fused_kernel(const float* __restrict__ rep, const int64_t* __restrict__ batch,
+                                                        int n_batch, int64_t item_offset, float l2_reg, int reg_mode,
+                                                        const float* __restrict__ w, float loss_scale,
+                                                        float* __restrict__ g_rep, float* __restrict__ g_w,
+                                                        float* __restrict__ loss_out, float* scratch) {
+  constexpr int D = G * VPL * 4;
+  constexpr int SPB = 256 / G;  // samples per block
+  __shared__ float s_loss[SPB];
+  __shared__ float s_w[HAS_W ? SPB : 1][HAS_W ? D : 1];
+  const int gib = threadIdx.x / G, gl = threadIdx.x & (G - 1);
+  const int smp = blockIdx.x * SPB + gib;
+  const bool active = smp < n_batch;
+  int64_t ru = 0, rp = 0, rn = 0;
+  if (active) {
+    ru = batch[3 * (size_t)smp];
+    rp = batch[3 * (size_t)smp + 1] + item_offset;
+    rn = batch[3 * (size_t)smp + 2] + item_offset;
+  }
+  float4 u[VPL], p[VPL], n[VPL], wv[VPL];
+  float pos = 0.f, neg = 0.f, l2 = 0.f;
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    const int c = (gl + t * G) * 4;
+    u[t] = p[t] = n[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wv[t] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (active) {
+      u[t] = ldg_f4(rep + (size_t)ru * D + c);
+      p[t] = ldg_f4(rep + (size_t)rp * D + c);
+      n[t] = ldg_f4(rep + (size_t)rn * D + c);
+      if constexpr (HAS_W) wv[t] = ldg_f4(w + c);
+    }
+    pos += u[t].x * p[t].x * wv[t].x + u[t].y * p[t].y * wv[t].y + u[t].z * p[t].z * wv[t].z + u[t].w * p[t].w * wv[t].w;
+    neg += u[t].x * n[t].x * wv[t].x + u[t].y * n[t].y * wv[t].y + u[t].z * n[t].z * wv[t].z + u[t].w * n[t].w * wv[t].w;
+    l2 += u[t].x * u[t].x + u[t].y * u[t].y + u[t].z * u[t].z + u[t].w * u[t].w;
+    l2 += p[t].x * p[t].x + p[t].y * p[t].y + p[t].z * p[t].z + p[t].w * p[t].w;
+    l2 += n[t].x * n[t].x + n[t].y * n[t].y + n[t].z * n[t].z + n[t].w * n[t].w;
+  }
+  pos = group_sum<G>(pos);
+  neg = group_sum<G>(neg);
+  l2 = group_sum<G>(l2);
+  const float x = neg - pos;
+  const float inv_b = 1.f / (float)n_batch;
+  float loss = softplus_t(x);
+  if (reg_mode == 1) loss += l2_reg * l2;
+  const float coef = loss_scale * inv_b * sigmoid_t(x);
+  const float rc = (reg_mode == 1) ? 2.f * l2_reg * loss_scale * inv_b : 0.f;
+  if (active) {
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int c = (gl + t * G) * 4;
+      const float4 cw = make_float4(coef * wv[t].x, coef * wv[t].y, coef * wv[t].z, coef * wv[t].w);
+      float4 gu = make_float4(cw.x * (n[t].x - p[t].x) + rc * u[t].x, cw.y * (n[t].y - p[t].y) + rc * u[t].y,
+                              cw.z * (n[t].z - p[t].z) + rc * u[t].z, cw.w * (n[t].w - p[t].w) + rc * u[t].w);
+      float4 gp = make_float4(-cw.x * u[t].x + rc * p[t].x, -cw.y * u[t].y + rc * p[t].y, -cw.z * u[t].z + rc * p[t].z,
+                              -cw.w * u[t].w + rc * p[t].w);
+      float4 gn = make_float4(cw.x * u[t].x + rc * n[t].x, cw.y * u[t].y + rc * n[t].y, cw.z * u[t].z + rc * n[t].z,
+                              cw.w * u[t].w + rc * n[t].w);
+      red_add_f4(g_rep + (size_t)ru * D + c, gu);
+      red_add_f4(g_rep + (size_t)rp * D + c, gp);
+      red_add_f4(g_rep + (size_t)rn * D + c, gn);
+      if constexpr (HAS_W) {  // d(score)/dw = u * (n - p)
+        s_w[gib][c + 0] = coef * u[t].x * (n[t].x - p[t].x);
+        s_w[gib][c + 1] = coef * u[t].y * (n[t].y - p[t].y);
+        s_w[gib][c + 2] = coef * u[t].z * (n[t].z - p[t].z);
+        s_w[gib][c + 3] = coef * u[t].w * (n[t].w - p[t].w);
+      }
+    }
+  } else if constexpr (HAS_W) {
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int c = (gl + t * G) * 4;
+      s_w[gib][c] = s_w[gib][c + 1] = s_w[gib][c + 2] = s_w[gib][c + 3] = 0.f;
+    }
+  }
+  if (gl == 0) s_loss[gib] = active ? loss : 0.f;
+  __syncthreads();
+  // block partials -> scratch[1 + block], scratch[1 + gridDim + block*D + d]
+  float* part_loss = scratch + 4;
+  float* part_w = scratch + 4 + gridDim.x;
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < SPB; ++i) acc += s_loss[i];
+    part_loss[blockIdx.x] = acc;
+  }
+  if constexpr (HAS_W) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float acc = 0.f;
+      for (int i = 0; i < SPB; ++i) acc += s_w[i][d];
+      part_w[(size_t)blockIdx.x * D + d] = acc;
+    }
+  }
+  if (!last_block_ticket(scratch)) return;
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (unsigned i = 0; i < gridDim.x; ++i) acc += __ldcg(part_loss + i);
+    *loss_out += loss_scale * acc * inv_b;
+  }
+  if (HAS_W) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float acc = 0.f;
+      for (unsigned i = 0; i < gridDim.x; ++i) acc += __ldcg(part_w + (size_t)i * D + d);
+      g_w[d] = acc;
+    }
+  }
+}
+
+// LightGCN regulariser on layer-0 rows (model.py:114-117)
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) bpr_l2_emb0_kernel(const float* __restrict__ emb0, const int64_t* __restrict__ batch,
+                                                          int n_batch, int64_t item_offset, float l2_reg,
+                                                          float* __restrict__ g_emb0, float* __restrict__ loss_out,
+                                                          float* scratch) {
+  constexpr int D = G * VPL * 4;
+  constexpr int SPB = 256 / G;
+  __shared__ float s_loss[SPB];
+  const int gib = threadIdx.x / G, gl = threadIdx.x & (G - 1);
+  const int smp = blockIdx.x * SPB + gib;
+  const bool active = smp < n_batch;
+  const float inv_b = 1.f / (float)n_batch;
+  const float rc = 2.f * l2_reg * inv_b;
+  float l2 = 0.f;
+  if (active) {
+    int64_t rows[3] = {batch[3 * (size_t)smp], batch[3 * (size_t)smp + 1] + item_offset,
+                       batch[3 * (size_t)smp + 2] + item_offset};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) {
+        const int c = (gl + t * G) * 4;
+        const float4 e = ldg_f4(emb0 + (size_t)rows[q] * D + c);
+        l2 += e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+        red_add_f4(g_emb0 + (size_t)rows[q] * D + c, make_float4(rc * e.x, rc * e.y, rc * e.z, rc * e.w));
+      }
+    }
+  }
+  l2 = group_sum<G>(l2);
+  if (gl == 0) s_loss[gib] = active ? l2 : 0.f;
+  __syncthreads();
+  float* part_loss = scratch + 4;
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < SPB; ++i) acc += s_loss[i];
+    part_loss[blockIdx.x] = acc;
+  }
+  if (!last_block_ticket(scratch)) return;
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (unsigned i = 0; i < gridDim.x; ++i) acc += __ldcg(part_loss + i);
+    *loss_out += l2_reg * acc * inv_b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- Adam
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
+                                                   float eps, const int64_t* __restrict__ step_ptr) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step_ptr + 1);
+    const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+    s_step_size = (float)((double)lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = (float)(1.0 - (double)beta1), w2 = (float)(1.0 - (double)beta2);
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 gg = ld_f4(g + 4 * i);
+    float4 mm = ld_f4(m + 4 * i), vv = ld_f4(v + 4 * i), pp = ld_f4(p + 4 * i);
+#define B2_ADAM1(c)                                                            \
+    mm.c = mm.c + w1 * (gg.c - mm.c);            /* exp_avg.lerp_(grad, 1-b1) */ \
+    vv.c = vv.c * beta2 + (w2 * gg.c) * gg.c;    /* mul_(b2).addcmul_(g,g,1-b2) */ \
+    pp.c = pp.c - step_size * (mm.c / (sqrtf(vv.c) / bc2_sqrt + eps));
+    B2_ADAM1(x) B2_ADAM1(y) B2_ADAM1(z) B2_ADAM1(w)
+    st_f4(m + 4 * i, mm); st_f4(v + 4 * i, vv); st_f4(p + 4 * i, pp);
+  }
+  // tail (n not a multiple of 4)
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float gg = g[i];
+    float mm = m[i], vv = v[i];
+    mm = mm + w1 * (gg - mm);
+    vv = vv * beta2 + (w2 * gg) * gg;
+    p[i] = p[i] - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    m[i] = mm; v[i] = vv;
+  }
+#undef B2_ADAM1
+}
+
+__global__ void step_advance_kernel(int64_t* step, int64_t* step_b, const float* loss, double* loss_accum, int n_batch) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (step) *step += 1;
+    if (step_b) *step_b += 1;
+    if (loss && loss_accum) {  // AverageMeter.update(loss.item(), B)  (utils.py:286-289)
+      loss_accum[0] += (double)(*loss) * (double)n_batch;
+      loss_accum[1] += (double)n_batch;
+    }
+  }
+}
+
+template <int G, int VPL>
+static int launch_bpr(const float* rep, const int64_t* batch, int nb, int64_t off, float l2_reg, int reg_mode,
+                      const float* w, float loss_scale, float* g_rep, float* g_w, float* loss_out, float* scratch,
+                      cudaStream_t st) {
+  const int grid = ceil_div(nb, 256 / G);
+  if (w) bpr_fused_kernel<G, VPL, true><<<grid, 256, 0, st>>>(rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch);
+  else bpr_fused_kernel<G, VPL, false><<<grid, 256, 0, st>>>(rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch);
+  B2_LAUNCHED();
+  return 0;
+}
+
+}  // namespace b200rec
+using namespace b200rec;
+
+#define B2_DISPATCH_D(d, ...)                                                                                     \
+  switch (d) {                                                                                                    \
+    case 16: { constexpr int G = 4, VPL = 1; __VA_ARGS__; } break;                                                       \
+    case 32: { constexpr int G = 8, VPL = 1; __VA_ARGS__; } break;                                                       \
+    case 64: { constexpr int G = 16, VPL = 1; __VA_ARGS__; } break;                                                      \
+    case 128: { constexpr int G = 32, VPL = 1; __VA_ARGS__; } break;                                                     \
+    case 256: { constexpr int G = 32, VPL = 2; __VA_ARGS__; } break;                                                     \
+    default: return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", __func__, "embedding size must be 16/32/64/128/256"); \
+  }
+
+extern "C" int b200rec_bpr_sample(const int32_t* user_ptr, const int32_t* user_items, int32_t n_users, int32_t n_items,
+                                  uint64_t seed, const int64_t* step, int32_t batch, int64_t* out_batch, void* stream) {
+  B2_REQUIRE(user_ptr && user_items && step && out_batch && n_users > 0 && n_items > 0 && batch > 0, "bad argument");
+  bpr_sample_kernel<<<ceil_div(batch, 128), 128, 0, (cudaStream_t)stream>>>(user_ptr, user_items, n_users, n_items, seed,
+                                                                           step, batch, out_batch);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_gather_rows(const float* table, int32_t d, const int64_t* idx, int64_t offset, int32_t n,
+                                   float* out, float* sqnorm, void* stream) {
+  B2_REQUIRE(table && idx && out && n >= 0, "bad argument");
+  if (n == 0) return 0;
+  B2_DISPATCH_D(d, (gather_rows_kernel<G, VPL><<<ceil_div(n, 256 / G), 256, 0, (cudaStream_t)stream>>>(table, idx, offset, n, out, sqnorm)));
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_scatter_add_rows(float* table, int32_t d, const int64_t* idx, int64_t offset, int32_t n,
+                                        const float* src, void* stream) {
+  B2_REQUIRE(table && idx && src && n >= 0, "bad argument");
+  if (n == 0) return 0;
+  B2_DISPATCH_D(d, (scatter_add_rows_kernel<G, VPL><<<ceil_div(n, 256 / G), 256, 0, (cudaStream_t)stream>>>(table, idx, offset, n, src)));
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int64_t b200rec_bpr_scratch_floats(int32_t n_batch, int32_t d) {
+  if (d < 16) d = 16;
+  const int64_t blocks = (n_batch + (256 / (d / 4 > 32 ? 32 : d / 4)) - 1) / (256 / (d / 4 > 32 ? 32 : d / 4));
+  return 4 + blocks * (int64_t)(d + 1);
+}
+
+extern "C" int b200rec_bpr_fwd_bwd(const float* rep, int32_t d, const int64_t* batch, int32_t n_batch, int64_t item_offset,
+                                   float l2_reg, int32_t reg_mode, const float* w, float loss_scale, float* g_rep,
+                                   float* g_w, float* loss_out, float* block_scratch, void* stream) {
+  B2_REQUIRE(rep && batch && g_rep && loss_out && block_scratch && n_batch > 0, "bad argument");
+  B2_REQUIRE(reg_mode == 0 || reg_mode == 1, "reg_mode must be 0 or 1 (layer-0 L2 is b200rec_bpr_l2_emb0)");
+  B2_REQUIRE(!w || g_w, "g_w required with w");
+  B2_DISPATCH_D(d, { int rc = launch_bpr<G, VPL>(rep, batch, n_batch, item_offset, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, block_scratch, (cudaStream_t)stream); if (rc) return rc; });
+  return 0;
+}
+
+extern "C" int b200rec_bpr_l2_emb0(const float* emb0, int32_t d, const int64_t* batch, int32_t n_batch, int64_t item_offset,
+                                   float l2_reg, float* g_emb0, float* loss_out, float* block_scratch, void* stream) {
+  B2_REQUIRE(emb0 && batch && g_emb0 && loss_out && block_scratch && n_batch > 0, "bad argument");
+  B2_DISPATCH_D(d, (bpr_l2_emb0_kernel<G, VPL><<<ceil_div(n_batch, 256 / G), 256, 0, (cudaStream_t)stream>>>(emb0, batch, n_batch, item_offset, l2_reg, g_emb0, loss_out, block_scratch)));
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                 float beta1, float beta2, float eps, const int64_t* step, void* stream) {
+  B2_REQUIRE(param && grad && exp_avg && exp_avg_sq && step && n > 0, "bad argument");
+  B2_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, "16-byte alignment");
+  int grid = ceil_div(n / 4 + 1, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_dropout_mask(int32_t nnz, float p, uint64_t seed, const int64_t* step, uint32_t* keep_bits,
+                                    void* stream) {
+  B2_REQUIRE(nnz > 0 && step && keep_bits && p >= 0.f && p < 1.f, "bad argument");
+  const int n_words = (nnz + 31) >> 5;
+  dropout_mask_kernel<<<ceil_div(n_words, 256), 256, 0, (cudaStream_t)stream>>>(nnz, (float)(1.0 - (double)p), seed, step,
+                                                                               keep_bits);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_step_advance(int64_t* step, int64_t* step_b, const float* loss, double* loss_accum, int32_t n_batch,
+                                    void* stream) {
+  step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step, step_b, loss, loss_accum, n_batch);
+  B2_LAUNCHED();
+  return 0;
+}

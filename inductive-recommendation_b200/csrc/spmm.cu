@@ -1,0 +1,356 @@
+// CSR SpMM with fused epilogue: the propagation leaf (model.py:106, :4184, :4196 dgl.ops.gspmm 'mul','sum').
+//
+// Mapping: one group of G = D/4 lanes owns one work item (a row, or a chunk of a hub row).  Each lane keeps a
+// float4 slice of the row sum, so a gathered neighbour row is one 128-bit load per lane, 256 B (D=64, two rows per
+// warp) or 512 B (D=128) fully coalesced.  Column ids / values are loaded G at a time, coalesced, and broadcast
+// with width-G shuffles; U neighbour rows are in flight per lane before the FMAs retire them.  The sum runs in CSR
+// order, so results do not depend on the grid, the item order or (multi-GPU) the row partition.
+#include "common.cuh"
+
+namespace b200rec {
+
+struct SpmmParams {
+  const int32_t* colidx;
+  const float* vals;
+  const float* nbr_scale;
+  const float* row_scale;
+  const int32_t* eid;
+  const uint32_t* keep_bits;
+  const int32_t* item_start;
+  const int32_t* item_end;
+  const int32_t* item_dst;
+  int n_items;
+  const float* x;
+  float* y;
+  const float* addend;
+  float* out;
+  float out_scale;
+  float post_scale;
+  float* partial;
+};
+
+template <int G, int VPL>
+__device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int gl, float4 (&acc)[VPL]) {
+  constexpr int D = G * VPL * 4;
+  float sc = p.post_scale;
+  if (p.row_scale) sc *= __ldg(p.row_scale + row);
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    const size_t off = (size_t)row * D + (size_t)(gl + t * G) * 4;
+    float4 s = make_float4(acc[t].x * sc, acc[t].y * sc, acc[t].z * sc, acc[t].w * sc);
+    if (p.y) st_f4(p.y + off, s);
+    if (p.out) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.addend) a = ld_f4(p.addend + off);
+      const float os = p.out_scale;
+      st_f4(p.out + off, make_float4((a.x + s.x) * os, (a.y + s.y) * os, (a.z + s.z) * os, (a.w + s.w) * os));
+    }
+  }
+}
+
+template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID>
+__global__ void __launch_bounds__(256) spmm_items_kernel(const SpmmParams p) {
+  constexpr int D = G * VPL * 4;
+  constexpr int U = (G >= 8) ? 8 : G;  // neighbour rows in flight per lane
+  constexpr int GPW = 32 / G;          // groups per warp
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int item = warp * GPW + lane / G;
+  int start = 0, end = 0, dst = 0;
+  if (item < p.n_items) {
+    start = __ldg(p.item_start + item);
+    end = __ldg(p.item_end + item);
+    dst = __ldg(p.item_dst + item);
+  }
+  int maxlen = end - start;
+  if (GPW > 1) {
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  }
+  float4 acc[VPL];
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* __restrict__ xg = p.x + (size_t)gl * 4;
+
+  for (int base = 0; base < maxlen; base += G) {
+    const int k = start + base + gl;
+    int c = -1;
+    float v = 1.f;
+    if (k < end) {
+      c = ld_stream_i32(p.colidx + k);
+      if (HAS_VALS) v = ld_stream_f32(p.vals + k);
+      if (HAS_MASK) {
+        const int e = HAS_EID ? ld_stream_i32(p.eid + k) : k;
+        if (!((__ldg(p.keep_bits + (e >> 5)) >> (e & 31)) & 1u)) c = -1;
+      }
+      if (HAS_NBR && c >= 0) v *= __ldg(p.nbr_scale + c);
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < G; j0 += U) {
+      if (base + j0 >= maxlen) break;  // warp-uniform
+      float4 xv[U][VPL];
+      float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cc = __shfl_sync(0xffffffffu, c, j0 + u, G);
+        vv[u] = __shfl_sync(0xffffffffu, v, j0 + u, G);
+        if (cc >= 0) {
+          const float* r = xg + (size_t)cc * D;
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) xv[u][t] = ldg_f4(r + t * G * 4);
+        } else {
+          vv[u] = 0.f;
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) xv[u][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) {
+          acc[t].x = fmaf(vv[u], xv[u][t].x, acc[t].x);
+          acc[t].y = fmaf(vv[u], xv[u][t].y, acc[t].y);
+          acc[t].z = fmaf(vv[u], xv[u][t].z, acc[t].z);
+          acc[t].w = fmaf(vv[u], xv[u][t].w, acc[t].w);
+        }
+      }
+    }
+  }
+  if (item >= p.n_items) return;
+  if (dst >= 0) {
+    epilogue_row<G, VPL>(p, dst, gl, acc);
+  } else {  // a chunk of a split row: raw partial sum, scaled by the reducer
+    const int slot = ~dst;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) st_f4(p.partial + (size_t)slot * D + (size_t)(gl + t * G) * 4, acc[t]);
+  }
+}
+
+// one group per split row: add its slots in slot order, then the common epilogue
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) spmm_long_reduce_kernel(const SpmmParams p, const int32_t* long_row,
+                                                                const int32_t* long_slot0, const int32_t* long_nslot,
+                                                                int n_long) {
+  constexpr int D = G * VPL * 4;
+  const int gidx = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G);
+  const int gl = threadIdx.x & (G - 1);
+  if (gidx >= n_long) return;
+  const int row = long_row[gidx], s0 = long_slot0[gidx], ns = long_nslot[gidx];
+  float4 acc[VPL];
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < ns; ++s) {
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const float4 v = ld_f4(p.partial + (size_t)(s0 + s) * D + (size_t)(gl + t * G) * 4);
+      acc[t].x += v.x; acc[t].y += v.y; acc[t].z += v.z; acc[t].w += v.w;
+    }
+  }
+  epilogue_row<G, VPL>(p, row, gl, acc);
+}
+
+template <int G, int VPL>
+static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t st) {
+  constexpr int GPW = 32 / G;
+  const int items_per_block = 8 * GPW;
+  if (a->n_items > 0) {
+    const int grid = ceil_div(a->n_items, items_per_block);
+    const bool hv = p.vals != nullptr, hn = p.nbr_scale != nullptr, hm = p.keep_bits != nullptr, he = p.eid != nullptr && hm;
+#define B2_SPMM_CASE(V, N, M, E)                                                  \
+  if (hv == V && hn == N && hm == M && he == E) {                                 \
+    spmm_items_kernel<G, VPL, V, N, M, E><<<grid, 256, 0, st>>>(p);               \
+    B2_LAUNCHED();                                                                \
+  } else
+    B2_SPMM_CASE(true, false, false, false)   // normalised adjacency
+    B2_SPMM_CASE(false, false, false, false)  // template features, eval
+    B2_SPMM_CASE(false, false, true, false)   // template features, training (edge dropout)
+    B2_SPMM_CASE(false, true, false, false)   // transposed features (backward), eval-mode graph
+    B2_SPMM_CASE(false, true, true, true)     // transposed features (backward), dropout mask by edge id
+    B2_SPMM_CASE(true, false, true, false)    // valued operand with dropout
+    B2_SPMM_CASE(true, true, false, false)
+    { return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "operand combination (vals/nbr_scale/keep_bits/eid) not instantiated"); }
+#undef B2_SPMM_CASE
+  }
+  if (a->n_long > 0) {
+    const int groups_per_block = 256 / G;
+    spmm_long_reduce_kernel<G, VPL><<<ceil_div(a->n_long, groups_per_block), 256, 0, st>>>(
+        p, a->long_row, a->long_slot0, a->long_nslot, a->n_long);
+    B2_LAUNCHED();
+  }
+  return 0;
+}
+
+static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint32_t* keep_bits, float post_scale,
+                         float* y, const float* addend, float* out, float out_scale, cudaStream_t st) {
+  B2_REQUIRE(a && x, "null operand");
+  B2_REQUIRE(y || out, "no output");
+  B2_REQUIRE(a->n_items == 0 || (a->item_start && a->item_end && a->item_dst && a->colidx), "csr plan missing");
+  B2_REQUIRE(a->n_long == 0 || (a->partial && a->long_row && a->long_slot0 && a->long_nslot), "long-row plan missing");
+  SpmmParams p;
+  p.colidx = a->colidx; p.vals = a->vals; p.nbr_scale = a->nbr_scale; p.row_scale = a->row_scale; p.eid = a->eid;
+  p.keep_bits = keep_bits;
+  p.item_start = a->item_start; p.item_end = a->item_end; p.item_dst = a->item_dst; p.n_items = a->n_items;
+  p.x = x; p.y = y; p.addend = addend; p.out = out; p.out_scale = out_scale; p.post_scale = post_scale;
+  p.partial = a->partial;
+  switch (d) {
+    case 16: return launch_spmm<4, 1>(a, p, st);
+    case 32: return launch_spmm<8, 1>(a, p, st);
+    case 64: return launch_spmm<16, 1>(a, p, st);
+    case 128: return launch_spmm<32, 1>(a, p, st);
+    case 256: return launch_spmm<32, 2>(a, p, st);
+    default: return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "embedding size must be 16/32/64/128/256");
+  }
+}
+
+// ---- adjacency normalisation (model.py:89-98) ----------------------------------------------------------
+__global__ void adj_dinv_kernel(const int32_t* rowptr, const float* mult, int n_rows, float* dinv) {
+  const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= n_rows) return;
+  const int s = rowptr[warp], e = rowptr[warp + 1];
+  float deg;
+  if (mult) {
+    // np.sum(adj, axis=1) accumulates the fp32 multiplicities; they are small integers, so any order is exact
+    float acc = 0.f;
+    for (int k = s + lane; k < e; k += 32) acc += mult[k];
+    deg = warp_sum(acc);
+  } else {
+    deg = (float)(e - s);
+  }
+  deg = fmaxf(1.f, deg);
+  if (lane == 0) dinv[warp] = (float)(1.0 / sqrt((double)deg));  // deg^-0.5 correctly rounded to fp32
+}
+__global__ void adj_vals_kernel(const int32_t* rowptr, const int32_t* colidx, const float* mult, int n_rows,
+                                const float* dinv, float* vals) {
+  const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= n_rows) return;
+  const int s = rowptr[warp], e = rowptr[warp + 1];
+  const float dr = dinv[warp];
+  for (int k = s + lane; k < e; k += 32) {
+    const float m = mult ? mult[k] : 1.f;
+    vals[k] = __fmul_rn(__fmul_rn(dr, m), dinv[colidx[k]]);  // d_mat.dot(adj).dot(d_mat): (d_r * a) * d_c
+  }
+}
+
+}  // namespace b200rec
+
+using namespace b200rec;
+
+extern "C" int b200rec_adj_normalize(const int32_t* rowptr, const int32_t* colidx, const float* mult, int32_t n_rows,
+                                     float* dinv, float* vals, void* stream) {
+  B2_REQUIRE(rowptr && colidx && dinv && vals && n_rows > 0, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div((long long)n_rows * 32, 256);
+  adj_dinv_kernel<<<grid, 256, 0, st>>>(rowptr, mult, n_rows, dinv);
+  B2_LAUNCHED();
+  adj_vals_kernel<<<grid, 256, 0, st>>>(rowptr, colidx, mult, n_rows, dinv, vals);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_spmm_f32(const b200rec_csr* a, const float* x, int32_t d, const uint32_t* keep_bits,
+                                float post_scale, float* y, const float* addend, float* out, float out_scale,
+                                void* stream) {
+  return spmm_dispatch(a, x, d, keep_bits, post_scale, y, addend, out, out_scale, (cudaStream_t)stream);
+}
+
+extern "C" int b200rec_propagate_fwd(const b200rec_csr* a, const float* x0, int32_t d, int32_t n_layers, float* buf0,
+                                     float* buf1, float* mean_out, void* stream) {
+  B2_REQUIRE(a && x0 && mean_out && n_layers >= 0, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_layers == 0) {
+    B2_CUDA(cudaMemcpyAsync(mean_out, x0, (size_t)a->n_rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  B2_REQUIRE(n_layers == 1 || buf0, "buf0 required for n_layers >= 2");
+  B2_REQUIRE(n_layers <= 2 || buf1, "buf1 required for n_layers >= 3");
+  float* bufs[2] = {buf0, buf1};
+  const float inv = 1.f / (float)(n_layers + 1);
+  const float* src = x0;
+  for (int k = 0; k < n_layers; ++k) {
+    const bool last = (k == n_layers - 1);
+    float* y = last ? nullptr : bufs[k & 1];
+    const float* addend = (k == 0) ? x0 : mean_out;  // running layer sum lives in mean_out
+    int rc = spmm_dispatch(a, src, d, nullptr, 1.f, y, addend, mean_out, last ? inv : 1.f, st);
+    if (rc) return rc;
+    src = y;
+  }
+  return 0;
+}
+
+extern "C" int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32_t d, int32_t n_layers, float* buf0,
+                                     float* buf1, float* dx0_out, void* stream) {
+  B2_REQUIRE(a && g && dx0_out && n_layers >= 0, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv = 1.f / (float)(n_layers + 1);
+  if (n_layers == 0) {
+    B2_CUDA(cudaMemcpyAsync(dx0_out, g, (size_t)a->n_rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  B2_REQUIRE(n_layers == 1 || buf0, "buf0 required for n_layers >= 2");
+  B2_REQUIRE(n_layers <= 2 || buf1, "buf1 required for n_layers >= 3");
+  float* bufs[2] = {buf0, buf1};
+  const float* src = g;  // H_0 = G
+  for (int k = 1; k <= n_layers; ++k) {
+    const bool last = (k == n_layers);
+    float* dstp = last ? dx0_out : bufs[k & 1];
+    int rc = spmm_dispatch(a, src, d, nullptr, 1.f, nullptr, g, dstp, last ? inv : 1.f, st);  // H_k = G + A H_{k-1}
+    if (rc) return rc;
+    src = dstp;
+  }
+  return 0;
+}
+
+extern "C" int b200rec_plan_build_host(const int32_t* rowptr, int32_t n_rows, int32_t chunk, int32_t* n_items,
+                                       int32_t* n_long, int32_t* n_slots, int32_t* item_start, int32_t* item_end,
+                                       int32_t* item_dst, int32_t* long_row, int32_t* long_slot0,
+                                       int32_t* long_nslot) {
+  B2_REQUIRE(rowptr && n_rows >= 0 && chunk >= 32 && n_items && n_long && n_slots, "bad argument");
+  // sizes
+  long long items = 0, longs = 0, slots = 0;
+  int maxlen = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    const int len = rowptr[r + 1] - rowptr[r];
+    if (len < 0) return fail(B200REC_ERR_ARG, "%s: %s", __func__, "rowptr not monotone");
+    if (len > chunk) {
+      const int pieces = (len + chunk - 1) / chunk;
+      items += pieces; slots += pieces; longs += 1;
+      if (chunk > maxlen) maxlen = chunk;
+    } else {
+      items += 1;
+      if (len > maxlen) maxlen = len;
+    }
+  }
+  *n_items = (int32_t)items; *n_long = (int32_t)longs; *n_slots = (int32_t)slots;
+  if (!item_start) return 0;
+  B2_REQUIRE(item_end && item_dst && (longs == 0 || (long_row && long_slot0 && long_nslot)), "null output");
+  // counting sort by length, longest first, stable in (row, piece) order -> deterministic
+  int* bucket = new int[(size_t)maxlen + 2]();
+  auto each_item = [&](auto&& fn) {
+    int slot = 0, li = 0;
+    for (int r = 0; r < n_rows; ++r) {
+      const int s = rowptr[r], len = rowptr[r + 1] - s;
+      if (len > chunk) {
+        const int pieces = (len + chunk - 1) / chunk;
+        if (long_row) { long_row[li] = r; long_slot0[li] = slot; long_nslot[li] = pieces; }
+        ++li;
+        for (int q = 0; q < pieces; ++q) {
+          const int b = s + q * chunk, e = (b + chunk < s + len) ? b + chunk : s + len;
+          fn(b, e, ~(slot + q));
+        }
+        slot += pieces;
+      } else {
+        fn(s, s + len, r);
+      }
+    }
+  };
+  each_item([&](int b, int e, int) { bucket[maxlen - (e - b)]++; });
+  int run = 0;
+  for (int i = 0; i <= maxlen; ++i) { int c = bucket[i]; bucket[i] = run; run += c; }
+  each_item([&](int b, int e, int dst) {
+    const int pos = bucket[maxlen - (e - b)]++;
+    item_start[pos] = b; item_end[pos] = e; item_dst[pos] = dst;
+  });
+  delete[] bucket;
+  return 0;
+}

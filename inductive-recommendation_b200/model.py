@@ -1,0 +1,275 @@
+"""Drop-in for the reference's model.py, hot-path classes only: MF, LightGCN, IGCN, IMF.
+
+Surface kept from /root/reference/model.py: get_model (:20-25), BasicModel (:35-53), MF (:56-76), LightGCN (:79-127),
+IGCN (:4107-4220), IMF (:4290-4297) -- same constructor config keys, attributes (embedding, w, user_map, item_map,
+norm_adj, feat_mat, alpha, row_sum), methods (get_rep, bpr_forward, predict, generate_graph, generate_feat,
+update_feat_mat, feat_mat_anneal, save, load) and state_dict keys.  The arithmetic the reference hands to DGL / ATen
+(gspmm, index gather/put, mm) runs in libb200rec's sm_100a kernels through b200rec.ops; there is no CPU path, models
+must live on a CUDA device.  Out of scope: NGCF proper, SGL/HALF, DOSE_*, ItemKNN, Popularity,
+MultiVAE, NeuMF, IMCGAE, IDCF.
+
+Additions: `recommend()` (fused score + mask + top-K, used by trainer.eval instead of predict + topk), an eval-mode
+cache of get_rep() (the reference re-propagates for every 512-user batch, model.py:123), `dropout_rng` config key
+('device' = Philox mask drawn in a kernel, 'host' = the reference's CPU torch.rand draw, model.py:4020).
+"""
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.init import normal_
+
+from b200rec import graph as b2graph
+from b200rec import ops
+from utils import graph_rank_nodes
+
+
+def get_model(config, dataset):
+    config = config.copy()
+    config['dataset'] = dataset
+    cls = getattr(sys.modules[__name__], config['name'])
+    return cls(config)
+
+
+class BasicModel(nn.Module):
+    def __init__(self, model_config):
+        super().__init__()
+        self.config = model_config
+        self.name = model_config['name']
+        self.device = torch.device(model_config['device'])
+        self.n_users = model_config['dataset'].n_users
+        self.n_items = model_config['dataset'].n_items
+        self.trainable = True
+        self._rep_cache = None
+
+    def predict(self, users):
+        raise NotImplementedError
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path, map_location=self.device))
+
+    # ---- shared helpers ----
+    def item_table(self):
+        """(table, row offset of item 0, users table)"""
+        raise NotImplementedError
+
+    def _cache_key(self):
+        return None
+
+    def _cached_rep(self, compute):
+        """eval-mode memo of get_rep(): valid while no parameter / graph / alpha changed."""
+        if self.training or torch.is_grad_enabled():
+            return compute()
+        key = self._cache_key()
+        if self._rep_cache is None or self._rep_cache[0] != key:
+            self._rep_cache = (key, compute())
+        return self._rep_cache[1]
+
+    def recommend(self, users, k, excl_a=None, excl_b=None, banned=None, precision=0):
+        """Fused full-rank scoring + masking + top-K (trainer.py:152-169): returns (ids int32 [b,k], scores [b,k]),
+        ordered (score desc, item id asc)."""
+        with torch.no_grad():
+            table_u, table_i = self.score_tables()
+            return ops.score_topk(table_u, users.contiguous(), table_i, k, excl_a, excl_b, banned, precision)
+
+
+class MF(BasicModel):
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.embedding_size = model_config['embedding_size']
+        self.user_embedding = nn.Embedding(self.n_users, self.embedding_size)
+        self.item_embedding = nn.Embedding(self.n_items, self.embedding_size)
+        normal_(self.user_embedding.weight, std=0.1)
+        normal_(self.item_embedding.weight, std=0.1)
+        self.to(device=self.device)
+        # one contiguous [U+I, D] buffer behind both tables so the fused kernels see a single row space
+        joint = torch.cat([self.user_embedding.weight.data, self.item_embedding.weight.data], dim=0).contiguous()
+        self._joint = joint
+        self.user_embedding.weight = nn.Parameter(joint[:self.n_users])
+        self.item_embedding.weight = nn.Parameter(joint[self.n_users:])
+
+    def get_rep(self):
+        return self._joint
+
+    def score_tables(self):
+        return self.user_embedding.weight.data, self.item_embedding.weight.data
+
+    def bpr_forward(self, users, pos_items, neg_items):
+        ue = ops.gather_rows(self.user_embedding.weight, users)
+        pe = ops.gather_rows(self.item_embedding.weight, pos_items)
+        ne = ops.gather_rows(self.item_embedding.weight, neg_items)
+        l2_norm_sq = (ue * ue).sum(1) + (pe * pe).sum(1) + (ne * ne).sum(1)
+        return ue, pe, ne, l2_norm_sq
+
+    def predict(self, users):
+        with torch.no_grad():
+            return ops.score_dense(self.user_embedding.weight.data, users.contiguous(), self.item_embedding.weight.data)
+
+
+class LightGCN(BasicModel):
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.embedding_size = model_config['embedding_size']
+        self.n_layers = model_config['n_layers']
+        self.embedding = nn.Embedding(self.n_users + self.n_items, self.embedding_size)
+        self.norm_adj = self.generate_graph(model_config['dataset'])
+        normal_(self.embedding.weight, std=0.1)
+        self.to(device=self.device)
+
+    def generate_graph(self, dataset):
+        """D^-1/2 A D^-1/2 as a device CSR operand (b200rec.graph.CsrOperand; it also answers .indices()/.values()/
+        .shape like the reference's sparse tensor)."""
+        users, items = dataset.train_pairs()
+        return b2graph.build_norm_adj(dataset.n_users, dataset.n_items, torch.from_numpy(np.ascontiguousarray(users)),
+                                      torch.from_numpy(np.ascontiguousarray(items)), device=self.device)
+
+    def layer0(self):
+        return self.embedding.weight
+
+    def _cache_key(self):
+        return (self.embedding.weight._version, self.embedding.weight.data_ptr(), id(self.norm_adj))
+
+    def get_rep(self):
+        return self._cached_rep(lambda: ops.propagate(self.norm_adj, self.layer0(), self.n_layers))
+
+    def score_tables(self):
+        rep = self.get_rep()
+        return rep, rep[self.n_users:]
+
+    def bpr_forward(self, users, pos_items, neg_items):
+        rep = self.get_rep()
+        w = self.embedding.weight
+        ue = ops.gather_rows(w, users)
+        pe = ops.gather_rows(w, pos_items, self.n_users)
+        ne = ops.gather_rows(w, neg_items, self.n_users)
+        l2_norm_sq = (ue * ue).sum(1) + (pe * pe).sum(1) + (ne * ne).sum(1)
+        users_r = ops.gather_rows(rep, users)
+        pos_items_r = ops.gather_rows(rep, pos_items, self.n_users)
+        neg_items_r = ops.gather_rows(rep, neg_items, self.n_users)
+        return users_r, pos_items_r, neg_items_r, l2_norm_sq
+
+    def predict(self, users):
+        with torch.no_grad():
+            rep = self.get_rep()
+            return ops.score_dense(rep, users.contiguous(), rep[self.n_users:])
+
+
+class IGCN(BasicModel):
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.embedding_size = model_config['embedding_size']
+        self.n_layers = model_config['n_layers']
+        self.dropout = model_config['dropout']
+        self.feature_ratio = model_config['feature_ratio']
+        self.dropout_rng = model_config.get('dropout_rng', 'device')
+        self.dropout_seed = model_config.get('dropout_seed', 2021)
+        self._drop_step = None
+        self.norm_adj = self.generate_graph(model_config['dataset'])
+        self.alpha = 1.
+        self.delta = model_config.get('delta', 0.99)
+        self.feat_mat, self.user_map, self.item_map, self.row_sum = \
+            self.generate_feat(model_config['dataset'], ranking_metric=model_config.get('ranking_metric', 'sort'))
+        self.update_feat_mat()
+        self.embedding = nn.Embedding(self.feat_mat.n_cols, self.embedding_size)
+        self.w = nn.Parameter(torch.ones([self.embedding_size], dtype=torch.float32, device=self.device))
+        normal_(self.embedding.weight, std=0.1)
+        self.to(device=self.device)
+
+    generate_graph = LightGCN.generate_graph
+
+    def update_feat_mat(self):
+        """F[r, :] = row_sum[r] ** ((alpha-1)/2 - 0.5): only the per-row scale vector changes."""
+        self.row_scale = self.feat_mat.row_scale(self.alpha)
+        self._rep_cache = None
+
+    def feat_mat_anneal(self):
+        self.alpha *= self.delta
+        self.update_feat_mat()
+
+    def generate_feat(self, dataset, is_updating=False, ranking_metric=None):
+        """Template maps + feature operand.  is_updating=True keeps the stored maps, so nodes that joined after
+        training (ids beyond the old ranges) are expressed through template columns only -- the inductive path."""
+        n_users, n_items = dataset.n_users, dataset.n_items
+        if not is_updating:
+            if self.feature_ratio < 1.:
+                ranked_users, ranked_items = graph_rank_nodes(dataset, ranking_metric)
+                core_users = ranked_users[:int(self.n_users * self.feature_ratio)]
+                core_items = ranked_items[:int(self.n_items * self.feature_ratio)]
+            else:
+                core_users = np.arange(self.n_users, dtype=np.int64)
+                core_items = np.arange(self.n_items, dtype=np.int64)
+            user_map = {int(u): k for k, u in enumerate(core_users)}
+            item_map = {int(i): k for k, i in enumerate(core_items)}
+        else:
+            user_map, item_map = self.user_map, self.item_map
+            self.n_users, self.n_items = n_users, n_items
+        ut = np.full(n_users, -1, dtype=np.int64)
+        it = np.full(n_items, -1, dtype=np.int64)
+        ut[np.fromiter(user_map.keys(), np.int64, len(user_map))] = np.fromiter(user_map.values(), np.int64, len(user_map))
+        it[np.fromiter(item_map.keys(), np.int64, len(item_map))] = np.fromiter(item_map.values(), np.int64, len(item_map))
+        users, items = dataset.train_pairs()
+        feat, _, _ = b2graph.build_feat(n_users, n_items, torch.from_numpy(np.ascontiguousarray(users)),
+                                        torch.from_numpy(np.ascontiguousarray(items)), torch.from_numpy(ut),
+                                        torch.from_numpy(it), device=self.device)
+        return feat, user_map, item_map, feat.row_sum
+
+    def _keep_bits(self):
+        """edge-dropout mask for this call (training only), in the coalesced row-major edge order."""
+        nnz = self.feat_mat.nnz
+        if self.dropout_rng == 'host':
+            rnd = torch.rand(nnz)  # CPU generator, exactly the reference's draw
+            keep = torch.floor((1 - self.dropout) + rnd).type(torch.bool)
+            return ops.pack_keep_bits(keep.to(self.device))
+        if self._drop_step is None:
+            self._drop_step = torch.zeros(1, dtype=torch.int64, device=self.device)
+        bits = ops.dropout_bits(nnz, self.dropout, self.dropout_seed, self._drop_step)
+        ops.step_advance(self._drop_step)
+        return bits
+
+    def layer0(self):
+        if self.training and self.dropout > 0.:
+            return ops.inductive_layer(self.feat_mat, self.embedding.weight, self.row_scale, self._keep_bits(),
+                                       1. / (1. - self.dropout))
+        return ops.inductive_layer(self.feat_mat, self.embedding.weight, self.row_scale)
+
+    def _cache_key(self):
+        return (self.embedding.weight._version, self.embedding.weight.data_ptr(), id(self.norm_adj), id(self.feat_mat),
+                self.alpha)
+
+    def get_rep(self):
+        return self._cached_rep(lambda: ops.propagate(self.norm_adj, self.layer0(), self.n_layers))
+
+    score_tables = LightGCN.score_tables
+    predict = LightGCN.predict
+
+    def bpr_forward(self, users, pos_items, neg_items):
+        rep = self.get_rep()
+        users_r = ops.gather_rows(rep, users)
+        pos_items_r = ops.gather_rows(rep, pos_items, self.n_users)
+        neg_items_r = ops.gather_rows(rep, neg_items, self.n_users)
+        l2_norm_sq = (users_r * users_r).sum(1) + (pos_items_r * pos_items_r).sum(1) + (neg_items_r * neg_items_r).sum(1)
+        return users_r, pos_items_r, neg_items_r, l2_norm_sq
+
+    def save(self, path):
+        params = {'sate_dict': self.state_dict(), 'user_map': self.user_map, 'item_map': self.item_map,
+                  'alpha': self.alpha}  # key spelling kept for checkpoint compatibility with the reference
+        torch.save(params, path)
+
+    def load(self, path):
+        params = torch.load(path, map_location=self.device, weights_only=False)
+        self.load_state_dict(params['sate_dict'])
+        self.user_map = params['user_map']
+        self.item_map = params['item_map']
+        self.alpha = params['alpha']
+        self.feat_mat, _, _, self.row_sum = self.generate_feat(self.config['dataset'], is_updating=True)
+        self.update_feat_mat()
+
+
+class IMF(IGCN):
+    """IGCN without propagation: the inductive layer only (reference config sets n_layers = 0)."""
+
+    def get_rep(self):
+        return self._cached_rep(self.layer0)

@@ -1,0 +1,354 @@
+"""Drop-in for the reference's trainer.py, hot-path classes only: BasicTrainer, BPRTrainer, IGCNTrainer.
+
+Surface kept from /root/reference/trainer.py: get_trainer (:16-22); BasicTrainer (:25-253) with train, eval,
+calculate_metrics, inductive_eval, initialize_optimizer, record and the attributes topks / epoch / best_ndcg /
+save_path / opt / dataloader / test_user_loader; BPRTrainer (:403-429); IGCNTrainer (:518-561).  Config keys are the
+reference's (config.py); optional extras: 'fused' (default True: CUDA-graphed libb200rec step with on-device
+sampling), 'sampler' ('device' | 'host': draw triples on device, or iterate the DataLoader like the reference),
+'seed', 'eval_precision' (0 exact fp32, 1 tcgen05 bf16 candidates + exact re-score).
+Out of scope: DOSE*/SGL/HALF/IDCF/BCE/ML trainers.
+
+What changes underneath: one training step is a replayed CUDA graph (b200rec.engine.BprEngine); evaluation computes
+the representation once, then runs the fused score + mask + top-K kernel over large user chunks and a hit-matrix
+kernel, instead of a re-propagation, a dense [512, n_items] score matrix, Python exclusion lists and two device
+synchronisations per 512 users (trainer.py:150-170).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch.optim import SGD, Adam  # noqa: F401  (resolved by name from the config, like the reference)
+from torch.utils.data import DataLoader, TensorDataset
+
+from b200rec import ops
+from b200rec.engine import BprEngine
+from dataset import AuxiliaryDataset
+from utils import AverageMeter
+
+
+def get_trainer(config, dataset, model):
+    config = config.copy()
+    config['dataset'] = dataset
+    config['model'] = model
+    cls = getattr(sys.modules[__name__], config['name'])
+    return cls(config)
+
+
+class BasicTrainer:
+    def __init__(self, trainer_config):
+        self.config = trainer_config
+        self.name = trainer_config['name']
+        self.dataset = trainer_config['dataset']
+        self.model = trainer_config['model']
+        self.topks = trainer_config['topks']
+        self.device = torch.device(trainer_config['device'])
+        self.n_epochs = trainer_config['n_epochs']
+        self.max_patience = trainer_config.get('max_patience', 50)
+        self.val_interval = trainer_config.get('val_interval', 1)
+        self.epoch = 0
+        self.best_ndcg = -np.inf
+        self.save_path = None
+        self.opt = None
+        self.eval_precision = trainer_config.get('eval_precision', 0)
+        self.eval_chunk = max(int(trainer_config['test_batch_size']), 16384)
+        test_user = TensorDataset(torch.arange(self.dataset.n_users, dtype=torch.int64, device=self.device))
+        self.test_user_loader = DataLoader(test_user, batch_size=trainer_config['test_batch_size'])
+        self.engine = None
+
+    def initialize_optimizer(self):
+        opt = getattr(sys.modules[__name__], self.config['optimizer'])
+        self.opt = opt(self.model.parameters(), lr=self.config['lr'])
+
+    def train_one_epoch(self):
+        raise NotImplementedError
+
+    def record(self, writer, stage, metrics):
+        for metric in metrics:
+            for k in self.topks:
+                writer.add_scalar('{:s}_{:s}/{:s}_{:s}@{:d}'.format(self.model.name, self.name, stage, metric, k),
+                                  metrics[metric][k], self.epoch)
+
+    def train(self, verbose=True, writer=None):
+        if not self.model.trainable:
+            results, metrics, _ = self.eval('val')
+            if verbose:
+                print('Validation result. {:s}'.format(results))
+            return metrics['NDCG'][self.topks[4]]
+        os.makedirs('checkpoints', exist_ok=True)
+        patience = self.max_patience
+        for self.epoch in range(self.n_epochs):
+            start_time = time.time()
+            self.model.train()
+            loss = self.train_one_epoch()
+            _, metrics, _ = self.eval('train')
+            consumed_time = time.time() - start_time
+            if verbose:
+                print('Epoch {:d}/{:d}, Loss: {:.6f}, Time: {:.3f}s'.format(self.epoch, self.n_epochs, loss, consumed_time))
+            if writer:
+                writer.add_scalar('{:s}_{:s}/train_loss'.format(self.model.name, self.name), loss, self.epoch)
+                self.record(writer, 'train', metrics)
+            if (self.epoch + 1) % self.val_interval != 0:
+                continue
+            start_time = time.time()
+            results, metrics, _ = self.eval('val')
+            consumed_time = time.time() - start_time
+            if verbose:
+                print('Validation result. {:s}Time: {:.3f}s'.format(results, consumed_time))
+            if writer:
+                self.record(writer, 'validation', metrics)
+            ndcg = metrics['NDCG'][self.topks[4]]
+            if ndcg > self.best_ndcg:
+                if self.save_path:
+                    os.remove(self.save_path)
+                self.save_path = os.path.join('checkpoints', '{:s}_{:s}_{:s}_{:.3f}.pth'.format(
+                    self.model.name, self.name, self.dataset.name, ndcg * 100))
+                self.best_ndcg = ndcg
+                self.model.save(self.save_path)
+                patience = self.max_patience
+                print('Best NDCG, save model to {:s}'.format(self.save_path))
+            else:
+                patience -= self.val_interval
+                if patience <= 0:
+                    print('Early stopping!')
+                    break
+        self.model.load(self.save_path)
+        return self.best_ndcg
+
+    # ------------------------------------------------------------------------------------------------ metrics
+    def hit_matrix(self, eval_data, rec_items):
+        """hit[u, j] = rec_items[u, j] in eval_data[u]  (device kernel; eval rows as sorted CSR)"""
+        if hasattr(eval_data, 'ptr'):  # lazy CSR-backed lists
+            ptr, idx = np.asarray(eval_data.ptr, dtype=np.int64), np.asarray(eval_data.idx, dtype=np.int64)
+        else:
+            lens = np.fromiter((len(x) for x in eval_data), dtype=np.int64, count=len(eval_data))
+            ptr = np.zeros(len(eval_data) + 1, dtype=np.int64)
+            np.cumsum(lens, out=ptr[1:])
+            idx = np.concatenate([np.asarray(x, dtype=np.int64) for x in eval_data if len(x)]) if ptr[-1] else \
+                np.zeros(0, dtype=np.int64)
+        rows = np.repeat(np.arange(len(ptr) - 1, dtype=np.int64), np.diff(ptr))
+        idx = idx[np.lexsort((idx, rows))]
+        dev = self.device
+        ptr_d = torch.from_numpy(ptr.astype(np.int32)).to(dev)
+        idx_d = torch.from_numpy(idx.astype(np.int32)).to(dev) if idx.size else torch.zeros(1, dtype=torch.int32, device=dev)
+        rec_d = rec_items if isinstance(rec_items, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rec_items))
+        rec_d = rec_d.to(device=dev, dtype=torch.int32).contiguous()
+        return ops.hit_matrix(rec_d, 0, ptr_d, idx_d).cpu().numpy(), np.diff(ptr).astype(np.int32)
+
+    def calculate_metrics(self, eval_data, rec_items):
+        """Precision / Recall / NDCG @k for every k in topks, averaged over users with at least one eval item."""
+        hit, n_eval = self.hit_matrix(eval_data, rec_items)
+        results = {'Precision': {}, 'Recall': {}, 'NDCG': {}}
+        has_items = n_eval > 0
+        for k in self.topks:
+            h = hit[:, :k]
+            n_hit = h.sum(axis=1)
+            with np.errstate(invalid='ignore', divide='ignore'):
+                recall = n_hit / n_eval
+            discount = np.log2(np.arange(2, k + 2, dtype=np.float32))[None, :]
+            dcg = (h / discount).sum(axis=1)
+            ideal = (np.arange(k)[None, :] < np.minimum(n_eval, k)[:, None]).astype(np.float32)
+            idcg = (ideal / discount).sum(axis=1)
+            with np.errstate(invalid='ignore', divide='ignore'):
+                ndcg = dcg / idcg
+            results['Precision'][k] = (n_hit / k)[has_items].mean()
+            results['Recall'][k] = recall[has_items].mean()
+            results['NDCG'][k] = ndcg[has_items].mean()
+        return results
+
+    def recommend_all(self, val_or_test, banned_items=None):
+        """top-max(topks) item ids for every user: int32 [n_users, K] on device"""
+        self.model.eval()
+        dev = self.device
+        excl_a = excl_b = None
+        if val_or_test != 'train':
+            excl_a = self.dataset.csr('train', device=dev)
+            if val_or_test == 'test':
+                excl_b = self.dataset.csr('val', device=dev)
+        banned = None
+        if banned_items is not None:
+            b = np.asarray(banned_items)
+            if b.size:
+                lo, hi = int(b.min()), int(b.max()) + 1
+                if hi - lo != b.size or np.unique(b).size != b.size:
+                    raise NotImplementedError('banned_items must be a contiguous id range (inductive_eval passes np.arange)')
+                banned = (lo, hi)
+        k = max(self.topks)
+        n_users = self.dataset.n_users
+        out = []
+        with torch.no_grad():
+            for s in range(0, n_users, self.eval_chunk):
+                users = torch.arange(s, min(n_users, s + self.eval_chunk), dtype=torch.int64, device=dev)
+                ids, _ = self.model.recommend(users, k, excl_a, excl_b, banned, precision=self.eval_precision)
+                out.append(ids)
+        return torch.cat(out, dim=0)
+
+    def eval(self, val_or_test, banned_items=None):
+        eval_data = getattr(self.dataset, val_or_test + '_data')
+        rec_items = self.recommend_all(val_or_test, banned_items)
+        metrics = self.calculate_metrics(eval_data, rec_items)
+        precison = recall = ndcg = ''
+        for k in self.topks:
+            precison += '{:.3f}, '.format(metrics['Precision'][k] * 100.)
+            recall += '{:.3f}, '.format(metrics['Recall'][k] * 100.)
+            ndcg += '{:.3f}, '.format(metrics['NDCG'][k] * 100.)
+        results = 'Precision: {:s}Recall: {:s}NDCG: {:s}'.format(precison, recall, ndcg)
+        return results, metrics, []
+
+    def inductive_eval(self, n_old_users, n_old_items):
+        """Six test passes over {all, old, new} users x {all, old, new} items; ids >= n_old_* are the new nodes."""
+        ds = self.dataset
+        full = [list(x) for x in ds.test_data]
+        n_users, n_items = ds.n_users, ds.n_items
+
+        def run(tag, user_range, item_filter, banned):
+            data = [[] for _ in range(n_users)]
+            for u in user_range:
+                items = full[u]
+                if item_filter is not None:
+                    items = [i for i in items if item_filter(i)]
+                data[u] = items
+            ds.test_data = data
+            results, metrics, _ = self.eval('test', banned_items=banned)
+            print('{:s} result. {:s}'.format(tag, results))
+            return metrics
+
+        out = {}
+        try:
+            out['all_all'] = run('All users and all items', range(n_users), None, None)
+            out['old_all'] = run('Old users and all items', range(n_old_users), None, None)
+            out['new_all'] = run('New users and all items', range(n_old_users, n_users), None, None)
+            out['all_old'] = run('All users and old items', range(n_users), lambda i: i < n_old_items,
+                                 np.arange(n_old_items, n_items))
+            out['all_new'] = run('All users and new items', range(n_users), lambda i: i >= n_old_items,
+                                 np.arange(n_old_items))
+            out['old_old'] = run('Old users and old items', range(n_old_users), lambda i: i < n_old_items,
+                                 np.arange(n_old_items, n_items))
+        finally:
+            ds.test_data = full
+        return out
+
+
+class BPRTrainer(BasicTrainer):
+    def __init__(self, trainer_config):
+        super().__init__(trainer_config)
+        self.batch_size = trainer_config['batch_size']
+        self.dataloader = DataLoader(self.dataset, batch_size=self.batch_size,
+                                     num_workers=trainer_config['dataloader_num_workers'])
+        self.initialize_optimizer()
+        self.l2_reg = trainer_config['l2_reg']
+        self.fused = trainer_config.get('fused', True) and self.config['optimizer'] == 'Adam'
+        self.sampler = trainer_config.get('sampler', 'device')
+        self.seed = trainer_config.get('seed', 2021)
+        self.aux_reg = 0.0
+
+    def _aux_dataset(self):
+        return None
+
+    def _engine(self):
+        if self.engine is None:
+            self.engine = BprEngine(self.model, self.dataset, self.opt, self.batch_size, self.l2_reg,
+                                    aux_reg=self.aux_reg, aux_dataset=self._aux_dataset(), seed=self.seed,
+                                    partition=self.config.get('partition'))
+        return self.engine
+
+    def steps_per_epoch(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def _host_batches(self):
+        for batch_data in self.dataloader:
+            yield batch_data[:, 0, :].to(dtype=torch.int64)
+
+    def train_one_epoch(self):
+        if not self.fused:
+            return self._train_one_epoch_autograd()
+        eng = self._engine()
+        eng.reset_meter()
+        if self.sampler == 'host':
+            for inputs in self._host_batches():
+                if inputs.shape[0] != self.batch_size:  # ragged last batch: one eager step through autograd
+                    self._autograd_step(inputs.to(self.device), None)
+                    continue
+                eng.step(host_batch=inputs.pin_memory())
+        else:
+            for _ in range(self.steps_per_epoch()):
+                eng.step()
+        eng.sync_optimizer_state()
+        return eng.meter_avg()
+
+    # ---- reference-shaped loop through autograd (any optimiser; also the parity path for bpr_forward) ----
+    def _loss(self, inputs, aux_inputs):
+        users, pos_items, neg_items = inputs[:, 0].contiguous(), inputs[:, 1].contiguous(), inputs[:, 2].contiguous()
+        users_r, pos_items_r, neg_items_r, l2_norm_sq = self.model.bpr_forward(users, pos_items, neg_items)
+        pos_scores = torch.sum(users_r * pos_items_r, dim=1)
+        neg_scores = torch.sum(users_r * neg_items_r, dim=1)
+        return F.softplus(neg_scores - pos_scores).mean() + self.l2_reg * l2_norm_sq.mean()
+
+    def _autograd_step(self, inputs, aux_inputs):
+        loss = self._loss(inputs, aux_inputs)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        self.model._rep_cache = None
+        return loss.item()
+
+    def _train_one_epoch_autograd(self):
+        losses = AverageMeter()
+        for inputs in self._host_batches():
+            inputs = inputs.to(self.device)
+            losses.update(self._autograd_step(inputs, None), inputs.shape[0])
+        return losses.avg
+
+
+class IGCNTrainer(BPRTrainer):
+    def __init__(self, trainer_config):
+        super().__init__(trainer_config)
+        self.aux_dataset = AuxiliaryDataset(self.dataset, self.model.user_map, self.model.item_map)
+        self.aux_dataloader = DataLoader(self.aux_dataset, batch_size=self.batch_size,
+                                         num_workers=trainer_config['dataloader_num_workers'])
+        self.aux_reg = trainer_config['aux_reg']
+
+    def _aux_dataset(self):
+        return self.aux_dataset
+
+    def _loss(self, inputs, aux_inputs):
+        loss = super()._loss(inputs, aux_inputs)
+        m = self.model
+        users, pos_items, neg_items = aux_inputs[:, 0].contiguous(), aux_inputs[:, 1].contiguous(), aux_inputs[:, 2].contiguous()
+        tu = len(m.user_map)
+        users_r = ops.gather_rows(m.embedding.weight, users)
+        pos_items_r = ops.gather_rows(m.embedding.weight, pos_items, tu)
+        neg_items_r = ops.gather_rows(m.embedding.weight, neg_items, tu)
+        pos_scores = torch.sum(users_r * pos_items_r * m.w[None, :], dim=1)
+        neg_scores = torch.sum(users_r * neg_items_r * m.w[None, :], dim=1)
+        return loss + self.aux_reg * F.softplus(neg_scores - pos_scores).mean()
+
+    def train_one_epoch(self):
+        if not self.fused:
+            losses = AverageMeter()
+            for batch_data, a_batch_data in zip(self.dataloader, self.aux_dataloader):
+                inputs = batch_data[:, 0, :].to(device=self.device, dtype=torch.int64)
+                aux = a_batch_data[:, 0, :].to(device=self.device, dtype=torch.int64)
+                losses.update(self._autograd_step(inputs, aux), inputs.shape[0])
+            loss = losses.avg
+        else:
+            eng = self._engine()
+            eng.reset_meter()
+            eng.refresh_row_scale()
+            if self.sampler == 'host':
+                for batch_data, a_batch_data in zip(self.dataloader, self.aux_dataloader):
+                    inputs = batch_data[:, 0, :].to(dtype=torch.int64)
+                    aux = a_batch_data[:, 0, :].to(dtype=torch.int64)
+                    if inputs.shape[0] != self.batch_size:
+                        self._autograd_step(inputs.to(self.device), aux.to(self.device))
+                        continue
+                    eng.step(host_batch=inputs.pin_memory(), host_aux_batch=aux.pin_memory())
+            else:
+                for _ in range(self.steps_per_epoch()):
+                    eng.step()
+            eng.sync_optimizer_state()
+            loss = eng.meter_avg()
+        self.model.feat_mat_anneal()
+        return loss

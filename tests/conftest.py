@@ -34,3 +34,44 @@ def golden():
 
 def lists_from_csr(indptr, items):
     return [items[indptr[u]:indptr[u + 1]].tolist() for u in range(len(indptr) - 1)]
+
+
+def golden_dataset(g, device="cuda"):
+    """SyntheticDataset over the graph stored in a golden fixture"""
+    import torch
+    import dataset
+    from b200rec import synth
+    t = lambda k: torch.from_numpy(np.asarray(g[k], dtype=np.int64))  # noqa: E731
+    graph = synth.SynthGraph(int(g["n_users"]), int(g["n_items"]), t("train_indptr"), t("train_items"),
+                             t("val_indptr"), t("val_items"), t("test_indptr"), t("test_items"))
+    return dataset.get_dataset({"name": "SyntheticDataset", "device": device, "graph": graph})
+
+
+def golden_maps(g):
+    return (dict(zip(g["user_map_keys"].tolist(), g["user_map_vals"].tolist())),
+            dict(zip(g["item_map_keys"].tolist(), g["item_map_vals"].tolist())))
+
+
+MODEL_CFG = {
+    "lightgcn_tiny": {"name": "LightGCN", "embedding_size": 64, "n_layers": 3},
+    "lightgcn_d128": {"name": "LightGCN", "embedding_size": 128, "n_layers": 4},
+    "mf_tiny": {"name": "MF", "embedding_size": 64},
+    "igcn_tiny": {"name": "IGCN", "embedding_size": 64, "n_layers": 3, "dropout": 0.3, "feature_ratio": 1.0},
+    "igcn_fr_tiny": {"name": "IGCN", "embedding_size": 64, "n_layers": 2, "dropout": 0.3, "feature_ratio": 0.5},
+    "imf_tiny": {"name": "IMF", "embedding_size": 64, "n_layers": 0, "dropout": 0.3, "feature_ratio": 1.0},
+}
+
+
+def golden_model(g, name, device="cuda", **extra):
+    """drop-in model carrying the reference's initial weights from the fixture"""
+    import torch
+    import model as M
+    ds = golden_dataset(g, device)
+    m = M.get_model(dict(MODEL_CFG[name], device=device, **extra), ds)
+    with torch.no_grad():
+        if name.startswith("mf"):
+            m.user_embedding.weight.copy_(torch.from_numpy(g["user_emb0"]))
+            m.item_embedding.weight.copy_(torch.from_numpy(g["item_emb0"]))
+        else:
+            m.embedding.weight.copy_(torch.from_numpy(g["emb0"]))
+    return ds, m

@@ -1,0 +1,70 @@
+"""CPU: libb200rec.so loads and exports every symbol declared in include/b200rec.h; the binding table in
+b200rec/_abi.py lists exactly those symbols; compute entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO
+from b200rec import _abi
+
+
+def _declared():
+    text = open(os.path.join(REPO, "include", "b200rec.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200rec_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _abi.load()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert sorted(_abi.PROTOTYPES) == names
+    assert lib.b200rec_version() >= 100
+
+
+def test_plan_build_host_long_rows_and_order():
+    lib = _abi.load()
+    lens = np.array([3, 0, 2500, 1, 70, 1024, 1025], dtype=np.int32)
+    rp = np.zeros(len(lens) + 1, dtype=np.int32)
+    np.cumsum(lens, out=rp[1:])
+    ni, nl, ns = C.c_int32(), C.c_int32(), C.c_int32()
+    null = C.c_void_p(0)
+    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, C.addressof(ni), C.addressof(nl), C.addressof(ns),
+                                       null, null, null, null, null, null) == 0
+    assert (ni.value, nl.value, ns.value) == (5 + 3 + 2, 2, 5)
+    a = [np.empty(ni.value, dtype=np.int32) for _ in range(3)]
+    b = [np.empty(nl.value, dtype=np.int32) for _ in range(3)]
+    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, C.addressof(ni), C.addressof(nl), C.addressof(ns),
+                                       a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+                                       b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data) == 0
+    start, end, dst = a
+    ln = end - start
+    assert (np.diff(ln) <= 0).all()                      # longest first
+    assert ln.sum() == lens.sum()
+    assert sorted(dst[dst >= 0].tolist()) == [0, 1, 3, 4, 5]
+    assert sorted((~dst[dst < 0]).tolist()) == [0, 1, 2, 3, 4]
+    assert b[0].tolist() == [2, 6] and b[1].tolist() == [0, 3] and b[2].tolist() == [3, 2]
+    # every nnz covered exactly once
+    cover = np.zeros(lens.sum(), dtype=np.int32)
+    for s, e in zip(start, end):
+        cover[s:e] += 1
+    assert (cover == 1).all()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from b200rec import ops
+    with pytest.raises(_abi.B200RecError):
+        ops.score_dense(torch.zeros(4, 64), torch.zeros(2, dtype=torch.int64), torch.zeros(4, 64))
+    import model
+    import dataset
+    from b200rec import synth
+    ds = dataset.get_dataset({'name': 'SyntheticDataset', 'device': 'cpu', 'graph': synth.generate(50, 60, 400, seed=1)})
+    with pytest.raises(_abi.B200RecError):
+        model.get_model({'name': 'LightGCN', 'embedding_size': 64, 'n_layers': 2, 'device': 'cpu'}, ds)

@@ -1,0 +1,190 @@
+"""GPU parity tests, drop-in surface: model.py / trainer.py of this repo against fixtures produced by the unmodified
+reference (tests/golden, oracle/make_golden.py).  Same inputs (graph, initial weights, recorded batch and dropout
+draw) -> same representations, loss, gradients, post-Adam weights (fp32, 1e-5 relative) and the same top-K ids and
+metrics."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import MODEL_CFG, golden_maps, golden_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOPKS = [1, 5, 10, 15, 20]
+ALL = ["lightgcn_tiny", "lightgcn_d128", "mf_tiny", "igcn_tiny", "igcn_fr_tiny", "imf_tiny"]
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _trainer(g, name, ds, m, **extra):
+    import trainer as T
+    is_igcn = MODEL_CFG[name]["name"] in ("IGCN", "IMF")
+    cfg = {"name": "IGCNTrainer" if is_igcn else "BPRTrainer", "optimizer": "Adam", "lr": float(g["lr"]),
+           "l2_reg": float(g["l2_reg"]), "aux_reg": float(g["aux_reg"]), "device": DEV, "n_epochs": 1,
+           "batch_size": int(g["batch"].shape[0]), "dataloader_num_workers": 0, "test_batch_size": 128, "topks": TOPKS}
+    cfg.update(extra)
+    return T.get_trainer(cfg, ds, m)
+
+
+def _keep_bits(g):
+    from b200rec import ops
+    keep = np.unpackbits(g["drop_keep"])[: int(g["drop_nnz"])].astype(bool)
+    return ops.pack_keep_bits(torch.from_numpy(keep).to(DEV))
+
+
+@pytest.mark.parametrize("name", ["igcn_tiny", "igcn_fr_tiny", "imf_tiny"])
+def test_template_features(golden, name):
+    g = golden(name)
+    ds, m = golden_model(g, name)
+    assert (m.user_map, m.item_map) == golden_maps(g)                          # template choice (graph_rank_nodes)
+    r, c, _ = m.feat_mat.fwd.to_coo()
+    assert np.array_equal(np.stack([_np(r), _np(c)]), g["feat_idx"])           # F structure: bit-exact
+    assert np.array_equal(_np(m.row_sum), g["row_sum"])
+    np.testing.assert_allclose(_np(m.row_scale)[_np(r)], g["feat_val_a1"], rtol=1e-6)
+    m.feat_mat_anneal()
+    assert abs(m.alpha - float(g["alpha_after"])) < 1e-12
+    np.testing.assert_allclose(_np(m.row_scale)[_np(r)], g["feat_val_anneal"], rtol=1e-6)
+    # transposed operand is consistent with the forward one
+    tr, tc = _np(m.feat_mat.bwd.to_coo()[0]), _np(m.feat_mat.bwd.to_coo()[1])
+    eid = _np(m.feat_mat.bwd.eid)
+    assert np.array_equal(_np(r)[eid], tc) and np.array_equal(_np(c)[eid], tr)
+
+
+@pytest.mark.parametrize("name", [n for n in ALL if not n.startswith("mf")])
+def test_get_rep_eval(golden, name):
+    g = golden(name)
+    ds, m = golden_model(g, name)
+    m.eval()
+    with torch.no_grad():
+        rep = m.get_rep()
+        assert m.get_rep() is rep      # eval-mode cache
+    np.testing.assert_allclose(_np(rep), g["rep_eval"], rtol=1e-5, atol=1e-7)
+    sc = m.predict(torch.arange(8, device=DEV))
+    np.testing.assert_allclose(_np(sc), g["scores_head"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_bpr_forward_autograd_path(golden, name):
+    """the reference-shaped loop: bpr_forward -> torch loss -> backward -> torch.optim.Adam"""
+    g = golden(name)
+    ds, m = golden_model(g, name, dropout_rng="host")
+    tr = _trainer(g, name, ds, m, fused=False)
+    m.train()
+    batch = torch.from_numpy(g["batch"]).to(DEV)
+    is_igcn = "drop_keep" in g
+    if is_igcn:
+        bits = _keep_bits(g)
+        m._keep_bits = lambda: bits          # inject the reference's recorded torch.rand draw
+    ur, pr, nr, l2 = m.bpr_forward(batch[:, 0].contiguous(), batch[:, 1].contiguous(), batch[:, 2].contiguous())
+    np.testing.assert_allclose(_np(ur), g["users_r"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(_np(pr), g["pos_r"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(_np(nr), g["neg_r"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(_np(l2), g["l2_norm_sq"], rtol=1e-5)
+    aux = torch.from_numpy(g["aux_batch"]).to(DEV) if "aux_batch" in g else None
+    loss = tr._loss(batch, aux)
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    tr.opt.zero_grad()
+    loss.backward()
+    if name.startswith("mf"):
+        np.testing.assert_allclose(_np(m.user_embedding.weight.grad), g["grad_user"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(_np(m.item_embedding.weight.grad), g["grad_item"], rtol=1e-4, atol=1e-9)
+    else:
+        np.testing.assert_allclose(_np(m.embedding.weight.grad), g["grad_emb"], rtol=1e-4, atol=1e-9)
+    if "grad_w" in g:
+        np.testing.assert_allclose(_np(m.w.grad), g["grad_w"], rtol=1e-4, atol=1e-9)
+    tr.opt.step()
+    if name.startswith("mf"):
+        np.testing.assert_allclose(_np(m.user_embedding.weight), g["user_emb1"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(_np(m.item_embedding.weight), g["item_emb1"], rtol=1e-5, atol=2e-6)
+    else:
+        np.testing.assert_allclose(_np(m.embedding.weight), g["emb1"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_engine_step(golden, name, use_graph):
+    """the CUDA-graphed fused step fed the reference's recorded batch: loss, gradient and post-Adam weights"""
+    g = golden(name)
+    ds, m = golden_model(g, name)
+    tr = _trainer(g, name, ds, m)
+    m.train()
+    eng = tr._engine()
+    eng.use_graph = use_graph
+    hb = torch.from_numpy(g["batch"]).pin_memory()
+    ha = torch.from_numpy(g["aux_batch"]).pin_memory() if "aux_batch" in g else None
+    hk = _keep_bits(g) if "drop_keep" in g else None
+    eng.step(host_batch=hb, host_aux_batch=ha, host_keep_bits=hk)
+    assert abs(eng.last_loss() - float(g["loss"])) < 2e-6
+    assert abs(eng.meter_avg() - float(g["loss"])) < 2e-6
+    if name.startswith("mf"):
+        np.testing.assert_allclose(_np(m.user_embedding.weight.grad), g["grad_user"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(_np(m.user_embedding.weight), g["user_emb1"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(_np(m.item_embedding.weight), g["item_emb1"], rtol=1e-5, atol=2e-6)
+    else:
+        np.testing.assert_allclose(_np(m.embedding.weight.grad), g["grad_emb"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(_np(m.embedding.weight), g["emb1"], rtol=1e-5, atol=2e-6)
+    if "grad_w" in g:
+        np.testing.assert_allclose(_np(m.w.grad), g["grad_w"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(_np(m.w), g["w1"], rtol=1e-5, atol=2e-6)
+    eng.sync_optimizer_state()
+    assert int(tr.opt.state[next(iter(m.parameters()))]["step"]) == 1
+
+
+@pytest.mark.parametrize("name", ["lightgcn_tiny", "mf_tiny", "igcn_tiny", "lightgcn_d128"])
+def test_eval_topk_and_metrics(golden, name):
+    g = golden(name)
+    ds, m = golden_model(g, name)
+    tr = _trainer(g, name, ds, m)
+    for split in ("train", "val", "test"):
+        rec = _np(tr.recommend_all(split))
+        ref_ids, ref_val = g["topk_ids_" + split], g["topk_val_" + split]
+        sep = np.ones_like(ref_ids, dtype=bool)
+        d = np.abs(np.diff(ref_val, axis=1)) > 1e-6
+        sep[:, 1:] &= d
+        sep[:, :-1] &= d
+        assert sep.mean() > 0.99
+        assert np.array_equal(rec[sep], ref_ids[sep])
+        _, metrics, _ = tr.eval(split)
+        for mname in ("Precision", "Recall", "NDCG"):
+            ours = np.array([metrics[mname][k] for k in TOPKS])
+            np.testing.assert_allclose(ours, g["metric_%s_%s" % (mname, split)], rtol=1e-5, atol=1e-7)
+    _, metrics, _ = tr.eval("test", banned_items=np.arange(int(g["banned_lo"]), int(g["banned_hi"])))
+    for mname in ("Precision", "Recall", "NDCG"):
+        ours = np.array([metrics[mname][k] for k in TOPKS])
+        np.testing.assert_allclose(ours, g["metric_%s_test_banned" % mname], rtol=1e-5, atol=1e-7)
+
+
+def test_train_epoch_device_sampler_runs_and_learns(golden):
+    g = golden("lightgcn_tiny")
+    ds, m = golden_model(g, "lightgcn_tiny")
+    tr = _trainer(g, "lightgcn_tiny", ds, m, lr=5e-3)
+    m.train()
+    l0 = tr.train_one_epoch()
+    for _ in range(5):
+        l1 = tr.train_one_epoch()
+    assert np.isfinite(l0) and l1 < l0
+    _, metrics, _ = tr.eval("val")
+    assert 0.0 <= metrics["Recall"][20] <= 1.0
+    # host-sampler mode (the reference's DataLoader batches, H2D per step) also runs
+    tr2 = _trainer(g, "lightgcn_tiny", ds, m, sampler="host")
+    assert np.isfinite(tr2.train_one_epoch())
+
+
+def test_checkpoint_roundtrip(golden, tmp_path):
+    g = golden("igcn_fr_tiny")
+    ds, m = golden_model(g, "igcn_fr_tiny")
+    m.feat_mat_anneal()
+    p = str(tmp_path / "m.pth")
+    m.save(p)
+    ck = torch.load(p, weights_only=False)
+    assert set(ck) == {"sate_dict", "user_map", "item_map", "alpha"}          # reference checkpoint layout
+    assert set(ck["sate_dict"]) == {"embedding.weight", "w"}
+    ds2, m2 = golden_model(g, "igcn_fr_tiny")
+    with torch.no_grad():
+        m2.embedding.weight.zero_()
+    m2.load(p)
+    m.eval(); m2.eval()
+    with torch.no_grad():
+        assert torch.equal(m.get_rep(), m2.get_rep())
