@@ -146,9 +146,11 @@ int b200rec_bpr_l2_emb0(const float* emb0, int32_t d, const int64_t* batch, int3
                         float l2_reg, float* g_emb0, float* loss_out, float* block_scratch, void* stream);
 
 /* Dense Adam, the arithmetic of torch.optim.Adam defaults (trainer.py:44-46): no weight decay / amsgrad.
- * step (device int64 scalar) is the count BEFORE this update; the kernel uses step+1 for the bias corrections. */
+ * step (device int64 scalar) is the count BEFORE this update; the kernel uses step+1 for the bias corrections.
+ * Hyper-parameters are doubles: torch forms 1-beta, lr/bias_correction1 and sqrt(bias_correction2) in double before
+ * the fp32 kernels see them, and so does this one. */
 int b200rec_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                      float lr, float beta1, float beta2, float eps, const int64_t* step, void* stream);
+                      double lr, double beta1, double beta2, double eps, const int64_t* step, void* stream);
 /* End of an optimiser step: *step += 1, *step_b += 1 (each if non-NULL; e.g. the Adam count and the sampler count),
  * and AverageMeter.update(loss, B) (utils.py:286-289) on device: loss_accum[0] += *loss * n_batch,
  * loss_accum[1] += n_batch (if both given). */

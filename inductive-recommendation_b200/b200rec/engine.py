@@ -97,6 +97,7 @@ class BprEngine:
                     self.aux_ptr, self.aux_items = aux_dataset.csr('train', device=dev)
         self.use_graph = use_graph
         self._graphs = {}
+        self._kernels = {}
         self.steps_done = 0
 
     # ------------------------------------------------------------------------------------------------ one step
@@ -167,8 +168,11 @@ class BprEngine:
             snap = [t.clone() for t in self._state_tensors()]
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
+            from . import _abi
+            n0 = _abi.launch_count()
             with torch.cuda.stream(s):
                 self._body(sample, draw_mask)
+            self._kernels[(sample, draw_mask)] = _abi.launch_count() - n0
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             for t, c in zip(self._state_tensors(), snap):
@@ -207,6 +211,10 @@ class BprEngine:
             self._run(True)
         self.model._rep_cache = None  # kernels update parameters in place, behind autograd's version counter
         self.steps_done += 1
+
+    def kernels_per_step(self, sample=True, draw_mask=True):
+        """libb200rec kernel launches inside one step (counted while the step was warmed up for capture)"""
+        return self._kernels.get((sample, draw_mask))
 
     def refresh_row_scale(self):
         """after IGCN.feat_mat_anneal(): the graph reads the scale vector in place"""

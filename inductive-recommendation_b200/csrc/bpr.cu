@@ -296,18 +296,18 @@ __global__ void __launch_bounds__(256) bpr_l2_emb0_kernel(const float* __restric
 
 // ---------------------------------------------------------------------------------------------- Adam
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
+                                                   float* __restrict__ v, int64_t n, double lr, double beta1d, double beta2d,
                                                    float eps, const int64_t* __restrict__ step_ptr) {
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     const double t = (double)(*step_ptr + 1);
-    const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
-    s_step_size = (float)((double)lr / bc1);
+    const double bc1 = 1.0 - pow(beta1d, t), bc2 = 1.0 - pow(beta2d, t);
+    s_step_size = (float)(lr / bc1);
     s_bc2_sqrt = (float)sqrt(bc2);
   }
   __syncthreads();
   const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-  const float w1 = (float)(1.0 - (double)beta1), w2 = (float)(1.0 - (double)beta2);
+  const float w1 = (float)(1.0 - beta1d), w2 = (float)(1.0 - beta2d), beta2 = (float)beta2d;
   const int64_t n4 = n >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 gg = ld_f4(g + 4 * i);
@@ -418,13 +418,13 @@ extern "C" int b200rec_bpr_l2_emb0(const float* emb0, int32_t d, const int64_t* 
   return 0;
 }
 
-extern "C" int b200rec_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                                 float beta1, float beta2, float eps, const int64_t* step, void* stream) {
+extern "C" int b200rec_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                                 double beta1, double beta2, double eps, const int64_t* step, void* stream) {
   B2_REQUIRE(param && grad && exp_avg && exp_avg_sq && step && n > 0, "bad argument");
   B2_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, "16-byte alignment");
   int grid = ceil_div(n / 4 + 1, 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, (float)eps, step);
   B2_LAUNCHED();
   return 0;
 }

@@ -9,7 +9,7 @@
 
 namespace b200rec {
 
-constexpr int TU = 64;  // users per block
+constexpr int TU = 64;  // users per block (dense kernel; the top-K kernel uses 16 * UPT)
 constexpr int TI = 64;  // items per tile
 constexpr int KMAX = 128;
 
@@ -63,27 +63,28 @@ struct TopkParams {
   Cand* partial;  // [n_split, n_users, k]
 };
 
-// dynamic smem: us[D][TU] | it[D][TI] | cand[TU][cap] | thr[TU] | cnt[TU]
-template <int D>
+// dynamic smem: us[D][TUK] | it[D][TI] | cand[TUK][cap] | thr[TUK] | cnt[TUK];  TUK = 16 * UPT users per block
+template <int D, int UPT>
 __global__ void __launch_bounds__(256) score_topk_f32_kernel(const TopkParams p) {
+  constexpr int TUK = 16 * UPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* us = reinterpret_cast<float*>(smem_raw);
-  float* it = us + D * TU;
+  float* it = us + D * TUK;
   Cand* cand = reinterpret_cast<Cand*>(it + D * TI);
-  float* thr = reinterpret_cast<float*>(cand + (size_t)TU * p.cap);
-  int* cnt = reinterpret_cast<int*>(thr + TU);
-  __shared__ int64_t s_user[TU];
+  float* thr = reinterpret_cast<float*>(cand + (size_t)TUK * p.cap);
+  int* cnt = reinterpret_cast<int*>(thr + TUK);
+  __shared__ int64_t s_user[TUK];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4 users x 4 items each
-  const int u0 = blockIdx.x * TU;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, UPT users x 4 items each
+  const int u0 = blockIdx.x * TUK;
   const int cap = p.cap, K = p.k;
   // item range of this split, aligned to TI
   const int tiles_total = (p.n_items + TI - 1) / TI;
   const int tiles_per = (tiles_total + p.n_split - 1) / p.n_split;
   const int tile_lo = blockIdx.y * tiles_per, tile_hi = min(tiles_total, tile_lo + tiles_per);
 
-  if (tid < TU) {
+  if (tid < TUK) {
     const int u = u0 + tid;
     s_user[tid] = (u < p.n_users) ? p.users[u] : -1;
     thr[tid] = -INFINITY;
@@ -91,12 +92,12 @@ __global__ void __launch_bounds__(256) score_topk_f32_kernel(const TopkParams p)
   }
   __syncthreads();
   // user tile, transposed to [d][user]
-  for (int e = tid; e < TU * (D / 4); e += 256) {
+  for (int e = tid; e < TUK * (D / 4); e += 256) {
     const int r = e / (D / 4), c4 = e % (D / 4);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (s_user[r] >= 0) v = ldg_f4(p.rep_users + (size_t)s_user[r] * D + c4 * 4);
-    us[(c4 * 4 + 0) * TU + r] = v.x; us[(c4 * 4 + 1) * TU + r] = v.y;
-    us[(c4 * 4 + 2) * TU + r] = v.z; us[(c4 * 4 + 3) * TU + r] = v.w;
+    us[(c4 * 4 + 0) * TUK + r] = v.x; us[(c4 * 4 + 1) * TUK + r] = v.y;
+    us[(c4 * 4 + 2) * TUK + r] = v.z; us[(c4 * 4 + 3) * TUK + r] = v.w;
   }
 
   for (int tile = tile_lo; tile < tile_hi; ++tile) {
@@ -110,25 +111,27 @@ __global__ void __launch_bounds__(256) score_topk_f32_kernel(const TopkParams p)
       it[(c4 * 4 + 2) * TI + r] = v.z; it[(c4 * 4 + 3) * TI + r] = v.w;
     }
     __syncthreads();
-    float acc[4][4];
+    float acc[UPT][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < UPT; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
 #pragma unroll 8
     for (int d = 0; d < D; ++d) {
-      const float4 uu = *reinterpret_cast<const float4*>(us + d * TU + ty * 4);
-      const float4 vv = *reinterpret_cast<const float4*>(it + d * TI + tx * 4);
-      const float ua[4] = {uu.x, uu.y, uu.z, uu.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+      float ua[UPT];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < UPT; ++a) ua[a] = us[d * TUK + ty * UPT + a];
+      const float4 vv = *reinterpret_cast<const float4*>(it + d * TI + tx * 4);
+      const float va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int a = 0; a < UPT; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ua[a], va[b], acc[a][b]);
     }
     // candidates
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int r = ty * 4 + a;
+    for (int a = 0; a < UPT; ++a) {
+      const int r = ty * UPT + a;
       const int64_t user = s_user[r];
       if (user < 0) continue;
       const float t = thr[r];
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(256) score_topk_f32_kernel(const TopkParams p)
     }
     __syncthreads();
     // compaction: rows that could overflow on the next tile keep their K best and raise the threshold
-    for (int r = warp; r < TU; r += 8) {
+    for (int r = warp; r < TUK; r += 8) {
       const int c = cnt[r];
       if (c > cap - TI) {
         Cand* row = cand + (size_t)r * cap;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256) score_topk_f32_kernel(const TopkParams p)
   }
   __syncthreads();
   // final: sort every row, emit K (padding: -inf / -1 when fewer than K unmasked items were seen)
-  for (int r = warp; r < TU; r += 8) {
+  for (int r = warp; r < TUK; r += 8) {
     if (s_user[r] < 0) continue;
     const int c = cnt[r];
     Cand* row = cand + (size_t)r * cap;
@@ -270,8 +273,9 @@ static int next_pow2(int v) {
   while (p < v) p <<= 1;
   return p;
 }
-static int choose_split(int n_users, int n_items, int k) {
-  const int user_tiles = ceil_div(n_users, TU);
+static int topk_upt(int d) { return d >= 256 ? 2 : 4; }
+static int choose_split(int n_users, int n_items, int k, int d) {
+  const int user_tiles = ceil_div(n_users, 16 * topk_upt(d));
   const int tiles_total = ceil_div(n_items, TI);
   int split = ceil_div(2 * 148, user_tiles);
   if (split > tiles_total) split = tiles_total;
@@ -310,9 +314,9 @@ extern "C" int b200rec_score_dense_f32(const float* rep_users, const int64_t* us
 
 extern "C" int64_t b200rec_score_topk_workspace(int32_t n_batch_users, int32_t n_items, int32_t d, int32_t k,
                                                 int32_t precision) {
-  (void)d; (void)precision;
+  (void)precision;
   if (k < 1) k = 1;
-  const int split = choose_split(n_batch_users, n_items, k);
+  const int split = choose_split(n_batch_users, n_items, k, d);
   return (int64_t)split * n_batch_users * k * (int64_t)sizeof(Cand) + 256;
 }
 
@@ -333,17 +337,18 @@ extern "C" int b200rec_score_topk(const float* rep_users, const int64_t* users, 
   p.excl_ptr_a = excl_ptr_a; p.excl_idx_a = excl_idx_a; p.excl_ptr_b = excl_ptr_b; p.excl_idx_b = excl_idx_b;
   p.banned_lo = banned_lo; p.banned_hi = banned_hi; p.k = k;
   p.cap = next_pow2(k + TI);
-  p.n_split = choose_split(n_batch_users, n_items, k);
+  p.n_split = choose_split(n_batch_users, n_items, k, d);
   p.partial = reinterpret_cast<Cand*>(workspace);
-  dim3 grid(ceil_div(n_batch_users, TU), p.n_split);
-#define B2_TOPK(DD)                                                                                                   \
+  const int upt = topk_upt(d), tuk = 16 * upt;
+  dim3 grid(ceil_div(n_batch_users, tuk), p.n_split);
+#define B2_TOPK(DD, UPT)                                                                                                   \
   case DD: {                                                                                                          \
-    const size_t smem = (size_t)DD * (TU + TI) * sizeof(float) + (size_t)TU * p.cap * sizeof(Cand) + TU * 8;          \
-    B2_CUDA(cudaFuncSetAttribute(score_topk_f32_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    score_topk_f32_kernel<DD><<<grid, 256, smem, st>>>(p);                                                            \
+    const size_t smem = (size_t)DD * (tuk + TI) * sizeof(float) + (size_t)tuk * p.cap * sizeof(Cand) + tuk * 8;       \
+    B2_CUDA(cudaFuncSetAttribute(score_topk_f32_kernel<DD, UPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    score_topk_f32_kernel<DD, UPT><<<grid, 256, smem, st>>>(p);                                                            \
   } break;
   switch (d) {
-    B2_TOPK(16) B2_TOPK(32) B2_TOPK(64) B2_TOPK(128) B2_TOPK(256)
+    B2_TOPK(16, 4) B2_TOPK(32, 4) B2_TOPK(64, 4) B2_TOPK(128, 4) B2_TOPK(256, 2)
     default: return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", __func__, "embedding size must be 16/32/64/128/256");
   }
 #undef B2_TOPK

@@ -293,7 +293,7 @@ extern "C" int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32
   const float* src = g;  // H_0 = G
   for (int k = 1; k <= n_layers; ++k) {
     const bool last = (k == n_layers);
-    float* dstp = last ? dx0_out : bufs[k & 1];
+    float* dstp = last ? dx0_out : bufs[(k - 1) & 1];
     int rc = spmm_dispatch(a, src, d, nullptr, 1.f, nullptr, g, dstp, last ? inv : 1.f, st);  // H_k = G + A H_{k-1}
     if (rc) return rc;
     src = dstp;
