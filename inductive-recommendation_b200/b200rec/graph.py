@@ -16,11 +16,23 @@ import torch
 
 from . import _abi
 
-CHUNK = 1024  # rows longer than this are split into chunk-sized work items (deterministic two-pass reduce)
+CHUNK_MAX = 1024
+
+
+def auto_chunk(nnz):
+    """Rows longer than `chunk` are split into chunk-sized work items (deterministic two-pass reduce).  One lane group
+    walks its item serially (~8 neighbour rows per memory round trip), so the longest item is the kernel's critical
+    path: size it so that there are a few items per resident group (148 SMs x 32 groups), within [64, 1024]."""
+    target = max(1, nnz // (148 * 32 * 4))
+    c = 64
+    while c < target and c < CHUNK_MAX:
+        c *= 2
+    return c
+
 
 
 class CsrOperand:
-    def __init__(self, rowptr, colidx, n_cols, vals=None, nbr_scale=None, row_scale=None, eid=None, chunk=CHUNK,
+    def __init__(self, rowptr, colidx, n_cols, vals=None, nbr_scale=None, row_scale=None, eid=None, chunk=None,
                  max_d=256):
         _abi.require_cuda(rowptr, colidx, vals, nbr_scale, row_scale, eid)
         assert rowptr.dtype == torch.int32 and colidx.dtype == torch.int32
@@ -30,7 +42,7 @@ class CsrOperand:
         self.n_cols = int(n_cols)
         self.nnz = colidx.numel()
         self.device = rowptr.device
-        self.chunk = chunk
+        self.chunk = chunk if chunk is not None else auto_chunk(self.nnz)
         self._build_plan(max_d)
         self._struct = None
 

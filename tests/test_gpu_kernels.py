@@ -53,7 +53,7 @@ def test_spmm_bit_exact_vs_c_oracle_with_hub_rows(d):
     vals = rng.standard_normal(rows.size).astype(np.float32)
     x = rng.standard_normal((n_cols, d)).astype(np.float32)
     op = graph.CsrOperand(torch.from_numpy(rp_).to(DEV), torch.from_numpy(cols.astype(np.int32)).to(DEV), n_cols,
-                          vals=torch.from_numpy(vals).to(DEV))
+                          vals=torch.from_numpy(vals).to(DEV), chunk=1024)
     assert op.n_long >= 1
     xd = torch.from_numpy(x).to(DEV)
     y = torch.empty((n_rows, d), device=DEV)
