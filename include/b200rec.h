@@ -61,6 +61,7 @@ typedef struct {
   const int32_t* item_start; /* [n_items] */
   const int32_t* item_end;   /* [n_items] */
   const int32_t* item_dst;   /* [n_items] row id, or ~slot for a piece of a long row */
+  const int32_t* item_row;   /* [n_items] the row the item belongs to (needed only with dst_flags) */
   int32_t n_long;            /* rows that were split */
   const int32_t* long_row;   /* [n_long] */
   const int32_t* long_slot0; /* [n_long] first slot */
@@ -73,7 +74,7 @@ typedef struct {
  * Call once with the output arrays NULL to get the sizes, allocate, call again to fill. */
 int b200rec_plan_build_host(const int32_t* rowptr /*HOST [n_rows+1]*/, int32_t n_rows, int32_t chunk,
                             int32_t* n_items, int32_t* n_long, int32_t* n_slots,
-                            int32_t* item_start, int32_t* item_end, int32_t* item_dst,
+                            int32_t* item_start, int32_t* item_end, int32_t* item_dst, int32_t* item_row,
                             int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot);
 
 /* Symmetric-normalised adjacency values (model.py:89-98 LightGCN.generate_graph; utils.py:42-50).
@@ -93,16 +94,28 @@ int b200rec_adj_normalize(const int32_t* rowptr, const int32_t* colidx, const fl
 int b200rec_spmm_f32(const b200rec_csr* a /*HOST struct of device pointers*/, const float* x, int32_t d,
                      const uint32_t* keep_bits, float post_scale,
                      float* y, const float* addend, float* out, float out_scale, void* stream);
+/* Same, with two per-row byte masks that let a caller skip work whose result it does not need / knows to be zero:
+ *   dst_flags [n_rows]: only rows with a non-zero flag are computed and written (others are left untouched);
+ *   src_flags [n_cols]: gathered rows with a zero flag are all-zero in x and are not read.
+ * Results on the computed rows are bit-identical to the unmasked call. */
+int b200rec_spmm_f32_ex(const b200rec_csr* a, const float* x, int32_t d, const uint32_t* keep_bits, float post_scale,
+                        float* y, const float* addend, float* out, float out_scale,
+                        const uint8_t* dst_flags, const uint8_t* src_flags, void* stream);
 
 /* L-layer propagation + layer mean (model.py:100-110 LightGCN.get_rep; :4193-4199 IGCN.get_rep):
  *   X_{k+1} = A X_k,  mean_out = (X_0 + ... + X_L) / (L+1).  buf0/buf1: [n_rows, D] scratch (L >= 2 needs both).
- * The running sum lives in mean_out; the last layer writes only the mean (no (L+1) x N x D stack). */
+ * The running sum lives in mean_out; the last layer writes only the mean (no (L+1) x N x D stack).
+ * needed_rows (optional byte mask [n_rows]): the caller will only read these rows of mean_out (a BPR step reads the
+ * <= 3B sampled rows, model.py:118-119), so the LAST layer is computed for them only; other rows of mean_out then
+ * hold an unfinished sum.  NULL = all rows. */
 int b200rec_propagate_fwd(const b200rec_csr* a, const float* x0, int32_t d, int32_t n_layers,
-                          float* buf0, float* buf1, float* mean_out, void* stream);
+                          float* buf0, float* buf1, float* mean_out, const uint8_t* needed_rows, void* stream);
 /* Backward of the above w.r.t. X_0 given G = dLoss/d(mean_out) (the autograd of model.py:100-110):
- *   dX0 = (1/(L+1)) sum_k A^k G, evaluated as H <- G + A H (A is bit-wise symmetric, so the forward CSR serves). */
+ *   dX0 = (1/(L+1)) sum_k A^k G, evaluated as H <- G + A H (A is bit-wise symmetric, so the forward CSR serves).
+ * nonzero_rows (optional byte mask [n_rows]): rows of G outside it are all-zero (G has <= 3B non-zero rows), so the
+ * first hop does not gather them.  NULL = dense G. */
 int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32_t d, int32_t n_layers,
-                          float* buf0, float* buf1, float* dx0_out, void* stream);
+                          float* buf0, float* buf1, float* dx0_out, const uint8_t* nonzero_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BPR sampling -- the distribution of BasicDataset.__getitem__ (dataset.py:119-131): user uniform over
@@ -115,6 +128,10 @@ int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32_t d, int32
 int b200rec_bpr_sample(const int32_t* user_ptr, const int32_t* user_items, int32_t n_users, int32_t n_items,
                        uint64_t seed, const int64_t* step /*device scalar*/, int32_t batch,
                        int64_t* out_batch, void* stream);
+
+/* Byte mask of the table rows a batch touches: flags[user] = flags[item_offset+pos] = flags[item_offset+neg] = 1.
+ * flags [n_rows] must be zeroed by the caller first.  Feeds needed_rows / nonzero_rows of the propagation calls. */
+int b200rec_mark_rows(const int64_t* batch /*[B,3]*/, int32_t n_batch, int64_t item_offset, uint8_t* flags, void* stream);
 
 /* Row gather / scatter-add used by the autograd-compatible bpr_forward (model.py:118-119 rep[idx,:] and its
  * index_put_(accumulate) backward).  idx int64 [n]; offset is added to every index (n_users for items). */

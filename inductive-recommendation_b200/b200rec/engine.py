@@ -76,6 +76,7 @@ class BprEngine:
             self.m, self.v = st['exp_avg'], st['exp_avg_sq']
             self.adam_step.fill_(int(st['step']))
             self.g_rep = torch.zeros((n, D), **f32)
+            self.row_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
             self.rep = torch.empty((n, D), **f32)
             L = model.n_layers
             self.bufs = [torch.empty((n, D), **f32) if L >= 2 + i else None for i in range(2)]
@@ -106,14 +107,14 @@ class BprEngine:
         if self.partition is not None:
             self.partition.propagate_fwd(m.norm_adj, x0, m.n_layers, self.bufs, self.rep)
         else:
-            ops.propagate_fwd(m.norm_adj, x0, m.n_layers, self.bufs, self.rep)
+            ops.propagate_fwd(m.norm_adj, x0, m.n_layers, self.bufs, self.rep, needed_rows=self.row_flags)
 
     def _propagate_bwd(self, out):
         m = self.model
         if self.partition is not None:
             self.partition.propagate_bwd(m.norm_adj, self.g_rep, m.n_layers, self.bufs, out)
         else:
-            ops.propagate_bwd(m.norm_adj, self.g_rep, m.n_layers, self.bufs, out)
+            ops.propagate_bwd(m.norm_adj, self.g_rep, m.n_layers, self.bufs, out, nonzero_rows=self.row_flags)
 
     def _body(self, sample, draw_mask=True):
         m, B = self.model, self.B
@@ -122,6 +123,11 @@ class BprEngine:
             ops.bpr_sample(self.user_ptr, self.user_items, self.dataset.n_users, self.dataset.n_items, self.seed,
                            self.sample_step, B, out=self.batch)
         self.loss.zero_()
+        if self.kind != 'MF':
+            # the step reads rep only at the <= 3B sampled rows, and G is non-zero only there: the last forward layer
+            # and the first backward hop are restricted to them (bit-identical on the rows that matter)
+            self.row_flags.zero_()
+            ops.mark_rows(self.batch, nu, self.row_flags)
         if self.kind == 'MF':
             self.grad.zero_()
             ops.bpr_fwd_bwd(self.table, self.batch, nu, self.l2_reg, 1, self.grad, self.loss, self.scratch)

@@ -53,17 +53,17 @@ class CsrOperand:
         null = C.c_void_p(0)
         _abi.check(lib.b200rec_plan_build_host(rp.ctypes.data, self.n_rows, self.chunk, C.addressof(n_items),
                                                C.addressof(n_long), C.addressof(n_slots), null, null, null, null, null,
-                                               null), "plan_build_host(size)")
+                                               null, null), "plan_build_host(size)")
         ni, nl, ns = n_items.value, n_long.value, n_slots.value
-        a = [np.empty(max(ni, 1), dtype=np.int32) for _ in range(3)]
+        a = [np.empty(max(ni, 1), dtype=np.int32) for _ in range(4)]
         b = [np.empty(max(nl, 1), dtype=np.int32) for _ in range(3)]
         _abi.check(lib.b200rec_plan_build_host(rp.ctypes.data, self.n_rows, self.chunk, C.addressof(n_items),
                                                C.addressof(n_long), C.addressof(n_slots),
-                                               a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+                                               a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
                                                b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data), "plan_build_host")
         dev = self.device
         self.n_items, self.n_long, self.n_slots = ni, nl, ns
-        self.item_start, self.item_end, self.item_dst = (torch.from_numpy(x[:max(ni, 1)]).to(dev) for x in a)
+        self.item_start, self.item_end, self.item_dst, self.item_row = (torch.from_numpy(x[:max(ni, 1)]).to(dev) for x in a)
         self.long_row, self.long_slot0, self.long_nslot = (torch.from_numpy(x[:max(nl, 1)]).to(dev) for x in b)
         self.partial = torch.empty((max(ns, 1), max_d), dtype=torch.float32, device=dev) if ns else None
         self.max_d = max_d
@@ -77,6 +77,7 @@ class CsrOperand:
             s.nbr_scale, s.row_scale, s.eid = p(self.nbr_scale), p(self.row_scale), p(self.eid)
             s.n_items = self.n_items
             s.item_start, s.item_end, s.item_dst = p(self.item_start), p(self.item_end), p(self.item_dst)
+            s.item_row = p(self.item_row)
             s.n_long = self.n_long
             s.long_row, s.long_slot0, s.long_nslot = p(self.long_row), p(self.long_slot0), p(self.long_nslot)
             s.n_slots = self.n_slots
@@ -98,19 +99,12 @@ class CsrOperand:
         o.__dict__.update(self.__dict__)
         o._struct = None
         keep_long = (self.long_row[:self.n_long] >= lo) & (self.long_row[:self.n_long] < hi) if self.n_long else None
-        dst = self.item_dst[:self.n_items]
-        is_row = dst >= 0
-        keep = is_row & (dst >= lo) & (dst < hi)
-        if self.n_long:
-            # pieces of split rows: slot -> owning long row
-            slot_owner = torch.repeat_interleave(self.long_row[:self.n_long].long(), self.long_nslot[:self.n_long].long())
-            piece = ~is_row
-            owner = torch.zeros_like(dst, dtype=torch.int64)
-            owner[piece] = slot_owner[(~dst[piece]).long()]
-            keep |= piece & (owner >= lo) & (owner < hi)
+        row = self.item_row[:self.n_items]
+        keep = (row >= lo) & (row < hi)
         o.item_start = self.item_start[:self.n_items][keep].contiguous()
         o.item_end = self.item_end[:self.n_items][keep].contiguous()
         o.item_dst = self.item_dst[:self.n_items][keep].contiguous()
+        o.item_row = self.item_row[:self.n_items][keep].contiguous()
         o.n_items = int(o.item_start.numel())
         if self.n_long:
             o.long_row = self.long_row[:self.n_long][keep_long].contiguous()
@@ -121,7 +115,7 @@ class CsrOperand:
                 if getattr(o, name).numel() == 0:
                     setattr(o, name, torch.zeros(1, dtype=torch.int32, device=self.device))
         if o.n_items == 0:
-            for name in ("item_start", "item_end", "item_dst"):
+            for name in ("item_start", "item_end", "item_dst", "item_row"):
                 setattr(o, name, torch.zeros(1, dtype=torch.int32, device=self.device))
         return o
 
@@ -171,7 +165,7 @@ def _coalesce(rows, cols, n_rows, n_cols):
     return rp.to(torch.int32), c.to(torch.int32), mult
 
 
-def build_norm_adj(n_users, n_items, users, items, device=None):
+def build_norm_adj(n_users, n_items, users, items, device=None, chunk=None):
     """users/items: int64 tensors of the E train pairs (train_array, dataset.py:149-151), any order, duplicates allowed
     (they are summed, like scipy's COO->CSR in utils.py:47-49).  Returns (CsrOperand with .vals/.dinv, mult)."""
     device = torch.device(device) if device is not None else users.device
@@ -186,7 +180,7 @@ def build_norm_adj(n_users, n_items, users, items, device=None):
     _abi.require_cuda(rowptr)
     _abi.check(lib.b200rec_adj_normalize(_abi.ptr(rowptr), _abi.ptr(colidx), _abi.ptr(mult), n, _abi.ptr(dinv),
                                          _abi.ptr(vals), _abi.stream_ptr()), "adj_normalize")
-    op = CsrOperand(rowptr, colidx, n, vals=vals)
+    op = CsrOperand(rowptr, colidx, n, vals=vals, chunk=chunk)
     op.dinv = dinv
     op.mult = mult
     return op

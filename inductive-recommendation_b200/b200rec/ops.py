@@ -19,25 +19,31 @@ def _lib():
 
 
 # ------------------------------------------------------------------------------------------------ raw calls
-def spmm(op, x, keep_bits=None, post_scale=1.0, y=None, addend=None, out=None, out_scale=1.0):
-    _abi.require_cuda(x, keep_bits, y, addend, out)
+def spmm(op, x, keep_bits=None, post_scale=1.0, y=None, addend=None, out=None, out_scale=1.0, dst_flags=None,
+         src_flags=None):
+    _abi.require_cuda(x, keep_bits, y, addend, out, dst_flags, src_flags)
     d = x.shape[1]
     assert x.dtype == torch.float32 and x.shape[0] >= op.n_cols
     assert op.partial is None or d <= op.max_d
-    check(_lib().b200rec_spmm_f32(C.byref(op.struct()), ptr(x), d, ptr(keep_bits), post_scale, ptr(y), ptr(addend),
-                                  ptr(out), out_scale, stream_ptr()), "spmm_f32")
+    if dst_flags is None and src_flags is None:
+        check(_lib().b200rec_spmm_f32(C.byref(op.struct()), ptr(x), d, ptr(keep_bits), post_scale, ptr(y), ptr(addend),
+                                      ptr(out), out_scale, stream_ptr()), "spmm_f32")
+    else:
+        check(_lib().b200rec_spmm_f32_ex(C.byref(op.struct()), ptr(x), d, ptr(keep_bits), post_scale, ptr(y),
+                                         ptr(addend), ptr(out), out_scale, ptr(dst_flags), ptr(src_flags),
+                                         stream_ptr()), "spmm_f32_ex")
 
 
-def propagate_fwd(op, x0, n_layers, bufs, mean_out):
-    _abi.require_cuda(x0, mean_out)
+def propagate_fwd(op, x0, n_layers, bufs, mean_out, needed_rows=None):
+    _abi.require_cuda(x0, mean_out, needed_rows)
     check(_lib().b200rec_propagate_fwd(C.byref(op.struct()), ptr(x0), x0.shape[1], n_layers, ptr(bufs[0]), ptr(bufs[1]),
-                                       ptr(mean_out), stream_ptr()), "propagate_fwd")
+                                       ptr(mean_out), ptr(needed_rows), stream_ptr()), "propagate_fwd")
 
 
-def propagate_bwd(op, g, n_layers, bufs, dx0):
-    _abi.require_cuda(g, dx0)
+def propagate_bwd(op, g, n_layers, bufs, dx0, nonzero_rows=None):
+    _abi.require_cuda(g, dx0, nonzero_rows)
     check(_lib().b200rec_propagate_bwd(C.byref(op.struct()), ptr(g), g.shape[1], n_layers, ptr(bufs[0]), ptr(bufs[1]),
-                                       ptr(dx0), stream_ptr()), "propagate_bwd")
+                                       ptr(dx0), ptr(nonzero_rows), stream_ptr()), "propagate_bwd")
 
 
 def bpr_sample(user_ptr, user_items, n_users, n_items, seed, step, batch_size, out=None):
@@ -47,6 +53,12 @@ def bpr_sample(user_ptr, user_items, n_users, n_items, seed, step, batch_size, o
     check(_lib().b200rec_bpr_sample(ptr(user_ptr), ptr(user_items), n_users, n_items, C.c_uint64(seed), ptr(step),
                                     batch_size, ptr(out), stream_ptr()), "bpr_sample")
     return out
+
+
+def mark_rows(batch, item_offset, flags):
+    """flags (uint8 [n_rows], zeroed by the caller) <- 1 at every row the batch touches"""
+    _abi.require_cuda(batch, flags)
+    check(_lib().b200rec_mark_rows(ptr(batch), batch.shape[0], item_offset, ptr(flags), stream_ptr()), "mark_rows")
 
 
 def bpr_scratch(batch_size, d, device):

@@ -78,6 +78,14 @@ __global__ void dropout_mask_kernel(int nnz, float keep_base, uint64_t seed, con
   bits[w] = word;
 }
 
+// rows a BPR batch touches: flags[u] = flags[off+pos] = flags[off+neg] = 1 (flags pre-zeroed)
+__global__ void mark_rows_kernel(const int64_t* __restrict__ batch, int n_batch, int64_t item_offset, uint8_t* __restrict__ flags) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * n_batch) return;
+  const int64_t r = batch[t] + ((t % 3) ? item_offset : 0);
+  flags[r] = 1;
+}
+
 // ---------------------------------------------------------------------------------------------- gather / scatter
 template <int G, int VPL>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
@@ -372,6 +380,13 @@ extern "C" int b200rec_bpr_sample(const int32_t* user_ptr, const int32_t* user_i
   B2_REQUIRE(user_ptr && user_items && step && out_batch && n_users > 0 && n_items > 0 && batch > 0, "bad argument");
   bpr_sample_kernel<<<ceil_div(batch, 128), 128, 0, (cudaStream_t)stream>>>(user_ptr, user_items, n_users, n_items, seed,
                                                                            step, batch, out_batch);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_mark_rows(const int64_t* batch, int32_t n_batch, int64_t item_offset, uint8_t* flags, void* stream) {
+  B2_REQUIRE(batch && flags && n_batch > 0, "bad argument");
+  mark_rows_kernel<<<ceil_div(3 * n_batch, 256), 256, 0, (cudaStream_t)stream>>>(batch, n_batch, item_offset, flags);
   B2_LAUNCHED();
   return 0;
 }

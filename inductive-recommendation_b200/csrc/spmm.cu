@@ -16,9 +16,12 @@ struct SpmmParams {
   const float* row_scale;
   const int32_t* eid;
   const uint32_t* keep_bits;
+  const uint8_t* dst_flags;  // optional: only rows with a non-zero flag are computed (others left untouched)
+  const uint8_t* src_flags;  // optional: gathered rows with a zero flag are known to be all-zero and are skipped
   const int32_t* item_start;
   const int32_t* item_end;
   const int32_t* item_dst;
+  const int32_t* item_row;
   int n_items;
   const float* x;
   float* y;
@@ -48,26 +51,39 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int g
   }
 }
 
-template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID>
-__global__ void __launch_bounds__(256) spmm_items_kernel(const SpmmParams p) {
+// Inner-loop economics (ncu, C2 shape): the LSU data pipe is the busiest unit -- every gathered 256 B row costs two
+// wavefronts whether it hits L1 or not -- so everything else is kept off that pipe and off the issue slots:
+//  * (column, value) pairs are loaded G at a time, coalesced, and parked in shared memory as one 64-bit word; each
+//    neighbour then costs ONE broadcast LDS.64 instead of two SHFLs;
+//  * edges that contribute nothing (past the row end, dropped by the edge-dropout mask, or whose source row is
+//    flagged all-zero) are squeezed out with a ballot/popc compaction before the gather loop; the slack of the last
+//    sub-block is padded with (first column of the row, weight 0), so the loop body carries no predicates or selects.
+template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID, bool HAS_SRCF>
+__global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(const SpmmParams p) {
   constexpr int D = G * VPL * 4;
   constexpr int U = (G >= 8) ? 8 : G;  // neighbour rows in flight per lane
   constexpr int GPW = 32 / G;          // groups per warp
+  constexpr bool COMPACT = HAS_MASK || HAS_SRCF;
+  __shared__ int2 s_cv[256];
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   const int item = warp * GPW + lane / G;
+  int2* my_cv = s_cv + (threadIdx.x & ~(G - 1));  // this group's G slots
   int start = 0, end = 0, dst = 0;
   if (item < p.n_items) {
     start = __ldg(p.item_start + item);
     end = __ldg(p.item_end + item);
     dst = __ldg(p.item_dst + item);
+    if (p.dst_flags && !__ldg(p.dst_flags + __ldg(p.item_row + item))) end = start;  // row not needed this call
   }
+  const bool live = end > start;
   int maxlen = end - start;
   if (GPW > 1) {
 #pragma unroll
     for (int o = G; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
   }
+  const int cfirst = live ? __ldg(p.colidx + start) : 0;  // padding target: a row this sum reads anyway
   float4 acc[VPL];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -75,35 +91,50 @@ __global__ void __launch_bounds__(256) spmm_items_kernel(const SpmmParams p) {
 
   for (int base = 0; base < maxlen; base += G) {
     const int k = start + base + gl;
-    int c = -1;
-    float v = 1.f;
-    if (k < end) {
+    int c = cfirst;
+    float v = 0.f;
+    bool valid = k < end;
+    if (valid) {
       c = ld_stream_i32(p.colidx + k);
-      if (HAS_VALS) v = ld_stream_f32(p.vals + k);
+      v = HAS_VALS ? ld_stream_f32(p.vals + k) : 1.f;
       if (HAS_MASK) {
         const int e = HAS_EID ? ld_stream_i32(p.eid + k) : k;
-        if (!((__ldg(p.keep_bits + (e >> 5)) >> (e & 31)) & 1u)) c = -1;
+        valid = ((__ldg(p.keep_bits + (e >> 5)) >> (e & 31)) & 1u) != 0u;
       }
-      if (HAS_NBR && c >= 0) v *= __ldg(p.nbr_scale + c);
+      if (HAS_SRCF) valid = valid && (__ldg(p.src_flags + c) != 0);
+      if (HAS_NBR && valid) v *= __ldg(p.nbr_scale + c);
     }
+    int cnt;  // contributing edges of this group in this block of G; cntmax: warp-uniform loop bound
+    if (COMPACT) {
+      const unsigned bal = __ballot_sync(0xffffffffu, valid);
+      const unsigned gm = (G == 32) ? bal : ((bal >> (lane & ~(G - 1))) & ((1u << (G & 31)) - 1u));
+      cnt = __popc(gm);
+      const int rank = __popc(gm & ((1u << gl) - 1u));
+      my_cv[gl] = make_int2(cfirst, 0);  // pad
+      __syncwarp();
+      if (valid) my_cv[rank] = make_int2(c, __float_as_int(v));
+    } else {
+      cnt = min(G, max(end - start - base, 0));
+      my_cv[gl] = valid ? make_int2(c, __float_as_int(v)) : make_int2(cfirst, 0);
+    }
+    int cntmax = cnt;
+    if (GPW > 1) {
+#pragma unroll
+      for (int o = G; o < 32; o <<= 1) cntmax = max(cntmax, __shfl_xor_sync(0xffffffffu, cntmax, o));
+    }
+    __syncwarp();
 #pragma unroll
     for (int j0 = 0; j0 < G; j0 += U) {
-      if (base + j0 >= maxlen) break;  // warp-uniform
+      if (j0 >= cntmax) break;  // warp-uniform
       float4 xv[U][VPL];
       float vv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int cc = __shfl_sync(0xffffffffu, c, j0 + u, G);
-        vv[u] = __shfl_sync(0xffffffffu, v, j0 + u, G);
-        if (cc >= 0) {
-          const float* r = xg + (size_t)cc * D;
+        const int2 cv = my_cv[j0 + u];  // broadcast LDS.64
+        vv[u] = __int_as_float(cv.y);
+        const float* r = xg + (size_t)((unsigned)cv.x * (unsigned)D);
 #pragma unroll
-          for (int t = 0; t < VPL; ++t) xv[u][t] = ldg_f4(r + t * G * 4);
-        } else {
-          vv[u] = 0.f;
-#pragma unroll
-          for (int t = 0; t < VPL; ++t) xv[u][t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int t = 0; t < VPL; ++t) xv[u][t] = ldg_f4(r + t * G * 4);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -116,8 +147,10 @@ __global__ void __launch_bounds__(256) spmm_items_kernel(const SpmmParams p) {
         }
       }
     }
+    __syncwarp();  // slots are rewritten by the next block
   }
   if (item >= p.n_items) return;
+  if (p.dst_flags && !__ldg(p.dst_flags + __ldg(p.item_row + item))) return;
   if (dst >= 0) {
     epilogue_row<G, VPL>(p, dst, gl, acc);
   } else {  // a chunk of a split row: raw partial sum, scaled by the reducer
@@ -127,7 +160,7 @@ __global__ void __launch_bounds__(256) spmm_items_kernel(const SpmmParams p) {
   }
 }
 
-// one group per split row: add its slots in slot order, then the common epilogue
+// one group per split row: add its slots in slot order (4 slot loads in flight), then the common epilogue
 template <int G, int VPL>
 __global__ void __launch_bounds__(256) spmm_long_reduce_kernel(const SpmmParams p, const int32_t* long_row,
                                                                 const int32_t* long_slot0, const int32_t* long_nslot,
@@ -137,13 +170,29 @@ __global__ void __launch_bounds__(256) spmm_long_reduce_kernel(const SpmmParams 
   const int gl = threadIdx.x & (G - 1);
   if (gidx >= n_long) return;
   const int row = long_row[gidx], s0 = long_slot0[gidx], ns = long_nslot[gidx];
+  if (p.dst_flags && !__ldg(p.dst_flags + row)) return;
   float4 acc[VPL];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < ns; ++s) {
+  const float* base = p.partial + (size_t)s0 * D + (size_t)gl * 4;
+  int s = 0;
+  for (; s + 4 <= ns; s += 4) {
+    float4 v[4][VPL];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) v[q][t] = ld_f4(base + (size_t)(s + q) * D + t * G * 4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) {
+        acc[t].x += v[q][t].x; acc[t].y += v[q][t].y; acc[t].z += v[q][t].z; acc[t].w += v[q][t].w;
+      }
+  }
+  for (; s < ns; ++s) {
 #pragma unroll
     for (int t = 0; t < VPL; ++t) {
-      const float4 v = ld_f4(p.partial + (size_t)(s0 + s) * D + (size_t)(gl + t * G) * 4);
+      const float4 v = ld_f4(base + (size_t)s * D + t * G * 4);
       acc[t].x += v.x; acc[t].y += v.y; acc[t].z += v.z; acc[t].w += v.w;
     }
   }
@@ -157,19 +206,21 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
   if (a->n_items > 0) {
     const int grid = ceil_div(a->n_items, items_per_block);
     const bool hv = p.vals != nullptr, hn = p.nbr_scale != nullptr, hm = p.keep_bits != nullptr, he = p.eid != nullptr && hm;
-#define B2_SPMM_CASE(V, N, M, E)                                                  \
-  if (hv == V && hn == N && hm == M && he == E) {                                 \
-    spmm_items_kernel<G, VPL, V, N, M, E><<<grid, 256, 0, st>>>(p);               \
+    const bool hs = p.src_flags != nullptr;
+#define B2_SPMM_CASE(V, N, M, E, S)                                               \
+  if (hv == V && hn == N && hm == M && he == E && hs == S) {                      \
+    spmm_items_kernel<G, VPL, V, N, M, E, S><<<grid, 256, 0, st>>>(p);            \
     B2_LAUNCHED();                                                                \
   } else
-    B2_SPMM_CASE(true, false, false, false)   // normalised adjacency
-    B2_SPMM_CASE(false, false, false, false)  // template features, eval
-    B2_SPMM_CASE(false, false, true, false)   // template features, training (edge dropout)
-    B2_SPMM_CASE(false, true, false, false)   // transposed features (backward), eval-mode graph
-    B2_SPMM_CASE(false, true, true, true)     // transposed features (backward), dropout mask by edge id
-    B2_SPMM_CASE(true, false, true, false)    // valued operand with dropout
-    B2_SPMM_CASE(true, true, false, false)
-    { return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "operand combination (vals/nbr_scale/keep_bits/eid) not instantiated"); }
+    B2_SPMM_CASE(true, false, false, false, false)   // normalised adjacency
+    B2_SPMM_CASE(true, false, false, false, true)    // normalised adjacency, sparse source (first backward hop)
+    B2_SPMM_CASE(false, false, false, false, false)  // template features, eval
+    B2_SPMM_CASE(false, false, true, false, false)   // template features, training (edge dropout)
+    B2_SPMM_CASE(false, true, false, false, false)   // transposed features (backward), eval-mode graph
+    B2_SPMM_CASE(false, true, true, true, false)     // transposed features (backward), dropout mask by edge id
+    B2_SPMM_CASE(true, false, true, false, false)    // valued operand with dropout
+    B2_SPMM_CASE(true, true, false, false, false)
+    { return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "operand combination (vals/nbr_scale/keep_bits/eid/src_flags) not instantiated"); }
 #undef B2_SPMM_CASE
   }
   if (a->n_long > 0) {
@@ -182,15 +233,19 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
 }
 
 static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint32_t* keep_bits, float post_scale,
-                         float* y, const float* addend, float* out, float out_scale, cudaStream_t st) {
+                         float* y, const float* addend, float* out, float out_scale, const uint8_t* dst_flags,
+                         const uint8_t* src_flags, cudaStream_t st) {
   B2_REQUIRE(a && x, "null operand");
   B2_REQUIRE(y || out, "no output");
   B2_REQUIRE(a->n_items == 0 || (a->item_start && a->item_end && a->item_dst && a->colidx), "csr plan missing");
   B2_REQUIRE(a->n_long == 0 || (a->partial && a->long_row && a->long_slot0 && a->long_nslot), "long-row plan missing");
+  B2_REQUIRE(!dst_flags || a->item_row, "dst_flags needs item_row in the plan");
+  B2_REQUIRE((long long)a->n_cols * d < (1ll << 32), "gathered table must have < 2^32 elements");
   SpmmParams p;
   p.colidx = a->colidx; p.vals = a->vals; p.nbr_scale = a->nbr_scale; p.row_scale = a->row_scale; p.eid = a->eid;
-  p.keep_bits = keep_bits;
-  p.item_start = a->item_start; p.item_end = a->item_end; p.item_dst = a->item_dst; p.n_items = a->n_items;
+  p.keep_bits = keep_bits; p.dst_flags = dst_flags; p.src_flags = src_flags;
+  p.item_start = a->item_start; p.item_end = a->item_end; p.item_dst = a->item_dst; p.item_row = a->item_row;
+  p.n_items = a->n_items;
   p.x = x; p.y = y; p.addend = addend; p.out = out; p.out_scale = out_scale; p.post_scale = post_scale;
   p.partial = a->partial;
   switch (d) {
@@ -251,11 +306,18 @@ extern "C" int b200rec_adj_normalize(const int32_t* rowptr, const int32_t* colid
 extern "C" int b200rec_spmm_f32(const b200rec_csr* a, const float* x, int32_t d, const uint32_t* keep_bits,
                                 float post_scale, float* y, const float* addend, float* out, float out_scale,
                                 void* stream) {
-  return spmm_dispatch(a, x, d, keep_bits, post_scale, y, addend, out, out_scale, (cudaStream_t)stream);
+  return spmm_dispatch(a, x, d, keep_bits, post_scale, y, addend, out, out_scale, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b200rec_spmm_f32_ex(const b200rec_csr* a, const float* x, int32_t d, const uint32_t* keep_bits,
+                                   float post_scale, float* y, const float* addend, float* out, float out_scale,
+                                   const uint8_t* dst_flags, const uint8_t* src_flags, void* stream) {
+  return spmm_dispatch(a, x, d, keep_bits, post_scale, y, addend, out, out_scale, dst_flags, src_flags,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int b200rec_propagate_fwd(const b200rec_csr* a, const float* x0, int32_t d, int32_t n_layers, float* buf0,
-                                     float* buf1, float* mean_out, void* stream) {
+                                     float* buf1, float* mean_out, const uint8_t* needed_rows, void* stream) {
   B2_REQUIRE(a && x0 && mean_out && n_layers >= 0, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_layers == 0) {
@@ -271,7 +333,9 @@ extern "C" int b200rec_propagate_fwd(const b200rec_csr* a, const float* x0, int3
     const bool last = (k == n_layers - 1);
     float* y = last ? nullptr : bufs[k & 1];
     const float* addend = (k == 0) ? x0 : mean_out;  // running layer sum lives in mean_out
-    int rc = spmm_dispatch(a, src, d, nullptr, 1.f, y, addend, mean_out, last ? inv : 1.f, st);
+    // only the last layer can be restricted: every earlier layer feeds rows that the needed rows read
+    int rc = spmm_dispatch(a, src, d, nullptr, 1.f, y, addend, mean_out, last ? inv : 1.f, last ? needed_rows : nullptr,
+                           nullptr, st);
     if (rc) return rc;
     src = y;
   }
@@ -279,7 +343,7 @@ extern "C" int b200rec_propagate_fwd(const b200rec_csr* a, const float* x0, int3
 }
 
 extern "C" int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32_t d, int32_t n_layers, float* buf0,
-                                     float* buf1, float* dx0_out, void* stream) {
+                                     float* buf1, float* dx0_out, const uint8_t* nonzero_rows, void* stream) {
   B2_REQUIRE(a && g && dx0_out && n_layers >= 0, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const float inv = 1.f / (float)(n_layers + 1);
@@ -294,7 +358,9 @@ extern "C" int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32
   for (int k = 1; k <= n_layers; ++k) {
     const bool last = (k == n_layers);
     float* dstp = last ? dx0_out : bufs[(k - 1) & 1];
-    int rc = spmm_dispatch(a, src, d, nullptr, 1.f, nullptr, g, dstp, last ? inv : 1.f, st);  // H_k = G + A H_{k-1}
+    // H_k = G + A H_{k-1}; on the first hop H_0 = G is zero outside nonzero_rows, so those gathers are skipped
+    int rc = spmm_dispatch(a, src, d, nullptr, 1.f, nullptr, g, dstp, last ? inv : 1.f, nullptr,
+                           (k == 1) ? nonzero_rows : nullptr, st);
     if (rc) return rc;
     src = dstp;
   }
@@ -303,7 +369,7 @@ extern "C" int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32
 
 extern "C" int b200rec_plan_build_host(const int32_t* rowptr, int32_t n_rows, int32_t chunk, int32_t* n_items,
                                        int32_t* n_long, int32_t* n_slots, int32_t* item_start, int32_t* item_end,
-                                       int32_t* item_dst, int32_t* long_row, int32_t* long_slot0,
+                                       int32_t* item_dst, int32_t* item_row, int32_t* long_row, int32_t* long_slot0,
                                        int32_t* long_nslot) {
   B2_REQUIRE(rowptr && n_rows >= 0 && chunk >= 32 && n_items && n_long && n_slots, "bad argument");
   // sizes
@@ -336,20 +402,21 @@ extern "C" int b200rec_plan_build_host(const int32_t* rowptr, int32_t n_rows, in
         ++li;
         for (int q = 0; q < pieces; ++q) {
           const int b = s + q * chunk, e = (b + chunk < s + len) ? b + chunk : s + len;
-          fn(b, e, ~(slot + q));
+          fn(b, e, ~(slot + q), r);
         }
         slot += pieces;
       } else {
-        fn(s, s + len, r);
+        fn(s, s + len, r, r);
       }
     }
   };
-  each_item([&](int b, int e, int) { bucket[maxlen - (e - b)]++; });
+  each_item([&](int b, int e, int, int) { bucket[maxlen - (e - b)]++; });
   int run = 0;
   for (int i = 0; i <= maxlen; ++i) { int c = bucket[i]; bucket[i] = run; run += c; }
-  each_item([&](int b, int e, int dst) {
+  each_item([&](int b, int e, int dst, int row) {
     const int pos = bucket[maxlen - (e - b)]++;
     item_start[pos] = b; item_end[pos] = e; item_dst[pos] = dst;
+    if (item_row) item_row[pos] = row;
   });
   delete[] bucket;
   return 0;

@@ -220,3 +220,38 @@ def test_hit_matrix():
     rec = torch.tensor([[9, 1, 3], [3, 9, 0], [8, -1, 5]], dtype=torch.int32, device=DEV)
     hit = ops.hit_matrix(rec, 0, ptr, idx)
     assert _np(hit).tolist() == [[1, 0, 1], [0, 0, 0], [1, 0, 0]]
+
+
+def test_spmm_row_and_source_masks_are_bit_identical(golden):
+    """dst_flags / src_flags skip work without changing a bit of the rows that are computed"""
+    from b200rec import graph, ops
+    g = golden("lightgcn_tiny")
+    users, items = rp.pairs_from_csr(g["train_indptr"], g["train_items"])
+    op = graph.build_norm_adj(int(g["n_users"]), int(g["n_items"]), torch.from_numpy(users), torch.from_numpy(items), DEV,
+                              chunk=64)   # small chunk: hub rows are split, so the piece -> row lookup is exercised
+    assert op.n_long > 0
+    n, d = op.n_rows, 64
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn((n, d), device=DEV, generator=gen)
+    full = torch.empty_like(x)
+    ops.spmm(op, x, y=full)
+    flags = (torch.rand(n, device=DEV, generator=gen) < 0.2).to(torch.uint8)
+    part = torch.full_like(x, 7.0)
+    ops.spmm(op, x, y=part, dst_flags=flags)
+    sel = flags.bool()
+    assert torch.equal(part[sel], full[sel]) and bool((part[~sel] == 7.0).all())
+    xs = x * sel[:, None]                      # source rows outside the mask are zero
+    ref = torch.empty_like(x); ops.spmm(op, xs, y=ref)
+    got = torch.empty_like(x); ops.spmm(op, xs, y=got, src_flags=flags)
+    assert torch.equal(got, ref)
+    # the propagation entry points: restricted last layer / sparse first hop
+    L = 3
+    bufs = [torch.empty_like(x), torch.empty_like(x)]
+    m_full, m_part = torch.empty_like(x), torch.empty_like(x)
+    ops.propagate_fwd(op, x, L, bufs, m_full)
+    ops.propagate_fwd(op, x, L, bufs, m_part, needed_rows=flags)
+    assert torch.equal(m_part[sel], m_full[sel])
+    d_full, d_part = torch.empty_like(x), torch.empty_like(x)
+    ops.propagate_bwd(op, xs, L, bufs, d_full)
+    ops.propagate_bwd(op, xs, L, bufs, d_part, nonzero_rows=flags)
+    assert torch.equal(d_part, d_full)
