@@ -42,8 +42,8 @@ uint64_t b200rec_launch_count(void);
  * A work item is a slice [item_start, item_end) of the nnz arrays that belongs to one row.  Rows with
  * at most `chunk` entries are one item whose item_dst is the row id; longer rows (hubs of the
  * power-law graph, IGCN's two shared template columns) are split into chunk-sized items whose item_dst
- * is ~slot (negative) -- they write a partial row into `partial[slot]`, and a second deterministic
- * kernel adds the slots of each long row in slot order.  Items are sorted by length, longest first.
+ * is ~slot (negative) -- they write a partial row into `partial[slot]`, and whichever lane group parks the last
+ * chunk of a row adds that row's slots in slot order (deterministic) and writes the row.  Items are sorted by length, longest first.
  * The decomposition is built once per graph by b200rec_plan_build().
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -66,7 +66,9 @@ typedef struct {
   const int32_t* long_row;   /* [n_long] */
   const int32_t* long_slot0; /* [n_long] first slot */
   const int32_t* long_nslot; /* [n_long] */
+  int32_t* long_cnt;         /* [n_long] arrival counters, zero-initialised once by the caller (self-resetting) */
   int32_t n_slots;
+  const int32_t* slot_long;  /* [n_slots] index (into long_*) of the split row a slot belongs to */
   float* partial;            /* [n_slots, D] scratch for split rows (caller-owned, D = largest D used) */
 } b200rec_csr;
 
@@ -75,7 +77,7 @@ typedef struct {
 int b200rec_plan_build_host(const int32_t* rowptr /*HOST [n_rows+1]*/, int32_t n_rows, int32_t chunk,
                             int32_t* n_items, int32_t* n_long, int32_t* n_slots,
                             int32_t* item_start, int32_t* item_end, int32_t* item_dst, int32_t* item_row,
-                            int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot);
+                            int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot, int32_t* slot_long);
 
 /* Symmetric-normalised adjacency values (model.py:89-98 LightGCN.generate_graph; utils.py:42-50).
  * deg[r] = max(1, sum of multiplicities in row r); dinv = deg^-1/2 (fp32, correctly rounded);

@@ -53,18 +53,22 @@ class CsrOperand:
         null = C.c_void_p(0)
         _abi.check(lib.b200rec_plan_build_host(rp.ctypes.data, self.n_rows, self.chunk, C.addressof(n_items),
                                                C.addressof(n_long), C.addressof(n_slots), null, null, null, null, null,
-                                               null, null), "plan_build_host(size)")
+                                               null, null, null), "plan_build_host(size)")
         ni, nl, ns = n_items.value, n_long.value, n_slots.value
         a = [np.empty(max(ni, 1), dtype=np.int32) for _ in range(4)]
         b = [np.empty(max(nl, 1), dtype=np.int32) for _ in range(3)]
+        sl = np.zeros(max(ns, 1), dtype=np.int32)
         _abi.check(lib.b200rec_plan_build_host(rp.ctypes.data, self.n_rows, self.chunk, C.addressof(n_items),
                                                C.addressof(n_long), C.addressof(n_slots),
                                                a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
-                                               b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data), "plan_build_host")
+                                               b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, sl.ctypes.data),
+                   "plan_build_host")
         dev = self.device
         self.n_items, self.n_long, self.n_slots = ni, nl, ns
         self.item_start, self.item_end, self.item_dst, self.item_row = (torch.from_numpy(x[:max(ni, 1)]).to(dev) for x in a)
         self.long_row, self.long_slot0, self.long_nslot = (torch.from_numpy(x[:max(nl, 1)]).to(dev) for x in b)
+        self.slot_long = torch.from_numpy(sl).to(dev)
+        self.long_cnt = torch.zeros(max(nl, 1), dtype=torch.int32, device=dev)
         self.partial = torch.empty((max(ns, 1), max_d), dtype=torch.float32, device=dev) if ns else None
         self.max_d = max_d
 
@@ -81,6 +85,7 @@ class CsrOperand:
             s.n_long = self.n_long
             s.long_row, s.long_slot0, s.long_nslot = p(self.long_row), p(self.long_slot0), p(self.long_nslot)
             s.n_slots = self.n_slots
+            s.slot_long, s.long_cnt = p(self.slot_long), p(self.long_cnt)
             s.partial = p(self.partial)
             self._struct = s
         return self._struct
@@ -98,7 +103,6 @@ class CsrOperand:
         o = object.__new__(CsrOperand)
         o.__dict__.update(self.__dict__)
         o._struct = None
-        keep_long = (self.long_row[:self.n_long] >= lo) & (self.long_row[:self.n_long] < hi) if self.n_long else None
         row = self.item_row[:self.n_items]
         keep = (row >= lo) & (row < hi)
         o.item_start = self.item_start[:self.n_items][keep].contiguous()
@@ -106,14 +110,6 @@ class CsrOperand:
         o.item_dst = self.item_dst[:self.n_items][keep].contiguous()
         o.item_row = self.item_row[:self.n_items][keep].contiguous()
         o.n_items = int(o.item_start.numel())
-        if self.n_long:
-            o.long_row = self.long_row[:self.n_long][keep_long].contiguous()
-            o.long_slot0 = self.long_slot0[:self.n_long][keep_long].contiguous()
-            o.long_nslot = self.long_nslot[:self.n_long][keep_long].contiguous()
-            o.n_long = int(o.long_row.numel())
-            for name in ("long_row", "long_slot0", "long_nslot"):
-                if getattr(o, name).numel() == 0:
-                    setattr(o, name, torch.zeros(1, dtype=torch.int32, device=self.device))
         if o.n_items == 0:
             for name in ("item_start", "item_end", "item_dst", "item_row"):
                 setattr(o, name, torch.zeros(1, dtype=torch.int32, device=self.device))

@@ -30,6 +30,11 @@ struct SpmmParams {
   float out_scale;
   float post_scale;
   float* partial;
+  const int32_t* slot_long;   // [n_slots] index of the split row a slot belongs to
+  const int32_t* long_row;
+  const int32_t* long_slot0;
+  const int32_t* long_nslot;
+  int32_t* long_cnt;          // [n_long] arrival counters (zero between launches: the finisher resets its own)
 };
 
 template <int G, int VPL>
@@ -153,50 +158,48 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   if (p.dst_flags && !__ldg(p.dst_flags + __ldg(p.item_row + item))) return;
   if (dst >= 0) {
     epilogue_row<G, VPL>(p, dst, gl, acc);
-  } else {  // a chunk of a split row: raw partial sum, scaled by the reducer
-    const int slot = ~dst;
-#pragma unroll
-    for (int t = 0; t < VPL; ++t) st_f4(p.partial + (size_t)slot * D + (size_t)(gl + t * G) * 4, acc[t]);
+    return;
   }
-}
-
-// one group per split row: add its slots in slot order (4 slot loads in flight), then the common epilogue
-template <int G, int VPL>
-__global__ void __launch_bounds__(256) spmm_long_reduce_kernel(const SpmmParams p, const int32_t* long_row,
-                                                                const int32_t* long_slot0, const int32_t* long_nslot,
-                                                                int n_long) {
-  constexpr int D = G * VPL * 4;
-  const int gidx = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G);
-  const int gl = threadIdx.x & (G - 1);
-  if (gidx >= n_long) return;
-  const int row = long_row[gidx], s0 = long_slot0[gidx], ns = long_nslot[gidx];
-  if (p.dst_flags && !__ldg(p.dst_flags + row)) return;
-  float4 acc[VPL];
+  // A chunk of a split (hub) row: park the raw partial sum; the group that parks the LAST chunk of the row adds all
+  // chunk sums in slot order (so the result does not depend on which group finishes last) and runs the epilogue.
+  const int slot = ~dst;
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) __stcg(reinterpret_cast<float4*>(p.partial + (size_t)slot * D + (size_t)(gl + t * G) * 4), acc[t]);
+  const int li = __ldg(p.slot_long + slot);
+  const int ns = __ldg(p.long_nslot + li);
+  __threadfence();
+  __syncwarp();
+  int old = 0;
+  if (gl == 0) old = atomicAdd(p.long_cnt + li, 1);
+  old = __shfl_sync(0xffffffffu, old, 0, G);
+  if (old != ns - 1) return;
+  if (gl == 0) p.long_cnt[li] = 0;
+  __threadfence();
+  const float* pbase = p.partial + (size_t)__ldg(p.long_slot0 + li) * D + (size_t)gl * 4;
 #pragma unroll
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* base = p.partial + (size_t)s0 * D + (size_t)gl * 4;
-  int s = 0;
-  for (; s + 4 <= ns; s += 4) {
-    float4 v[4][VPL];
+  int sidx = 0;
+  for (; sidx + 8 <= ns; sidx += 8) {
+    float4 v8[8][VPL];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 8; ++q)
 #pragma unroll
-      for (int t = 0; t < VPL; ++t) v[q][t] = ld_f4(base + (size_t)(s + q) * D + t * G * 4);
+      for (int t = 0; t < VPL; ++t) v8[q][t] = __ldcg(reinterpret_cast<const float4*>(pbase + (size_t)(sidx + q) * D + t * G * 4));
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 8; ++q)
 #pragma unroll
       for (int t = 0; t < VPL; ++t) {
-        acc[t].x += v[q][t].x; acc[t].y += v[q][t].y; acc[t].z += v[q][t].z; acc[t].w += v[q][t].w;
+        acc[t].x += v8[q][t].x; acc[t].y += v8[q][t].y; acc[t].z += v8[q][t].z; acc[t].w += v8[q][t].w;
       }
   }
-  for (; s < ns; ++s) {
+  for (; sidx < ns; ++sidx) {
 #pragma unroll
     for (int t = 0; t < VPL; ++t) {
-      const float4 v = ld_f4(base + (size_t)s * D + t * G * 4);
-      acc[t].x += v.x; acc[t].y += v.y; acc[t].z += v.z; acc[t].w += v.w;
+      const float4 v1 = __ldcg(reinterpret_cast<const float4*>(pbase + (size_t)sidx * D + t * G * 4));
+      acc[t].x += v1.x; acc[t].y += v1.y; acc[t].z += v1.z; acc[t].w += v1.w;
     }
   }
-  epilogue_row<G, VPL>(p, row, gl, acc);
+  epilogue_row<G, VPL>(p, __ldg(p.long_row + li), gl, acc);
 }
 
 template <int G, int VPL>
@@ -223,12 +226,6 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
     { return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "operand combination (vals/nbr_scale/keep_bits/eid/src_flags) not instantiated"); }
 #undef B2_SPMM_CASE
   }
-  if (a->n_long > 0) {
-    const int groups_per_block = 256 / G;
-    spmm_long_reduce_kernel<G, VPL><<<ceil_div(a->n_long, groups_per_block), 256, 0, st>>>(
-        p, a->long_row, a->long_slot0, a->long_nslot, a->n_long);
-    B2_LAUNCHED();
-  }
   return 0;
 }
 
@@ -238,7 +235,8 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
   B2_REQUIRE(a && x, "null operand");
   B2_REQUIRE(y || out, "no output");
   B2_REQUIRE(a->n_items == 0 || (a->item_start && a->item_end && a->item_dst && a->colidx), "csr plan missing");
-  B2_REQUIRE(a->n_long == 0 || (a->partial && a->long_row && a->long_slot0 && a->long_nslot), "long-row plan missing");
+  B2_REQUIRE(a->n_long == 0 || (a->partial && a->long_row && a->long_slot0 && a->long_nslot && a->slot_long && a->long_cnt),
+             "long-row plan missing");
   B2_REQUIRE(!dst_flags || a->item_row, "dst_flags needs item_row in the plan");
   B2_REQUIRE((long long)a->n_cols * d < (1ll << 32), "gathered table must have < 2^32 elements");
   SpmmParams p;
@@ -247,7 +245,8 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
   p.item_start = a->item_start; p.item_end = a->item_end; p.item_dst = a->item_dst; p.item_row = a->item_row;
   p.n_items = a->n_items;
   p.x = x; p.y = y; p.addend = addend; p.out = out; p.out_scale = out_scale; p.post_scale = post_scale;
-  p.partial = a->partial;
+  p.partial = a->partial; p.slot_long = a->slot_long; p.long_row = a->long_row; p.long_slot0 = a->long_slot0;
+  p.long_nslot = a->long_nslot; p.long_cnt = a->long_cnt;
   switch (d) {
     case 16: return launch_spmm<4, 1>(a, p, st);
     case 32: return launch_spmm<8, 1>(a, p, st);
@@ -370,7 +369,7 @@ extern "C" int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32
 extern "C" int b200rec_plan_build_host(const int32_t* rowptr, int32_t n_rows, int32_t chunk, int32_t* n_items,
                                        int32_t* n_long, int32_t* n_slots, int32_t* item_start, int32_t* item_end,
                                        int32_t* item_dst, int32_t* item_row, int32_t* long_row, int32_t* long_slot0,
-                                       int32_t* long_nslot) {
+                                       int32_t* long_nslot, int32_t* slot_long) {
   B2_REQUIRE(rowptr && n_rows >= 0 && chunk >= 32 && n_items && n_long && n_slots, "bad argument");
   // sizes
   long long items = 0, longs = 0, slots = 0;
@@ -399,6 +398,7 @@ extern "C" int b200rec_plan_build_host(const int32_t* rowptr, int32_t n_rows, in
       if (len > chunk) {
         const int pieces = (len + chunk - 1) / chunk;
         if (long_row) { long_row[li] = r; long_slot0[li] = slot; long_nslot[li] = pieces; }
+        if (slot_long) for (int q = 0; q < pieces; ++q) slot_long[slot + q] = li;
         ++li;
         for (int q = 0; q < pieces; ++q) {
           const int b = s + q * chunk, e = (b + chunk < s + len) ? b + chunk : s + len;

@@ -36,13 +36,15 @@ def test_plan_build_host_long_rows_and_order():
     ni, nl, ns = C.c_int32(), C.c_int32(), C.c_int32()
     null = C.c_void_p(0)
     assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, C.addressof(ni), C.addressof(nl), C.addressof(ns),
-                                       null, null, null, null, null, null, null) == 0
+                                       null, null, null, null, null, null, null, null) == 0
     assert (ni.value, nl.value, ns.value) == (5 + 3 + 2, 2, 5)
     a = [np.empty(ni.value, dtype=np.int32) for _ in range(4)]
     b = [np.empty(nl.value, dtype=np.int32) for _ in range(3)]
+    sl = np.empty(ns.value, dtype=np.int32)
     assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, C.addressof(ni), C.addressof(nl), C.addressof(ns),
                                        a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
-                                       b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data) == 0
+                                       b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, sl.ctypes.data) == 0
+    assert sl.tolist() == [0, 0, 0, 1, 1]
     start, end, dst, row = a
     assert np.array_equal(row[dst >= 0], dst[dst >= 0]) and set(row[dst < 0].tolist()) == {2, 6}
     ln = end - start
