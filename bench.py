@@ -154,14 +154,16 @@ def run_own(args, rank, world):
     _, _, _, d, n_layers = synth.SHAPES[workload]
     graph = build_graph(workload, dev)
     ds = D.get_dataset({"name": "SyntheticDataset", "device": dev, "graph": graph})
-    torch.manual_seed(2021)
+    torch.manual_seed(2021)  # same seed on every rank: the shards are slices of one initialisation
     partition = None
-    if world > 1:
-        from b200rec.dist import RowPartition
-        partition = "pending"
     m = M.get_model({"name": "LightGCN", "embedding_size": d, "n_layers": n_layers, "device": dev}, ds)
     if world > 1:
-        partition = RowPartition(m.norm_adj, rank, world, d)
+        from b200rec.dist import DimShard, RowPartition, shard_model_dims
+        if args.parallelism == "row":
+            partition = RowPartition(m.norm_adj, rank, world)
+        else:
+            shard_model_dims(m, DimShard(rank, world))
+            d = m.embedding_size
     tr = T.get_trainer({"name": "BPRTrainer", "optimizer": "Adam", "lr": LR, "l2_reg": L2_REG, "device": dev,
                         "n_epochs": 1, "batch_size": BATCH, "dataloader_num_workers": 0, "test_batch_size": 512,
                         "topks": TOPKS, "partition": partition}, ds, m)
@@ -299,7 +301,9 @@ def run_own(args, rank, world):
                 "config": {"workload": workload + ": " + WORKLOAD_DOC[workload], "batch": BATCH,
                            "steps_per_epoch": steps_per_epoch, "optimizer": "Adam", "sampler": "device (Philox)",
                            "l2": "flushed between timed steps (write of %d MiB)" % (flush_buf.numel() >> 20),
-                           "parallelism": "single GPU" if world == 1 else "row-partitioned graph x%d, per-layer all-gather" % world},
+                           "parallelism": "single GPU" if world == 1 else (
+                               "row-partitioned graph x%d, per-layer block exchange" % world if partition is not None else
+                               "embedding dimension sharded x%d (%d columns per GPU), one [B,3] all-reduce per step" % (world, d))},
                 "ms_per_step_l2_warm": t_warm, "epochs_per_sec_l2_warm": 1e3 / (t_warm * steps_per_epoch),
                 "e2e": {"value": e2e_value, "unit": "epochs/s", "h2d_bytes_per_step": BATCH * 3 * 8,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_net, "last_loss": loss},
@@ -318,6 +322,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="dim", choices=["dim", "row"],
+                    help="multi-GPU decomposition: embedding-dimension sharding (default) or the row partition")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

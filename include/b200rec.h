@@ -13,7 +13,8 @@
  *   - return 0 on success, negative b200rec_status otherwise; b200rec_last_error() gives the text
  *     (thread-local).  There is no CPU fallback: without a CUDA device every compute call fails.
  *   - indices are int32 (all BASELINE shapes have nnz < 2^31), embeddings fp32 row-major [rows, D],
- *     D in {16, 32, 64, 128, 256}.
+ *     D in {8, 16, 32, 64, 128, 256} (8 and 16 exist for embedding-dimension sharding: D/P columns per GPU;
+ *     the scoring entry points need D >= 16).
  */
 #ifndef B200REC_H
 #define B200REC_H
@@ -159,6 +160,16 @@ int b200rec_bpr_fwd_bwd(const float* rep, int32_t d, const int64_t* batch /*[B,3
                         int64_t item_offset, float l2_reg, int32_t reg_mode, const float* w,
                         float loss_scale, float* g_rep, float* g_w, float* loss_out,
                         float* block_scratch, void* stream);
+/* The same step when the embedding DIMENSION is sharded over P GPUs (each rank holds D/P columns of every table:
+ * propagation, Adam and all gradients are column-separable, only the two dot products couple the ranks):
+ *   phase 1: dots[B,3] <- this rank's partial (pos, neg, sum of squares) per sample;
+ *   caller : all-reduce(dots, SUM) over the ranks (48 KB at B = 2048);
+ *   phase 2: gradients for this rank's columns from the reduced dots; *loss_out += loss_weight * (loss terms), so a
+ *            caller that gives rank 0 weight 1 and the others 0 obtains the global loss by summing the ranks. */
+int b200rec_bpr_fwd_bwd_sharded(const float* rep, int32_t d, const int64_t* batch, int32_t n_batch,
+                                int64_t item_offset, float l2_reg, int32_t reg_mode, const float* w,
+                                float loss_scale, float* g_rep, float* g_w, float* loss_out, float* block_scratch,
+                                float* dots /*[B,3]*/, int32_t phase, float loss_weight, void* stream);
 /* LightGCN's layer-0 regulariser (model.py:114-117): g_emb0 += l2_reg * d(mean ||e_u||^2+||e_p||^2+||e_n||^2)/de,
  * *loss_out += l2_reg * mean(l2). */
 int b200rec_bpr_l2_emb0(const float* emb0, int32_t d, const int64_t* batch, int32_t n_batch, int64_t item_offset,

@@ -1,0 +1,151 @@
+"""Multi-GPU decompositions of the hot path (one process per GPU, torch.distributed / NCCL over NVLink).
+
+The reference has no multi-device code.  Two decompositions are built, both bit-identical
+to the single-GPU result on every output element:
+
+* `RowPartition` -- the scheme BASELINE.json names: contiguous row blocks of the [users | items] index space,
+  balanced by nnz; rank p computes rows [r_p, r_{p+1}) of every propagated table and the blocks are all-gathered
+  after each layer (backward: the same, A is symmetric).  Per-row sums are untouched by the partition.  Exchange volume
+  per layer is (P-1)/P * N * D * 4 bytes per rank, which is communication-bound for P >= 4.
+
+* `DimShard` -- shard the embedding DIMENSION instead: every rank holds D/P columns of every [N, D] table.  Propagation
+  (X <- A X), the layer mean, the inductive layer, all gradients and Adam act on each column independently, so the
+  L forward and L backward layers need NO exchange at all; the only coupling is the BPR score <u, i> = sum over
+  columns, one all-reduce of a [B, 3] fp32 tensor (24 KB at B = 2048) per step.  Evaluation all-gathers the columns of
+  the final representation once and shards the USERS of the score / top-K sweep.  This is the default for training.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class DimShard:
+    def __init__(self, rank=0, world=1, group=None):
+        self.rank, self.world, self.group = rank, world, group
+
+    def cols(self, d):
+        assert d % self.world == 0, "embedding_size must be divisible by the number of GPUs"
+        w = d // self.world
+        return self.rank * w, (self.rank + 1) * w
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def gather_cols(self, local):
+        """[N, D/P] on every rank -> [N, D] on every rank"""
+        if self.world == 1:
+            return local
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather(parts, local.contiguous(), group=self.group)
+        return torch.cat(parts, dim=1)
+
+    def user_range(self, n_users):
+        per = (n_users + self.world - 1) // self.world
+        return min(n_users, self.rank * per), min(n_users, (self.rank + 1) * per)
+
+    def gather_user_rows(self, local, n_users):
+        """rows of the rank's user_range -> all rows on every rank (user-sharded evaluation)"""
+        if self.world == 1:
+            return local
+        per = (n_users + self.world - 1) // self.world
+        pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad, group=self.group)
+        return torch.cat(parts, dim=0)[:n_users]
+
+
+def shard_model_dims(model, shard):
+    """Keep only this rank's columns of every embedding parameter (call before the optimiser is created).
+    Every rank must have built the model from the same seed, so the slices are slices of ONE initialisation."""
+    import torch.nn as nn
+    if shard.world == 1:
+        model._dim_shard = shard
+        return model
+    d = model.embedding_size
+    lo, hi = shard.cols(d)
+    if type(model).__name__ == 'MF':
+        joint = model._joint[:, lo:hi].contiguous()
+        model._joint = joint
+        model.user_embedding.weight = nn.Parameter(joint[:model.n_users])
+        model.item_embedding.weight = nn.Parameter(joint[model.n_users:])
+        model.user_embedding.embedding_dim = model.item_embedding.embedding_dim = hi - lo
+    else:
+        model.embedding.weight = nn.Parameter(model.embedding.weight.data[:, lo:hi].contiguous())
+        model.embedding.embedding_dim = hi - lo
+        if hasattr(model, 'w'):
+            model.w = nn.Parameter(model.w.data[lo:hi].contiguous())
+    model.full_embedding_size = d
+    model.embedding_size = hi - lo
+    model._dim_shard = shard
+    model._rep_cache = None
+    return model
+
+
+def nnz_balanced_bounds(rowptr, world):
+    """split points r_0 = 0 <= r_1 <= ... <= r_P = n_rows with about nnz/P entries per block"""
+    rp = np.asarray(rowptr, dtype=np.int64)
+    n = len(rp) - 1
+    targets = (np.arange(1, world) * rp[-1]) // world
+    cuts = np.searchsorted(rp, targets, side='left')
+    return [0] + [int(min(max(c, 0), n)) for c in cuts] + [n]
+
+
+class RowPartition:
+    """Row-partitioned propagation with a per-layer exchange of the row blocks."""
+
+    def __init__(self, adj, rank, world, group=None, bounds=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.bounds = bounds if bounds is not None else nnz_balanced_bounds(adj.rowptr.cpu().numpy(), world)
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.n_local_rows = self.hi - self.lo
+        self.local_op = adj.row_slice(self.lo, self.hi)
+
+    def exchange(self, buf):
+        """in place: after the call every rank holds every row block of `buf` ([n_rows, D])"""
+        if self.world == 1:
+            return
+        works = []
+        for p in range(self.world):
+            blk = buf[self.bounds[p]:self.bounds[p + 1]]
+            if blk.numel():
+                works.append(dist.broadcast(blk, src=p, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+
+    def propagate_fwd(self, adj, x0, n_layers, bufs, mean_out, needed_rows=None):
+        """same contract as ops.propagate_fwd; x0 must be complete on every rank, mean_out is complete on return"""
+        from . import ops
+        if n_layers == 0:
+            mean_out.copy_(x0)
+            return
+        inv = 1.0 / (n_layers + 1)
+        src = x0
+        for k in range(n_layers):
+            last = k == n_layers - 1
+            y = None if last else bufs[k & 1]
+            ops.spmm(self.local_op, src, y=y, addend=x0 if k == 0 else mean_out, out=mean_out,
+                     out_scale=inv if last else 1.0, dst_flags=needed_rows if last else None)
+            if not last:
+                self.exchange(y)
+                src = y
+        self.exchange(mean_out)
+
+    def propagate_bwd(self, adj, g, n_layers, bufs, dx0, nonzero_rows=None):
+        """dx0 rows [lo, hi) are valid on return (each rank updates only the parameters it owns)"""
+        from . import ops
+        if n_layers == 0:
+            dx0.copy_(g)
+            return
+        inv = 1.0 / (n_layers + 1)
+        src = g
+        for k in range(1, n_layers + 1):
+            last = k == n_layers
+            dst = dx0 if last else bufs[(k - 1) & 1]
+            ops.spmm(self.local_op, src, addend=g, out=dst, out_scale=inv if last else 1.0,
+                     src_flags=nonzero_rows if k == 1 else None)
+            if not last:
+                self.exchange(dst)
+                src = dst

@@ -25,7 +25,7 @@ def _adam_state(opt, p):
 
 class BprEngine:
     def __init__(self, model, dataset, opt, batch_size, l2_reg, aux_reg=0.0, aux_dataset=None, seed=2021,
-                 use_graph=True, partition=None):
+                 use_graph=True, partition=None, dim_shard=None):
         self.model, self.dataset, self.opt = model, dataset, opt
         self.kind = type(model).__name__
         if self.kind not in ('LightGCN', 'IGCN', 'IMF', 'MF'):
@@ -38,6 +38,10 @@ class BprEngine:
         self.lr, (self.b1, self.b2), self.eps = g['lr'], g['betas'], g['eps']
         self.B, self.l2_reg, self.aux_reg, self.seed = batch_size, float(l2_reg), float(aux_reg), seed
         self.partition = partition
+        self.shard = dim_shard if dim_shard is not None else getattr(model, '_dim_shard', None)
+        if self.shard is not None and self.shard.world == 1:
+            self.shard = None
+        assert not (self.shard is not None and partition is not None), 'choose one decomposition'
         dev = model.device
         self.dev = dev
         D = model.embedding_size
@@ -50,6 +54,7 @@ class BprEngine:
         self.loss = torch.zeros(1, **f32)
         self.loss_accum = torch.zeros(2, dtype=torch.float64, device=dev)
         self.scratch = ops.bpr_scratch(batch_size, D, dev)
+        self.dots = torch.zeros((batch_size, 3), **f32)  # per-sample (pos, neg, l2) partials when the dimension is sharded
         self.user_ptr, self.user_items = dataset.csr('train', device=dev)
         n = model.n_users + model.n_items
         self.n = n
@@ -116,6 +121,27 @@ class BprEngine:
         else:
             ops.propagate_bwd(m.norm_adj, self.g_rep, m.n_layers, self.bufs, out, nonzero_rows=self.row_flags)
 
+    def _bpr(self, rep, batch, item_offset, l2_reg, reg_mode, g_rep, w=None, g_w=None, loss_scale=1.0):
+        if self.shard is None:
+            ops.bpr_fwd_bwd(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, w=w, g_w=g_w,
+                            loss_scale=loss_scale)
+            return
+        # embedding dimension sharded over the ranks: partial dot products -> all-reduce -> this rank's gradient columns
+        ops.bpr_fwd_bwd_sharded(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, self.dots, 1,
+                                w=w, g_w=g_w, loss_scale=loss_scale)
+        self.shard.all_reduce_sum(self.dots)
+        ops.bpr_fwd_bwd_sharded(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, self.dots, 2,
+                                loss_weight=1.0 if self.shard.rank == 0 else 0.0, w=w, g_w=g_w, loss_scale=loss_scale)
+
+    def _adam(self, param, grad, m, v):
+        if self.partition is not None and param is self.table:
+            lo, hi = self.partition.lo, self.partition.hi  # each rank updates the rows it owns, then the blocks are exchanged
+            if hi > lo:
+                ops.adam_step(param[lo:hi], grad[lo:hi], m[lo:hi], v[lo:hi], self.adam_step, self.lr, self.b1, self.b2, self.eps)
+            self.partition.exchange(param)
+            return
+        ops.adam_step(param, grad, m, v, self.adam_step, self.lr, self.b1, self.b2, self.eps)
+
     def _body(self, sample, draw_mask=True):
         m, B = self.model, self.B
         nu = m.n_users
@@ -130,16 +156,16 @@ class BprEngine:
             ops.mark_rows(self.batch, nu, self.row_flags)
         if self.kind == 'MF':
             self.grad.zero_()
-            ops.bpr_fwd_bwd(self.table, self.batch, nu, self.l2_reg, 1, self.grad, self.loss, self.scratch)
-            ops.adam_step(self.table, self.grad, self.m, self.v, self.adam_step, self.lr, self.b1, self.b2, self.eps)
+            self._bpr(self.table, self.batch, nu, self.l2_reg, 1, self.grad)
+            self._adam(self.table, self.grad, self.m, self.v)
         elif self.kind == 'LightGCN':
             self.g_rep.zero_()
             self._propagate_fwd(self.table)
-            ops.bpr_fwd_bwd(self.rep, self.batch, nu, 0.0, 0, self.g_rep, self.loss, self.scratch)
+            self._bpr(self.rep, self.batch, nu, 0.0, 0, self.g_rep)
             self._propagate_bwd(self.grad)
             if self.l2_reg != 0.0:
                 ops.bpr_l2_emb0(self.table, self.batch, nu, self.l2_reg, self.grad, self.loss, self.scratch)
-            ops.adam_step(self.table, self.grad, self.m, self.v, self.adam_step, self.lr, self.b1, self.b2, self.eps)
+            self._adam(self.table, self.grad, self.m, self.v)
         else:  # IGCN / IMF
             p = float(m.dropout)
             keep, inv_keep = None, 1.0
@@ -153,15 +179,14 @@ class BprEngine:
             self.g_rep.zero_()
             ops.spmm(self.feat_fwd, self.table, keep_bits=keep, post_scale=inv_keep, y=self.x0)
             self._propagate_fwd(self.x0)
-            ops.bpr_fwd_bwd(self.rep, self.batch, nu, self.l2_reg, 1 if self.l2_reg != 0.0 else 0, self.g_rep, self.loss,
-                            self.scratch)
+            self._bpr(self.rep, self.batch, nu, self.l2_reg, 1 if self.l2_reg != 0.0 else 0, self.g_rep)
             self._propagate_bwd(self.dx0)
             ops.spmm(self.feat_bwd, self.dx0, keep_bits=keep, post_scale=inv_keep, y=self.grad)
             if self.aux is not None:
-                ops.bpr_fwd_bwd(self.table, self.aux_batch, len(m.user_map), 0.0, 0, self.grad, self.loss, self.scratch,
-                                w=m.w.data, g_w=self.g_w, loss_scale=self.aux_reg)
-                ops.adam_step(m.w.data, self.g_w, self.m_w, self.v_w, self.adam_step, self.lr, self.b1, self.b2, self.eps)
-            ops.adam_step(self.table, self.grad, self.m, self.v, self.adam_step, self.lr, self.b1, self.b2, self.eps)
+                self._bpr(self.table, self.aux_batch, len(m.user_map), 0.0, 0, self.grad, w=m.w.data, g_w=self.g_w,
+                          loss_scale=self.aux_reg)
+                self._adam(m.w.data, self.g_w, self.m_w, self.v_w)
+            self._adam(self.table, self.grad, self.m, self.v)
         ops.step_advance(self.adam_step, self.sample_step, self.loss, self.loss_accum, B)
 
     def _run(self, sample, draw_mask=True):
@@ -231,10 +256,15 @@ class BprEngine:
         self.loss_accum.zero_()
 
     def meter_avg(self):
-        a = self.loss_accum.cpu()
+        a = self.loss_accum.clone()
+        if self.shard is not None:  # rank 0 carries the BPR term, every rank its own columns' L2 term
+            self.shard.all_reduce_sum(a[:1])
+        a = a.cpu()
         return float(a[0] / a[1]) if float(a[1]) > 0 else 0.0
 
     def last_loss(self):
+        if self.shard is not None:
+            return float(self.shard.all_reduce_sum(self.loss.clone()).item())
         return float(self.loss.item())
 
     def sync_optimizer_state(self):

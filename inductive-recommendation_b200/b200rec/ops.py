@@ -74,6 +74,15 @@ def bpr_fwd_bwd(rep, batch, item_offset, l2_reg, reg_mode, g_rep, loss_out, scra
                                      stream_ptr()), "bpr_fwd_bwd")
 
 
+def bpr_fwd_bwd_sharded(rep, batch, item_offset, l2_reg, reg_mode, g_rep, loss_out, scratch, dots, phase, loss_weight=1.0,
+                        w=None, g_w=None, loss_scale=1.0):
+    _abi.require_cuda(rep, batch, g_rep, loss_out, scratch, dots, w, g_w)
+    check(_lib().b200rec_bpr_fwd_bwd_sharded(ptr(rep), rep.shape[1], ptr(batch), batch.shape[0], item_offset, l2_reg,
+                                             reg_mode, ptr(w), loss_scale, ptr(g_rep), ptr(g_w), ptr(loss_out),
+                                             ptr(scratch), ptr(dots), phase, loss_weight, stream_ptr()),
+          "bpr_fwd_bwd_sharded")
+
+
 def bpr_l2_emb0(emb0, batch, item_offset, l2_reg, g_emb0, loss_out, scratch):
     _abi.require_cuda(emb0, batch, g_emb0, loss_out, scratch)
     check(_lib().b200rec_bpr_l2_emb0(ptr(emb0), emb0.shape[1], ptr(batch), batch.shape[0], item_offset, l2_reg,

@@ -154,7 +154,11 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* __restrict_
                                                         int n_batch, int64_t item_offset, float l2_reg, int reg_mode,
                                                         const float* __restrict__ w, float loss_scale,
                                                         float* __restrict__ g_rep, float* __restrict__ g_w,
-                                                        float* __restrict__ loss_out, float* scratch) {
+                                                        float* __restrict__ loss_out, float* scratch,
+                                                        float* __restrict__ dots, int dots_mode, float loss_weight) {
+  // dots_mode 0: everything in one launch.  Embedding-dimension sharding (each rank holds D/P columns) splits it:
+  // 1 = write this rank's partial (pos, neg, l2) per sample to dots[B,3] and stop; after the caller's all-reduce,
+  // 2 = take the full (pos, neg, l2) from dots and produce this rank's columns of the gradient.
   constexpr int D = G * VPL * 4;
   constexpr int SPB = 256 / G;  // samples per block
   __shared__ float s_loss[SPB];
@@ -190,10 +194,20 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* __restrict_
   pos = group_sum<G>(pos);
   neg = group_sum<G>(neg);
   l2 = group_sum<G>(l2);
+  if (dots_mode == 1) {
+    if (active && gl == 0) {
+      dots[3 * (size_t)smp] = pos; dots[3 * (size_t)smp + 1] = neg; dots[3 * (size_t)smp + 2] = l2;
+    }
+    return;
+  }
+  if (dots_mode == 2 && active) {
+    pos = dots[3 * (size_t)smp]; neg = dots[3 * (size_t)smp + 1]; l2 = dots[3 * (size_t)smp + 2];
+  }
   const float x = neg - pos;
   const float inv_b = 1.f / (float)n_batch;
   float loss = softplus_t(x);
   if (reg_mode == 1) loss += l2_reg * l2;
+  loss *= loss_weight;
   const float coef = loss_scale * inv_b * sigmoid_t(x);
   const float rc = (reg_mode == 1) ? 2.f * l2_reg * loss_scale * inv_b : 0.f;
   if (active) {
@@ -354,10 +368,10 @@ __global__ void step_advance_kernel(int64_t* step, int64_t* step_b, const float*
 template <int G, int VPL>
 static int launch_bpr(const float* rep, const int64_t* batch, int nb, int64_t off, float l2_reg, int reg_mode,
                       const float* w, float loss_scale, float* g_rep, float* g_w, float* loss_out, float* scratch,
-                      cudaStream_t st) {
+                      float* dots, int dots_mode, float loss_weight, cudaStream_t st) {
   const int grid = ceil_div(nb, 256 / G);
-  if (w) bpr_fused_kernel<G, VPL, true><<<grid, 256, 0, st>>>(rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch);
-  else bpr_fused_kernel<G, VPL, false><<<grid, 256, 0, st>>>(rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch);
+  if (w) bpr_fused_kernel<G, VPL, true><<<grid, 256, 0, st>>>(rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight);
+  else bpr_fused_kernel<G, VPL, false><<<grid, 256, 0, st>>>(rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight);
   B2_LAUNCHED();
   return 0;
 }
@@ -367,12 +381,13 @@ using namespace b200rec;
 
 #define B2_DISPATCH_D(d, ...)                                                                                     \
   switch (d) {                                                                                                    \
+    case 8: { constexpr int G = 2, VPL = 1; __VA_ARGS__; } break;                                                        \
     case 16: { constexpr int G = 4, VPL = 1; __VA_ARGS__; } break;                                                       \
     case 32: { constexpr int G = 8, VPL = 1; __VA_ARGS__; } break;                                                       \
     case 64: { constexpr int G = 16, VPL = 1; __VA_ARGS__; } break;                                                      \
     case 128: { constexpr int G = 32, VPL = 1; __VA_ARGS__; } break;                                                     \
     case 256: { constexpr int G = 32, VPL = 2; __VA_ARGS__; } break;                                                     \
-    default: return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", __func__, "embedding size must be 16/32/64/128/256"); \
+    default: return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", __func__, "embedding size must be 8/16/32/64/128/256"); \
   }
 
 extern "C" int b200rec_bpr_sample(const int32_t* user_ptr, const int32_t* user_items, int32_t n_users, int32_t n_items,
@@ -410,8 +425,11 @@ extern "C" int b200rec_scatter_add_rows(float* table, int32_t d, const int64_t* 
 }
 
 extern "C" int64_t b200rec_bpr_scratch_floats(int32_t n_batch, int32_t d) {
-  if (d < 16) d = 16;
-  const int64_t blocks = (n_batch + (256 / (d / 4 > 32 ? 32 : d / 4)) - 1) / (256 / (d / 4 > 32 ? 32 : d / 4));
+  int g = d / 4;  // lanes per sample
+  if (g < 2) g = 2;
+  if (g > 32) g = 32;
+  const int64_t samples_per_block = 256 / g;
+  const int64_t blocks = (n_batch + samples_per_block - 1) / samples_per_block;
   return 4 + blocks * (int64_t)(d + 1);
 }
 
@@ -421,7 +439,21 @@ extern "C" int b200rec_bpr_fwd_bwd(const float* rep, int32_t d, const int64_t* b
   B2_REQUIRE(rep && batch && g_rep && loss_out && block_scratch && n_batch > 0, "bad argument");
   B2_REQUIRE(reg_mode == 0 || reg_mode == 1, "reg_mode must be 0 or 1 (layer-0 L2 is b200rec_bpr_l2_emb0)");
   B2_REQUIRE(!w || g_w, "g_w required with w");
-  B2_DISPATCH_D(d, { int rc = launch_bpr<G, VPL>(rep, batch, n_batch, item_offset, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, block_scratch, (cudaStream_t)stream); if (rc) return rc; });
+  B2_DISPATCH_D(d, { int rc = launch_bpr<G, VPL>(rep, batch, n_batch, item_offset, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, block_scratch, nullptr, 0, 1.f, (cudaStream_t)stream); if (rc) return rc; });
+  return 0;
+}
+
+extern "C" int b200rec_bpr_fwd_bwd_sharded(const float* rep, int32_t d, const int64_t* batch, int32_t n_batch,
+                                           int64_t item_offset, float l2_reg, int32_t reg_mode, const float* w,
+                                           float loss_scale, float* g_rep, float* g_w, float* loss_out,
+                                           float* block_scratch, float* dots, int32_t phase, float loss_weight,
+                                           void* stream) {
+  B2_REQUIRE(rep && batch && dots && block_scratch && n_batch > 0, "bad argument");
+  B2_REQUIRE(phase == 1 || phase == 2, "phase must be 1 (partial dots) or 2 (gradients from reduced dots)");
+  B2_REQUIRE(phase == 1 || (g_rep && loss_out), "phase 2 needs g_rep and loss_out");
+  B2_REQUIRE(reg_mode == 0 || reg_mode == 1, "reg_mode must be 0 or 1");
+  B2_REQUIRE(!w || g_w || phase == 1, "g_w required with w");
+  B2_DISPATCH_D(d, { int rc = launch_bpr<G, VPL>(rep, batch, n_batch, item_offset, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, block_scratch, dots, phase, loss_weight, (cudaStream_t)stream); if (rc) return rc; });
   return 0;
 }
 

@@ -248,12 +248,13 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
   p.partial = a->partial; p.slot_long = a->slot_long; p.long_row = a->long_row; p.long_slot0 = a->long_slot0;
   p.long_nslot = a->long_nslot; p.long_cnt = a->long_cnt;
   switch (d) {
+    case 8: return launch_spmm<2, 1>(a, p, st);
     case 16: return launch_spmm<4, 1>(a, p, st);
     case 32: return launch_spmm<8, 1>(a, p, st);
     case 64: return launch_spmm<16, 1>(a, p, st);
     case 128: return launch_spmm<32, 1>(a, p, st);
     case 256: return launch_spmm<32, 2>(a, p, st);
-    default: return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "embedding size must be 16/32/64/128/256");
+    default: return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "embedding size must be 8/16/32/64/128/256");
   }
 }
 

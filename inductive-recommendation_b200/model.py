@@ -68,6 +68,11 @@ class BasicModel(nn.Module):
             self._rep_cache = (key, compute())
         return self._rep_cache[1]
 
+    def _all_columns(self, rep):
+        """with the embedding dimension sharded over GPUs (b200rec.dist.DimShard) scoring needs every column"""
+        shard = getattr(self, '_dim_shard', None)
+        return rep if shard is None or shard.world == 1 else shard.gather_cols(rep)
+
     def recommend(self, users, k, excl_a=None, excl_b=None, banned=None, precision=0):
         """Fused full-rank scoring + masking + top-K (trainer.py:152-169): returns (ids int32 [b,k], scores [b,k]),
         ordered (score desc, item id asc)."""
@@ -95,7 +100,8 @@ class MF(BasicModel):
         return self._joint
 
     def score_tables(self):
-        return self.user_embedding.weight.data, self.item_embedding.weight.data
+        joint = self._all_columns(self._joint)
+        return joint[:self.n_users], joint[self.n_users:]
 
     def bpr_forward(self, users, pos_items, neg_items):
         ue = ops.gather_rows(self.user_embedding.weight, users)
@@ -106,7 +112,8 @@ class MF(BasicModel):
 
     def predict(self, users):
         with torch.no_grad():
-            return ops.score_dense(self.user_embedding.weight.data, users.contiguous(), self.item_embedding.weight.data)
+            tu, ti = self.score_tables()
+            return ops.score_dense(tu, users.contiguous(), ti)
 
 
 class LightGCN(BasicModel):
@@ -137,6 +144,9 @@ class LightGCN(BasicModel):
 
     def score_tables(self):
         rep = self.get_rep()
+        if getattr(self, '_full_src', None) is not rep:  # column all-gather once per cached representation
+            self._full_src, self._full_rep = rep, self._all_columns(rep)
+        rep = self._full_rep
         return rep, rep[self.n_users:]
 
     def bpr_forward(self, users, pos_items, neg_items):
@@ -153,8 +163,8 @@ class LightGCN(BasicModel):
 
     def predict(self, users):
         with torch.no_grad():
-            rep = self.get_rep()
-            return ops.score_dense(rep, users.contiguous(), rep[self.n_users:])
+            rep, items = self.score_tables()
+            return ops.score_dense(rep, users.contiguous(), items)
 
 
 class IGCN(BasicModel):

@@ -177,13 +177,19 @@ class BasicTrainer:
                 banned = (lo, hi)
         k = max(self.topks)
         n_users = self.dataset.n_users
+        shard = getattr(self.model, '_dim_shard', None)
+        u_lo, u_hi = (0, n_users) if shard is None or shard.world == 1 else shard.user_range(n_users)
         out = []
         with torch.no_grad():
-            for s in range(0, n_users, self.eval_chunk):
-                users = torch.arange(s, min(n_users, s + self.eval_chunk), dtype=torch.int64, device=dev)
+            self.model.score_tables()  # collective (column all-gather) when sharded: every rank takes part
+            for s in range(u_lo, u_hi, self.eval_chunk):  # multi-GPU: each rank scores its own block of users
+                users = torch.arange(s, min(u_hi, s + self.eval_chunk), dtype=torch.int64, device=dev)
                 ids, _ = self.model.recommend(users, k, excl_a, excl_b, banned, precision=self.eval_precision)
                 out.append(ids)
-        return torch.cat(out, dim=0)
+        ids = torch.cat(out, dim=0) if out else torch.zeros((0, k), dtype=torch.int32, device=dev)
+        if shard is not None and shard.world > 1:
+            ids = shard.gather_user_rows(ids, n_users)
+        return ids
 
     def eval(self, val_or_test, banned_items=None):
         eval_data = getattr(self.dataset, val_or_test + '_data')

@@ -1,0 +1,87 @@
+"""CPU: host-side logic of the multi-GPU decompositions (b200rec/dist.py) -- partition bounds, work-item slicing, and a
+world_size-2 gloo run of the collectives the engine uses (block exchange, column gather, user-row gather, dot-product
+all-reduce).  No kernels run here; the GPU tests compare the multi-rank results with the single-rank ones."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, REPO
+
+
+def test_nnz_balanced_bounds():
+    from b200rec.dist import nnz_balanced_bounds
+    rng = np.random.default_rng(0)
+    lens = rng.integers(0, 50, 1000)
+    lens[17] = 5000
+    rp = np.zeros(1001, dtype=np.int64)
+    np.cumsum(lens, out=rp[1:])
+    for world in (1, 2, 4, 8):
+        b = nnz_balanced_bounds(rp, world)
+        assert b[0] == 0 and b[-1] == 1000 and len(b) == world + 1 and all(x <= y for x, y in zip(b, b[1:]))
+        per = [rp[b[p + 1]] - rp[b[p]] for p in range(world)]
+        assert sum(per) == rp[-1]
+        assert max(per) <= rp[-1] / world + 5000 + 50   # within one (hub) row of the ideal share
+    assert nnz_balanced_bounds(np.zeros(5, dtype=np.int64), 4) == [0, 0, 0, 0, 4]  # empty graph
+
+
+def test_dim_shard_ranges():
+    from b200rec.dist import DimShard
+    for world in (1, 2, 4, 8):
+        cols = [DimShard(r, world).cols(64) for r in range(world)]
+        assert cols[0][0] == 0 and cols[-1][1] == 64 and all(a[1] == b[0] for a, b in zip(cols, cols[1:]))
+        ur = [DimShard(r, world).user_range(1001) for r in range(world)]
+        assert ur[0][0] == 0 and ur[-1][1] == 1001 and all(a[1] == b[0] for a, b in zip(ur, ur[1:]))
+    with pytest.raises(AssertionError):
+        DimShard(0, 3).cols(64)
+
+
+def _worker(rank, world, port, out):
+    sys.path[:0] = [PKG, REPO]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200rec.dist import DimShard, RowPartition, nnz_balanced_bounds
+    shard = DimShard(rank, world)
+    # column gather: every rank ends with the full table
+    full = torch.arange(6 * 8, dtype=torch.float32).reshape(6, 8)
+    lo, hi = shard.cols(8)
+    assert torch.equal(shard.gather_cols(full[:, lo:hi].contiguous()), full)
+    # dot-product all-reduce (the only coupling of a dimension-sharded BPR step)
+    u, v = torch.randn(5, 8, generator=torch.Generator().manual_seed(1)), torch.randn(5, 8, generator=torch.Generator().manual_seed(2))
+    part = (u[:, lo:hi] * v[:, lo:hi]).sum(1)
+    assert torch.allclose(shard.all_reduce_sum(part.clone()), (u * v).sum(1), atol=1e-6)
+    # user-sharded evaluation rows
+    ids = torch.arange(11 * 3, dtype=torch.int32).reshape(11, 3)
+    a, b = shard.user_range(11)
+    assert torch.equal(shard.gather_user_rows(ids[a:b].contiguous(), 11), ids)
+    # row-block exchange with uneven blocks
+    class _Adj:  # only what RowPartition reads
+        rowptr = torch.tensor([0, 1, 1, 9, 10, 12, 12, 20], dtype=torch.int32)
+        def row_slice(self, lo, hi):
+            return (lo, hi)
+    part = RowPartition(_Adj(), rank, world)
+    assert part.bounds == nnz_balanced_bounds(_Adj.rowptr.numpy(), world)
+    table = torch.arange(7 * 4, dtype=torch.float32).reshape(7, 4)
+    mine = torch.full_like(table, -1.0)
+    mine[part.lo:part.hi] = table[part.lo:part.hi]
+    part.exchange(mine)
+    assert torch.equal(mine, table)
+    out.put(rank)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_collectives():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(out.get(timeout=5) for _ in range(2)) == [0, 1]

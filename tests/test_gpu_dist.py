@@ -1,0 +1,20 @@
+"""GPU, >= 2 devices: run tests/dist_gpu_check.py under torchrun (NCCL).  Skipped on a single-GPU box; the host-side
+logic is covered on CPU by tests/test_dist_cpu.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_multi_gpu_parity():
+    n = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+           "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "dist_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DIST_GPU_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
