@@ -273,7 +273,7 @@ def run_own(args, rank, world):
 
     # ---- full-rank evaluation (users/s): representation + fused score/mask/top-20 + metrics ----
     eval_info = None
-    if rank == 0 and workload != "c4":
+    if workload != "c4":  # every rank takes part: the sweep is user-sharded and gathers the columns collectively
         m.eval()
         tr.eval("test")
         torch.cuda.synchronize()
@@ -311,6 +311,8 @@ def run_own(args, rank, world):
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "eval": eval_info, "clocks": clocks.summary()}
         print(json.dumps(line), flush=True)
     if world > 1:
+        eng.close()
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 

@@ -101,7 +101,8 @@ class BprEngine:
                 self.aux = aux_dataset
                 if aux_dataset is not None:
                     self.aux_ptr, self.aux_items = aux_dataset.csr('train', device=dev)
-        self.use_graph = use_graph
+        import os
+        self.use_graph = use_graph and os.environ.get('B200REC_NO_GRAPH', '0') != '1'
         self._graphs = {}
         self._kernels = {}
         self.steps_done = 0
@@ -209,7 +210,8 @@ class BprEngine:
             for t, c in zip(self._state_tensors(), snap):
                 t.copy_(c)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: the NCCL watchdog thread may touch CUDA while a sharded step (with its all-reduce) is captured
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._body(sample, draw_mask)
             for t, c in zip(self._state_tensors(), snap):  # capture does not execute, but keep state exact anyway
                 t.copy_(c)
@@ -246,6 +248,12 @@ class BprEngine:
     def kernels_per_step(self, sample=True, draw_mask=True):
         """libb200rec kernel launches inside one step (counted while the step was warmed up for capture)"""
         return self._kernels.get((sample, draw_mask))
+
+    def close(self):
+        """drop the captured graphs (needed before torch.distributed.destroy_process_group() when a graph holds
+        NCCL kernels: tearing the communicator down under a live graph blocks)"""
+        torch.cuda.synchronize()
+        self._graphs.clear()
 
     def refresh_row_scale(self):
         """after IGCN.feat_mat_anneal(): the graph reads the scale vector in place"""

@@ -21,6 +21,10 @@ def main():
     from b200rec import ops
     from b200rec.dist import DimShard, RowPartition, shard_model_dims
     topks = [1, 5, 10, 15, 20]
+    engines = []
+
+    def log(*a):
+        print('[rank %d]' % rank, *a, flush=True)
 
     def trainer_for(g, name, ds, m, **extra):
         is_igcn = MODEL_CFG[name]["name"] in ("IGCN", "IMF")
@@ -37,6 +41,7 @@ def main():
         shard = DimShard(rank, world)
         shard_model_dims(m, shard)
         tr = trainer_for(g, name, ds, m)
+        log('dim', name, 'built')
         # evaluation before the step: user-sharded top-K ids equal the reference's
         rec = tr.recommend_all("test").cpu().numpy()
         ref_ids, ref_val = g["topk_ids_test"], g["topk_val_test"]
@@ -45,8 +50,10 @@ def main():
         sep[:, 1:] &= dd
         sep[:, :-1] &= dd
         assert np.array_equal(rec[sep], ref_ids[sep]), name
+        log('dim', name, 'eval ok')
         m.train()
         eng = tr._engine()
+        engines.append(eng)
         hb = torch.from_numpy(g["batch"]).pin_memory()
         ha = torch.from_numpy(g["aux_batch"]).pin_memory() if "aux_batch" in g else None
         hk = None
@@ -54,6 +61,7 @@ def main():
             keep = np.unpackbits(g["drop_keep"])[: int(g["drop_nnz"])].astype(bool)
             hk = ops.pack_keep_bits(torch.from_numpy(keep).to(dev))
         eng.step(host_batch=hb, host_aux_batch=ha, host_keep_bits=hk)
+        log('dim', name, 'step done')
         assert abs(eng.last_loss() - float(g["loss"])) < 2e-6, (name, eng.last_loss(), float(g["loss"]))
         assert abs(eng.meter_avg() - float(g["loss"])) < 2e-6
         if name.startswith("mf"):
@@ -79,6 +87,7 @@ def main():
         multi = torch.empty_like(x0)
         part.propagate_fwd(m.norm_adj, x0, L, bufs, multi)
         assert torch.equal(single, multi), name + ": row-partitioned forward differs"
+        log('row', name, 'fwd ok')
         gsrc = torch.randn(x0.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
         d1, d2 = torch.empty_like(x0), torch.empty_like(x0)
         ops.propagate_bwd(m.norm_adj, gsrc, L, bufs, d1)
@@ -87,13 +96,21 @@ def main():
         tr = trainer_for(g, name, ds, m, partition=part)
         m.train()
         eng = tr._engine()
+        engines.append(eng)
+        log('row', name, 'bwd ok')
         eng.step(host_batch=torch.from_numpy(g["batch"]).pin_memory())
+        log('row', name, 'step done')
         assert abs(eng.last_loss() - float(g["loss"])) < 2e-6
         np.testing.assert_allclose(m.embedding.weight.data.cpu().numpy(), g["emb1"], rtol=1e-5, atol=5e-6)
     dist.barrier()
+    for e in engines:
+        e.close()
+    del engines
+    torch.cuda.synchronize()
     if rank == 0:
-        print("DIST_GPU_CHECK_OK world=%d" % world)
+        print("DIST_GPU_CHECK_OK world=%d" % world, flush=True)
     dist.destroy_process_group()
+    log("exit")
 
 
 if __name__ == "__main__":
