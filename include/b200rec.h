@@ -52,7 +52,9 @@ typedef struct {
   int32_t n_cols;            /* rows of the gathered table */
   int32_t nnz;
   const int32_t* rowptr;     /* [n_rows+1] */
-  const int32_t* colidx;     /* [nnz] ascending inside a row */
+  const int32_t* colidx;     /* [nnz] ascending inside a row; with col_hint != 0 bit 31 marks a "hot" column */
+  int32_t col_hint;          /* 0: plain ids; 1: hot rows allocate in L1, others L1::no_allocate;
+                                2: hot rows L2::evict_last, others L2::evict_first (table larger than L2) */
   const float* vals;         /* [nnz] per-edge value, or NULL (all ones) */
   const float* nbr_scale;    /* [n_cols] multiplies each gathered row, or NULL */
   const float* row_scale;    /* [n_rows] multiplies the finished row sum, or NULL */
@@ -76,6 +78,7 @@ typedef struct {
 /* Build the decomposition on the HOST (one-time, per graph).  All pointers here are HOST pointers.
  * Call once with the output arrays NULL to get the sizes, allocate, call again to fill. */
 int b200rec_plan_build_host(const int32_t* rowptr /*HOST [n_rows+1]*/, int32_t n_rows, int32_t chunk,
+                            int32_t phase_split /*rows < this are scheduled first (n_users), 0 = one phase*/,
                             int32_t* n_items, int32_t* n_long, int32_t* n_slots,
                             int32_t* item_start, int32_t* item_end, int32_t* item_dst, int32_t* item_row,
                             int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot, int32_t* slot_long);

@@ -37,6 +37,35 @@ struct SpmmParams {
   int32_t* long_cnt;          // [n_long] arrival counters (zero between launches: the finisher resets its own)
 };
 
+// Cache-policy hints for the neighbour-row gathers.  The column ids handed to the kernel carry a "hot" flag in bit 31
+// (b200rec.graph: the highest-degree rows, as many as fit the cache level that matters for this table size):
+//  HINT 2 (table larger than L2, e.g. 2M x 1M x 128): hot rows are loaded L2::evict_last, all other rows
+//         L2::evict_first, so the ~100 MB of rows that serve about half of all gathers stay resident in the 126 MB L2
+//         instead of being washed out by the 1.5 GB stream of cold rows;
+//  HINT 1 (table L2-resident): hot rows allocate in L1, cold rows are loaded L1::no_allocate.
+__device__ __forceinline__ uint64_t make_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t make_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_f4_policy(const float* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_f4_no_l1(const float* ptr) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  return v;
+}
+
 template <int G, int VPL>
 __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int gl, float4 (&acc)[VPL]) {
   constexpr int D = G * VPL * 4;
@@ -63,7 +92,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int g
 //  * edges that contribute nothing (past the row end, dropped by the edge-dropout mask, or whose source row is
 //    flagged all-zero) are squeezed out with a ballot/popc compaction before the gather loop; the slack of the last
 //    sub-block is padded with (first column of the row, weight 0), so the loop body carries no predicates or selects.
-template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID, bool HAS_SRCF>
+template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID, bool HAS_SRCF, int HINT>
 __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(const SpmmParams p) {
   constexpr int D = G * VPL * 4;
   constexpr int U = (G >= 8) ? 8 : G;  // neighbour rows in flight per lane
@@ -88,7 +117,9 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
 #pragma unroll
     for (int o = G; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
   }
-  const int cfirst = live ? __ldg(p.colidx + start) : 0;  // padding target: a row this sum reads anyway
+  const int cfirst = live ? (__ldg(p.colidx + start) & 0x7fffffff) : 0;  // padding target: a row this sum reads anyway
+  uint64_t pol_hot = 0, pol_cold = 0;
+  if (HINT == 2) { pol_hot = make_policy_evict_last(); pol_cold = make_policy_evict_first(); }
   float4 acc[VPL];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -106,8 +137,8 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
         const int e = HAS_EID ? ld_stream_i32(p.eid + k) : k;
         valid = ((__ldg(p.keep_bits + (e >> 5)) >> (e & 31)) & 1u) != 0u;
       }
-      if (HAS_SRCF) valid = valid && (__ldg(p.src_flags + c) != 0);
-      if (HAS_NBR && valid) v *= __ldg(p.nbr_scale + c);
+      if (HAS_SRCF) valid = valid && (__ldg(p.src_flags + (c & 0x7fffffff)) != 0);
+      if (HAS_NBR && valid) v *= __ldg(p.nbr_scale + (c & 0x7fffffff));
     }
     int cnt;  // contributing edges of this group in this block of G; cntmax: warp-uniform loop bound
     if (COMPACT) {
@@ -137,9 +168,23 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
       for (int u = 0; u < U; ++u) {
         const int2 cv = my_cv[j0 + u];  // broadcast LDS.64
         vv[u] = __int_as_float(cv.y);
-        const float* r = xg + (size_t)((unsigned)cv.x * (unsigned)D);
+        const float* r = xg + (size_t)(((unsigned)cv.x & 0x7fffffffu) * (unsigned)D);
+        if (HINT == 2) {
+          const uint64_t pol = (cv.x < 0) ? pol_hot : pol_cold;
 #pragma unroll
-        for (int t = 0; t < VPL; ++t) xv[u][t] = ldg_f4(r + t * G * 4);
+          for (int t = 0; t < VPL; ++t) xv[u][t] = ldg_f4_policy(r + t * G * 4, pol);
+        } else if (HINT == 1) {
+          if (cv.x < 0) {
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) xv[u][t] = ldg_f4(r + t * G * 4);
+          } else {
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) xv[u][t] = ldg_f4_no_l1(r + t * G * 4);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) xv[u][t] = ldg_f4(r + t * G * 4);
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -210,21 +255,28 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
     const int grid = ceil_div(a->n_items, items_per_block);
     const bool hv = p.vals != nullptr, hn = p.nbr_scale != nullptr, hm = p.keep_bits != nullptr, he = p.eid != nullptr && hm;
     const bool hs = p.src_flags != nullptr;
-#define B2_SPMM_CASE(V, N, M, E, S)                                               \
-  if (hv == V && hn == N && hm == M && he == E && hs == S) {                      \
-    spmm_items_kernel<G, VPL, V, N, M, E, S><<<grid, 256, 0, st>>>(p);            \
+    const int hint = a->col_hint;
+#define B2_SPMM_CASE_H(V, N, M, E, S, H)                                          \
+  if (hv == V && hn == N && hm == M && he == E && hs == S && hint == H) {         \
+    spmm_items_kernel<G, VPL, V, N, M, E, S, H><<<grid, 256, 0, st>>>(p);         \
     B2_LAUNCHED();                                                                \
   } else
-    B2_SPMM_CASE(true, false, false, false, false)   // normalised adjacency
-    B2_SPMM_CASE(true, false, false, false, true)    // normalised adjacency, sparse source (first backward hop)
+#define B2_SPMM_CASE(V, N, M, E, S) B2_SPMM_CASE_H(V, N, M, E, S, 0)
+    B2_SPMM_CASE_H(true, false, false, false, false, 0)   // normalised adjacency
+    B2_SPMM_CASE_H(true, false, false, false, false, 1)
+    B2_SPMM_CASE_H(true, false, false, false, false, 2)
+    B2_SPMM_CASE_H(true, false, false, false, true, 0)    // normalised adjacency, sparse source (first backward hop)
+    B2_SPMM_CASE_H(true, false, false, false, true, 1)
+    B2_SPMM_CASE_H(true, false, false, false, true, 2)
     B2_SPMM_CASE(false, false, false, false, false)  // template features, eval
     B2_SPMM_CASE(false, false, true, false, false)   // template features, training (edge dropout)
     B2_SPMM_CASE(false, true, false, false, false)   // transposed features (backward), eval-mode graph
     B2_SPMM_CASE(false, true, true, true, false)     // transposed features (backward), dropout mask by edge id
     B2_SPMM_CASE(true, false, true, false, false)    // valued operand with dropout
     B2_SPMM_CASE(true, true, false, false, false)
-    { return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "operand combination (vals/nbr_scale/keep_bits/eid/src_flags) not instantiated"); }
+    { return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "operand combination (vals/nbr_scale/keep_bits/eid/src_flags/col_hint) not instantiated"); }
 #undef B2_SPMM_CASE
+#undef B2_SPMM_CASE_H
   }
   return 0;
 }
@@ -238,6 +290,7 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
   B2_REQUIRE(a->n_long == 0 || (a->partial && a->long_row && a->long_slot0 && a->long_nslot && a->slot_long && a->long_cnt),
              "long-row plan missing");
   B2_REQUIRE(!dst_flags || a->item_row, "dst_flags needs item_row in the plan");
+  B2_REQUIRE(a->col_hint >= 0 && a->col_hint <= 2, "col_hint must be 0, 1 or 2");
   B2_REQUIRE((long long)a->n_cols * d < (1ll << 32), "gathered table must have < 2^32 elements");
   SpmmParams p;
   p.colidx = a->colidx; p.vals = a->vals; p.nbr_scale = a->nbr_scale; p.row_scale = a->row_scale; p.eid = a->eid;
@@ -367,7 +420,7 @@ extern "C" int b200rec_propagate_bwd(const b200rec_csr* a, const float* g, int32
   return 0;
 }
 
-extern "C" int b200rec_plan_build_host(const int32_t* rowptr, int32_t n_rows, int32_t chunk, int32_t* n_items,
+extern "C" int b200rec_plan_build_host(const int32_t* rowptr, int32_t n_rows, int32_t chunk, int32_t phase_split, int32_t* n_items,
                                        int32_t* n_long, int32_t* n_slots, int32_t* item_start, int32_t* item_end,
                                        int32_t* item_dst, int32_t* item_row, int32_t* long_row, int32_t* long_slot0,
                                        int32_t* long_nslot, int32_t* slot_long) {
@@ -411,11 +464,17 @@ extern "C" int b200rec_plan_build_host(const int32_t* rowptr, int32_t n_rows, in
       }
     }
   };
-  each_item([&](int b, int e, int, int) { bucket[maxlen - (e - b)]++; });
+  // two phases (rows < phase_split first, e.g. all user rows, then all item rows), each longest-first: the rows of
+  // one phase gather from the other side of the bipartite graph only, so each phase has the cache to itself
+  delete[] bucket;
+  const int nb = maxlen + 1;
+  bucket = new int[2 * (size_t)nb + 2]();
+  auto key = [&](int b, int e, int row) { return ((phase_split > 0 && row >= phase_split) ? nb : 0) + (maxlen - (e - b)); };
+  each_item([&](int b, int e, int, int row) { bucket[key(b, e, row)]++; });
   int run = 0;
-  for (int i = 0; i <= maxlen; ++i) { int c = bucket[i]; bucket[i] = run; run += c; }
+  for (int i = 0; i < 2 * nb; ++i) { int c = bucket[i]; bucket[i] = run; run += c; }
   each_item([&](int b, int e, int dst, int row) {
-    const int pos = bucket[maxlen - (e - b)]++;
+    const int pos = bucket[key(b, e, row)]++;
     item_start[pos] = b; item_end[pos] = e; item_dst[pos] = dst;
     if (item_row) item_row[pos] = row;
   });

@@ -131,7 +131,8 @@ class LightGCN(BasicModel):
         .shape like the reference's sparse tensor)."""
         users, items = dataset.train_pairs()
         return b2graph.build_norm_adj(dataset.n_users, dataset.n_items, torch.from_numpy(np.ascontiguousarray(users)),
-                                      torch.from_numpy(np.ascontiguousarray(items)), device=self.device)
+                                      torch.from_numpy(np.ascontiguousarray(items)), device=self.device,
+                                      d=self.embedding_size)
 
     def layer0(self):
         return self.embedding.weight

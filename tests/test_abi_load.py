@@ -35,13 +35,13 @@ def test_plan_build_host_long_rows_and_order():
     np.cumsum(lens, out=rp[1:])
     ni, nl, ns = C.c_int32(), C.c_int32(), C.c_int32()
     null = C.c_void_p(0)
-    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, C.addressof(ni), C.addressof(nl), C.addressof(ns),
+    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, 0, C.addressof(ni), C.addressof(nl), C.addressof(ns),
                                        null, null, null, null, null, null, null, null) == 0
     assert (ni.value, nl.value, ns.value) == (5 + 3 + 2, 2, 5)
     a = [np.empty(ni.value, dtype=np.int32) for _ in range(4)]
     b = [np.empty(nl.value, dtype=np.int32) for _ in range(3)]
     sl = np.empty(ns.value, dtype=np.int32)
-    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, C.addressof(ni), C.addressof(nl), C.addressof(ns),
+    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, 0, C.addressof(ni), C.addressof(nl), C.addressof(ns),
                                        a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
                                        b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, sl.ctypes.data) == 0
     assert sl.tolist() == [0, 0, 0, 1, 1]
@@ -53,6 +53,14 @@ def test_plan_build_host_long_rows_and_order():
     assert sorted(dst[dst >= 0].tolist()) == [0, 1, 3, 4, 5]
     assert sorted((~dst[dst < 0]).tolist()) == [0, 1, 2, 3, 4]
     assert b[0].tolist() == [2, 6] and b[1].tolist() == [0, 3] and b[2].tolist() == [3, 2]
+    # two phases: rows < 4 first, each phase longest-first
+    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, 4, C.addressof(ni), C.addressof(nl), C.addressof(ns),
+                                       a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
+                                       b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, sl.ctypes.data) == 0
+    first = row < 4
+    assert first[:first.sum()].all() and not first[first.sum():].any()
+    for ph in (first, ~first):
+        assert (np.diff((end - start)[ph]) <= 0).all()
     # every nnz covered exactly once
     cover = np.zeros(lens.sum(), dtype=np.int32)
     for s, e in zip(start, end):
