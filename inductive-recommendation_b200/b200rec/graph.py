@@ -19,10 +19,11 @@ from . import _abi
 CHUNK_MAX = 1024
 
 
-def auto_chunk(nnz):
-    """Rows longer than `chunk` are split into chunk-sized work items (deterministic two-pass reduce).  One lane group
-    walks its item serially (~8 neighbour rows per memory round trip), so the longest item is the kernel's critical
-    path: size it so that there are a few items per resident group (148 SMs x 32 groups), within [64, 1024]."""
+def auto_chunk(nnz, d=None):
+    """Rows longer than `chunk` are split into chunk-sized work items (deterministic ordered reduce by the lane group that
+    parks the row's last chunk).  One lane group walks its item serially, about 8 neighbour rows per memory round trip, so
+    the longest item is a critical path (ncu, C2 shape with 1024-edge items: SMs 54 % active); every extra chunk costs a
+    partial-row round trip through L2.  Measured sweet spot: a few items per resident lane group, within [64, 1024]."""
     target = max(1, nnz // (148 * 32 * 4))
     c = 64
     while c < target and c < CHUNK_MAX:
@@ -30,10 +31,9 @@ def auto_chunk(nnz):
     return c
 
 
-
 class CsrOperand:
     def __init__(self, rowptr, colidx, n_cols, vals=None, nbr_scale=None, row_scale=None, eid=None, chunk=None,
-                 max_d=256, phase_split=0):
+                 max_d=256, phase_split=0, d=None):
         _abi.require_cuda(rowptr, colidx, vals, nbr_scale, row_scale, eid)
         assert rowptr.dtype == torch.int32 and colidx.dtype == torch.int32
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
@@ -42,7 +42,7 @@ class CsrOperand:
         self.n_cols = int(n_cols)
         self.nnz = colidx.numel()
         self.device = rowptr.device
-        self.chunk = chunk if chunk is not None else auto_chunk(self.nnz)
+        self.chunk = chunk if chunk is not None else auto_chunk(self.nnz, d)
         self.phase_split = int(phase_split)
         self.col_hint = 0
         self._build_plan(max_d)
@@ -215,7 +215,7 @@ def build_norm_adj(n_users, n_items, users, items, device=None, chunk=None, d=No
     _abi.check(lib.b200rec_adj_normalize(_abi.ptr(rowptr), _abi.ptr(colidx), _abi.ptr(mult), n, _abi.ptr(dinv),
                                          _abi.ptr(vals), _abi.stream_ptr()), "adj_normalize")
     import os
-    op = CsrOperand(rowptr, colidx, n, vals=vals, chunk=chunk,
+    op = CsrOperand(rowptr, colidx, n, vals=vals, chunk=chunk, d=d,
                     phase_split=0 if os.environ.get("B200REC_NO_PHASE", "0") == "1" else n_users)
     if d is not None:
         op.apply_cache_hints(d, n_users)

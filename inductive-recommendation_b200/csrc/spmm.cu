@@ -5,6 +5,7 @@
 // warp) or 512 B (D=128) fully coalesced.  Column ids / values are loaded G at a time, coalesced, and broadcast
 // with width-G shuffles; U neighbour rows are in flight per lane before the FMAs retire them.  The sum runs in CSR
 // order, so results do not depend on the grid, the item order or (multi-GPU) the row partition.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200rec {
@@ -95,15 +96,18 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int g
 template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID, bool HAS_SRCF, int HINT>
 __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(const SpmmParams p) {
   constexpr int D = G * VPL * 4;
-  constexpr int U = (G >= 8) ? 8 : G;  // neighbour rows in flight per lane
-  constexpr int GPW = 32 / G;          // groups per warp
+  constexpr int U = 8;                    // neighbour rows in flight per lane
+  constexpr int GPW = 32 / G;             // groups per warp
+  constexpr int EB = (G >= 16) ? G : 16;  // edges staged per group per block (narrow rows: several edges per lane)
+  constexpr int EPL = EB / G;             // edges loaded per lane per block
   constexpr bool COMPACT = HAS_MASK || HAS_SRCF;
-  __shared__ int2 s_cv[256];
+  constexpr int CVS = (G == 32) ? EB : EB + 1;  // slot stride per group: +1 keeps the groups' broadcast reads off one bank
+  __shared__ int2 s_cv[(256 / G) * CVS];
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   const int item = warp * GPW + lane / G;
-  int2* my_cv = s_cv + (threadIdx.x & ~(G - 1));  // this group's G slots
+  int2* my_cv = s_cv + (threadIdx.x / G) * CVS;  // this group's EB slots
   int start = 0, end = 0, dst = 0;
   if (item < p.n_items) {
     start = __ldg(p.item_start + item);
@@ -125,34 +129,40 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* __restrict__ xg = p.x + (size_t)gl * 4;
 
-  for (int base = 0; base < maxlen; base += G) {
-    const int k = start + base + gl;
-    int c = cfirst;
-    float v = 0.f;
-    bool valid = k < end;
-    if (valid) {
-      c = ld_stream_i32(p.colidx + k);
-      v = HAS_VALS ? ld_stream_f32(p.vals + k) : 1.f;
-      if (HAS_MASK) {
-        const int e = HAS_EID ? ld_stream_i32(p.eid + k) : k;
-        valid = ((__ldg(p.keep_bits + (e >> 5)) >> (e & 31)) & 1u) != 0u;
-      }
-      if (HAS_SRCF) valid = valid && (__ldg(p.src_flags + (c & 0x7fffffff)) != 0);
-      if (HAS_NBR && valid) v *= __ldg(p.nbr_scale + (c & 0x7fffffff));
-    }
-    int cnt;  // contributing edges of this group in this block of G; cntmax: warp-uniform loop bound
+  for (int base = 0; base < maxlen; base += EB) {
+    int cnt = 0;  // contributing edges of this group in this block of EB; cntmax: warp-uniform loop bound
     if (COMPACT) {
-      const unsigned bal = __ballot_sync(0xffffffffu, valid);
-      const unsigned gm = (G == 32) ? bal : ((bal >> (lane & ~(G - 1))) & ((1u << (G & 31)) - 1u));
-      cnt = __popc(gm);
-      const int rank = __popc(gm & ((1u << gl) - 1u));
-      my_cv[gl] = make_int2(cfirst, 0);  // pad
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) my_cv[e * G + gl] = make_int2(cfirst, 0);  // pad
       __syncwarp();
-      if (valid) my_cv[rank] = make_int2(c, __float_as_int(v));
-    } else {
-      cnt = min(G, max(end - start - base, 0));
-      my_cv[gl] = valid ? make_int2(c, __float_as_int(v)) : make_int2(cfirst, 0);
     }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int k = start + base + e * G + gl;
+      int c = cfirst;
+      float v = 0.f;
+      bool valid = k < end;
+      if (valid) {
+        c = ld_stream_i32(p.colidx + k);
+        v = HAS_VALS ? ld_stream_f32(p.vals + k) : 1.f;
+        if (HAS_MASK) {
+          const int eidx = HAS_EID ? ld_stream_i32(p.eid + k) : k;
+          valid = ((__ldg(p.keep_bits + (eidx >> 5)) >> (eidx & 31)) & 1u) != 0u;
+        }
+        if (HAS_SRCF) valid = valid && (__ldg(p.src_flags + (c & 0x7fffffff)) != 0);
+        if (HAS_NBR && valid) v *= __ldg(p.nbr_scale + (c & 0x7fffffff));
+      }
+      if (COMPACT) {
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        const unsigned gm = (G == 32) ? bal : ((bal >> (lane & ~(G - 1))) & ((1u << (G & 31)) - 1u));
+        const int rank = cnt + __popc(gm & ((1u << gl) - 1u));
+        if (valid) my_cv[rank] = make_int2(c, __float_as_int(v));
+        cnt += __popc(gm);
+      } else {
+        my_cv[e * G + gl] = valid ? make_int2(c, __float_as_int(v)) : make_int2(cfirst, 0);
+      }
+    }
+    if (!COMPACT) cnt = min(EB, max(end - start - base, 0));
     int cntmax = cnt;
     if (GPW > 1) {
 #pragma unroll
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
     }
     __syncwarp();
 #pragma unroll
-    for (int j0 = 0; j0 < G; j0 += U) {
+    for (int j0 = 0; j0 < EB; j0 += U) {
       if (j0 >= cntmax) break;  // warp-uniform
       float4 xv[U][VPL];
       float vv[U];
@@ -250,7 +260,15 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
 template <int G, int VPL>
 static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t st) {
   constexpr int GPW = 32 / G;
-  const int items_per_block = 8 * GPW;
+  // threads per block: 256 measured best or equal on every shape (C2: 57-58 us at 32/64/256 for D=64; C4 D=16:
+  // 1.86 ms at 256 vs 4.9 ms at 32); B200REC_SPMM_TPB overrides for experiments
+  static int tpb = 0;
+  if (!tpb) {
+    const char* e = getenv("B200REC_SPMM_TPB");
+    tpb = e ? atoi(e) : 256;
+    if (tpb != 32 && tpb != 64 && tpb != 128 && tpb != 256) tpb = 256;
+  }
+  const int items_per_block = (tpb / 32) * GPW;
   if (a->n_items > 0) {
     const int grid = ceil_div(a->n_items, items_per_block);
     const bool hv = p.vals != nullptr, hn = p.nbr_scale != nullptr, hm = p.keep_bits != nullptr, he = p.eid != nullptr && hm;
@@ -258,7 +276,7 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
     const int hint = a->col_hint;
 #define B2_SPMM_CASE_H(V, N, M, E, S, H)                                          \
   if (hv == V && hn == N && hm == M && he == E && hs == S && hint == H) {         \
-    spmm_items_kernel<G, VPL, V, N, M, E, S, H><<<grid, 256, 0, st>>>(p);         \
+    spmm_items_kernel<G, VPL, V, N, M, E, S, H><<<grid, tpb, 0, st>>>(p);         \
     B2_LAUNCHED();                                                                \
   } else
 #define B2_SPMM_CASE(V, N, M, E, S) B2_SPMM_CASE_H(V, N, M, E, S, 0)

@@ -38,7 +38,7 @@ def test_adjacency_structure_bit_exact_values_1ulp(golden, name):
     np.testing.assert_allclose(_np(v2), a2.data, rtol=3e-7)
 
 
-@pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("d", [8, 16, 32, 64, 128, 256])
 def test_spmm_bit_exact_vs_c_oracle_with_hub_rows(d):
     from b200rec import graph, ops
     rng = np.random.default_rng(d)
@@ -111,7 +111,7 @@ def test_sampler_and_dropout_bit_exact_vs_c_oracle(golden):
 
 
 @pytest.mark.parametrize("d,with_w,reg_mode", [(64, False, 0), (64, False, 1), (128, False, 1), (64, True, 0), (32, True, 0),
-                                               (256, False, 1), (16, False, 0)])
+                                               (256, False, 1), (16, False, 0), (8, False, 1), (8, True, 0)])
 def test_bpr_fused_matches_torch_fp32(d, with_w, reg_mode):
     from b200rec import ops
     gen = torch.Generator(device=DEV).manual_seed(d + reg_mode)
