@@ -303,7 +303,8 @@ def run_own(args, rank, world):
                            "l2": "flushed between timed steps (write of %d MiB)" % (flush_buf.numel() >> 20),
                            "parallelism": "single GPU" if world == 1 else (
                                "row-partitioned graph x%d, per-layer block exchange" % world if partition is not None else
-                               "embedding dimension sharded x%d (%d columns per GPU), one [B,3] all-reduce per step" % (world, d))},
+                               "embedding dimension sharded x%d (%d columns per GPU) x %d replicas, one [B,3] all-reduce per "
+                               "step; evaluation user-sharded x%d" % (m._dim_shard.world, d, world // m._dim_shard.world, world))},
                 "ms_per_step_l2_warm": t_warm, "epochs_per_sec_l2_warm": 1e3 / (t_warm * steps_per_epoch),
                 "e2e": {"value": e2e_value, "unit": "epochs/s", "h2d_bytes_per_step": BATCH * 3 * 8,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_net, "last_loss": loss},

@@ -20,11 +20,40 @@ import torch.distributed as dist
 
 
 class DimShard:
-    def __init__(self, rank=0, world=1, group=None):
-        self.rank, self.world, self.group = rank, world, group
+    """rank r of `world` holds columns [cols(d)] of every table.  Shards narrower than `min_cols` columns are not worth
+    having (the SpMM becomes per-edge-overhead-bound: C2 one layer 57 us at 64 columns, 42 at 32, 40 at 16, 50 at 8), so
+    the column split stops at P' = the largest power of two <= world with D / P' >= min_cols, and the world is arranged
+    as world / P' identical replicas of a P'-way shard group (same seed, same sampler stream -> same numbers, no traffic
+    between replicas).  Evaluation always shards the USERS over the whole world."""
+
+    def __init__(self, rank=0, world=1, group=None, min_cols=None):
+        import os
+        self.world_rank, self.world_size, self.world_group = rank, world, group
+        self.min_cols = int(os.environ.get("B200REC_MIN_COLS", "16")) if min_cols is None else min_cols
+        self.rank, self.world, self.group = rank, world, group  # shard-group coordinates, fixed by configure()
+        self._configured = world == 1
+
+    def configure(self, d):
+        """collective (every rank of the world calls it with the same d): pick P' and create the shard groups"""
+        if self._configured:
+            return self
+        p = 1
+        while p * 2 <= self.world_size and d % (p * 2) == 0 and d // (p * 2) >= self.min_cols:
+            p *= 2
+        self.world = p
+        self.rank = self.world_rank % p
+        self.replica = self.world_rank // p
+        self.group = self.world_group
+        if p != self.world_size:
+            for rep in range(self.world_size // p):  # every rank creates every group, in the same order
+                g = dist.new_group(list(range(rep * p, (rep + 1) * p)))
+                if rep == self.replica:
+                    self.group = g
+        self._configured = True
+        return self
 
     def cols(self, d):
-        assert d % self.world == 0, "embedding_size must be divisible by the number of GPUs"
+        assert d % self.world == 0, "embedding_size must be divisible by the shard count"
         w = d // self.world
         return self.rank * w, (self.rank + 1) * w
 
@@ -34,7 +63,7 @@ class DimShard:
         return t
 
     def gather_cols(self, local):
-        """[N, D/P] on every rank -> [N, D] on every rank"""
+        """[N, D/P'] on every rank of a shard group -> [N, D] on every rank"""
         if self.world == 1:
             return local
         parts = [torch.empty_like(local) for _ in range(self.world)]
@@ -42,18 +71,18 @@ class DimShard:
         return torch.cat(parts, dim=1)
 
     def user_range(self, n_users):
-        per = (n_users + self.world - 1) // self.world
-        return min(n_users, self.rank * per), min(n_users, (self.rank + 1) * per)
+        per = (n_users + self.world_size - 1) // self.world_size
+        return min(n_users, self.world_rank * per), min(n_users, (self.world_rank + 1) * per)
 
     def gather_user_rows(self, local, n_users):
-        """rows of the rank's user_range -> all rows on every rank (user-sharded evaluation)"""
-        if self.world == 1:
+        """rows of the rank's user_range -> all rows on every rank (user-sharded evaluation over the whole world)"""
+        if self.world_size == 1:
             return local
-        per = (n_users + self.world - 1) // self.world
+        per = (n_users + self.world_size - 1) // self.world_size
         pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         pad[: local.shape[0]] = local
-        parts = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(parts, pad, group=self.group)
+        parts = [torch.empty_like(pad) for _ in range(self.world_size)]
+        dist.all_gather(parts, pad, group=self.world_group)
         return torch.cat(parts, dim=0)[:n_users]
 
 
@@ -61,10 +90,11 @@ def shard_model_dims(model, shard):
     """Keep only this rank's columns of every embedding parameter (call before the optimiser is created).
     Every rank must have built the model from the same seed, so the slices are slices of ONE initialisation."""
     import torch.nn as nn
+    d = model.embedding_size
+    shard.configure(d)
     if shard.world == 1:
         model._dim_shard = shard
         return model
-    d = model.embedding_size
     lo, hi = shard.cols(d)
     if type(model).__name__ == 'MF':
         joint = model._joint[:, lo:hi].contiguous()

@@ -265,7 +265,7 @@ class BprEngine:
 
     def meter_avg(self):
         a = self.loss_accum.clone()
-        if self.shard is not None:  # rank 0 carries the BPR term, every rank its own columns' L2 term
+        if self.shard is not None:  # shard rank 0 carries the BPR term, every rank its own columns' L2 term
             self.shard.all_reduce_sum(a[:1])
         a = a.cpu()
         return float(a[0] / a[1]) if float(a[1]) > 0 else 0.0

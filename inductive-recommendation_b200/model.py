@@ -71,7 +71,7 @@ class BasicModel(nn.Module):
     def _all_columns(self, rep):
         """with the embedding dimension sharded over GPUs (b200rec.dist.DimShard) scoring needs every column"""
         shard = getattr(self, '_dim_shard', None)
-        return rep if shard is None or shard.world == 1 else shard.gather_cols(rep)
+        return rep if shard is None else shard.gather_cols(rep)
 
     def recommend(self, users, k, excl_a=None, excl_b=None, banned=None, precision=0):
         """Fused full-rank scoring + masking + top-K (trainer.py:152-169): returns (ids int32 [b,k], scores [b,k]),

@@ -120,6 +120,16 @@ class BasicTrainer:
     # ------------------------------------------------------------------------------------------------ metrics
     def hit_matrix(self, eval_data, rec_items):
         """hit[u, j] = rec_items[u, j] in eval_data[u]  (device kernel; eval rows as sorted CSR)"""
+        dev = self.device
+        for split in ('train', 'val', 'test'):  # the dataset's own lists: use its cached device CSR
+            if eval_data is getattr(self.dataset, split + '_data', None):
+                ptr_d, idx_d = self.dataset.csr(split, device=dev)
+                if idx_d.numel() == 0:
+                    idx_d = torch.zeros(1, dtype=torch.int32, device=dev)
+                rec_d = rec_items if isinstance(rec_items, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rec_items))
+                rec_d = rec_d.to(device=dev, dtype=torch.int32).contiguous()
+                n_eval = (ptr_d[1:] - ptr_d[:-1]).cpu().numpy().astype(np.int32)
+                return ops.hit_matrix(rec_d, 0, ptr_d, idx_d).cpu().numpy(), n_eval
         if hasattr(eval_data, 'ptr'):  # lazy CSR-backed lists
             ptr, idx = np.asarray(eval_data.ptr, dtype=np.int64), np.asarray(eval_data.idx, dtype=np.int64)
         else:
@@ -130,7 +140,6 @@ class BasicTrainer:
                 np.zeros(0, dtype=np.int64)
         rows = np.repeat(np.arange(len(ptr) - 1, dtype=np.int64), np.diff(ptr))
         idx = idx[np.lexsort((idx, rows))]
-        dev = self.device
         ptr_d = torch.from_numpy(ptr.astype(np.int32)).to(dev)
         idx_d = torch.from_numpy(idx.astype(np.int32)).to(dev) if idx.size else torch.zeros(1, dtype=torch.int32, device=dev)
         rec_d = rec_items if isinstance(rec_items, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rec_items))
@@ -178,7 +187,7 @@ class BasicTrainer:
         k = max(self.topks)
         n_users = self.dataset.n_users
         shard = getattr(self.model, '_dim_shard', None)
-        u_lo, u_hi = (0, n_users) if shard is None or shard.world == 1 else shard.user_range(n_users)
+        u_lo, u_hi = (0, n_users) if shard is None else shard.user_range(n_users)
         out = []
         with torch.no_grad():
             self.model.score_tables()  # collective (column all-gather) when sharded: every rank takes part
@@ -187,7 +196,7 @@ class BasicTrainer:
                 ids, _ = self.model.recommend(users, k, excl_a, excl_b, banned, precision=self.eval_precision)
                 out.append(ids)
         ids = torch.cat(out, dim=0) if out else torch.zeros((0, k), dtype=torch.int32, device=dev)
-        if shard is not None and shard.world > 1:
+        if shard is not None:
             ids = shard.gather_user_rows(ids, n_users)
         return ids
 

@@ -32,12 +32,17 @@ def test_nnz_balanced_bounds():
 def test_dim_shard_ranges():
     from b200rec.dist import DimShard
     for world in (1, 2, 4, 8):
-        cols = [DimShard(r, world).cols(64) for r in range(world)]
+        cols = [DimShard(r, world, min_cols=1).cols(64) for r in range(world)]
         assert cols[0][0] == 0 and cols[-1][1] == 64 and all(a[1] == b[0] for a, b in zip(cols, cols[1:]))
         ur = [DimShard(r, world).user_range(1001) for r in range(world)]
         assert ur[0][0] == 0 and ur[-1][1] == 1001 and all(a[1] == b[0] for a, b in zip(ur, ur[1:]))
     with pytest.raises(AssertionError):
         DimShard(0, 3).cols(64)
+    # the column split stops at min_cols: 8 ranks, D=64, min 16 columns -> 4-way shards x 2 replicas (no process group
+    # is needed to compute the coordinates when the split covers the whole world)
+    s = DimShard(5, 8, min_cols=8)
+    s.configure(64)
+    assert (s.world, s.rank) == (8, 5)
 
 
 def _worker(rank, world, port, out):
@@ -45,7 +50,7 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from b200rec.dist import DimShard, RowPartition, nnz_balanced_bounds
-    shard = DimShard(rank, world)
+    shard = DimShard(rank, world, min_cols=1).configure(8)
     # column gather: every rank ends with the full table
     full = torch.arange(6 * 8, dtype=torch.float32).reshape(6, 8)
     lo, hi = shard.cols(8)
@@ -70,6 +75,11 @@ def _worker(rank, world, port, out):
     mine[part.lo:part.hi] = table[part.lo:part.hi]
     part.exchange(mine)
     assert torch.equal(mine, table)
+    # replicas: with min_cols = D the columns are not split, each rank is its own shard group
+    rep = DimShard(rank, world, min_cols=8).configure(8)
+    assert (rep.world, rep.rank, rep.replica) == (1, 0, rank) and rep.cols(8) == (0, 8)
+    assert torch.equal(rep.gather_cols(full), full)
+    assert torch.equal(rep.gather_user_rows(ids[a:b].contiguous(), 11), ids)   # users still shard over the world
     out.put(rank)
     dist.destroy_process_group()
 
