@@ -207,8 +207,10 @@ int b200rec_score_dense_f32(const float* rep_users, const int64_t* users, int32_
  *   for each listed user: score all items, drop items in its exclusion rows (train, and val when testing:
  *   excl_ptr_a/excl_idx_a and optional excl_ptr_b/excl_idx_b, sorted CSR by user, trainer.py:155-165) and items in
  *   [banned_lo, banned_hi) (trainer.py:166-167), return the K best as (score desc, item id asc).
- * precision 0: exact fp32 CUDA-core path;  1: tcgen05 bf16 candidate pass + exact fp32 re-score (same ids and
- *   scores as precision 0 by construction: the candidate margin bounds the bf16 error).
+ * precision 0: exact fp32 CUDA-core path;  1 (D = 64 / 128): TMA-fed tcgen05 bf16 candidate pass + exact fp32 re-score
+ *   (same ids and scores as precision 0 by construction: the candidate margin bounds the bf16 error).
+ * out_overflow [b] (required for precision 1, optional otherwise): 1 for a user whose candidate list overflowed --
+ *   its output row is not valid and must be recomputed with precision 0; always 0 for precision 0.
  * workspace: device scratch, size from b200rec_score_topk_workspace(). */
 int64_t b200rec_score_topk_workspace(int32_t n_batch_users, int32_t n_items, int32_t d, int32_t k, int32_t precision);
 int b200rec_score_topk(const float* rep_users, const int64_t* users, int32_t n_batch_users,
@@ -216,7 +218,8 @@ int b200rec_score_topk(const float* rep_users, const int64_t* users, int32_t n_b
                        const int32_t* excl_ptr_a, const int32_t* excl_idx_a,
                        const int32_t* excl_ptr_b, const int32_t* excl_idx_b,
                        int32_t banned_lo, int32_t banned_hi, int32_t k, int32_t precision,
-                       int32_t* out_ids /*[b,K]*/, float* out_scores /*[b,K]*/, void* workspace, void* stream);
+                       int32_t* out_ids /*[b,K]*/, float* out_scores /*[b,K]*/, int32_t* out_overflow /*[b]*/,
+                       void* workspace, void* stream);
 /* hit[u,j] = rec[u,j] in eval row u (trainer.py:117-121), eval rows sorted CSR. */
 int b200rec_hit_matrix(const int32_t* rec_ids, int32_t n_rows, int32_t k, int64_t user0,
                        const int32_t* eval_ptr, const int32_t* eval_idx, float* hit, void* stream);

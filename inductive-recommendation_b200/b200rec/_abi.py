@@ -59,7 +59,7 @@ PROTOTYPES = {
     "b200rec_dropout_mask": (C.c_int, [_I32, _F, _U64, _P, _P, _P]),
     "b200rec_score_dense_f32": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P]),
     "b200rec_score_topk_workspace": (C.c_int64, [_I32, _I32, _I32, _I32, _I32]),
-    "b200rec_score_topk": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "b200rec_score_topk": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "b200rec_hit_matrix": (C.c_int, [_P, _I32, _I32, _I64, _P, _P, _P, _P]),
 }
 

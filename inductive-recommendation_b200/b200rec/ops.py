@@ -128,9 +128,18 @@ def score_topk(rep_users, users, rep_items, k, excl_a=None, excl_b=None, banned=
     ea = excl_a if excl_a is not None else (None, None)
     eb = excl_b if excl_b is not None else (None, None)
     lo, hi = banned if banned is not None else (0, 0)
+    if precision == 1 and d not in (64, 128):
+        precision = 0  # the tensor-core path is built for D = 64 / 128
+    ovf = torch.zeros(nb, dtype=torch.int32, device=rep_users.device) if precision == 1 else None
     check(_lib().b200rec_score_topk(ptr(rep_users), ptr(users), nb, ptr(rep_items), ni, d, ptr(ea[0]), ptr(ea[1]),
-                                    ptr(eb[0]), ptr(eb[1]), lo, hi, k, precision, ptr(ids), ptr(sc), ptr(ws),
+                                    ptr(eb[0]), ptr(eb[1]), lo, hi, k, precision, ptr(ids), ptr(sc), ptr(ovf), ptr(ws),
                                     stream_ptr()), "score_topk")
+    if precision == 1:
+        bad = torch.nonzero(ovf).flatten()
+        score_topk.last_overflow = int(bad.numel())  # rows that fell back to the exact path (diagnostics / tests)
+        if bad.numel():  # candidate list overflow (pathological score distribution): exact path for those users
+            ids2, sc2 = score_topk(rep_users, users[bad].contiguous(), rep_items, k, excl_a, excl_b, banned, precision=0)
+            ids[bad], sc[bad] = ids2, sc2
     return ids, sc
 
 

@@ -291,6 +291,13 @@ using namespace b200rec;
 
 extern "C" int64_t b200rec_score_topk_workspace(int32_t n_batch_users, int32_t n_items, int32_t d, int32_t k,
                                                 int32_t precision);
+// score_tc.cu
+int64_t b200rec_score_topk_tc_workspace(int nb, int ni, int d);
+bool b200rec_score_topk_tc_supported(int d);
+int b200rec_score_topk_tc(const float* rep_users, const int64_t* users, int nb, const float* rep_items, int ni, int d,
+                          const int32_t* ea_ptr, const int32_t* ea_idx, const int32_t* eb_ptr, const int32_t* eb_idx, int blo,
+                          int bhi, int k, int32_t* out_ids, float* out_scores, int32_t* out_overflow, void* workspace,
+                          cudaStream_t st);
 
 extern "C" int b200rec_score_dense_f32(const float* rep_users, const int64_t* users, int32_t n_batch_users,
                                        const float* rep_items, int32_t n_items, int32_t d, float* scores, void* stream) {
@@ -316,6 +323,7 @@ extern "C" int64_t b200rec_score_topk_workspace(int32_t n_batch_users, int32_t n
                                                 int32_t precision) {
   (void)precision;
   if (k < 1) k = 1;
+  if (precision == 1 && b200rec_score_topk_tc_supported(d)) return b200rec_score_topk_tc_workspace(n_batch_users, n_items, d);
   const int split = choose_split(n_batch_users, n_items, k, d);
   return (int64_t)split * n_batch_users * k * (int64_t)sizeof(Cand) + 256;
 }
@@ -324,14 +332,21 @@ extern "C" int b200rec_score_topk(const float* rep_users, const int64_t* users, 
                                   const float* rep_items, int32_t n_items, int32_t d, const int32_t* excl_ptr_a,
                                   const int32_t* excl_idx_a, const int32_t* excl_ptr_b, const int32_t* excl_idx_b,
                                   int32_t banned_lo, int32_t banned_hi, int32_t k, int32_t precision, int32_t* out_ids,
-                                  float* out_scores, void* workspace, void* stream) {
+                                  float* out_scores, int32_t* out_overflow, void* workspace, void* stream) {
   B2_REQUIRE(rep_users && users && rep_items && out_ids && out_scores && workspace, "null argument");
   B2_REQUIRE(n_batch_users > 0 && n_items > 0, "empty input");
   B2_REQUIRE(k >= 1 && k <= KMAX, "k must be in [1,128]");
   B2_REQUIRE(!excl_ptr_a || excl_idx_a, "exclusion CSR a incomplete");
   B2_REQUIRE(!excl_ptr_b || excl_idx_b, "exclusion CSR b incomplete");
-  B2_REQUIRE(precision == 0, "only precision 0 (exact fp32) is built in this version");
+  B2_REQUIRE(precision == 0 || precision == 1, "precision must be 0 (exact fp32) or 1 (tcgen05 bf16 candidates + exact re-score)");
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == 1) {
+    B2_REQUIRE(b200rec_score_topk_tc_supported(d), "precision 1 supports embedding size 64 / 128");
+    B2_REQUIRE(out_overflow, "precision 1 needs out_overflow");
+    return b200rec_score_topk_tc(rep_users, users, n_batch_users, rep_items, n_items, d, excl_ptr_a, excl_idx_a, excl_ptr_b,
+                                 excl_idx_b, banned_lo, banned_hi, k, out_ids, out_scores, out_overflow, workspace, st);
+  }
+  if (out_overflow) B2_CUDA(cudaMemsetAsync(out_overflow, 0, (size_t)n_batch_users * sizeof(int32_t), st));
   TopkParams p;
   p.rep_users = rep_users; p.users = users; p.n_users = n_batch_users; p.rep_items = rep_items; p.n_items = n_items;
   p.excl_ptr_a = excl_ptr_a; p.excl_idx_a = excl_idx_a; p.excl_ptr_b = excl_ptr_b; p.excl_idx_b = excl_idx_b;

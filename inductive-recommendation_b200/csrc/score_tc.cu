@@ -1,0 +1,523 @@
+// Full-rank evaluation, tensor-core path (north_star (4); model.py:122-127 predict + trainer.py:152-169 mask + topk):
+// a TMA-fed tcgen05 bf16 user x item score GEMM whose epilogue never writes the score matrix.
+//
+//   prep kernel     : gather the user rows, convert users / items to bf16 (K-major), row norms, max item norm
+//   score_tc_kernel : one CTA per 128 users; warp 0 = TMA producer (item tiles, ring of STAGES), warp 1 = tcgen05.mma
+//                     issuer (128 x BN x 16 UMMAs, fp32 accumulators in TMEM, two accumulator stages), warps 2-5 =
+//                     epilogue: tcgen05.ld 32 columns at a time, running max, and only values above the row's cut-off
+//                     are looked at individually, tested against the user's sorted train / val rows and the banned
+//                     range, and appended to the row's candidate list.  The cut-off is (K-th best approximate score so
+//                     far) - 2 eps; it is re-derived by a warp-cooperative sort of the row's list at a few scheduled
+//                     tile indices (the list then holds a superset of the K best seen so far).
+//   rescore kernel  : exact fp32 scores (the same fmaf chain in d-order as the precision-0 path and the C oracle) for the
+//                     candidates, final (score desc, id asc) top-K.
+// Exactness: |approx - exact| <= eps_u = 1.05 * 2^-7 * ||u|| * max_i ||v_i|| (two bf16 roundings, Cauchy-Schwarz; fp32
+// accumulation error is three orders smaller).  If T is the exact K-th best score, every true top-K item has
+// approx >= T - eps and the K-th best approx is <= T + eps, so "approx >= K-th best approx - 2 eps" keeps all of them.
+// The ids and scores returned are therefore identical to the exact path by construction; a row whose candidate list
+// overflows is flagged and must be redone by the caller with precision 0.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace b200rec {
+
+constexpr int TC_M = 128;      // users per CTA (UMMA M, cta_group::1)
+constexpr int TC_CAP = 1024;   // candidate slots per user row
+struct Cand {
+  float s;
+  int id;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a mis-programmed pipeline must abort the launch (trap -> CUDA error), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > 40000000u) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major operand tile with 128-byte swizzle (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B): start>>4, LBO (unused) 1,
+// SBO = 1024 B >> 4, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B  (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ prep
+// rows -> bf16 (row-major, D contiguous = K-major), ||row||_2, optional gather, optional global max of the norms
+template <int D>
+__global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ table, const int64_t* __restrict__ gather,
+                                                      int n_rows, __nv_bfloat16* __restrict__ out, float* __restrict__ norms,
+                                                      unsigned* __restrict__ max_norm_bits) {
+  constexpr int G = D / 4;  // lanes per row (D = 64 -> 16, 128 -> 32)
+  const int gi = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G), gl = threadIdx.x & (G - 1);
+  float ss = 0.f;
+  if (gi < n_rows) {
+    const int64_t src = gather ? gather[gi] : gi;
+    const float4 v = ldg_f4(table + (size_t)src * D + gl * 4);
+    ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<unsigned*>(&a);
+    pk.y = *reinterpret_cast<unsigned*>(&b);
+    *reinterpret_cast<uint2*>(out + (size_t)gi * D + gl * 4) = pk;
+  }
+  ss = group_sum<G>(ss);
+  if (gi < n_rows && gl == 0) {
+    const float nrm = sqrtf(ss);
+    norms[gi] = nrm;
+    if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nrm));  // non-negative floats order like their bits
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ main kernel
+struct TcParams {
+  const int64_t* users;      // [b] absolute user ids (exclusion rows are indexed by them)
+  int n_users, n_items, k;
+  const int32_t *excl_ptr_a, *excl_idx_a, *excl_ptr_b, *excl_idx_b;
+  int banned_lo, banned_hi;
+  const float* unorm;        // [b]
+  const unsigned* vmax_bits; // max item norm
+  Cand* cand;                // [b, TC_CAP]
+  int* cand_cnt;             // [b]
+  int* overflow;             // [b]
+};
+
+__device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) { return a.s > b.s || (a.s == b.s && a.id < b.id); }
+__device__ __forceinline__ void warp_sort_desc(Cand* c, int np, int lane) {
+  for (int k = 2; k <= np; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < np; t += 32) {
+        const int o = t ^ j;
+        if (o > t) {
+          const bool up = ((t & k) == 0);
+          const Cand a = c[t], b = c[o];
+          if (cand_before(b, a) == up) { c[t] = b; c[o] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+__device__ __forceinline__ bool row_has(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t row, int key) {
+  if (!ptr) return false;
+  int lo = __ldg(ptr + row), hi = __ldg(ptr + row + 1);
+  const int end = hi;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(idx + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo < end && __ldg(idx + lo) == key;
+}
+
+template <int D, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tm_users,
+                                                          const __grid_constant__ CUtensorMap tm_items, const TcParams p) {
+  constexpr int KB = D / 64;                        // 128-byte K blocks
+  constexpr uint32_t A_BYTES = TC_M * D * 2, B_STAGE_BYTES = BN * D * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B atoms need 1024 B alignment
+  uint8_t* sA = smem;                               // [KB][128 rows][128 B]
+  uint8_t* sB = smem + A_BYTES;                     // [STAGES][KB][BN rows][128 B]
+  Cand* sort_area = reinterpret_cast<Cand*>(sB + (size_t)STAGES * B_STAGE_BYTES);  // [4 warps][TC_CAP]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sort_area + 4 * TC_CAP);
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + STAGES;        // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty = tfull + 2;           // [2]
+  uint64_t* afull = tempty + 2;           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * TC_M;
+  const int n_tiles = (p.n_items + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+    mbar_init(afull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 accumulator stages x BN fp32 columns = 512 columns, allocated and freed by this warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(afull, A_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + (size_t)kb * TC_M * 128, &tm_users, kb * 64, u0, afull);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(empty + s, ((t / STAGES) & 1) ^ 1);
+        mbar_expect_tx(full + s, B_STAGE_BYTES);
+        uint8_t* dst = sB + (size_t)s * B_STAGE_BYTES;
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(dst + (size_t)kb * BN * 128, &tm_items, kb * 64, t * BN, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_M, BN);
+      mbar_wait(afull, 0);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % STAGES, as = t & 1;
+        mbar_wait(tempty + as, ((t >> 1) & 1) ^ 1);  // epilogue drained this accumulator stage
+        mbar_wait(full + s, (t / STAGES) & 1);       // item tile landed
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K=16 per 64-wide K block; +32 B inside the swizzle atom per step
+            const uint64_t ad = umma_desc_sw128(a0 + kb * TC_M * 128 + k * 32);
+            const uint64_t bd = umma_desc_sw128(b0 + kb * BN * 128 + k * 32);
+            tc_mma_bf16(tmem_base + as * BN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+        }
+        tc_commit(empty + s);    // smem stage free when these MMAs retire
+        tc_commit(tfull + as);   // accumulator ready
+      }
+    }
+  } else {
+    // ===== epilogue: thread <-> TMEM lane <-> user row =====
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int u = u0 + row;
+    const bool active = u < p.n_users;
+    const int64_t user = active ? p.users[u] : 0;
+    Cand* my_list = p.cand + (size_t)(active ? u : 0) * TC_CAP;
+    Cand* my_sort = sort_area + (size_t)(warp - 2) * TC_CAP;
+    const float vmax = __uint_as_float(*p.vmax_bits);
+    const float margin = active ? 2.f * 1.05f * 0.0078125f * p.unorm[u] * vmax : 0.f;
+    float cut = -INFINITY;  // candidates need approx >= cut = (K-th best approx so far) - margin
+    int cnt = 0;
+    bool ovf = false;
+    const int K = p.k;
+    // refinement schedule (same recurrence in every thread): after tile 0, then whenever the expected number of new
+    // candidates since the last refinement reaches TC_CAP/8
+    float expect_acc = 0.f, seen_at_refine = 0.f;
+
+    auto refine = [&]() {
+      // Warp-cooperative, row by row.  Only a LOWER bound of the K-th best approximate score is needed (a lower cut
+      // just admits a few more candidates), so instead of sorting the list a value bisection finds a pivot with
+      // K <= #(entries >= pivot) <= 2K in a handful of counting passes over a shared-memory copy, and the band above
+      // (pivot - margin) is kept by a ballot compaction.  (A full bitonic sort here cost 13.5 M of the 20 M warp
+      // instructions of a CTA sweep.)
+      for (int r = 0; r < 32; ++r) {
+        const int rc = __shfl_sync(0xffffffffu, cnt, r);
+        const bool ract = __shfl_sync(0xffffffffu, (int)active, r) != 0;
+        if (!ract || rc < K) continue;  // fewer than K so far: keep everything, no cut yet
+        Cand* list = reinterpret_cast<Cand*>(__shfl_sync(0xffffffffu, (unsigned long long)my_list, r));
+        const float rmargin = __shfl_sync(0xffffffffu, margin, r);
+        const float rcut = __shfl_sync(0xffffffffu, cut, r);
+        float mx = -INFINITY, mn = INFINITY;
+        for (int t = lane; t < rc; t += 32) {
+          const Cand c = list[t];
+          my_sort[t] = c;
+          mx = fmaxf(mx, c.s);
+          mn = fminf(mn, c.s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        __syncwarp();
+        // invariant: #(entries >= lo) >= K  (the previous K-th best is still in the list; or lo = min and rc >= K)
+        float lo = (rcut > -INFINITY) ? rcut + rmargin : mn;
+        lo = fminf(lo, mx);
+        float hi = mx;
+        for (int itn = 0; itn < 14; ++itn) {
+          const float pv = 0.5f * (lo + hi);
+          if (!(pv > lo && pv < hi)) break;
+          int c = 0;
+          for (int t = lane; t < rc; t += 32) c += (my_sort[t].s >= pv) ? 1 : 0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+          if (c >= K) {
+            lo = pv;
+            if (c <= 2 * K) break;
+          } else {
+            hi = pv;
+          }
+        }
+        const float ncut = lo - rmargin;
+        int base = 0;
+        for (int t0 = 0; t0 < rc; t0 += 32) {
+          const int t = t0 + lane;
+          const bool kp = t < rc && my_sort[t].s >= ncut;
+          const unsigned bal = __ballot_sync(0xffffffffu, kp);
+          if (kp) list[base + __popc(bal & ((1u << lane) - 1u))] = my_sort[t];
+          base += __popc(bal);
+        }
+        __syncwarp();
+        if (lane == r) { cnt = base; cut = ncut; }
+      }
+    };
+
+    for (int t = 0; t < n_tiles; ++t) {
+      const int as = t & 1;
+      mbar_wait(tfull + as, (t >> 1) & 1);
+      tc_fence_after();
+      const int i0 = t * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+        float m = __uint_as_float(v[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        if (active && m >= cut) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sc = __uint_as_float(v[j]);
+            const int item = i0 + c * 32 + j;
+            if (sc >= cut && item < p.n_items) {
+              if (item >= p.banned_lo && item < p.banned_hi) continue;
+              if (row_has(p.excl_ptr_a, p.excl_idx_a, user, item)) continue;
+              if (row_has(p.excl_ptr_b, p.excl_idx_b, user, item)) continue;
+              if (cnt < TC_CAP) my_list[cnt++] = Cand{sc, item};
+              else ovf = true;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + as);  // 4 epilogue warps -> barrier count 4
+      // scheduled refinement
+      bool do_refine = false;
+      if (t == 0) do_refine = true;
+      else {
+        expect_acc += (float)BN * (float)K / seen_at_refine;
+        if (expect_acc >= (float)(TC_CAP / 8)) do_refine = true;
+      }
+      if (t == n_tiles - 1) do_refine = true;
+      if (do_refine) {
+        __syncwarp();
+        refine();
+        seen_at_refine = (float)(t + 1) * (float)BN;
+        expect_acc = 0.f;
+      }
+    }
+    if (active) {
+      p.cand_cnt[u] = cnt;
+      p.overflow[u] = ovf ? 1 : 0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ exact re-score + top-K
+template <int D>
+__global__ void __launch_bounds__(128) tc_rescore_kernel(const float* __restrict__ rep_users, const int64_t* __restrict__ users,
+                                                         int n_users, const float* __restrict__ rep_items,
+                                                         const Cand* __restrict__ cand, const int* __restrict__ cand_cnt, int k,
+                                                         int32_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  Cand* buf = reinterpret_cast<Cand*>(raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * 4 + warp;
+  if (u >= n_users) return;
+  Cand* row = buf + (size_t)warp * TC_CAP;
+  const int n = cand_cnt[u];
+  const float* ur = rep_users + (size_t)users[u] * D;
+  int np = 32;
+  while (np < n) np <<= 1;
+  for (int t = lane; t < np; t += 32) {
+    Cand c{-INFINITY, INT32_MAX};
+    if (t < n) {
+      const int id = cand[(size_t)u * TC_CAP + t].id;
+      const float* vr = rep_items + (size_t)id * D;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) acc = fmaf(__ldg(ur + d), __ldg(vr + d), acc);  // the oracle's chain, d = 0..D-1
+      c = Cand{acc, id};
+    }
+    row[t] = c;
+  }
+  __syncwarp();
+  warp_sort_desc(row, np, lane);
+  for (int j = lane; j < k; j += 32) {
+    const bool ok = j < n;
+    out_ids[(size_t)u * k + j] = ok ? row[j].id : -1;
+    out_scores[(size_t)u * k + j] = ok ? row[j].s : -INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+// bf16 [rows, D] row-major; box = 64 columns (128 B, SWIZZLE_128B) x box_rows
+static int make_map(CUtensorMap* m, const void* base, int rows, int d, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B200REC_ERR_CUDA, "%s: %s", "score_topk_tc", "cuTensorMapEncodeTiled not available");
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200REC_ERR_CUDA, "%s: %s", "score_topk_tc", "cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace b200rec
+using namespace b200rec;
+
+// workspace carve-up shared by the size query and the launch
+struct TcWorkspace {
+  size_t users_bf16, items_bf16, unorm, vnorm, vmax, cand, cnt, ovf, total;
+};
+static TcWorkspace tc_layout(int nb, int ni, int d) {
+  TcWorkspace w;
+  size_t o = 0;
+  w.users_bf16 = o; o = align_up(o + (size_t)nb * d * 2, 1024);
+  w.items_bf16 = o; o = align_up(o + (size_t)ni * d * 2, 1024);
+  w.unorm = o; o = align_up(o + (size_t)nb * 4, 256);
+  w.vnorm = o; o = align_up(o + (size_t)ni * 4, 256);
+  w.vmax = o; o = align_up(o + 4, 256);
+  w.cand = o; o = align_up(o + (size_t)nb * TC_CAP * sizeof(Cand), 256);
+  w.cnt = o; o = align_up(o + (size_t)nb * 4, 256);
+  w.ovf = o; o = align_up(o + (size_t)nb * 4, 256);
+  w.total = o + 1024;
+  return w;
+}
+
+int64_t b200rec_score_topk_tc_workspace(int nb, int ni, int d) { return (int64_t)tc_layout(nb, ni, d).total; }
+bool b200rec_score_topk_tc_supported(int d) { return d == 64 || d == 128; }
+
+template <int D, int BN, int STAGES>
+static int tc_launch(const float* rep_users, const int64_t* users, int nb, const float* rep_items, int ni,
+                     const int32_t* ea_ptr, const int32_t* ea_idx, const int32_t* eb_ptr, const int32_t* eb_idx, int blo, int bhi,
+                     int k, int32_t* out_ids, float* out_scores, int32_t* out_overflow, void* workspace, cudaStream_t st) {
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024));
+  const TcWorkspace w = tc_layout(nb, ni, D);
+  __nv_bfloat16* ub = reinterpret_cast<__nv_bfloat16*>(ws + w.users_bf16);
+  __nv_bfloat16* ib = reinterpret_cast<__nv_bfloat16*>(ws + w.items_bf16);
+  float* unorm = reinterpret_cast<float*>(ws + w.unorm);
+  float* vnorm = reinterpret_cast<float*>(ws + w.vnorm);
+  unsigned* vmax = reinterpret_cast<unsigned*>(ws + w.vmax);
+  Cand* cand = reinterpret_cast<Cand*>(ws + w.cand);
+  int* cnt = reinterpret_cast<int*>(ws + w.cnt);
+  int* ovf = out_overflow ? out_overflow : reinterpret_cast<int*>(ws + w.ovf);
+  B2_CUDA(cudaMemsetAsync(vmax, 0, 4, st));
+  constexpr int G = D / 4;
+  tc_prep_kernel<D><<<ceil_div((long long)nb * G, 256), 256, 0, st>>>(rep_users, users, nb, ub, unorm, nullptr);
+  B2_LAUNCHED();
+  tc_prep_kernel<D><<<ceil_div((long long)ni * G, 256), 256, 0, st>>>(rep_items, nullptr, ni, ib, vnorm, vmax);
+  B2_LAUNCHED();
+  CUtensorMap mu, mi;
+  int rc = make_map(&mu, ub, nb, D, TC_M);
+  if (rc) return rc;
+  rc = make_map(&mi, ib, ni, D, BN);
+  if (rc) return rc;
+  TcParams p;
+  p.users = users; p.n_users = nb; p.n_items = ni; p.k = k;
+  p.excl_ptr_a = ea_ptr; p.excl_idx_a = ea_idx; p.excl_ptr_b = eb_ptr; p.excl_idx_b = eb_idx;
+  p.banned_lo = blo; p.banned_hi = bhi; p.unorm = unorm; p.vmax_bits = vmax; p.cand = cand; p.cand_cnt = cnt; p.overflow = ovf;
+  const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 4 * TC_CAP * sizeof(Cand) + 256;
+  B2_CUDA(cudaFuncSetAttribute(score_tc_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  score_tc_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 192, smem, st>>>(mu, mi, p);
+  B2_LAUNCHED();
+  const size_t rsmem = 4 * TC_CAP * sizeof(Cand);
+  tc_rescore_kernel<D><<<ceil_div(nb, 4), 128, rsmem, st>>>(rep_users, users, nb, rep_items, cand, cnt, k, out_ids, out_scores);
+  B2_LAUNCHED();
+  return 0;
+}
+
+int b200rec_score_topk_tc(const float* rep_users, const int64_t* users, int nb, const float* rep_items, int ni, int d,
+                          const int32_t* ea_ptr, const int32_t* ea_idx, const int32_t* eb_ptr, const int32_t* eb_idx, int blo,
+                          int bhi, int k, int32_t* out_ids, float* out_scores, int32_t* out_overflow, void* workspace,
+                          cudaStream_t st) {
+  if (d == 64)
+    return tc_launch<64, 256, 4>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
+                                 out_scores, out_overflow, workspace, st);
+  if (d == 128)
+    return tc_launch<128, 256, 2>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
+                                  out_scores, out_overflow, workspace, st);
+  return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "score_topk_tc", "tensor-core scoring supports embedding size 64 / 128");
+}
