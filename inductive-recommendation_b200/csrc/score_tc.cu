@@ -23,7 +23,7 @@
 namespace b200rec {
 
 constexpr int TC_M = 128;      // users per CTA (UMMA M, cta_group::1)
-constexpr int TC_CAP = 1024;   // candidate slots per user row
+constexpr int TC_CAP = 512;    // candidate slots per user row
 struct Cand {
   float s;
   int id;
@@ -167,7 +167,7 @@ __device__ __forceinline__ bool row_has(const int32_t* __restrict__ ptr, const i
 }
 
 template <int D, int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tm_users,
+__global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant__ CUtensorMap tm_users,
                                                           const __grid_constant__ CUtensorMap tm_items, const TcParams p) {
   constexpr int KB = D / 64;                        // 128-byte K blocks
   constexpr uint32_t A_BYTES = TC_M * D * 2, B_STAGE_BYTES = BN * D * 2;
@@ -327,20 +327,35 @@ __global__ void __launch_bounds__(192, 1) score_tc_kernel(const __grid_constant_
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
-        float m = __uint_as_float(v[0]);
+        // maxima of the four groups of 8, then of the whole chunk: a group is scanned value by value only when its
+        // maximum reaches the cut (with 6-12 warps per SM every instruction's latency is exposed, so the common path
+        // must stay short and branch-free)
+        float gm[4];
 #pragma unroll
-        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        for (int q = 0; q < 4; ++q) {
+          float a = fmaxf(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+          float b = fmaxf(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+          float c2 = fmaxf(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+          float d2 = fmaxf(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+          gm[q] = fmaxf(fmaxf(a, b), fmaxf(c2, d2));
+        }
+        const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
         if (active && m >= cut) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sc = __uint_as_float(v[j]);
-            const int item = i0 + c * 32 + j;
-            if (sc >= cut && item < p.n_items) {
-              if (item >= p.banned_lo && item < p.banned_hi) continue;
-              if (row_has(p.excl_ptr_a, p.excl_idx_a, user, item)) continue;
-              if (row_has(p.excl_ptr_b, p.excl_idx_b, user, item)) continue;
-              if (cnt < TC_CAP) my_list[cnt++] = Cand{sc, item};
-              else ovf = true;
+          for (int q = 0; q < 4; ++q) {
+            if (gm[q] < cut) continue;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int j = q * 8 + jj;
+              const float sc = __uint_as_float(v[j]);
+              const int item = i0 + c * 32 + j;
+              if (sc >= cut && item < p.n_items) {
+                if (item >= p.banned_lo && item < p.banned_hi) continue;
+                if (row_has(p.excl_ptr_a, p.excl_idx_a, user, item)) continue;
+                if (row_has(p.excl_ptr_b, p.excl_idx_b, user, item)) continue;
+                if (cnt < TC_CAP) my_list[cnt++] = Cand{sc, item};
+                else ovf = true;
+              }
             }
           }
         }
@@ -514,10 +529,10 @@ int b200rec_score_topk_tc(const float* rep_users, const int64_t* users, int nb, 
                           int bhi, int k, int32_t* out_ids, float* out_scores, int32_t* out_overflow, void* workspace,
                           cudaStream_t st) {
   if (d == 64)
-    return tc_launch<64, 256, 4>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
+    return tc_launch<64, 128, 4>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
                                  out_scores, out_overflow, workspace, st);
   if (d == 128)
-    return tc_launch<128, 256, 2>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
+    return tc_launch<128, 128, 2>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
                                   out_scores, out_overflow, workspace, st);
   return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "score_topk_tc", "tensor-core scoring supports embedding size 64 / 128");
 }

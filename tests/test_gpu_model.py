@@ -134,11 +134,13 @@ def test_fused_engine_step(golden, name, use_graph):
     assert int(tr.opt.state[next(iter(m.parameters()))]["step"]) == 1
 
 
+@pytest.mark.parametrize("precision", [0, 1])
 @pytest.mark.parametrize("name", ["lightgcn_tiny", "mf_tiny", "igcn_tiny", "lightgcn_d128"])
-def test_eval_topk_and_metrics(golden, name):
+def test_eval_topk_and_metrics(golden, name, precision):
+    """precision 0 = exact fp32 CUDA-core scoring, 1 = tcgen05 bf16 candidates + exact re-score (same ids by construction)"""
     g = golden(name)
     ds, m = golden_model(g, name)
-    tr = _trainer(g, name, ds, m)
+    tr = _trainer(g, name, ds, m, eval_precision=precision)
     for split in ("train", "val", "test"):
         rec = _np(tr.recommend_all(split))
         ref_ids, ref_val = g["topk_ids_" + split], g["topk_val_" + split]
