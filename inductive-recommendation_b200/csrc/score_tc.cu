@@ -23,7 +23,7 @@
 namespace b200rec {
 
 constexpr int TC_M = 128;      // users per CTA (UMMA M, cta_group::1)
-constexpr int TC_CAP = 512;    // candidate slots per user row
+constexpr int TC_CAP = 1024;   // candidate slots per user row
 struct Cand {
   float s;
   int id;

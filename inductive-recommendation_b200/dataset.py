@@ -75,10 +75,10 @@ class BasicDataset(Dataset):
     def csr(self, split='train', device=None, sort=True):
         """(ptr int32 [n_users+1], idx int32) of `<split>_data`, items ascending per user, cached per device."""
         lists = getattr(self, split + '_data')
-        key = (split, str(device), id(lists))
+        key = (split, str(device))
         hit = self._csr_cache.get(key)
-        if hit is not None:
-            return hit
+        if hit is not None and hit[0] is lists:  # the entry keeps `lists` alive, so identity cannot be a recycled id
+            return hit[1]
         ptr, idx = _lists_to_csr(lists)
         if sort and idx.size:
             rows = np.repeat(np.arange(len(lists), dtype=np.int64), np.diff(ptr))
@@ -87,8 +87,7 @@ class BasicDataset(Dataset):
         out = (torch.from_numpy(ptr.astype(np.int32)), torch.from_numpy(idx.astype(np.int32)))
         if device is not None:
             out = tuple(t.to(device) for t in out)
-        self._csr_cache = {k: v for k, v in self._csr_cache.items() if k[0] != split or k[1] != str(device)}
-        self._csr_cache[key] = out
+        self._csr_cache[key] = (lists, out)
         return out
 
     def train_pairs(self):
@@ -168,6 +167,7 @@ class SyntheticDataset(BasicDataset):
         else:
             self.train_data, self.val_data, self.test_data = (_LazyLists(*self._np[s]) for s in ('train', 'val', 'test'))
         self._orig = {'train': self.train_data, 'val': self.val_data, 'test': self.test_data}
+        self._np_csr_cache = {}
         self.train_array = None  # use train_pairs()
 
     def __len__(self):
@@ -182,13 +182,13 @@ class SyntheticDataset(BasicDataset):
         if lists is not self._orig[split]:  # e.g. inductive_eval temporarily replaces test_data
             return super().csr(split, device, sort)
         key = (split, str(device), 'np')
-        hit = self._csr_cache.get(key)
+        hit = self._np_csr_cache.get(key)
         if hit is None:
             ptr, idx = self._np[split]  # generator output is already sorted per user
             hit = (torch.from_numpy(ptr.astype(np.int32)), torch.from_numpy(idx.astype(np.int32)))
             if device is not None:
                 hit = tuple(t.to(device) for t in hit)
-            self._csr_cache[key] = hit
+            self._np_csr_cache[key] = hit
         return hit
 
 

@@ -52,7 +52,8 @@ class BasicTrainer:
         self.best_ndcg = -np.inf
         self.save_path = None
         self.opt = None
-        self.eval_precision = trainer_config.get('eval_precision', 0)
+        # 1 = tcgen05 bf16 candidate pass + exact fp32 re-score (identical ids/scores, D = 64 / 128; falls back to 0 otherwise)
+        self.eval_precision = trainer_config.get('eval_precision', 1)
         self.eval_chunk = max(int(trainer_config['test_batch_size']), 16384)
         test_user = TensorDataset(torch.arange(self.dataset.n_users, dtype=torch.int64, device=self.device))
         self.test_user_loader = DataLoader(test_user, batch_size=trainer_config['test_batch_size'])

@@ -193,9 +193,59 @@ def run_case(tag, graph, model_cfg, trainer_cfg, out_dir, seed=2021, batch=256):
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def run_inductive_case(tag, full_graph, out_dir, seed=2021):
+    """IGCN built on the OLD nodes only, then re-pointed at the enlarged dataset the way IGCN.load does
+    (model.py:4213-4220: generate_feat(is_updating=True) + update_feat_mat) and evaluated with the reference's
+    inductive_eval (trainer.py:212-253); its six printed result lines are the fixture."""
+    old_graph, n_old_u, n_old_i = synth.inductive_split(full_graph, 0.8, 0.8)
+    tmp_old, tmp_new = tempfile.mkdtemp(), tempfile.mkdtemp()
+    synth.write_processed(old_graph, tmp_old)
+    synth.write_processed(full_graph, tmp_new)
+    ds_old = quiet(ref_dataset.get_dataset, {"name": "ProcessedDataset", "path": tmp_old, "device": CPU})
+    ds_new = quiet(ref_dataset.get_dataset, {"name": "ProcessedDataset", "path": tmp_new, "device": CPU})
+    ref_utils.set_seed(seed)
+    cfg = {"name": "IGCN", "embedding_size": 64, "n_layers": 3, "dropout": 0.3, "feature_ratio": 1.0, "device": CPU}
+    model = quiet(ref_model.get_model, cfg, ds_old)
+    out = {"emb0": model.embedding.weight.detach().numpy().copy(), "n_old_users": ds_old.n_users,
+           "n_old_items": ds_old.n_items, "old_n_items_attr": ds_old.n_items}
+    for name, g in (("old", old_graph), ("new", full_graph)):
+        for split in ("train", "val", "test"):
+            out["%s_%s_indptr" % (name, split)] = getattr(g, split + "_indptr").numpy()
+            out["%s_%s_items" % (name, split)] = getattr(g, split + "_items").numpy()
+    out["new_n_users"], out["new_n_items"] = ds_new.n_users, ds_new.n_items
+    # re-point the model at the enlarged dataset (what a driver has to do; the reference ships none)
+    model.config["dataset"] = ds_new
+    model.n_users, model.n_items = ds_new.n_users, ds_new.n_items
+    model.norm_adj = model.generate_graph(ds_new)
+    model.feat_mat, _, _, model.row_sum = model.generate_feat(ds_new, is_updating=True)
+    model.update_feat_mat()
+    model.eval()
+    with torch.no_grad():
+        out["rep_new"] = model.get_rep().numpy().copy()
+    out["feat_idx_new"], out["feat_val_new"] = coo_of(model.feat_mat)
+    tr = quiet(ref_trainer.get_trainer,
+               {"name": "IGCNTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 0.0, "aux_reg": 0.01, "device": CPU,
+                "dataloader_num_workers": 0, "topks": TOPKS, "n_epochs": 1, "batch_size": 256, "test_batch_size": 128},
+               ds_new, model)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        tr.inductive_eval(ds_old.n_users, ds_old.n_items)
+    lines = [l for l in buf.getvalue().splitlines() if "result." in l]
+    assert len(lines) == 6, lines
+    out["inductive_lines"] = np.array(lines)
+    path = os.path.join(out_dir, tag + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+    for l in lines:
+        print("   ", l)
+
+
 def main():
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--only-inductive" in sys.argv:
+        run_inductive_case("igcn_inductive", synth.generate(400, 600, 9000, seed=21), out_dir)
+        return
     g = synth.generate(300, 500, 6000, seed=7)
     bpr = {"name": "BPRTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 1e-4}
     igcn = {"name": "IGCNTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 0.0, "aux_reg": 0.01}
@@ -210,6 +260,7 @@ def main():
     # a D=128 / L=4 case (the C4 kernel configuration) on a graph with hub rows
     g2 = synth.generate(400, 300, 9000, seed=11, a_item=1.1)
     run_case("lightgcn_d128", g2, {"name": "LightGCN", "embedding_size": 128, "n_layers": 4}, bpr, out_dir)
+    run_inductive_case("igcn_inductive", synth.generate(400, 600, 9000, seed=21), out_dir)
 
 
 if __name__ == "__main__":

@@ -192,3 +192,54 @@ def test_checkpoint_roundtrip(golden, tmp_path):
     m.eval(); m2.eval()
     with torch.no_grad():
         assert torch.equal(m.get_rep(), m2.get_rep())
+
+
+def test_inductive_eval_matches_reference(golden, capsys):
+    """IGCN built on the old nodes, re-pointed at the enlarged dataset (generate_feat(is_updating=True), new adjacency),
+    then the six passes of inductive_eval (trainer.py:212-253): the printed result lines equal the reference's."""
+    import re
+    import dataset as D
+    import model as M
+    import trainer as T
+    from b200rec import synth
+    g = golden("igcn_inductive")
+    t = lambda k: torch.from_numpy(np.asarray(g[k], dtype=np.int64))  # noqa: E731
+
+    def ds_of(prefix, nu, ni):
+        graph = synth.SynthGraph(nu, ni, t(prefix + "_train_indptr"), t(prefix + "_train_items"), t(prefix + "_val_indptr"),
+                                 t(prefix + "_val_items"), t(prefix + "_test_indptr"), t(prefix + "_test_items"))
+        return D.get_dataset({"name": "SyntheticDataset", "device": DEV, "graph": graph})
+
+    n_old_u, n_old_i = int(g["n_old_users"]), int(g["n_old_items"])
+    ds_old = ds_of("old", n_old_u, n_old_i)
+    ds_new = ds_of("new", int(g["new_n_users"]), int(g["new_n_items"]))
+    m = M.get_model({"name": "IGCN", "embedding_size": 64, "n_layers": 3, "dropout": 0.3, "feature_ratio": 1.0,
+                     "device": DEV}, ds_old)
+    with torch.no_grad():
+        m.embedding.weight.copy_(torch.from_numpy(g["emb0"]))
+    # what a driver does to evaluate new users / items (the reference ships none; IGCN.load shows the sequence)
+    m.config["dataset"] = ds_new
+    m.n_users, m.n_items = ds_new.n_users, ds_new.n_items
+    m.norm_adj = m.generate_graph(ds_new)
+    m.feat_mat, _, _, m.row_sum = m.generate_feat(ds_new, is_updating=True)
+    m.update_feat_mat()
+    r, c, _ = m.feat_mat.fwd.to_coo()
+    assert np.array_equal(np.stack([_np(r), _np(c)]), g["feat_idx_new"])     # new nodes use template columns only
+    m.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(_np(m.get_rep()), g["rep_new"], rtol=1e-5, atol=1e-7)
+    tr = T.get_trainer({"name": "IGCNTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 0.0, "aux_reg": 0.01,
+                        "device": DEV, "dataloader_num_workers": 0, "topks": TOPKS, "n_epochs": 1, "batch_size": 256,
+                        "test_batch_size": 128}, ds_new, m)
+    capsys.readouterr()
+    tr.inductive_eval(n_old_u, n_old_i)
+    ours = [l for l in capsys.readouterr().out.splitlines() if "result." in l]
+    ref = [str(x) for x in g["inductive_lines"]]
+    assert len(ours) == 6
+    num = re.compile(r"-?\d+\.\d+")
+    for a, b in zip(ours, ref):
+        assert a.split(" result.")[0] == b.split(" result.")[0]
+        va, vb = [float(x) for x in num.findall(a)], [float(x) for x in num.findall(b)]
+        assert len(va) == len(vb) == 15
+        np.testing.assert_allclose(va, vb, atol=2e-3)   # printed with 3 decimals
+    assert ds_new.test_data is not None and len(ds_new.test_data) == ds_new.n_users  # test_data restored
