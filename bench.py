@@ -156,7 +156,10 @@ def run_own(args, rank, world):
     ds = D.get_dataset({"name": "SyntheticDataset", "device": dev, "graph": graph})
     torch.manual_seed(2021)  # same seed on every rank: the shards are slices of one initialisation
     partition = None
-    m = M.get_model({"name": "LightGCN", "embedding_size": d, "n_layers": n_layers, "device": dev}, ds)
+    model_cfg = {"lightgcn": {"name": "LightGCN", "embedding_size": d, "n_layers": n_layers},
+                 "igcn": {"name": "IGCN", "embedding_size": d, "n_layers": n_layers, "dropout": 0.3, "feature_ratio": 1.0},
+                 "mf": {"name": "MF", "embedding_size": d}}[args.model]
+    m = M.get_model(dict(model_cfg, device=dev), ds)
     if world > 1:
         from b200rec.dist import DimShard, RowPartition, shard_model_dims
         if args.parallelism == "row":
@@ -164,7 +167,8 @@ def run_own(args, rank, world):
         else:
             shard_model_dims(m, DimShard(rank, world))
             d = m.embedding_size
-    tr = T.get_trainer({"name": "BPRTrainer", "optimizer": "Adam", "lr": LR, "l2_reg": L2_REG, "device": dev,
+    tr = T.get_trainer({"name": "IGCNTrainer" if args.model == "igcn" else "BPRTrainer", "optimizer": "Adam", "lr": LR,
+                        "l2_reg": 0.0 if args.model == "igcn" else L2_REG, "aux_reg": 0.01, "device": dev,
                         "n_epochs": 1, "batch_size": BATCH, "dataloader_num_workers": 0, "test_batch_size": 512,
                         "topks": TOPKS, "partition": partition}, ds, m)
     m.train()
@@ -282,13 +286,22 @@ def run_own(args, rank, world):
         torch.cuda.synchronize()
         eval_s = time.perf_counter() - w0
         ke = timed_steps(lambda: tr.recommend_all("test"), 3, flush=True)
+        d_full = getattr(m, "full_embedding_size", m.embedding_size)
+        score_flops = 2.0 * ds.n_users * ds.n_items * d_full
+        pk = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
+        tf_peak = float(pk.get("bf16_tflops", 1590.0))
+        tf = score_flops / (min(ke) * 1e-3) / 1e12 * (1.0 / world)  # per GPU: the sweep is user-sharded
         eval_info = {"users_per_s_e2e": ds.n_users / eval_s, "users_per_s_kernels": ds.n_users / (min(ke) * 1e-3),
                      "k": max(TOPKS), "recall@20": float(metrics["Recall"][20]), "ndcg@20": float(metrics["NDCG"][20]),
+                     "precision": tr.eval_precision,
+                     "score_roofline": {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s",
+                                        "frac": tf / tf_peak, "note": "whole recommend_all sweep (propagation + prep + "
+                                        "tcgen05 score/candidates + exact re-score) per GPU; epilogue-latency-bound, see DESIGN 4.6"},
                      "includes": "get_rep + score/mask/top-K + D2H ids + hit matrix + metrics"}
 
     # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload on the host cores ----
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "lightgcn":
         n_cpu = 3 if workload != "c4" else 1
         s_cpu, threads = cpu_port_step_time(graph, workload, n_cpu, 1)
         cpu_baseline = {"value": 1.0 / (steps_per_epoch * s_cpu), "unit": "epochs/s", "cores": threads, "kind": "port",
@@ -298,7 +311,7 @@ def run_own(args, rank, world):
         line = {"metric": "bpr_epochs_per_sec", "value": value, "unit": "epochs/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload + ": " + WORKLOAD_DOC[workload], "batch": BATCH,
+                "config": {"workload": workload + ": " + WORKLOAD_DOC[workload].replace("LightGCN", model_cfg["name"]), "batch": BATCH,
                            "steps_per_epoch": steps_per_epoch, "optimizer": "Adam", "sampler": "device (Philox)",
                            "l2": "flushed between timed steps (write of %d MiB)" % (flush_buf.numel() >> 20),
                            "parallelism": "single GPU" if world == 1 else (
@@ -325,6 +338,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="lightgcn", choices=["lightgcn", "igcn", "mf"],
+                    help="lightgcn is the headline; igcn = inductive template-feature layer + propagation (config.py:18-23)")
     ap.add_argument("--parallelism", default="dim", choices=["dim", "row"],
                     help="multi-GPU decomposition: embedding-dimension sharding (default) or the row partition")
     args = ap.parse_args()

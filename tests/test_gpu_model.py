@@ -243,3 +243,48 @@ def test_inductive_eval_matches_reference(golden, capsys):
         assert len(va) == len(vb) == 15
         np.testing.assert_allclose(va, vb, atol=2e-3)   # printed with 3 decimals
     assert ds_new.test_data is not None and len(ds_new.test_data) == ds_new.n_users  # test_data restored
+
+
+def test_train_loop_checkpoints_and_early_stop(golden, tmp_path, monkeypatch, capsys):
+    """BasicTrainer.train (trainer.py:58-113): eval('train') + eval('val') per epoch, best-NDCG checkpoint rotation in
+    ./checkpoints, patience, reload of the best checkpoint at the end."""
+    import os
+    g = golden("lightgcn_tiny")
+    ds, m = golden_model(g, "lightgcn_tiny")
+    monkeypatch.chdir(tmp_path)
+    tr = _trainer(g, "lightgcn_tiny", ds, m, n_epochs=4, lr=5e-3, max_patience=2)
+    best = tr.train(verbose=True)
+    out = capsys.readouterr().out
+    assert out.count("Validation result.") >= 1 and "Epoch 0/4" in out
+    files = os.listdir(tmp_path / "checkpoints")
+    assert len(files) == 1 and files[0].startswith("LightGCN_BPRTrainer_SyntheticDataset_") and files[0].endswith(".pth")
+    assert abs(float(files[0].rsplit("_", 1)[1][:-4]) - best * 100) < 1e-3        # file name carries NDCG*100 (3 decimals)
+    assert tr.save_path == os.path.join("checkpoints", files[0]) and best == tr.best_ndcg > 0
+    sd = torch.load(tr.save_path)
+    assert list(sd) == ["embedding.weight"] and torch.equal(sd["embedding.weight"].to(DEV), m.embedding.weight.data)
+
+
+def test_degenerate_graph_rows_and_k_larger_than_catalogue():
+    """users without train items, items nobody interacted with (degree clamped to 1, model.py:92), K > unmasked items"""
+    import dataset as D
+    import model as M
+    import trainer as T
+    from b200rec import synth
+    tp = torch.tensor([0, 0, 3, 3, 4, 6], dtype=torch.int64)          # users 0 and 2 have no train items
+    ti = torch.tensor([1, 4, 7, 0, 2, 7], dtype=torch.int64)          # items 3, 5, 6, 8 are never used
+    e = torch.zeros(6, dtype=torch.int64)
+    graph = synth.SynthGraph(5, 9, tp, ti, e, ti[:0], tp, ti)          # test = train (just to have eval rows)
+    ds = D.get_dataset({"name": "SyntheticDataset", "device": DEV, "graph": graph})
+    m = M.get_model({"name": "LightGCN", "embedding_size": 64, "n_layers": 2, "device": DEV}, ds)
+    dinv = _np(m.norm_adj.dinv)
+    assert dinv[0] == 1.0 and dinv[5 + 3] == 1.0                        # isolated nodes: deg = max(1, 0)
+    tr = T.get_trainer({"name": "BPRTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 1e-4, "device": DEV, "n_epochs": 1,
+                        "batch_size": 64, "dataloader_num_workers": 0, "test_batch_size": 4, "topks": TOPKS}, ds, m)
+    m.train()
+    assert np.isfinite(tr.train_one_epoch())
+    assert set(_np(tr._engine().batch[:, 0]).tolist()) <= {1, 3, 4}     # the sampler never draws a user with an empty row
+    rec = _np(tr.recommend_all("val"))                                  # K = 20 > 9 items: padded with -1
+    assert rec.shape == (5, 20) and (rec[:, 9:] == -1).all()
+    assert sorted(rec[1, :6].tolist()) == [0, 2, 3, 5, 6, 8]            # user 1's train items 1, 4, 7 are masked
+    _, metrics, _ = tr.eval("test")
+    assert 0.0 <= metrics["Recall"][20] <= 1.0
