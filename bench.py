@@ -161,9 +161,11 @@ def run_own(args, rank, world):
                  "mf": {"name": "MF", "embedding_size": d}}[args.model]
     m = M.get_model(dict(model_cfg, device=dev), ds)
     if world > 1:
-        from b200rec.dist import DimShard, RowPartition, shard_model_dims
+        from b200rec.dist import DimShard, PeerRowPartition, RowPartition, shard_model_dims
         if args.parallelism == "row":
             partition = RowPartition(m.norm_adj, rank, world)
+        elif args.parallelism == "peer":
+            partition = PeerRowPartition(m.norm_adj, rank, world, d)
         else:
             shard_model_dims(m, DimShard(rank, world))
             d = m.embedding_size
@@ -315,7 +317,9 @@ def run_own(args, rank, world):
                            "steps_per_epoch": steps_per_epoch, "optimizer": "Adam", "sampler": "device (Philox)",
                            "l2": "flushed between timed steps (write of %d MiB)" % (flush_buf.numel() >> 20),
                            "parallelism": "single GPU" if world == 1 else (
-                               "row-partitioned graph x%d, per-layer block exchange" % world if partition is not None else
+                               ("row-partitioned graph x%d, exchange fused into the SpMM / Adam epilogues (NVLink peer stores) "
+                                "+ signal/wait hand-shake" % world) if args.parallelism == "peer" else
+                               "row-partitioned graph x%d, per-layer NCCL block exchange" % world if partition is not None else
                                "embedding dimension sharded x%d (%d columns per GPU) x %d replicas, one [B,3] all-reduce per "
                                "step; evaluation user-sharded x%d" % (m._dim_shard.world, d, world // m._dim_shard.world, world))},
                 "ms_per_step_l2_warm": t_warm, "epochs_per_sec_l2_warm": 1e3 / (t_warm * steps_per_epoch),
@@ -340,8 +344,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="lightgcn", choices=["lightgcn", "igcn", "mf"],
                     help="lightgcn is the headline; igcn = inductive template-feature layer + propagation (config.py:18-23)")
-    ap.add_argument("--parallelism", default="dim", choices=["dim", "row"],
-                    help="multi-GPU decomposition: embedding-dimension sharding (default) or the row partition")
+    ap.add_argument("--parallelism", default="dim", choices=["dim", "row", "peer"],
+                    help="multi-GPU decomposition: embedding-dimension sharding (default), the row partition with NCCL "
+                         "block exchange, or the row partition with the exchange fused into the kernels over peer memory")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

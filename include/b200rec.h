@@ -224,6 +224,33 @@ int b200rec_score_topk(const float* rep_users, const int64_t* users, int32_t n_b
 int b200rec_hit_matrix(const int32_t* rec_ids, int32_t n_rows, int32_t k, int64_t user0,
                        const int32_t* eval_ptr, const int32_t* eval_idx, float* hit, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Peer memory for the row-partitioned multi-GPU propagation (new: the reference has no multi-device code).
+ * b200rec_peer_alloc: cudaMalloc + zero + CUDA IPC handle (HOST, 64 bytes) that the other ranks of the node open with
+ * b200rec_peer_open.  b200rec_spmm_f32_peer is b200rec_spmm_f32_ex whose epilogue also stores every finished row of
+ * y / out into the same offset of up to 8 peer copies (an all-gather by push, fused into the SpMM).
+ * b200rec_peer_signal / _wait: per-layer hand-shake -- flags[my_rank] on every peer <- *epoch + epoch_add, then spin
+ * (bounded) until all flags of this rank reach that value, then *epoch += epoch_add.  `peer_flags` is a DEVICE array of
+ * n_peers pointers (one flag array per rank, this rank's own included).
+ * ------------------------------------------------------------------------------------------------ */
+int b200rec_spmm_f32_peer(const b200rec_csr* a, const float* x, int32_t d, const uint32_t* keep_bits, float post_scale,
+                          float* y, const float* addend, float* out, float out_scale,
+                          const uint8_t* dst_flags, const uint8_t* src_flags, int32_t n_peers,
+                          float* const* peer_y /*HOST [n_peers] device pointers, or NULL*/,
+                          float* const* peer_out /*HOST [n_peers], or NULL*/, void* stream);
+/* b200rec_adam_step on a row block whose updated parameters are also stored into the peers' tables. */
+int b200rec_adam_step_peer(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           double lr, double beta1, double beta2, double eps, const int64_t* step,
+                           int32_t n_peers, float* const* peer_param /*HOST [n_peers]*/, void* stream);
+int b200rec_peer_alloc(int64_t bytes, void** ptr_out /*HOST out*/, uint8_t* handle_out /*HOST [64]*/);
+int b200rec_peer_open(const uint8_t* handle /*HOST [64]*/, void** ptr_out /*HOST out*/);
+int b200rec_peer_close(void* ptr);
+int b200rec_peer_free(void* ptr);
+int b200rec_peer_signal(void* const* peer_flags, int32_t n_peers, int32_t my_rank, const int64_t* epoch, int64_t epoch_add,
+                        void* stream);
+int b200rec_peer_wait(const void* my_flags, int32_t n_peers, int64_t* epoch /*advanced by epoch_add on return*/,
+                      int64_t epoch_add, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,14 @@ PROTOTYPES = {
     "b200rec_score_dense_f32": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P]),
     "b200rec_score_topk_workspace": (C.c_int64, [_I32, _I32, _I32, _I32, _I32]),
     "b200rec_score_topk": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "b200rec_spmm_f32_peer": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P, _P, _I32, _P, _P, _P]),
+    "b200rec_adam_step_peer": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _P, _I32, _P, _P]),
+    "b200rec_peer_alloc": (C.c_int, [_I64, _P, _P]),
+    "b200rec_peer_open": (C.c_int, [_P, _P]),
+    "b200rec_peer_close": (C.c_int, [_P]),
+    "b200rec_peer_free": (C.c_int, [_P]),
+    "b200rec_peer_signal": (C.c_int, [_P, _I32, _I32, _P, _I64, _P]),
+    "b200rec_peer_wait": (C.c_int, [_P, _I32, _P, _I64, _P]),
     "b200rec_hit_matrix": (C.c_int, [_P, _I32, _I32, _I64, _P, _P, _P, _P]),
 }
 

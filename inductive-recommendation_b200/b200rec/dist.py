@@ -181,3 +181,148 @@ class RowPartition:
             if not last:
                 self.exchange(dst)
                 src = dst
+
+
+# ------------------------------------------------------------------------------------------------ peer memory (CUDA IPC)
+class _RawCuda:
+    """__cuda_array_interface__ view of a raw device pointer (so torch can wrap memory this library allocated)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def _wrap(ptr, nbytes, device):
+    return torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
+
+
+class PeerTable:
+    """one [rows, d] fp32 (or raw byte) buffer per rank, each mapped into every other rank of the node"""
+
+    def __init__(self, nbytes, rank, world, group, device):
+        import ctypes as C
+        from . import _abi
+        lib = _abi.load()
+        ptr = C.c_void_p(0)
+        handle = (C.c_uint8 * 64)()
+        _abi.check(lib.b200rec_peer_alloc(nbytes, C.byref(ptr), handle), "peer_alloc")
+        self.ptr, self.nbytes, self.rank, self.world = ptr.value, nbytes, rank, world
+        self.bytes = _wrap(self.ptr, nbytes, device)
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=device)
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine, group=group)
+        self.peer_ptrs = []
+        for r in range(world):
+            if r == rank:
+                self.peer_ptrs.append(self.ptr)
+                continue
+            h = (C.c_uint8 * 64)(*handles[r].cpu().tolist())
+            p = C.c_void_p(0)
+            _abi.check(lib.b200rec_peer_open(h, C.byref(p)), "peer_open")
+            self.peer_ptrs.append(p.value)
+
+    def others(self, byte_offset=0):
+        """HOST ctypes array of the other ranks' pointers (+ offset), as the *_peer entry points take them"""
+        import ctypes as C
+        ptrs = [p + byte_offset for r, p in enumerate(self.peer_ptrs) if r != self.rank]
+        return (C.c_void_p * max(len(ptrs), 1))(*ptrs)
+
+
+class PeerRowPartition(RowPartition):
+    """RowPartition whose per-layer exchange is fused into the producing kernels: the SpMM epilogue (and the Adam
+    update) store every finished row into all peers' tables over NVLink while the kernel is still gathering for its next
+    rows; what remains per layer is a two-kernel signal / wait hand-shake.  No NCCL on the data path."""
+
+    def __init__(self, adj, rank, world, d, group=None):
+        super().__init__(adj, rank, world, group)
+        import ctypes as C
+        dev = adj.device
+        n = adj.n_rows
+        self.d, self.n_rows = d, n
+        nb = n * d * 4
+        self._tables = {k: PeerTable(nb, rank, world, group, dev) for k in ("table", "buf0", "buf1", "rep")}
+        self.table, self.buf0, self.buf1, self.rep = (self._tables[k].bytes.view(torch.float32).view(n, d)
+                                                      for k in ("table", "buf0", "buf1", "rep"))
+        self._flags = PeerTable(256, rank, world, group, dev)
+        self.flag_ptrs = torch.tensor(self._flags.peer_ptrs, dtype=torch.int64, device=dev)  # device array of pointers
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.n_others = world - 1
+        self._C = C
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def _others(self, name):
+        return self._tables[name].others()
+
+    def _name_of(self, t):
+        for k in ("table", "buf0", "buf1", "rep"):
+            if t.data_ptr() == getattr(self, k).data_ptr():
+                return k
+        raise ValueError("tensor is not one of this partition's peer tables")
+
+    def handshake(self):
+        """everyone's pushed rows have landed AND everyone is done reading the tables of the previous phase"""
+        from . import _abi
+        from ._abi import check, ptr, stream_ptr
+        lib = _abi.load()
+        check(lib.b200rec_peer_signal(ptr(self.flag_ptrs), self.world, self.rank, ptr(self.epoch), 1, stream_ptr()), "peer_signal")
+        check(lib.b200rec_peer_wait(self._C.c_void_p(self._flags.ptr), self.world, ptr(self.epoch), 1, stream_ptr()), "peer_wait")
+
+    def exchange(self, buf):
+        self.handshake()  # the rows were pushed by the kernel that produced them
+
+    def _spmm(self, src, y=None, addend=None, out=None, out_scale=1.0, dst_flags=None, src_flags=None, push_y=False,
+              push_out=False):
+        from . import _abi
+        from ._abi import check, ptr, stream_ptr
+        C = self._C
+        py = self._others(self._name_of(y)) if push_y else None
+        po = self._others(self._name_of(out)) if push_out else None
+        check(_abi.load().b200rec_spmm_f32_peer(C.byref(self.local_op.struct()), ptr(src), src.shape[1], None, 1.0, ptr(y),
+                                                ptr(addend), ptr(out), out_scale, ptr(dst_flags), ptr(src_flags),
+                                                self.n_others, py, po, stream_ptr()), "spmm_f32_peer")
+
+    def propagate_fwd(self, adj, x0, n_layers, bufs, mean_out, needed_rows=None):
+        assert mean_out is self.rep and x0.shape[1] == self.d
+        if n_layers == 0:
+            mean_out.copy_(x0)
+            return
+        inv = 1.0 / (n_layers + 1)
+        bufs = [self.buf0, self.buf1]
+        src = x0
+        for k in range(n_layers):
+            last = k == n_layers - 1
+            y = None if last else bufs[k & 1]
+            self._spmm(src, y=y, addend=x0 if k == 0 else mean_out, out=mean_out, out_scale=inv if last else 1.0,
+                       dst_flags=needed_rows if last else None, push_y=not last, push_out=last)
+            self.handshake()
+            src = y
+
+    def propagate_bwd(self, adj, g, n_layers, bufs, dx0, nonzero_rows=None):
+        if n_layers == 0:
+            dx0.copy_(g)
+            return
+        inv = 1.0 / (n_layers + 1)
+        bufs = [self.buf0, self.buf1]
+        src = g
+        for k in range(1, n_layers + 1):
+            last = k == n_layers
+            dst = dx0 if last else bufs[(k - 1) & 1]
+            self._spmm(src, addend=g, out=dst, out_scale=inv if last else 1.0, src_flags=nonzero_rows if k == 1 else None,
+                       push_out=not last)
+            if not last:
+                self.handshake()
+                src = dst
+
+    def adam(self, param, grad, m, v, step, lr, b1, b2, eps):
+        """update the rows this rank owns and store them into every peer's table; hand-shakes on both sides"""
+        from . import _abi
+        from ._abi import check, ptr, stream_ptr
+        assert param.data_ptr() == self.table.data_ptr()
+        self.handshake()  # nobody still reads the old parameters (layer-0 L2 term, first forward layer)
+        lo, hi, d = self.lo, self.hi, self.d
+        if hi > lo:
+            off = lo * d * 4
+            check(_abi.load().b200rec_adam_step_peer(ptr(param[lo:hi]), ptr(grad[lo:hi]), ptr(m[lo:hi]), ptr(v[lo:hi]),
+                                                     (hi - lo) * d, lr, b1, b2, eps, ptr(step), self.n_others,
+                                                     self._tables["table"].others(off), stream_ptr()), "adam_step_peer")
+        self.handshake()

@@ -73,6 +73,10 @@ class BprEngine:
                 self.adam_step.fill_(int(st['step']))
         else:
             emb = model.embedding.weight
+            if partition is not None and hasattr(partition, 'table'):
+                # peer-memory row partition: the parameter table itself lives in memory the other ranks can store into
+                partition.table.copy_(emb.data)
+                emb.data = partition.table
             self.table = emb.data
             self.grad = torch.zeros_like(self.table)
             emb.grad = self.grad
@@ -82,9 +86,12 @@ class BprEngine:
             self.adam_step.fill_(int(st['step']))
             self.g_rep = torch.zeros((n, D), **f32)
             self.row_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
-            self.rep = torch.empty((n, D), **f32)
             L = model.n_layers
-            self.bufs = [torch.empty((n, D), **f32) if L >= 2 + i else None for i in range(2)]
+            if partition is not None and hasattr(partition, 'rep'):
+                self.rep, self.bufs = partition.rep, [partition.buf0, partition.buf1]
+            else:
+                self.rep = torch.empty((n, D), **f32)
+                self.bufs = [torch.empty((n, D), **f32) if L >= 2 + i else None for i in range(2)]
             if self.kind in ('IGCN', 'IMF'):
                 self.x0 = torch.empty((n, D), **f32)
                 self.dx0 = torch.empty((n, D), **f32)
@@ -135,6 +142,9 @@ class BprEngine:
                                 loss_weight=1.0 if self.shard.rank == 0 else 0.0, w=w, g_w=g_w, loss_scale=loss_scale)
 
     def _adam(self, param, grad, m, v):
+        if self.partition is not None and param is self.table and hasattr(self.partition, 'adam'):
+            self.partition.adam(param, grad, m, v, self.adam_step, self.lr, self.b1, self.b2, self.eps)
+            return
         if self.partition is not None and param is self.table:
             lo, hi = self.partition.lo, self.partition.hi  # each rank updates the rows it owns, then the blocks are exchanged
             if hi > lo:

@@ -317,9 +317,13 @@ __global__ void __launch_bounds__(256) bpr_l2_emb0_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------- Adam
+struct AdamPeers {
+  int n;
+  float* p[8];  // the same element range of the parameter table on the other ranks (row-partitioned multi-GPU)
+};
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, double lr, double beta1d, double beta2d,
-                                                   float eps, const int64_t* __restrict__ step_ptr) {
+                                                   float eps, const int64_t* __restrict__ step_ptr, const AdamPeers peers) {
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     const double t = (double)(*step_ptr + 1);
@@ -340,6 +344,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     pp.c = pp.c - step_size * (mm.c / (sqrtf(vv.c) / bc2_sqrt + eps));
     B2_ADAM1(x) B2_ADAM1(y) B2_ADAM1(z) B2_ADAM1(w)
     st_f4(m + 4 * i, mm); st_f4(v + 4 * i, vv); st_f4(p + 4 * i, pp);
+    for (int q = 0; q < peers.n; ++q) st_f4(peers.p[q] + 4 * i, pp);  // updated rows go straight to the peers' tables
   }
   // tail (n not a multiple of 4)
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
@@ -348,7 +353,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     float mm = m[i], vv = v[i];
     mm = mm + w1 * (gg - mm);
     vv = vv * beta2 + (w2 * gg) * gg;
-    p[i] = p[i] - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    const float pn = p[i] - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    p[i] = pn;
+    for (int q = 0; q < peers.n; ++q) peers.p[q][i] = pn;
     m[i] = mm; v[i] = vv;
   }
 #undef B2_ADAM1
@@ -471,7 +478,25 @@ extern "C" int b200rec_adam_step(float* param, const float* grad, float* exp_avg
   B2_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, "16-byte alignment");
   int grid = ceil_div(n / 4 + 1, 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, (float)eps, step);
+  AdamPeers none;
+  none.n = 0;
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, (float)eps, step, none);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_adam_step_peer(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                                      double beta1, double beta2, double eps, const int64_t* step, int32_t n_peers,
+                                      float* const* peer_param /*HOST [n_peers]*/, void* stream) {
+  B2_REQUIRE(param && grad && exp_avg && exp_avg_sq && step && n > 0, "bad argument");
+  B2_REQUIRE(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_param), "at most 8 peers");
+  B2_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, "16-byte alignment");
+  AdamPeers pr;
+  pr.n = n_peers;
+  for (int q = 0; q < 8; ++q) pr.p[q] = q < n_peers ? peer_param[q] : nullptr;
+  int grid = ceil_div(n / 4 + 1, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, (float)eps, step, pr);
   B2_LAUNCHED();
   return 0;
 }

@@ -36,6 +36,10 @@ struct SpmmParams {
   const int32_t* long_slot0;
   const int32_t* long_nslot;
   int32_t* long_cnt;          // [n_long] arrival counters (zero between launches: the finisher resets its own)
+  // row-partitioned multi-GPU: the same row is also stored into the peers' copies of y / out (all-gather by push)
+  int n_peer;
+  float* peer_y[8];
+  float* peer_out[8];
 };
 
 // Cache-policy hints for the neighbour-row gathers.  The column ids handed to the kernel carry a "hot" flag in bit 31
@@ -76,12 +80,19 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int g
   for (int t = 0; t < VPL; ++t) {
     const size_t off = (size_t)row * D + (size_t)(gl + t * G) * 4;
     float4 s = make_float4(acc[t].x * sc, acc[t].y * sc, acc[t].z * sc, acc[t].w * sc);
-    if (p.y) st_f4(p.y + off, s);
+    if (p.y) {
+      st_f4(p.y + off, s);
+      for (int q = 0; q < p.n_peer; ++q)
+        if (p.peer_y[q]) st_f4(p.peer_y[q] + off, s);  // NVLink store into the peer's table, overlapped with the gathers
+    }
     if (p.out) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.addend) a = ld_f4(p.addend + off);
       const float os = p.out_scale;
-      st_f4(p.out + off, make_float4((a.x + s.x) * os, (a.y + s.y) * os, (a.z + s.z) * os, (a.w + s.w) * os));
+      const float4 o4 = make_float4((a.x + s.x) * os, (a.y + s.y) * os, (a.z + s.z) * os, (a.w + s.w) * os);
+      st_f4(p.out + off, o4);
+      for (int q = 0; q < p.n_peer; ++q)
+        if (p.peer_out[q]) st_f4(p.peer_out[q] + off, o4);
     }
   }
 }
@@ -301,7 +312,8 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
 
 static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint32_t* keep_bits, float post_scale,
                          float* y, const float* addend, float* out, float out_scale, const uint8_t* dst_flags,
-                         const uint8_t* src_flags, cudaStream_t st) {
+                         const uint8_t* src_flags, cudaStream_t st, int n_peer = 0, float* const* peer_y = nullptr,
+                         float* const* peer_out = nullptr) {
   B2_REQUIRE(a && x, "null operand");
   B2_REQUIRE(y || out, "no output");
   B2_REQUIRE(a->n_items == 0 || (a->item_start && a->item_end && a->item_dst && a->colidx), "csr plan missing");
@@ -315,6 +327,11 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
   p.keep_bits = keep_bits; p.dst_flags = dst_flags; p.src_flags = src_flags;
   p.item_start = a->item_start; p.item_end = a->item_end; p.item_dst = a->item_dst; p.item_row = a->item_row;
   p.n_items = a->n_items;
+  p.n_peer = n_peer;
+  for (int q = 0; q < 8; ++q) {
+    p.peer_y[q] = (q < n_peer && peer_y) ? peer_y[q] : nullptr;
+    p.peer_out[q] = (q < n_peer && peer_out) ? peer_out[q] : nullptr;
+  }
   p.x = x; p.y = y; p.addend = addend; p.out = out; p.out_scale = out_scale; p.post_scale = post_scale;
   p.partial = a->partial; p.slot_long = a->slot_long; p.long_row = a->long_row; p.long_slot0 = a->long_slot0;
   p.long_nslot = a->long_nslot; p.long_cnt = a->long_cnt;
@@ -385,6 +402,16 @@ extern "C" int b200rec_spmm_f32_ex(const b200rec_csr* a, const float* x, int32_t
                                    const uint8_t* dst_flags, const uint8_t* src_flags, void* stream) {
   return spmm_dispatch(a, x, d, keep_bits, post_scale, y, addend, out, out_scale, dst_flags, src_flags,
                        (cudaStream_t)stream);
+}
+
+extern "C" int b200rec_spmm_f32_peer(const b200rec_csr* a, const float* x, int32_t d, const uint32_t* keep_bits,
+                                     float post_scale, float* y, const float* addend, float* out, float out_scale,
+                                     const uint8_t* dst_flags, const uint8_t* src_flags, int32_t n_peers,
+                                     float* const* peer_y /*HOST [n_peers] or NULL*/, float* const* peer_out /*HOST or NULL*/,
+                                     void* stream) {
+  B2_REQUIRE(n_peers >= 0 && n_peers <= 8, "at most 8 peers");
+  return spmm_dispatch(a, x, d, keep_bits, post_scale, y, addend, out, out_scale, dst_flags, src_flags, (cudaStream_t)stream,
+                       n_peers, peer_y, peer_out);
 }
 
 extern "C" int b200rec_propagate_fwd(const b200rec_csr* a, const float* x0, int32_t d, int32_t n_layers, float* buf0,

@@ -102,6 +102,47 @@ def main():
         log('row', name, 'step done')
         assert abs(eng.last_loss() - float(g["loss"])) < 2e-6
         np.testing.assert_allclose(m.embedding.weight.data.cpu().numpy(), g["emb1"], rtol=1e-5, atol=5e-6)
+    # ---- peer-memory row partition: the exchange is fused into the SpMM / Adam epilogues (NVLink stores) ----
+    if os.environ.get("B200REC_SKIP_PEER", "0") != "1":
+        from b200rec.dist import PeerRowPartition
+        for name in ("lightgcn_tiny", "lightgcn_d128"):
+            g = load_golden(name)
+            ds, m = golden_model(g, name, device=dev)
+            L = int(g["n_layers"])
+            x0 = m.embedding.weight.data.clone()
+            single = torch.empty_like(x0)
+            bufs = [torch.empty_like(x0), torch.empty_like(x0)]
+            ops.propagate_fwd(m.norm_adj, x0, L, bufs, single)
+            part = PeerRowPartition(m.norm_adj, rank, world, x0.shape[1])
+            log('peer', name, 'tables mapped')
+            part.table.copy_(x0)
+            torch.cuda.synchronize(); dist.barrier()
+            part.propagate_fwd(m.norm_adj, part.table, L, None, part.rep)
+            torch.cuda.synchronize()
+            assert torch.equal(single, part.rep), name + ": peer row-partitioned forward differs"
+            log('peer', name, 'fwd ok')
+            gsrc = torch.randn(x0.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+            d1, d2 = torch.empty_like(x0), torch.empty_like(x0)
+            ops.propagate_bwd(m.norm_adj, gsrc, L, bufs, d1)
+            part.propagate_bwd(m.norm_adj, gsrc, L, None, d2)
+            torch.cuda.synchronize()
+            assert torch.equal(d1[part.lo:part.hi], d2[part.lo:part.hi]), name + ": peer row-partitioned backward differs"
+            log('peer', name, 'bwd ok')
+            tr = trainer_for(g, name, ds, m, partition=part)
+            m.train()
+            eng = tr._engine()
+            engines.append(eng)
+            for use_graph in (False, True):
+                with torch.no_grad():
+                    m.embedding.weight.data.copy_(torch.from_numpy(g["emb0"]).to(dev))
+                    eng.m.zero_(); eng.v.zero_(); eng.adam_step.zero_()
+                torch.cuda.synchronize(); dist.barrier()
+                eng.use_graph = use_graph
+                eng.step(host_batch=torch.from_numpy(g["batch"]).pin_memory())
+                torch.cuda.synchronize()
+                assert abs(eng.last_loss() - float(g["loss"])) < 2e-6
+                np.testing.assert_allclose(m.embedding.weight.data.cpu().numpy(), g["emb1"], rtol=1e-5, atol=5e-6)
+                log('peer', name, 'engine step ok, graph =', use_graph)
     dist.barrier()
     for e in engines:
         e.close()
