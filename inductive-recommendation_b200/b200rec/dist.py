@@ -126,14 +126,31 @@ def nnz_balanced_bounds(rowptr, world):
 
 
 class RowPartition:
-    """Row-partitioned propagation with a per-layer exchange of the row blocks."""
+    """Row-partitioned propagation with a per-layer exchange of the row blocks.
+
+    Each rank owns one block of USER rows and one block of ITEM rows (both nnz-balanced over the ranks) rather than one
+    contiguous range of the joint index space: user rows gather from the item table and item rows from the (larger,
+    colder) user table, so a single range would give the ranks unequal cache behaviour (measured on C4, 2 GPUs: one rank
+    all users, the other all items -> 54.6 ms/step against 75.6 on one GPU)."""
 
     def __init__(self, adj, rank, world, group=None, bounds=None):
         self.rank, self.world, self.group = rank, world, group
-        self.bounds = bounds if bounds is not None else nnz_balanced_bounds(adj.rowptr.cpu().numpy(), world)
-        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
-        self.n_local_rows = self.hi - self.lo
-        self.local_op = adj.row_slice(self.lo, self.hi)
+        rp = adj.rowptr.cpu().numpy().astype(np.int64)
+        nu = int(getattr(adj, "phase_split", 0))
+        if bounds is not None:
+            self.blocks = [[(bounds[r], bounds[r + 1])] for r in range(world)]
+        elif 0 < nu < adj.n_rows:
+            ub = nnz_balanced_bounds(rp[: nu + 1], world)
+            ib = nnz_balanced_bounds(rp[nu:] - rp[nu], world)
+            self.blocks = [[(ub[r], ub[r + 1]), (nu + ib[r], nu + ib[r + 1])] for r in range(world)]
+        else:
+            b = nnz_balanced_bounds(rp, world)
+            self.blocks = [[(b[r], b[r + 1])] for r in range(world)]
+        self.bounds = [blk[0][0] for blk in self.blocks] + [self.blocks[-1][0][1]]  # first-block bounds (diagnostics)
+        self.my_blocks = [(lo, hi) for lo, hi in self.blocks[rank] if hi > lo]
+        self.lo, self.hi = self.blocks[rank][0]
+        self.n_local_rows = sum(hi - lo for lo, hi in self.my_blocks)
+        self.local_op = adj.row_slice(self.blocks[rank])
 
     def exchange(self, buf):
         """in place: after the call every rank holds every row block of `buf` ([n_rows, D])"""
@@ -141,9 +158,9 @@ class RowPartition:
             return
         works = []
         for p in range(self.world):
-            blk = buf[self.bounds[p]:self.bounds[p + 1]]
-            if blk.numel():
-                works.append(dist.broadcast(blk, src=p, group=self.group, async_op=True))
+            for lo, hi in self.blocks[p]:
+                if hi > lo:
+                    works.append(dist.broadcast(buf[lo:hi], src=p, group=self.group, async_op=True))
         for w in works:
             w.wait()
 
@@ -166,7 +183,7 @@ class RowPartition:
         self.exchange(mean_out)
 
     def propagate_bwd(self, adj, g, n_layers, bufs, dx0, nonzero_rows=None):
-        """dx0 rows [lo, hi) are valid on return (each rank updates only the parameters it owns)"""
+        """dx0 rows of this rank's blocks are valid on return (each rank updates only the parameters it owns)"""
         from . import ops
         if n_layers == 0:
             dx0.copy_(g)
@@ -319,8 +336,8 @@ class PeerRowPartition(RowPartition):
         from ._abi import check, ptr, stream_ptr
         assert param.data_ptr() == self.table.data_ptr()
         self.handshake()  # nobody still reads the old parameters (layer-0 L2 term, first forward layer)
-        lo, hi, d = self.lo, self.hi, self.d
-        if hi > lo:
+        d = self.d
+        for lo, hi in self.my_blocks:
             off = lo * d * 4
             check(_abi.load().b200rec_adam_step_peer(ptr(param[lo:hi]), ptr(grad[lo:hi]), ptr(m[lo:hi]), ptr(v[lo:hi]),
                                                      (hi - lo) * d, lr, b1, b2, eps, ptr(step), self.n_others,

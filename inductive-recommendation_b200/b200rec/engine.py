@@ -146,8 +146,7 @@ class BprEngine:
             self.partition.adam(param, grad, m, v, self.adam_step, self.lr, self.b1, self.b2, self.eps)
             return
         if self.partition is not None and param is self.table:
-            lo, hi = self.partition.lo, self.partition.hi  # each rank updates the rows it owns, then the blocks are exchanged
-            if hi > lo:
+            for lo, hi in self.partition.my_blocks:  # each rank updates the rows it owns, then the blocks are exchanged
                 ops.adam_step(param[lo:hi], grad[lo:hi], m[lo:hi], v[lo:hi], self.adam_step, self.lr, self.b1, self.b2, self.eps)
             self.partition.exchange(param)
             return

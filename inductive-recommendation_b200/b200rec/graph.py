@@ -135,14 +135,17 @@ class CsrOperand:
         o.nbr_scale, o.row_scale, o._struct = nbr_scale, row_scale, None
         return o
 
-    def row_slice(self, lo, hi):
-        """rows [lo, hi) as an operand that writes into the FULL output table at global row ids
-        (multi-GPU row partition: per-row sums are unchanged, so P-rank results equal 1-rank bit for bit)."""
+    def row_slice(self, lo, hi=None):
+        """rows [lo, hi) -- or a list of such ranges -- as an operand that writes into the FULL output table at global
+        row ids (multi-GPU row partition: per-row sums are unchanged, so P-rank results equal 1-rank bit for bit)."""
+        ranges = [(lo, hi)] if hi is not None else list(lo)
         o = object.__new__(CsrOperand)
         o.__dict__.update(self.__dict__)
         o._struct = None
         row = self.item_row[:self.n_items]
-        keep = (row >= lo) & (row < hi)
+        keep = torch.zeros_like(row, dtype=torch.bool)
+        for a, b in ranges:
+            keep |= (row >= a) & (row < b)
         o.item_start = self.item_start[:self.n_items][keep].contiguous()
         o.item_end = self.item_end[:self.n_items][keep].contiguous()
         o.item_dst = self.item_dst[:self.n_items][keep].contiguous()

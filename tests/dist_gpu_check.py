@@ -92,7 +92,8 @@ def main():
         d1, d2 = torch.empty_like(x0), torch.empty_like(x0)
         ops.propagate_bwd(m.norm_adj, gsrc, L, bufs, d1)
         part.propagate_bwd(m.norm_adj, gsrc, L, bufs, d2)
-        assert torch.equal(d1[part.lo:part.hi], d2[part.lo:part.hi]), name + ": row-partitioned backward differs"
+        for lo, hi in part.my_blocks:
+            assert torch.equal(d1[lo:hi], d2[lo:hi]), name + ": row-partitioned backward differs"
         tr = trainer_for(g, name, ds, m, partition=part)
         m.train()
         eng = tr._engine()
@@ -126,7 +127,8 @@ def main():
             ops.propagate_bwd(m.norm_adj, gsrc, L, bufs, d1)
             part.propagate_bwd(m.norm_adj, gsrc, L, None, d2)
             torch.cuda.synchronize()
-            assert torch.equal(d1[part.lo:part.hi], d2[part.lo:part.hi]), name + ": peer row-partitioned backward differs"
+            for lo, hi in part.my_blocks:
+                assert torch.equal(d1[lo:hi], d2[lo:hi]), name + ": peer row-partitioned backward differs"
             log('peer', name, 'bwd ok')
             tr = trainer_for(g, name, ds, m, partition=part)
             m.train()

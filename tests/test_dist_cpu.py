@@ -66,15 +66,20 @@ def _worker(rank, world, port, out):
     # row-block exchange with uneven blocks
     class _Adj:  # only what RowPartition reads
         rowptr = torch.tensor([0, 1, 1, 9, 10, 12, 12, 20], dtype=torch.int32)
-        def row_slice(self, lo, hi):
-            return (lo, hi)
-    part = RowPartition(_Adj(), rank, world)
-    assert part.bounds == nnz_balanced_bounds(_Adj.rowptr.numpy(), world)
-    table = torch.arange(7 * 4, dtype=torch.float32).reshape(7, 4)
-    mine = torch.full_like(table, -1.0)
-    mine[part.lo:part.hi] = table[part.lo:part.hi]
-    part.exchange(mine)
-    assert torch.equal(mine, table)
+        n_rows, phase_split = 7, 3
+        def row_slice(self, ranges):
+            return ranges
+    for split in (0, 3):  # one contiguous block per rank / one user block + one item block per rank
+        _Adj.phase_split = split
+        part = RowPartition(_Adj(), rank, world)
+        covered = sorted(r for blk in part.blocks for lo, hi in blk for r in range(lo, hi))
+        assert covered == list(range(7)) and len(part.blocks[rank]) == (2 if split else 1)
+        table = torch.arange(7 * 4, dtype=torch.float32).reshape(7, 4)
+        mine = torch.full_like(table, -1.0)
+        for lo, hi in part.my_blocks:
+            mine[lo:hi] = table[lo:hi]
+        part.exchange(mine)
+        assert torch.equal(mine, table)
     # replicas: with min_cols = D the columns are not split, each rank is its own shard group
     rep = DimShard(rank, world, min_cols=8).configure(8)
     assert (rep.world, rep.rank, rep.replica) == (1, 0, rank) and rep.cols(8) == (0, 8)
