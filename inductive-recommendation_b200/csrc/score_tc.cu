@@ -166,6 +166,18 @@ __device__ __forceinline__ bool row_has(const int32_t* __restrict__ ptr, const i
   return lo < end && __ldg(idx + lo) == key;
 }
 
+// Rare path of the epilogue, kept out of line so the unrolled scan stays a compare + predicated call per value
+// (the scan is latency-exposed: 6-12 warps per SM, every branch costs a pipeline bubble).
+__device__ __noinline__ void tc_append_candidate(const TcParams& p, int64_t user, float sc, int item, Cand* list, int& cnt,
+                                                 bool& ovf) {
+  if (item >= p.n_items) return;
+  if (item >= p.banned_lo && item < p.banned_hi) return;
+  if (row_has(p.excl_ptr_a, p.excl_idx_a, user, item)) return;
+  if (row_has(p.excl_ptr_b, p.excl_idx_b, user, item)) return;
+  if (cnt < TC_CAP) list[cnt++] = Cand{sc, item};
+  else ovf = true;
+}
+
 template <int D, int BN, int STAGES>
 __global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant__ CUtensorMap tm_users,
                                                           const __grid_constant__ CUtensorMap tm_items, const TcParams p) {
@@ -348,14 +360,7 @@ __global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant_
             for (int jj = 0; jj < 8; ++jj) {
               const int j = q * 8 + jj;
               const float sc = __uint_as_float(v[j]);
-              const int item = i0 + c * 32 + j;
-              if (sc >= cut && item < p.n_items) {
-                if (item >= p.banned_lo && item < p.banned_hi) continue;
-                if (row_has(p.excl_ptr_a, p.excl_idx_a, user, item)) continue;
-                if (row_has(p.excl_ptr_b, p.excl_idx_b, user, item)) continue;
-                if (cnt < TC_CAP) my_list[cnt++] = Cand{sc, item};
-                else ovf = true;
-              }
+              if (sc >= cut) tc_append_candidate(p, user, sc, i0 + c * 32 + j, my_list, cnt, ovf);
             }
           }
         }
