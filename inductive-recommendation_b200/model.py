@@ -52,10 +52,6 @@ class BasicModel(nn.Module):
         self.load_state_dict(torch.load(path, map_location=self.device))
 
     # ---- shared helpers ----
-    def item_table(self):
-        """(table, row offset of item 0, users table)"""
-        raise NotImplementedError
-
     def _cache_key(self):
         return None
 

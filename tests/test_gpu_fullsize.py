@@ -1,0 +1,145 @@
+"""GPU: size-independent properties at the BASELINE.json sizes, where the CPU oracle would take minutes to hours.
+C2 = Yelp2018-shaped (31 668 x 38 048, 1.56 M train edges, D=64, L=3); C4 = 2M x 1M, 100 M edges, D=128, L=4."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def c2():
+    import dataset as D
+    import model as M
+    from b200rec import synth
+    g = synth.generate_named("c2", seed=0, device=DEV)
+    ds = D.get_dataset({"name": "SyntheticDataset", "device": DEV, "graph": g})
+    torch.manual_seed(0)
+    m = M.get_model({"name": "LightGCN", "embedding_size": 64, "n_layers": 3, "device": DEV}, ds)
+    return ds, m
+
+
+def _dot(a, b):
+    return float((a.double() * b.double()).sum())
+
+
+def test_c2_graph_invariants(c2):
+    ds, m = c2
+    a = m.norm_adj
+    assert a.nnz == 2 * len(ds) and a.n_rows == ds.n_users + ds.n_items
+    r, c, v = a.to_coo()
+    assert bool((r[1:] * a.n_cols + c[1:] > r[:-1] * a.n_cols + c[:-1]).all())      # row-major sorted, no duplicates
+    assert bool(((r < ds.n_users) ^ (c < ds.n_users)).all())                          # bipartite: users <-> items only
+    # bit-wise symmetric values: the transpose has the same value multiset at mirrored positions
+    key = c * a.n_cols + r
+    order = torch.argsort(key)
+    assert torch.equal(v[order], v)
+    deg = (a.rowptr[1:] - a.rowptr[:-1]).float().clamp(min=1)
+    np.testing.assert_allclose(a.dinv.cpu().numpy(), (deg ** -0.5).cpu().numpy(), rtol=2e-7)
+
+
+def test_c2_propagation_linearity_and_adjoint(c2):
+    from b200rec import ops
+    ds, m = c2
+    a, n, L = m.norm_adj, m.n_users + m.n_items, 3
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x, y = (torch.randn((n, 64), device=DEV, generator=gen) for _ in range(2))
+    bufs = [torch.empty_like(x), torch.empty_like(x)]
+    px, py, pxy = (torch.empty_like(x) for _ in range(3))
+    ops.propagate_fwd(a, x, L, bufs, px)
+    ops.propagate_fwd(a, y, L, bufs, py)
+    ops.propagate_fwd(a, 2.0 * x - 0.5 * y, L, bufs, pxy)
+    torch.testing.assert_close(pxy, 2.0 * px - 0.5 * py, rtol=1e-4, atol=1e-5)       # linearity
+    by = torch.empty_like(x)
+    ops.propagate_bwd(a, y, L, bufs, by)
+    assert abs(_dot(px, y) - _dot(x, by)) <= 1e-5 * abs(_dot(px, y)) + 1e-6          # <P x, y> == <x, P^T y>
+    torch.testing.assert_close(by, py, rtol=1e-4, atol=1e-5)                          # P is symmetric (A is)
+    # determinism: same bits on a second launch (ordered hub reduction, no atomics)
+    px2 = torch.empty_like(x)
+    ops.propagate_fwd(a, x, L, bufs, px2)
+    assert torch.equal(px, px2)
+
+
+def test_c2_sampler_and_training_epoch(c2):
+    import trainer as T
+    ds, m = c2
+    tr = T.get_trainer({"name": "BPRTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 1e-4, "device": DEV, "n_epochs": 1,
+                        "batch_size": 2048, "dataloader_num_workers": 0, "test_batch_size": 512,
+                        "topks": [1, 5, 10, 15, 20]}, ds, m)
+    m.train()
+    eng = tr._engine()
+    ptr, idx = ds.csr("train", device=DEV)
+    for _ in range(3):
+        eng.step()
+        b = eng.batch
+        u, p, ng = b[:, 0], b[:, 1], b[:, 2]
+        assert bool(((ptr[u + 1] - ptr[u]) > 0).all())
+        key = ptr.long()  # membership by searching the user's sorted row
+        lo = key[u]
+        flat = idx.long()
+        pos_hit = torch.zeros_like(u, dtype=torch.bool)
+        neg_hit = torch.zeros_like(u, dtype=torch.bool)
+        for k in range(int((ptr[1:] - ptr[:-1]).max())):
+            inside = lo + k < key[u + 1]
+            cur = flat[(lo + k).clamp(max=flat.numel() - 1)]
+            pos_hit |= inside & (cur == p)
+            neg_hit |= inside & (cur == ng)
+            if k > 4000:
+                break
+        assert bool(pos_hit.all()) and not bool(neg_hit.any())
+    l0 = tr.train_one_epoch()
+    l1 = tr.train_one_epoch()
+    assert np.isfinite(l0) and l1 < l0 < 0.6932                                       # BPR loss starts at ln 2 and falls
+
+
+def test_c2_topk_properties(c2):
+    import trainer as T
+    ds, m = c2
+    tr = T.get_trainer({"name": "BPRTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 1e-4, "device": DEV, "n_epochs": 1,
+                        "batch_size": 2048, "dataloader_num_workers": 0, "test_batch_size": 512,
+                        "topks": [1, 5, 10, 15, 20]}, ds, m)
+    recs = {}
+    for prec in (0, 1):
+        tr.eval_precision = prec
+        recs[prec] = tr.recommend_all("test")
+    assert torch.equal(recs[0], recs[1])                                              # tcgen05 path == exact path, 31 668 users
+    rec = recs[0].long()
+    assert bool((rec >= 0).all()) and bool((rec < ds.n_items).all())
+    assert bool((torch.sort(rec, dim=1).values[:, 1:] != torch.sort(rec, dim=1).values[:, :-1]).all())  # no repeats
+    # no recommended item is a train or val item of that user
+    from b200rec import ops
+    for split in ("train", "val"):
+        p_, i_ = ds.csr(split, device=DEV)
+        assert float(ops.hit_matrix(recs[0], 0, p_, i_ if i_.numel() else torch.zeros(1, dtype=torch.int32, device=DEV)).sum()) == 0
+    # scores are non-increasing along K and consistent with predict()
+    m.eval()
+    users = torch.arange(0, 64, device=DEV)
+    sc = m.predict(users)
+    ids, vals = m.recommend(users, 20)
+    assert bool((vals[:, 1:] <= vals[:, :-1]).all())
+    assert torch.equal(torch.gather(sc, 1, ids.long()), vals)
+    assert torch.equal(vals[:, 0], sc.max(dim=1).values)
+
+
+def test_c4_spmm_adjoint_and_partition_of_rows():
+    """one layer at the 100 M-edge shape: <A x, y> == <x, A y>, and computing the rows in two halves gives the same bits"""
+    from b200rec import graph, ops, synth
+    g = synth.generate_named("c4", seed=0, device=DEV, heldout=False)
+    rows = torch.repeat_interleave(torch.arange(g.n_users, device=DEV), g.train_indptr[1:] - g.train_indptr[:-1])
+    a = graph.build_norm_adj(g.n_users, g.n_items, rows, g.train_items, DEV, d=128)
+    del rows
+    n = a.n_rows
+    assert a.nnz == 200_000_000 and a.n_long > 0
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.randn((n, 128), device=DEV, generator=gen)
+    y = torch.randn((n, 128), device=DEV, generator=gen)
+    ax, ay = torch.empty_like(x), torch.empty_like(x)
+    ops.spmm(a, x, y=ax)
+    ops.spmm(a, y, y=ay)
+    lhs, rhs = _dot(ax, y), _dot(x, ay)
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs) + 1e-3
+    half = torch.full_like(ax, float("nan"))
+    ops.spmm(a.row_slice(0, n // 2), x, y=half)
+    ops.spmm(a.row_slice(n // 2, n), x, y=half)
+    assert torch.equal(half, ax)

@@ -71,7 +71,6 @@ def test_sampler_contract(golden):
     assert u.min() >= 0 and u.max() < nu and n.min() >= 0 and n.max() < ni
     deg = np.diff(ptr)
     assert (deg[u] > 0).all()
-    key = set((ptr[1:].repeat(0)).tolist())  # noqa: F841
     train = set((np.repeat(np.arange(nu), deg) * ni + idx).tolist())
     assert all((int(a) * ni + int(c)) in train for a, c in zip(u[:5000], p[:5000]))       # positives are train items
     assert not any((int(a) * ni + int(c)) in train for a, c in zip(u[:5000], n[:5000]))   # negatives never are
