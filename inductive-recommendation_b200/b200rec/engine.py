@@ -110,17 +110,38 @@ class BprEngine:
                     self.aux_ptr, self.aux_items = aux_dataset.csr('train', device=dev)
         import os
         self.use_graph = use_graph and os.environ.get('B200REC_NO_GRAPH', '0') != '1'
+        self._side_stream = torch.cuda.Stream(device=dev)
         self._graphs = {}
         self._kernels = {}
         self.steps_done = 0
 
     # ------------------------------------------------------------------------------------------------ one step
-    def _propagate_fwd(self, x0):
+    def _propagate_fwd(self, x0, join=None):
+        """L x SpMM + layer mean into self.rep.  Only the LAST layer needs the batch (it is restricted to the sampled
+        rows), so `join` -- which makes the main stream wait for the side stream that draws the batch and marks its rows --
+        is called right before it: sampling overlaps the first L-1 layers inside the step graph."""
         m = self.model
+        L = m.n_layers
         if self.partition is not None:
-            self.partition.propagate_fwd(m.norm_adj, x0, m.n_layers, self.bufs, self.rep)
-        else:
-            ops.propagate_fwd(m.norm_adj, x0, m.n_layers, self.bufs, self.rep, needed_rows=self.row_flags)
+            if join:
+                join()
+            self.partition.propagate_fwd(m.norm_adj, x0, L, self.bufs, self.rep, needed_rows=self.row_flags)
+            return
+        if join is None or L < 2:
+            if join:
+                join()
+            ops.propagate_fwd(m.norm_adj, x0, L, self.bufs, self.rep, needed_rows=self.row_flags)
+            return
+        inv = 1.0 / (L + 1)
+        src = x0
+        for k in range(L):  # the layer loop of b200rec_propagate_fwd, opened up for the join
+            last = k == L - 1
+            if last:
+                join()
+            y = None if last else self.bufs[k & 1]
+            ops.spmm(m.norm_adj, src, y=y, addend=x0 if k == 0 else self.rep, out=self.rep, out_scale=inv if last else 1.0,
+                     dst_flags=self.row_flags if last else None)
+            src = y
 
     def _propagate_bwd(self, out):
         m = self.model
@@ -155,22 +176,29 @@ class BprEngine:
     def _body(self, sample, draw_mask=True):
         m, B = self.model, self.B
         nu = m.n_users
-        if sample:
-            ops.bpr_sample(self.user_ptr, self.user_items, self.dataset.n_users, self.dataset.n_items, self.seed,
-                           self.sample_step, B, out=self.batch)
+        main = torch.cuda.current_stream()
+        forked = self.kind == 'LightGCN' and self.partition is None and m.n_layers >= 2
+        side = self._side_stream if forked else main
+        if forked:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if sample:
+                ops.bpr_sample(self.user_ptr, self.user_items, self.dataset.n_users, self.dataset.n_items, self.seed,
+                               self.sample_step, B, out=self.batch)
+            if self.kind != 'MF':
+                # the step reads rep only at the <= 3B sampled rows, and G is non-zero only there: the last forward layer
+                # and the first backward hop are restricted to them (bit-identical on the rows that matter)
+                self.row_flags.zero_()
+                ops.mark_rows(self.batch, nu, self.row_flags)
+        join = (lambda: main.wait_stream(side)) if forked else None
         self.loss.zero_()
-        if self.kind != 'MF':
-            # the step reads rep only at the <= 3B sampled rows, and G is non-zero only there: the last forward layer
-            # and the first backward hop are restricted to them (bit-identical on the rows that matter)
-            self.row_flags.zero_()
-            ops.mark_rows(self.batch, nu, self.row_flags)
         if self.kind == 'MF':
             self.grad.zero_()
             self._bpr(self.table, self.batch, nu, self.l2_reg, 1, self.grad)
             self._adam(self.table, self.grad, self.m, self.v)
         elif self.kind == 'LightGCN':
             self.g_rep.zero_()
-            self._propagate_fwd(self.table)
+            self._propagate_fwd(self.table, join)
             self._bpr(self.rep, self.batch, nu, 0.0, 0, self.g_rep)
             self._propagate_bwd(self.grad)
             if self.l2_reg != 0.0:

@@ -125,8 +125,9 @@ def score_topk(rep_users, users, rep_items, k, excl_a=None, excl_b=None, banned=
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=rep_users.device)
     ids = torch.empty((nb, k), dtype=torch.int32, device=rep_users.device)
     sc = torch.empty((nb, k), dtype=torch.float32, device=rep_users.device)
-    ea = excl_a if excl_a is not None else (None, None)
-    eb = excl_b if excl_b is not None else (None, None)
+    # an exclusion CSR without entries (e.g. an empty validation split) is the same as none
+    ea = excl_a if excl_a is not None and excl_a[1].numel() else (None, None)
+    eb = excl_b if excl_b is not None and excl_b[1].numel() else (None, None)
     lo, hi = banned if banned is not None else (0, 0)
     if precision == 1 and d not in (64, 128):
         precision = 0  # the tensor-core path is built for D = 64 / 128
