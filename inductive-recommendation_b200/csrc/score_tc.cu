@@ -18,6 +18,7 @@
 // overflows is flagged and must be redone by the caller with precision 0.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200rec {
@@ -396,6 +397,292 @@ __global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ main kernel, v2
+// Same pipeline, different epilogue: ncu on v1 showed the tensor pipe 3 % busy with the MMA warp spinning on `tempty` --
+// four latency-exposed warps both drained TMEM and ran the branchy per-hit work (range / exclusion tests, list appends,
+// cut refinement).  Here the four DRAIN warps (2-5) only load 32 columns, reduce them to four group maxima, compare
+// with the row's cut and push the rare hit groups (row, first item, 8 scores) into a per-warp single-producer /
+// single-consumer ring in shared memory; two CONSUMER warps (6-7), each owning the rows of two drain warps, pop the
+// records, do the per-value tests, append to the row lists, and re-derive a row's cut when its list reaches
+// TC_REFINE_AT entries.  No locks: a row is touched by exactly one consumer; a stale cut only costs extra records.
+constexpr int TC_QCAP = 128;      // records per ring (power of two)
+constexpr int TC_REFINE_AT = 128; // list length that triggers a cut refinement
+struct __align__(16) HitRec {
+  float v[8];
+  int base;   // item id of v[0]
+  int row;    // row inside the CTA tile
+  int pad[2];
+};
+
+template <int D, int BN, int STAGES>
+__global__ void __launch_bounds__(256, (D == 64) ? 2 : 1) score_tc2_kernel(const __grid_constant__ CUtensorMap tm_users,
+                                                                            const __grid_constant__ CUtensorMap tm_items,
+                                                                            const TcParams p) {
+  constexpr int KB = D / 64;
+  constexpr uint32_t A_BYTES = TC_M * D * 2, B_STAGE_BYTES = BN * D * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + A_BYTES;
+  HitRec* queues = reinterpret_cast<HitRec*>(sB + (size_t)STAGES * B_STAGE_BYTES);      // [4][TC_QCAP]
+  Cand* sort_area = reinterpret_cast<Cand*>(queues + 4 * TC_QCAP);                        // [2 consumer warps][TC_CAP]
+  float* s_cut = reinterpret_cast<float*>(sort_area + 2 * TC_CAP);                        // [128]
+  int* s_cnt = reinterpret_cast<int*>(s_cut + TC_M);                                      // [128]
+  volatile int* s_tail = reinterpret_cast<volatile int*>(s_cnt + TC_M);                   // [4] records published
+  volatile int* s_head = s_tail + 4;                                                      // [4] records consumed
+  volatile int* s_done = s_head + 4;                                                      // [4] producer finished
+  uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(s_done) + 4);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* afull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * TC_M;
+  const int n_tiles = (p.n_items + BN - 1) / BN;
+
+  if (threadIdx.x < TC_M) { s_cut[threadIdx.x] = -INFINITY; s_cnt[threadIdx.x] = 0; }
+  if (threadIdx.x < 4) { s_tail[threadIdx.x] = 0; s_head[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+    mbar_init(afull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(afull, A_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + (size_t)kb * TC_M * 128, &tm_users, kb * 64, u0, afull);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(empty + s, ((t / STAGES) & 1) ^ 1);
+        mbar_expect_tx(full + s, B_STAGE_BYTES);
+        uint8_t* dst = sB + (size_t)s * B_STAGE_BYTES;
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(dst + (size_t)kb * BN * 128, &tm_items, kb * 64, t * BN, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_M, BN);
+      mbar_wait(afull, 0);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % STAGES, as = t & 1;
+        mbar_wait(tempty + as, ((t >> 1) & 1) ^ 1);
+        mbar_wait(full + s, (t / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = umma_desc_sw128(a0 + kb * TC_M * 128 + k * 32);
+            const uint64_t bd = umma_desc_sw128(b0 + kb * BN * 128 + k * 32);
+            tc_mma_bf16(tmem_base + as * BN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+        }
+        tc_commit(empty + s);
+        tc_commit(tfull + as);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== drain warps: TMEM -> group maxima -> hit records =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const bool active = (u0 + row) < p.n_users;
+    HitRec* q = queues + quad * TC_QCAP;
+    int tail = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int as = t & 1;
+      const float cut = active ? s_cut[row] : INFINITY;  // refreshed once per tile (the consumer may have raised it)
+      mbar_wait(tfull + as, (t >> 1) & 1);
+      tc_fence_after();
+      const int i0 = t * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+        unsigned hit4 = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float a = fmaxf(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+          const float b = fmaxf(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+          const float c2 = fmaxf(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+          const float d2 = fmaxf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+          if (fmaxf(fmaxf(a, b), fmaxf(c2, d2)) >= cut) hit4 |= 1u << g;
+        }
+        if (__any_sync(0xffffffffu, hit4 != 0)) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const bool mine = (hit4 >> g) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (bal == 0) continue;
+            const int n = __popc(bal);
+            // wait for room in the ring (bounded)
+            unsigned spins = 0;
+            while (tail + n - s_head[quad] > TC_QCAP) {
+              if (++spins > 200000000u) __trap();
+            }
+            if (mine) {
+              HitRec* r = q + ((tail + __popc(bal & ((1u << lane) - 1u))) & (TC_QCAP - 1));
+              *reinterpret_cast<uint4*>(&r->v[0]) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+              *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+              r->base = i0 + c * 32 + g * 8;
+              r->row = row;
+            }
+            tail += n;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) s_tail[quad] = tail;  // publish
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + as);
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) s_done[quad] = 1;
+  } else {
+    // ===== consumer warps: warp 6 owns the rows of quadrants 0,1; warp 7 those of 2,3 =====
+    const int cw = warp - 6;
+    Cand* my_sort = sort_area + (size_t)cw * TC_CAP;
+    const float vmax = __uint_as_float(*p.vmax_bits);
+    const int K = p.k;
+    int head[2] = {0, 0};
+
+    auto refine_row = [&](int row) {
+      // warp-cooperative: lower bound of the K-th best approximate score by value bisection, then keep the band above
+      // (bound - margin) with a ballot compaction (see the exactness argument at the top of the file)
+      const int u = u0 + row;
+      const int rc = min(s_cnt[row], TC_CAP);
+      if (rc < K) return;
+      Cand* list = p.cand + (size_t)u * TC_CAP;
+      const float margin = 2.f * 1.05f * 0.0078125f * __ldg(p.unorm + u) * vmax;
+      const float rcut = s_cut[row];
+      float mx = -INFINITY, mn = INFINITY;
+      for (int t = lane; t < rc; t += 32) {
+        const Cand c = list[t];
+        my_sort[t] = c;
+        mx = fmaxf(mx, c.s);
+        mn = fminf(mn, c.s);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      __syncwarp();
+      float lo = (rcut > -INFINITY) ? rcut + margin : mn;  // #(entries >= lo) >= K always holds
+      lo = fminf(lo, mx);
+      float hi = mx;
+      for (int itn = 0; itn < 14; ++itn) {
+        const float pv = 0.5f * (lo + hi);
+        if (!(pv > lo && pv < hi)) break;
+        int c = 0;
+        for (int t = lane; t < rc; t += 32) c += (my_sort[t].s >= pv) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (c >= K) { lo = pv; if (c <= 2 * K) break; } else { hi = pv; }
+      }
+      const float ncut = lo - margin;
+      int base = 0;
+      for (int t0 = 0; t0 < rc; t0 += 32) {
+        const int t = t0 + lane;
+        const bool kp = t < rc && my_sort[t].s >= ncut;
+        const unsigned bal = __ballot_sync(0xffffffffu, kp);
+        if (kp) list[base + __popc(bal & ((1u << lane) - 1u))] = my_sort[t];
+        base += __popc(bal);
+      }
+      __syncwarp();
+      if (lane == 0) { s_cnt[row] = base; s_cut[row] = ncut; }
+      __syncwarp();
+    };
+
+    unsigned idle = 0;
+    for (;;) {
+      bool progressed = false;
+      bool all_done = true;
+#pragma unroll
+      for (int qi = 0; qi < 2; ++qi) {
+        const int quad = cw * 2 + qi;
+        const int done = s_done[quad];      // read BEFORE the tail: done => the tail read below is final
+        __threadfence_block();
+        const int tl = s_tail[quad];
+        __threadfence_block();              // acquire: the records below were written before the tail was published
+        HitRec* q = queues + quad * TC_QCAP;
+        int h = head[qi];
+        while (h < tl) {
+          const int nrec = min(4, tl - h);
+          const int ri = lane >> 3, j = lane & 7;
+          if (ri < nrec) {
+            const HitRec* r = q + ((h + ri) & (TC_QCAP - 1));
+            const float sc = r->v[j];
+            const int row = r->row;
+            const int item = r->base + j;
+            const int u = u0 + row;
+            if (sc >= s_cut[row] && item < p.n_items && !(item >= p.banned_lo && item < p.banned_hi)) {
+              const int64_t user = p.users[u];
+              if (!row_has(p.excl_ptr_a, p.excl_idx_a, user, item) && !row_has(p.excl_ptr_b, p.excl_idx_b, user, item)) {
+                const int pos = atomicAdd(&s_cnt[row], 1);
+                if (pos < TC_CAP) p.cand[(size_t)u * TC_CAP + pos] = Cand{sc, item};
+                else p.overflow[u] = 1;
+              }
+            }
+          }
+          h += nrec;
+          progressed = true;
+        }
+        __syncwarp();
+        if (h != head[qi]) {
+          head[qi] = h;
+          __threadfence_block();
+          if (lane == 0) s_head[quad] = h;  // free the slots
+        }
+        if (!(done && h == tl)) all_done = false;
+        // rows of this quadrant whose list grew long: tighten their cut
+        __threadfence();  // list entries written by the lanes above are visible to the whole warp
+        const int row = quad * 32 + lane;
+        const bool need = (u0 + row) < p.n_users && s_cnt[row] >= TC_REFINE_AT;
+        unsigned needm = __ballot_sync(0xffffffffu, need);
+        while (needm) {
+          const int r = __ffs(needm) - 1;
+          needm &= needm - 1;
+          refine_row(quad * 32 + r);
+        }
+      }
+      if (all_done) break;
+      if (!progressed) { if (++idle > 400000000u) __trap(); } else idle = 0;
+    }
+    // final: exact lower bound pass for every row, publish counts
+    __threadfence();
+    for (int r = 0; r < 64; ++r) {
+      const int row = cw * 64 + r;
+      if ((u0 + row) >= p.n_users) continue;
+      refine_row(row);
+      if (lane == 0) p.cand_cnt[u0 + row] = min(s_cnt[row], TC_CAP);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ exact re-score + top-K
 template <int D>
 __global__ void __launch_bounds__(128) tc_rescore_kernel(const float* __restrict__ rep_users, const int64_t* __restrict__ users,
@@ -519,10 +806,24 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
   p.users = users; p.n_users = nb; p.n_items = ni; p.k = k;
   p.excl_ptr_a = ea_ptr; p.excl_idx_a = ea_idx; p.excl_ptr_b = eb_ptr; p.excl_idx_b = eb_idx;
   p.banned_lo = blo; p.banned_hi = bhi; p.unorm = unorm; p.vmax_bits = vmax; p.cand = cand; p.cand_cnt = cnt; p.overflow = ovf;
-  const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 4 * TC_CAP * sizeof(Cand) + 256;
-  B2_CUDA(cudaFuncSetAttribute(score_tc_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  score_tc_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 192, smem, st>>>(mu, mi, p);
-  B2_LAUNCHED();
+  static int use_v1 = -1;
+  if (use_v1 < 0) {
+    const char* e = getenv("B200REC_TC_V1");
+    use_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (use_v1) {
+    const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 4 * TC_CAP * sizeof(Cand) + 256;
+    B2_CUDA(cudaFuncSetAttribute(score_tc_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    score_tc_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 192, smem, st>>>(mu, mi, p);
+    B2_LAUNCHED();
+  } else {
+    B2_CUDA(cudaMemsetAsync(ovf, 0, (size_t)nb * sizeof(int), st));
+    const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 4 * TC_QCAP * sizeof(HitRec) +
+                        2 * TC_CAP * sizeof(Cand) + 2 * TC_M * 4 + 512;
+    B2_CUDA(cudaFuncSetAttribute(score_tc2_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 256, smem, st>>>(mu, mi, p);
+    B2_LAUNCHED();
+  }
   const size_t rsmem = 4 * TC_CAP * sizeof(Cand);
   tc_rescore_kernel<D><<<ceil_div(nb, 4), 128, rsmem, st>>>(rep_users, users, nb, rep_items, cand, cnt, k, out_ids, out_scores);
   B2_LAUNCHED();
@@ -534,7 +835,7 @@ int b200rec_score_topk_tc(const float* rep_users, const int64_t* users, int nb, 
                           int bhi, int k, int32_t* out_ids, float* out_scores, int32_t* out_overflow, void* workspace,
                           cudaStream_t st) {
   if (d == 64)
-    return tc_launch<64, 128, 4>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
+    return tc_launch<64, 128, 3>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
                                  out_scores, out_overflow, workspace, st);
   if (d == 128)
     return tc_launch<128, 128, 2>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
