@@ -403,8 +403,13 @@ __global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant_
 // cut refinement).  Here the four DRAIN warps (2-5) only load 32 columns, reduce them to four group maxima, compare
 // with the row's cut and push the rare hit groups (row, first item, 8 scores) into a per-warp single-producer /
 // single-consumer ring in shared memory; two CONSUMER warps (6-7), each owning the rows of two drain warps, pop the
-// records, do the per-value tests, append to the row lists, and re-derive a row's cut when its list reaches
-// TC_REFINE_AT entries.  No locks: a row is touched by exactly one consumer; a stale cut only costs extra records.
+// records, do the per-value tests, append to the row lists, and re-derive a row's cut when its list grows long.
+// No locks: a row is touched by exactly one consumer (one consumer warp per drain warp); a stale cut only costs extra
+// records.  The train / val exclusion test (a binary search in global memory per candidate) is NOT done here: with E
+// excluded items in a row, the (K+E)-th best approximate score over ALL items is a lower bound of the K-th best over the
+// allowed ones (at most E of the top K+E are excluded), so the cut is derived from rank K' = K + E and the exclusion
+// filter runs in the massively parallel re-score kernel.  (For a trained model the user's train items are its top
+// scorers anyway, so the candidate volume is the same as with an inline test.)
 constexpr int TC_QCAP = 128;      // records per ring (power of two)
 constexpr int TC_REFINE_AT = 128; // list length that triggers a cut refinement
 struct __align__(16) HitRec {
@@ -415,7 +420,7 @@ struct __align__(16) HitRec {
 };
 
 template <int D, int BN, int STAGES>
-__global__ void __launch_bounds__(256, (D == 64) ? 2 : 1) score_tc2_kernel(const __grid_constant__ CUtensorMap tm_users,
+__global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const __grid_constant__ CUtensorMap tm_users,
                                                                             const __grid_constant__ CUtensorMap tm_items,
                                                                             const TcParams p) {
   constexpr int KB = D / 64;
@@ -425,10 +430,11 @@ __global__ void __launch_bounds__(256, (D == 64) ? 2 : 1) score_tc2_kernel(const
   uint8_t* sA = smem;
   uint8_t* sB = smem + A_BYTES;
   HitRec* queues = reinterpret_cast<HitRec*>(sB + (size_t)STAGES * B_STAGE_BYTES);      // [4][TC_QCAP]
-  Cand* sort_area = reinterpret_cast<Cand*>(queues + 4 * TC_QCAP);                        // [2 consumer warps][TC_CAP]
-  float* s_cut = reinterpret_cast<float*>(sort_area + 2 * TC_CAP);                        // [128]
+  Cand* sort_area = reinterpret_cast<Cand*>(queues + 4 * TC_QCAP);                        // [4 consumer warps][TC_CAP]
+  float* s_cut = reinterpret_cast<float*>(sort_area + 4 * TC_CAP);                        // [128]
   int* s_cnt = reinterpret_cast<int*>(s_cut + TC_M);                                      // [128]
-  volatile int* s_tail = reinterpret_cast<volatile int*>(s_cnt + TC_M);                   // [4] records published
+  int* s_kk = s_cnt + TC_M;                                                               // [128] K' = K + #excluded
+  volatile int* s_tail = reinterpret_cast<volatile int*>(s_kk + TC_M);                    // [4] records published
   volatile int* s_head = s_tail + 4;                                                      // [4] records consumed
   volatile int* s_done = s_head + 4;                                                      // [4] producer finished
   uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(s_done) + 4);
@@ -443,7 +449,21 @@ __global__ void __launch_bounds__(256, (D == 64) ? 2 : 1) score_tc2_kernel(const
   const int u0 = blockIdx.x * TC_M;
   const int n_tiles = (p.n_items + BN - 1) / BN;
 
-  if (threadIdx.x < TC_M) { s_cut[threadIdx.x] = -INFINITY; s_cnt[threadIdx.x] = 0; }
+  if (threadIdx.x < TC_M) {
+    const int u = u0 + (int)threadIdx.x;
+    float cut0 = -INFINITY;
+    int kk = p.k;
+    if (u < p.n_users) {
+      const int64_t user = p.users[u];
+      if (p.excl_ptr_a) kk += p.excl_ptr_a[user + 1] - p.excl_ptr_a[user];
+      if (p.excl_ptr_b) kk += p.excl_ptr_b[user + 1] - p.excl_ptr_b[user];
+      if (kk > TC_CAP / 2) {  // a user with that many excluded items: exact path (flagged for the caller)
+        p.overflow[u] = 1;
+        cut0 = INFINITY;
+      }
+    }
+    s_cut[threadIdx.x] = cut0; s_cnt[threadIdx.x] = 0; s_kk[threadIdx.x] = kk;
+  }
   if (threadIdx.x < 4) { s_tail[threadIdx.x] = 0; s_head[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -556,19 +576,20 @@ __global__ void __launch_bounds__(256, (D == 64) ? 2 : 1) score_tc2_kernel(const
     __syncwarp();
     if (lane == 0) s_done[quad] = 1;
   } else {
-    // ===== consumer warps: warp 6 owns the rows of quadrants 0,1; warp 7 those of 2,3 =====
-    const int cw = warp - 6;
-    Cand* my_sort = sort_area + (size_t)cw * TC_CAP;
+    // ===== consumer warps: warp 6+q owns the ring and the 32 rows of drain quadrant q =====
+    const int quad = warp - 6;
+    Cand* my_sort = sort_area + (size_t)quad * TC_CAP;
+    HitRec* q = queues + quad * TC_QCAP;
     const float vmax = __uint_as_float(*p.vmax_bits);
-    const int K = p.k;
-    int head[2] = {0, 0};
+    int head = 0;
 
     auto refine_row = [&](int row) {
-      // warp-cooperative: lower bound of the K-th best approximate score by value bisection, then keep the band above
+      // warp-cooperative: lower bound of the K'-th best approximate score by value bisection, then keep the band above
       // (bound - margin) with a ballot compaction (see the exactness argument at the top of the file)
       const int u = u0 + row;
       const int rc = min(s_cnt[row], TC_CAP);
-      if (rc < K) return;
+      const int kk = s_kk[row];
+      if (rc < kk) return;
       Cand* list = p.cand + (size_t)u * TC_CAP;
       const float margin = 2.f * 1.05f * 0.0078125f * __ldg(p.unorm + u) * vmax;
       const float rcut = s_cut[row];
@@ -585,7 +606,7 @@ __global__ void __launch_bounds__(256, (D == 64) ? 2 : 1) score_tc2_kernel(const
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
       }
       __syncwarp();
-      float lo = (rcut > -INFINITY) ? rcut + margin : mn;  // #(entries >= lo) >= K always holds
+      float lo = (rcut > -INFINITY) ? rcut + margin : mn;  // #(entries >= lo) >= K' always holds
       lo = fminf(lo, mx);
       float hi = mx;
       for (int itn = 0; itn < 14; ++itn) {
@@ -595,7 +616,7 @@ __global__ void __launch_bounds__(256, (D == 64) ? 2 : 1) score_tc2_kernel(const
         for (int t = lane; t < rc; t += 32) c += (my_sort[t].s >= pv) ? 1 : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (c >= K) { lo = pv; if (c <= 2 * K) break; } else { hi = pv; }
+        if (c >= kk) { lo = pv; if (c <= kk + kk / 2 + 8) break; } else { hi = pv; }
       }
       const float ncut = lo - margin;
       int base = 0;
@@ -613,63 +634,52 @@ __global__ void __launch_bounds__(256, (D == 64) ? 2 : 1) score_tc2_kernel(const
 
     unsigned idle = 0;
     for (;;) {
-      bool progressed = false;
-      bool all_done = true;
-#pragma unroll
-      for (int qi = 0; qi < 2; ++qi) {
-        const int quad = cw * 2 + qi;
-        const int done = s_done[quad];      // read BEFORE the tail: done => the tail read below is final
-        __threadfence_block();
-        const int tl = s_tail[quad];
-        __threadfence_block();              // acquire: the records below were written before the tail was published
-        HitRec* q = queues + quad * TC_QCAP;
-        int h = head[qi];
-        while (h < tl) {
-          const int nrec = min(4, tl - h);
-          const int ri = lane >> 3, j = lane & 7;
-          if (ri < nrec) {
-            const HitRec* r = q + ((h + ri) & (TC_QCAP - 1));
-            const float sc = r->v[j];
-            const int row = r->row;
-            const int item = r->base + j;
-            const int u = u0 + row;
-            if (sc >= s_cut[row] && item < p.n_items && !(item >= p.banned_lo && item < p.banned_hi)) {
-              const int64_t user = p.users[u];
-              if (!row_has(p.excl_ptr_a, p.excl_idx_a, user, item) && !row_has(p.excl_ptr_b, p.excl_idx_b, user, item)) {
-                const int pos = atomicAdd(&s_cnt[row], 1);
-                if (pos < TC_CAP) p.cand[(size_t)u * TC_CAP + pos] = Cand{sc, item};
-                else p.overflow[u] = 1;
-              }
-            }
+      const int done = s_done[quad];      // read BEFORE the tail: done => the tail read below is final
+      __threadfence_block();
+      const int tl = s_tail[quad];
+      __threadfence_block();              // acquire: the records below were written before the tail was published
+      const bool progressed = head < tl;
+      while (head < tl) {
+        const int nrec = min(4, tl - head);
+        const int ri = lane >> 3, j = lane & 7;
+        if (ri < nrec) {
+          const HitRec* r = q + ((head + ri) & (TC_QCAP - 1));
+          const float sc = r->v[j];
+          const int row = r->row;
+          const int item = r->base + j;
+          if (sc >= s_cut[row] && item < p.n_items && !(item >= p.banned_lo && item < p.banned_hi)) {
+            const int pos = atomicAdd(&s_cnt[row], 1);
+            if (pos < TC_CAP) p.cand[(size_t)(u0 + row) * TC_CAP + pos] = Cand{sc, item};
+            else p.overflow[u0 + row] = 1;
           }
-          h += nrec;
-          progressed = true;
         }
-        __syncwarp();
-        if (h != head[qi]) {
-          head[qi] = h;
-          __threadfence_block();
-          if (lane == 0) s_head[quad] = h;  // free the slots
-        }
-        if (!(done && h == tl)) all_done = false;
-        // rows of this quadrant whose list grew long: tighten their cut
+        head += nrec;
+      }
+      __syncwarp();
+      if (progressed) {
+        __threadfence_block();
+        if (lane == 0) s_head[quad] = head;  // free the slots
+        // rows whose list grew long: tighten their cut
         __threadfence();  // list entries written by the lanes above are visible to the whole warp
         const int row = quad * 32 + lane;
-        const bool need = (u0 + row) < p.n_users && s_cnt[row] >= TC_REFINE_AT;
+        const int kk = s_kk[row];
+        const bool need = (u0 + row) < p.n_users && s_cnt[row] >= max(TC_REFINE_AT, min(2 * kk, 3 * TC_CAP / 4));
         unsigned needm = __ballot_sync(0xffffffffu, need);
         while (needm) {
           const int r = __ffs(needm) - 1;
           needm &= needm - 1;
           refine_row(quad * 32 + r);
         }
+        idle = 0;
+      } else {
+        if (done) break;                    // done was read before a tail that equals head: the ring is drained
+        if (++idle > 400000000u) __trap();
       }
-      if (all_done) break;
-      if (!progressed) { if (++idle > 400000000u) __trap(); } else idle = 0;
     }
-    // final: exact lower bound pass for every row, publish counts
+    // final: lower-bound pass for every row, publish counts
     __threadfence();
-    for (int r = 0; r < 64; ++r) {
-      const int row = cw * 64 + r;
+    for (int r = 0; r < 32; ++r) {
+      const int row = quad * 32 + r;
       if ((u0 + row) >= p.n_users) continue;
       refine_row(row);
       if (lane == 0) p.cand_cnt[u0 + row] = min(s_cnt[row], TC_CAP);
@@ -688,7 +698,8 @@ template <int D>
 __global__ void __launch_bounds__(128) tc_rescore_kernel(const float* __restrict__ rep_users, const int64_t* __restrict__ users,
                                                          int n_users, const float* __restrict__ rep_items,
                                                          const Cand* __restrict__ cand, const int* __restrict__ cand_cnt, int k,
-                                                         int32_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+                                                         int32_t* __restrict__ out_ids, float* __restrict__ out_scores,
+                                                         const TcParams p) {
   extern __shared__ __align__(16) unsigned char raw[];
   Cand* buf = reinterpret_cast<Cand*>(raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -703,18 +714,23 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(const float* __restrict
     Cand c{-INFINITY, INT32_MAX};
     if (t < n) {
       const int id = cand[(size_t)u * TC_CAP + t].id;
-      const float* vr = rep_items + (size_t)id * D;
-      float acc = 0.f;
+      // masks (trainer.py:155-167): train / val items of this user, banned range -- dropped before the exact score
+      const bool masked = (id >= p.banned_lo && id < p.banned_hi) || row_has(p.excl_ptr_a, p.excl_idx_a, users[u], id) ||
+                          row_has(p.excl_ptr_b, p.excl_idx_b, users[u], id);
+      if (!masked) {
+        const float* vr = rep_items + (size_t)id * D;
+        float acc = 0.f;
 #pragma unroll 8
-      for (int d = 0; d < D; ++d) acc = fmaf(__ldg(ur + d), __ldg(vr + d), acc);  // the oracle's chain, d = 0..D-1
-      c = Cand{acc, id};
+        for (int d = 0; d < D; ++d) acc = fmaf(__ldg(ur + d), __ldg(vr + d), acc);  // the oracle's chain, d = 0..D-1
+        c = Cand{acc, id};
+      }
     }
     row[t] = c;
   }
   __syncwarp();
   warp_sort_desc(row, np, lane);
   for (int j = lane; j < k; j += 32) {
-    const bool ok = j < n;
+    const bool ok = j < n && row[j].id != INT32_MAX;  // masked candidates sorted to the end
     out_ids[(size_t)u * k + j] = ok ? row[j].id : -1;
     out_scores[(size_t)u * k + j] = ok ? row[j].s : -INFINITY;
   }
@@ -819,13 +835,13 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
   } else {
     B2_CUDA(cudaMemsetAsync(ovf, 0, (size_t)nb * sizeof(int), st));
     const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 4 * TC_QCAP * sizeof(HitRec) +
-                        2 * TC_CAP * sizeof(Cand) + 2 * TC_M * 4 + 512;
+                        4 * TC_CAP * sizeof(Cand) + 3 * TC_M * 4 + 512;
     B2_CUDA(cudaFuncSetAttribute(score_tc2_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 256, smem, st>>>(mu, mi, p);
+    score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 320, smem, st>>>(mu, mi, p);
     B2_LAUNCHED();
   }
   const size_t rsmem = 4 * TC_CAP * sizeof(Cand);
-  tc_rescore_kernel<D><<<ceil_div(nb, 4), 128, rsmem, st>>>(rep_users, users, nb, rep_items, cand, cnt, k, out_ids, out_scores);
+  tc_rescore_kernel<D><<<ceil_div(nb, 4), 128, rsmem, st>>>(rep_users, users, nb, rep_items, cand, cnt, k, out_ids, out_scores, p);
   B2_LAUNCHED();
   return 0;
 }
