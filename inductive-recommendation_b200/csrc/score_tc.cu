@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant_
 // allowed ones (at most E of the top K+E are excluded), so the cut is derived from rank K' = K + E and the exclusion
 // filter runs in the massively parallel re-score kernel.  (For a trained model the user's train items are its top
 // scorers anyway, so the candidate volume is the same as with an inline test.)
-constexpr int TC_QCAP = 128;      // records per ring (power of two)
+constexpr int TC_QCAP = 64;       // records per ring (power of two); 8 rings: (quadrant, column half)
 constexpr int TC_REFINE_AT = 128; // list length that triggers a cut refinement
 struct __align__(16) HitRec {
   float v[8];
@@ -420,7 +420,7 @@ struct __align__(16) HitRec {
 };
 
 template <int D, int BN, int STAGES>
-__global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const __grid_constant__ CUtensorMap tm_users,
+__global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant__ CUtensorMap tm_users,
                                                                             const __grid_constant__ CUtensorMap tm_items,
                                                                             const TcParams p) {
   constexpr int KB = D / 64;
@@ -429,15 +429,15 @@ __global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + A_BYTES;
-  HitRec* queues = reinterpret_cast<HitRec*>(sB + (size_t)STAGES * B_STAGE_BYTES);      // [4][TC_QCAP]
-  Cand* sort_area = reinterpret_cast<Cand*>(queues + 4 * TC_QCAP);                        // [4 consumer warps][TC_CAP]
+  HitRec* queues = reinterpret_cast<HitRec*>(sB + (size_t)STAGES * B_STAGE_BYTES);      // [8][TC_QCAP]
+  Cand* sort_area = reinterpret_cast<Cand*>(queues + 8 * TC_QCAP);                        // [4 consumer warps][TC_CAP]
   float* s_cut = reinterpret_cast<float*>(sort_area + 4 * TC_CAP);                        // [128]
   int* s_cnt = reinterpret_cast<int*>(s_cut + TC_M);                                      // [128]
   int* s_kk = s_cnt + TC_M;                                                               // [128] K' = K + #excluded
-  volatile int* s_tail = reinterpret_cast<volatile int*>(s_kk + TC_M);                    // [4] records published
-  volatile int* s_head = s_tail + 4;                                                      // [4] records consumed
-  volatile int* s_done = s_head + 4;                                                      // [4] producer finished
-  uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(s_done) + 4);
+  volatile int* s_tail = reinterpret_cast<volatile int*>(s_kk + TC_M);                    // [8] records published
+  volatile int* s_head = s_tail + 8;                                                      // [8] records consumed
+  volatile int* s_done = s_head + 8;                                                      // [8] producer finished
+  uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(s_done) + 8);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -464,10 +464,10 @@ __global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const
     }
     s_cut[threadIdx.x] = cut0; s_cnt[threadIdx.x] = 0; s_kk[threadIdx.x] = kk;
   }
-  if (threadIdx.x < 4) { s_tail[threadIdx.x] = 0; s_head[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
+  if (threadIdx.x < 8) { s_tail[threadIdx.x] = 0; s_head[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
     mbar_init(afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -516,12 +516,16 @@ __global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const
         tc_commit(tfull + as);
       }
     }
-  } else if (warp < 6) {
-    // ===== drain warps: TMEM -> group maxima -> hit records =====
+  } else if (warp < 10) {
+    // ===== drain warps: TMEM -> group maxima -> hit records.  Two warps per TMEM lane quadrant (a warp may only touch
+    // lanes 32 * (warp % 4) ..), each taking half of a tile's columns: two drain warps per scheduler hide each other's
+    // tcgen05.ld / FMNMX latency.
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ring = quad * 2 + half;
     const int row = quad * 32 + lane;
     const bool active = (u0 + row) < p.n_users;
-    HitRec* q = queues + quad * TC_QCAP;
+    HitRec* q = queues + ring * TC_QCAP;
     int tail = 0;
     for (int t = 0; t < n_tiles; ++t) {
       const int as = t & 1;
@@ -530,7 +534,7 @@ __global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const
       tc_fence_after();
       const int i0 = t * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
         unsigned hit4 = 0;
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const
             const int n = __popc(bal);
             // wait for room in the ring (bounded)
             unsigned spins = 0;
-            while (tail + n - s_head[quad] > TC_QCAP) {
+            while (tail + n - s_head[ring] > TC_QCAP) {
               if (++spins > 200000000u) __trap();
             }
             if (mine) {
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const
             tail += n;
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) s_tail[quad] = tail;  // publish
+            if (lane == 0) s_tail[ring] = tail;  // publish
           }
         }
       }
@@ -574,14 +578,13 @@ __global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const
     }
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) s_done[quad] = 1;
+    if (lane == 0) s_done[ring] = 1;
   } else {
-    // ===== consumer warps: warp 6+q owns the ring and the 32 rows of drain quadrant q =====
-    const int quad = warp - 6;
+    // ===== consumer warps: warp 10+q owns the two rings and the 32 rows of drain quadrant q =====
+    const int quad = warp - 10;
     Cand* my_sort = sort_area + (size_t)quad * TC_CAP;
-    HitRec* q = queues + quad * TC_QCAP;
     const float vmax = __uint_as_float(*p.vmax_bits);
-    int head = 0;
+    int head2[2] = {0, 0};
 
     auto refine_row = [&](int row) {
       // warp-cooperative: lower bound of the K'-th best approximate score by value bisection, then keep the band above
@@ -634,31 +637,43 @@ __global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const
 
     unsigned idle = 0;
     for (;;) {
-      const int done = s_done[quad];      // read BEFORE the tail: done => the tail read below is final
-      __threadfence_block();
-      const int tl = s_tail[quad];
-      __threadfence_block();              // acquire: the records below were written before the tail was published
-      const bool progressed = head < tl;
-      while (head < tl) {
-        const int nrec = min(4, tl - head);
-        const int ri = lane >> 3, j = lane & 7;
-        if (ri < nrec) {
-          const HitRec* r = q + ((head + ri) & (TC_QCAP - 1));
-          const float sc = r->v[j];
-          const int row = r->row;
-          const int item = r->base + j;
-          if (sc >= s_cut[row] && item < p.n_items && !(item >= p.banned_lo && item < p.banned_hi)) {
-            const int pos = atomicAdd(&s_cnt[row], 1);
-            if (pos < TC_CAP) p.cand[(size_t)(u0 + row) * TC_CAP + pos] = Cand{sc, item};
-            else p.overflow[u0 + row] = 1;
-          }
-        }
-        head += nrec;
-      }
-      __syncwarp();
-      if (progressed) {
+      bool progressed = false, all_done = true;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int ring = quad * 2 + hf;
+        HitRec* q = queues + ring * TC_QCAP;
+        const int done = s_done[ring];      // read BEFORE the tail: done => the tail read below is final
         __threadfence_block();
-        if (lane == 0) s_head[quad] = head;  // free the slots
+        const int tl = s_tail[ring];
+        __threadfence_block();              // acquire: the records below were written before the tail was published
+        int head = head2[hf];
+        const bool any = head < tl;
+        while (head < tl) {
+          const int nrec = min(4, tl - head);
+          const int ri = lane >> 3, j = lane & 7;
+          if (ri < nrec) {
+            const HitRec* r = q + ((head + ri) & (TC_QCAP - 1));
+            const float sc = r->v[j];
+            const int row = r->row;
+            const int item = r->base + j;
+            if (sc >= s_cut[row] && item < p.n_items && !(item >= p.banned_lo && item < p.banned_hi)) {
+              const int pos = atomicAdd(&s_cnt[row], 1);
+              if (pos < TC_CAP) p.cand[(size_t)(u0 + row) * TC_CAP + pos] = Cand{sc, item};
+              else p.overflow[u0 + row] = 1;
+            }
+          }
+          head += nrec;
+        }
+        __syncwarp();
+        if (any) {
+          head2[hf] = head;
+          __threadfence_block();
+          if (lane == 0) s_head[ring] = head;  // free the slots
+          progressed = true;
+        }
+        if (!(done && head == tl)) all_done = false;
+      }
+      if (progressed) {
         // rows whose list grew long: tighten their cut
         __threadfence();  // list entries written by the lanes above are visible to the whole warp
         const int row = quad * 32 + lane;
@@ -672,7 +687,7 @@ __global__ void __launch_bounds__(320, (D == 64) ? 2 : 1) score_tc2_kernel(const
         }
         idle = 0;
       } else {
-        if (done) break;                    // done was read before a tail that equals head: the ring is drained
+        if (all_done) break;
         if (++idle > 400000000u) __trap();
       }
     }
@@ -834,10 +849,10 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
     B2_LAUNCHED();
   } else {
     B2_CUDA(cudaMemsetAsync(ovf, 0, (size_t)nb * sizeof(int), st));
-    const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 4 * TC_QCAP * sizeof(HitRec) +
+    const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 8 * TC_QCAP * sizeof(HitRec) +
                         4 * TC_CAP * sizeof(Cand) + 3 * TC_M * 4 + 512;
     B2_CUDA(cudaFuncSetAttribute(score_tc2_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 320, smem, st>>>(mu, mi, p);
+    score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 448, smem, st>>>(mu, mi, p);
     B2_LAUNCHED();
   }
   const size_t rsmem = 4 * TC_CAP * sizeof(Cand);
