@@ -86,6 +86,13 @@ class BprEngine:
             self.adam_step.fill_(int(st['step']))
             self.g_rep = torch.zeros((n, D), **f32)
             self.row_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+            # The two masked layers (last forward layer on the sampled rows, first backward hop from the sampled rows) can be
+            # given their own hub-row chunk (B200REC_SPARSE_CHUNK).  Measured on C2 (ms/step): same plan 0.377, chunk 128
+            # 0.387, 64 0.404, 32 0.435, 1024 0.494 -- the auto chunk is the optimum for them too, so the default is off.
+            import os
+            sc = int(os.environ.get('B200REC_SPARSE_CHUNK', '0'))
+            self.adj_sparse = model.norm_adj.replan(sc) if (partition is None and sc > 0 and sc != model.norm_adj.chunk) \
+                else model.norm_adj
             L = model.n_layers
             if partition is not None and hasattr(partition, 'rep'):
                 self.rep, self.bufs = partition.rep, [partition.buf0, partition.buf1]
@@ -127,28 +134,39 @@ class BprEngine:
                 join()
             self.partition.propagate_fwd(m.norm_adj, x0, L, self.bufs, self.rep, needed_rows=self.row_flags)
             return
-        if join is None or L < 2:
+        if L == 0:
             if join:
                 join()
-            ops.propagate_fwd(m.norm_adj, x0, L, self.bufs, self.rep, needed_rows=self.row_flags)
+            ops.propagate_fwd(m.norm_adj, x0, L, self.bufs, self.rep)
             return
         inv = 1.0 / (L + 1)
         src = x0
-        for k in range(L):  # the layer loop of b200rec_propagate_fwd, opened up for the join
+        for k in range(L):  # the layer loop of b200rec_propagate_fwd, opened up for the join and the sparse plan
             last = k == L - 1
-            if last:
+            if last and join:
                 join()
             y = None if last else self.bufs[k & 1]
-            ops.spmm(m.norm_adj, src, y=y, addend=x0 if k == 0 else self.rep, out=self.rep, out_scale=inv if last else 1.0,
-                     dst_flags=self.row_flags if last else None)
+            ops.spmm(self.adj_sparse if last else m.norm_adj, src, y=y, addend=x0 if k == 0 else self.rep, out=self.rep,
+                     out_scale=inv if last else 1.0, dst_flags=self.row_flags if last else None)
             src = y
 
     def _propagate_bwd(self, out):
         m = self.model
         if self.partition is not None:
             self.partition.propagate_bwd(m.norm_adj, self.g_rep, m.n_layers, self.bufs, out)
-        else:
-            ops.propagate_bwd(m.norm_adj, self.g_rep, m.n_layers, self.bufs, out, nonzero_rows=self.row_flags)
+            return
+        L = m.n_layers
+        if L == 0:
+            ops.propagate_bwd(m.norm_adj, self.g_rep, L, self.bufs, out)
+            return
+        inv = 1.0 / (L + 1)
+        src = self.g_rep
+        for k in range(1, L + 1):  # H_k = G + A H_{k-1}; the first hop reads only the <= 3B non-zero rows of G
+            last = k == L
+            dst = out if last else self.bufs[(k - 1) & 1]
+            ops.spmm(self.adj_sparse if k == 1 else m.norm_adj, src, addend=self.g_rep, out=dst, out_scale=inv if last else 1.0,
+                     src_flags=self.row_flags if k == 1 else None)
+            src = dst
 
     def _bpr(self, rep, batch, item_offset, l2_reg, reg_mode, g_rep, w=None, g_w=None, loss_scale=1.0):
         if self.shard is None:

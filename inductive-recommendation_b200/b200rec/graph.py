@@ -24,6 +24,9 @@ def auto_chunk(nnz, d=None):
     parks the row's last chunk).  One lane group walks its item serially, about 8 neighbour rows per memory round trip, so
     the longest item is a critical path (ncu, C2 shape with 1024-edge items: SMs 54 % active); every extra chunk costs a
     partial-row round trip through L2.  Measured sweet spot: a few items per resident lane group, within [64, 1024]."""
+    import os
+    if os.environ.get("B200REC_CHUNK"):
+        return int(os.environ["B200REC_CHUNK"])
     target = max(1, nnz // (148 * 32 * 4))
     c = 64
     while c < target and c < CHUNK_MAX:
@@ -127,6 +130,14 @@ class CsrOperand:
         enc[hot[self.colidx.long()]] |= -2 ** 31
         self.colidx_enc, self.col_hint, self.hot_rows, self._struct = enc, hint, int(hot.sum()), None
         return self
+
+    def replan(self, chunk):
+        """the same matrix with a different hub-row chunk (own work plan and scratch, shared CSR arrays)"""
+        o = CsrOperand(self.rowptr, self.colidx, self.n_cols, vals=self.vals, nbr_scale=self.nbr_scale,
+                       row_scale=self.row_scale, eid=self.eid, chunk=chunk, max_d=self.max_d, phase_split=self.phase_split)
+        if self.col_hint:
+            o.colidx_enc, o.col_hint = self.colidx_enc, self.col_hint
+        return o
 
     def with_scales(self, nbr_scale=None, row_scale=None):
         """same structure/plan, different per-node scale vectors (IGCN anneal: F's values change every epoch)"""

@@ -143,3 +143,52 @@ def test_c4_spmm_adjoint_and_partition_of_rows():
     ops.spmm(a.row_slice(0, n // 2), x, y=half)
     ops.spmm(a.row_slice(n // 2, n), x, y=half)
     assert torch.equal(half, ax)
+
+
+def test_c3_inductive_protocol():
+    """BASELINE config 3: IGCN on the old 80 % of an Amazon-book-shaped graph, then new users / items represented through
+    template aggregation only (generate_feat(is_updating=True)) and the six-way inductive_eval (trainer.py:212-253).
+    Size-independent checks: the old/new user split is a partition (user-weighted mean of the two recalls is the overall
+    recall), banned item ranges never appear, and the tensor-core and exact evaluation paths agree."""
+    import dataset as D
+    import model as M
+    import trainer as T
+    from b200rec import synth
+    full = synth.generate_named("c3", seed=0, device=DEV)
+    old, n_old_u, n_old_i = synth.inductive_split(full, 0.8, 0.8)
+    ds_old = D.get_dataset({"name": "SyntheticDataset", "device": DEV, "graph": old})
+    ds_new = D.get_dataset({"name": "SyntheticDataset", "device": DEV, "graph": full})
+    torch.manual_seed(0)
+    m = M.get_model({"name": "IGCN", "embedding_size": 64, "n_layers": 3, "dropout": 0.3, "feature_ratio": 1.0,
+                     "device": DEV}, ds_old)
+    cfg = {"name": "IGCNTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 0.0, "aux_reg": 0.01, "device": DEV,
+           "n_epochs": 1, "batch_size": 2048, "dataloader_num_workers": 0, "test_batch_size": 512, "topks": [1, 5, 10, 15, 20]}
+    tr = T.get_trainer(cfg, ds_old, m)
+    m.train()
+    eng = tr._engine()
+    for _ in range(20):
+        eng.step()
+    eng.sync_optimizer_state()
+    assert np.isfinite(eng.meter_avg())
+    t_rows = m.embedding.weight.shape[0]
+    # re-point at the enlarged dataset: new nodes get rows of F over the OLD template columns only
+    m.config["dataset"] = ds_new
+    m.n_users, m.n_items = ds_new.n_users, ds_new.n_items
+    m.norm_adj = m.generate_graph(ds_new)
+    m.feat_mat, _, _, m.row_sum = m.generate_feat(ds_new, is_updating=True)
+    m.update_feat_mat()
+    assert m.feat_mat.n_cols == t_rows and m.feat_mat.n_rows == ds_new.n_users + ds_new.n_items
+    tr2 = T.get_trainer(cfg, ds_new, m)
+    res = tr2.inductive_eval(n_old_u, n_old_i)
+    te_ptr = full.test_indptr.cpu().numpy()
+    has = np.diff(te_ptr) > 0
+    w_old, w_new = has[:n_old_u].sum(), has[n_old_u:].sum()
+    for k in (5, 20):
+        mix = (w_old * res["old_all"]["Recall"][k] + w_new * res["new_all"]["Recall"][k]) / (w_old + w_new)
+        assert abs(mix - res["all_all"]["Recall"][k]) < 1e-5
+    rec_old_items = tr2.recommend_all("test", banned_items=np.arange(n_old_i, ds_new.n_items))
+    assert int(rec_old_items.max()) < n_old_i                              # banned (new) items never recommended
+    rec_new_items = tr2.recommend_all("test", banned_items=np.arange(n_old_i))
+    assert int(rec_new_items[rec_new_items >= 0].min()) >= n_old_i
+    tr2.eval_precision = 0
+    assert torch.equal(tr2.recommend_all("test", banned_items=np.arange(n_old_i)), rec_new_items)  # exact == tcgen05
