@@ -102,29 +102,74 @@ class BasicDataset(Dataset):
                     f.write(' '.join([str(user)] + [str(i) for i in items]) + '\n')
 
 
+_CACHE_MAGIC = 'b200rec-lists-v1'
+
+
+def _parse_lists(file_path):
+    """`user item item ...` lines -> (ptr int64 [n_lines+1], idx int64 [tokens]) in file order (dataset.py:154-164 of
+    the reference builds Python lists line by line; here the tokens are converted in one numpy call)."""
+    with open(file_path, 'r') as f:
+        lines = f.read().strip().split('\n')
+    ntok = np.fromiter((len(line.split()) for line in lines), dtype=np.int64, count=len(lines))
+    flat = np.array(' '.join(lines).split(), dtype=np.int64) if ntok.sum() else np.zeros(0, np.int64)
+    tok_start = np.zeros(len(lines) + 1, dtype=np.int64)
+    np.cumsum(ntok, out=tok_start[1:])
+    keep = np.ones(flat.size, dtype=bool)
+    keep[tok_start[:-1][ntok > 0]] = False                             # every non-empty line leads with its user id
+    idx = flat[keep]
+    ptr = np.zeros(len(lines) + 1, dtype=np.int64)
+    np.cumsum(np.maximum(ntok - 1, 0), out=ptr[1:])
+    return ptr, idx
+
+
+def _read_lists_cached(file_path, use_cache=True):
+    """Binary cache beside the text file (`<name>.txt.b200rec.npz`: ptr, idx, and the size / mtime of the text it was
+    made from).  A stale or unreadable cache is ignored and rewritten; an unwritable directory just skips the cache."""
+    cache = file_path + '.b200rec.npz'
+    st = os.stat(file_path)
+    stamp = np.array([st.st_size, st.st_mtime_ns], dtype=np.int64)
+    if use_cache and os.path.exists(cache):
+        try:
+            with np.load(cache, allow_pickle=False) as z:
+                if str(z['magic']) == _CACHE_MAGIC and np.array_equal(z['stamp'], stamp):
+                    return z['ptr'], z['idx']
+        except Exception:
+            pass
+    ptr, idx = _parse_lists(file_path)
+    if use_cache:
+        try:
+            tmp = cache + '.tmp%d' % os.getpid()
+            with open(tmp, 'wb') as f:
+                np.savez(f, magic=np.array(_CACHE_MAGIC), stamp=stamp, ptr=ptr, idx=idx)
+            os.replace(tmp, cache)
+        except OSError:
+            pass
+    return ptr, idx
+
+
 class ProcessedDataset(BasicDataset):
-    """`<path>/{train,val,test}.txt`, one line per user: `user item item ...`."""
+    """`<path>/{train,val,test}.txt`, one line per user: `user item item ...` (reference dataset.py:140-164), with a
+    binary CSR cache written beside each file on first read (config key `cache`, default True)."""
 
     def __init__(self, dataset_config):
         super().__init__(dataset_config)
         path = dataset_config['path']
+        self._use_cache = bool(dataset_config.get('cache', True))
         self.train_data = self.read_data(os.path.join(path, 'train.txt'))
         self.val_data = self.read_data(os.path.join(path, 'val.txt'))
         self.test_data = self.read_data(os.path.join(path, 'test.txt'))
         assert len(self.train_data) == len(self.val_data) == len(self.test_data)
         self.n_users = len(self.train_data)
-        self.train_array = [[u, i] for u in range(self.n_users) for i in self.train_data[u]]
+        ptr, idx = _lists_to_csr(self.train_data)
+        users = np.repeat(np.arange(self.n_users, dtype=np.int64), np.diff(ptr))
+        self.train_array = np.stack([users, idx], axis=1).tolist()
 
     def read_data(self, file_path):
-        with open(file_path, 'r') as f:
-            lines = f.read().strip().split('\n')
-        data = []
-        for line in lines:
-            items = [int(tok) for tok in line.split(' ')[1:]]
-            if items:
-                self.n_items = max(self.n_items, max(items) + 1)
-            data.append(items)
-        return data
+        ptr, idx = _read_lists_cached(file_path, self._use_cache)
+        if idx.size:
+            self.n_items = max(self.n_items, int(idx.max()) + 1)
+        flat = idx.tolist()
+        return [flat[ptr[u]:ptr[u + 1]] for u in range(len(ptr) - 1)]
 
 
 class _LazyLists:

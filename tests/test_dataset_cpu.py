@@ -1,0 +1,94 @@
+"""ProcessedDataset: the text format of the reference (dataset.py:140-164) and the binary CSR cache beside it."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "inductive-recommendation_b200"))
+import dataset as D  # noqa: E402
+
+
+def _write(path, lists):
+    os.makedirs(path, exist_ok=True)
+    for sp in ("train", "val", "test"):
+        with open(os.path.join(path, sp + ".txt"), "w") as f:
+            for u, items in enumerate(lists[sp]):
+                f.write(" ".join([str(u)] + [str(i) for i in items]) + "\n")
+
+
+def _naive(path):
+    """The reference's line-by-line parse, restated."""
+    out = []
+    with open(path) as f:
+        for line in f.read().strip().split("\n"):
+            out.append([int(t) for t in line.split(" ")[1:]])
+    return out
+
+
+@pytest.fixture
+def lists():
+    rng = np.random.default_rng(3)
+    mk = lambda hi: [rng.choice(700, size=int(rng.integers(0, hi)), replace=False).tolist() for _ in range(150)]
+    d = {"train": mk(40), "val": mk(5), "test": mk(8)}
+    d["train"][0] = []          # a user with no interactions: the line is just the user id
+    d["train"][149] = [699]
+    return d
+
+
+def test_parse_matches_reference_semantics(tmp_path, lists):
+    p = str(tmp_path / "ds")
+    _write(p, lists)
+    ds = D.get_dataset({"name": "ProcessedDataset", "path": p, "device": "cpu"})
+    for sp in ("train", "val", "test"):
+        assert getattr(ds, sp + "_data") == _naive(os.path.join(p, sp + ".txt")) == lists[sp]
+    assert ds.n_users == 150 and ds.n_items == 700
+    assert ds.train_array == [[u, i] for u in range(150) for i in lists["train"][u]]
+    assert len(ds) == len(ds.train_array)
+    ptr, idx = ds.csr("train")
+    assert ptr[-1] == len(ds.train_array)
+    for u in (1, 77, 149):
+        assert idx[ptr[u]:ptr[u + 1]].tolist() == sorted(lists["train"][u])
+
+
+def test_cache_hit_stale_and_disabled(tmp_path, lists):
+    p = str(tmp_path / "ds")
+    _write(p, lists)
+    cfg = {"name": "ProcessedDataset", "path": p, "device": "cpu"}
+    D.get_dataset(cfg)
+    cache = os.path.join(p, "train.txt.b200rec.npz")
+    assert os.path.exists(cache)
+    # a hit must not touch the text: make it unparsable but keep size and mtime
+    txt = os.path.join(p, "val.txt")
+    st = os.stat(txt)
+    raw = open(txt, "rb").read()
+    open(txt, "wb").write(b"x" * len(raw))
+    os.utime(txt, ns=(st.st_atime_ns, st.st_mtime_ns))
+    ds = D.get_dataset(cfg)
+    assert ds.val_data == lists["val"]
+    open(txt, "wb").write(raw)
+    # a changed text invalidates the cache
+    lists["train"][5] = [1, 2, 3]
+    _write(p, lists)
+    ds = D.get_dataset(cfg)
+    assert ds.train_data[5] == [1, 2, 3]
+    # a corrupt cache is ignored and rewritten
+    open(cache, "wb").write(b"garbage")
+    ds = D.get_dataset(cfg)
+    assert ds.train_data == lists["train"]
+    assert np.load(cache)["ptr"][-1] == sum(len(x) for x in lists["train"])
+    # cache: False neither reads nor writes
+    q = str(tmp_path / "nocache")
+    _write(q, lists)
+    D.get_dataset({"name": "ProcessedDataset", "path": q, "device": "cpu", "cache": False})
+    assert not [f for f in os.listdir(q) if f.endswith(".npz")]
+
+
+def test_output_dataset_round_trip(tmp_path, lists):
+    p = str(tmp_path / "a")
+    _write(p, lists)
+    ds = D.get_dataset({"name": "ProcessedDataset", "path": p, "device": "cpu"})
+    q = str(tmp_path / "b")
+    ds.output_dataset(q)
+    ds2 = D.get_dataset({"name": "ProcessedDataset", "path": q, "device": "cpu"})
+    assert ds2.train_data == ds.train_data and ds2.test_data == ds.test_data and ds2.n_items == ds.n_items
