@@ -150,7 +150,7 @@ __device__ __forceinline__ float sigmoid_t(float x) {
 }
 
 template <int G, int VPL, bool HAS_W>
-__global__ void __launch_bounds__(256) bpr_fused_kernel(const float* __restrict__ rep, const int64_t* __restrict__ batch,
+__global__ void __launch_bounds__(256) bpr_fused_kernel(const float* rep, const int64_t* batch,
                                                         int n_batch, int64_t item_offset, float l2_reg, int reg_mode,
                                                         const float* __restrict__ w, float loss_scale,
                                                         float* __restrict__ g_rep, float* __restrict__ g_w,
@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* __restrict_
   const int gib = threadIdx.x / G, gl = threadIdx.x & (G - 1);
   const int smp = blockIdx.x * SPB + gib;
   const bool active = smp < n_batch;
+  pdl_trigger();
+  pdl_wait();  // rep / batch / dots come from the previous kernels of the step
   int64_t ru = 0, rp = 0, rn = 0;
   if (active) {
     ru = batch[3 * (size_t)smp];
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* __restrict_
 
 // LightGCN regulariser on layer-0 rows (model.py:114-117)
 template <int G, int VPL>
-__global__ void __launch_bounds__(256) bpr_l2_emb0_kernel(const float* __restrict__ emb0, const int64_t* __restrict__ batch,
+__global__ void __launch_bounds__(256) bpr_l2_emb0_kernel(const float* __restrict__ emb0, const int64_t* batch,
                                                           int n_batch, int64_t item_offset, float l2_reg,
                                                           float* __restrict__ g_emb0, float* __restrict__ loss_out,
                                                           float* scratch) {
@@ -285,6 +287,8 @@ __global__ void __launch_bounds__(256) bpr_l2_emb0_kernel(const float* __restric
   const float inv_b = 1.f / (float)n_batch;
   const float rc = 2.f * l2_reg * inv_b;
   float l2 = 0.f;
+  pdl_trigger();
+  pdl_wait();  // g_emb0 is the previous kernel's output
   if (active) {
     int64_t rows[3] = {batch[3 * (size_t)smp], batch[3 * (size_t)smp + 1] + item_offset,
                        batch[3 * (size_t)smp + 2] + item_offset};
@@ -321,7 +325,7 @@ struct AdamPeers {
   int n;
   float* p[8];  // the same element range of the parameter table on the other ranks (row-partitioned multi-GPU)
 };
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, double lr, double beta1d, double beta2d,
                                                    float eps, const int64_t* __restrict__ step_ptr, const AdamPeers peers) {
   __shared__ float s_step_size, s_bc2_sqrt;
@@ -331,6 +335,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     s_step_size = (float)(lr / bc1);
     s_bc2_sqrt = (float)sqrt(bc2);
   }
+  pdl_trigger();
+  pdl_wait();  // the bias corrections above (two fp64 pow) overlap the tail of the kernel that produces g
   __syncthreads();
   const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const float w1 = (float)(1.0 - beta1d), w2 = (float)(1.0 - beta2d), beta2 = (float)beta2d;
@@ -362,6 +368,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 __global__ void step_advance_kernel(int64_t* step, int64_t* step_b, const float* loss, double* loss_accum, int n_batch) {
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (step) *step += 1;
     if (step_b) *step_b += 1;
@@ -377,9 +384,8 @@ static int launch_bpr(const float* rep, const int64_t* batch, int nb, int64_t of
                       const float* w, float loss_scale, float* g_rep, float* g_w, float* loss_out, float* scratch,
                       float* dots, int dots_mode, float loss_weight, cudaStream_t st) {
   const int grid = ceil_div(nb, 256 / G);
-  if (w) bpr_fused_kernel<G, VPL, true><<<grid, 256, 0, st>>>(rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight);
-  else bpr_fused_kernel<G, VPL, false><<<grid, 256, 0, st>>>(rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight);
-  B2_LAUNCHED();
+  if (w) B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, true>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight);
+  else B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, false>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight);
   return 0;
 }
 
@@ -467,8 +473,7 @@ extern "C" int b200rec_bpr_fwd_bwd_sharded(const float* rep, int32_t d, const in
 extern "C" int b200rec_bpr_l2_emb0(const float* emb0, int32_t d, const int64_t* batch, int32_t n_batch, int64_t item_offset,
                                    float l2_reg, float* g_emb0, float* loss_out, float* block_scratch, void* stream) {
   B2_REQUIRE(emb0 && batch && g_emb0 && loss_out && block_scratch && n_batch > 0, "bad argument");
-  B2_DISPATCH_D(d, (bpr_l2_emb0_kernel<G, VPL><<<ceil_div(n_batch, 256 / G), 256, 0, (cudaStream_t)stream>>>(emb0, batch, n_batch, item_offset, l2_reg, g_emb0, loss_out, block_scratch)));
-  B2_LAUNCHED();
+  B2_DISPATCH_D(d, { B2_LAUNCH_PDL(bpr_l2_emb0_kernel<G, VPL>, ceil_div(n_batch, 256 / G), 256, 0, (cudaStream_t)stream, emb0, batch, n_batch, item_offset, l2_reg, g_emb0, loss_out, block_scratch); });
   return 0;
 }
 
@@ -480,8 +485,7 @@ extern "C" int b200rec_adam_step(float* param, const float* grad, float* exp_avg
   if (grid > 148 * 16) grid = 148 * 16;
   AdamPeers none;
   none.n = 0;
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, (float)eps, step, none);
-  B2_LAUNCHED();
+  B2_LAUNCH_PDL(adam_kernel, grid, 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, (float)eps, step, none);
   return 0;
 }
 
@@ -496,8 +500,7 @@ extern "C" int b200rec_adam_step_peer(float* param, const float* grad, float* ex
   for (int q = 0; q < 8; ++q) pr.p[q] = q < n_peers ? peer_param[q] : nullptr;
   int grid = ceil_div(n / 4 + 1, 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, (float)eps, step, pr);
-  B2_LAUNCHED();
+  B2_LAUNCH_PDL(adam_kernel, grid, 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, (float)eps, step, pr);
   return 0;
 }
 
@@ -513,7 +516,6 @@ extern "C" int b200rec_dropout_mask(int32_t nnz, float p, uint64_t seed, const i
 
 extern "C" int b200rec_step_advance(int64_t* step, int64_t* step_b, const float* loss, double* loss_accum, int32_t n_batch,
                                     void* stream) {
-  step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step, step_b, loss, loss_accum, n_batch);
-  B2_LAUNCHED();
+  B2_LAUNCH_PDL(step_advance_kernel, 1, 32, 0, (cudaStream_t)stream, step, step_b, loss, loss_accum, n_batch);
   return 0;
 }

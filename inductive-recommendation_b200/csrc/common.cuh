@@ -37,9 +37,53 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------
+// Kernels of one training step run back to back on one stream (and as consecutive nodes of the step graph).  Launched
+// with the programmatic-serialization attribute, a kernel's blocks may become resident while the previous kernel's
+// last wave drains: they read their STATIC inputs (work plan, CSR indices), then pdl_wait() until the previous grid has
+// completed and its writes are visible.  Rules kept by every kernel launched through launch_pdl():
+//   * pdl_wait() is executed by every block before the first access to anything another kernel of the step writes,
+//     and before its own first global write (so completion stays transitive along the chain);
+//   * pdl_trigger() only lets the NEXT grid start its prologue early; it promises nothing about this grid's data.
+// B200REC_NO_PDL=1 launches everything fully serialised.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define B2_LAUNCH_PDL(...)                           \
+  do {                                               \
+    B2_CUDA(b200rec::launch_pdl(__VA_ARGS__));       \
+    B2_LAUNCHED();                                   \
+  } while (0)
+
 // ---- device helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// coherent 128-bit load (never promoted to ld.global.nc): for tables the previous kernel of the step wrote, which a
+// programmatically launched grid may only read after pdl_wait()
+__device__ __forceinline__ float4 ldc_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint8_t ldc_u8(const uint8_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return (uint8_t)v;
+}
 __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 // streaming (evict-first) loads for data that is read exactly once (CSR arrays)
 __device__ __forceinline__ int ld_stream_i32(const int32_t* p) { return __ldcs(p); }

@@ -8,6 +8,10 @@
 #include <stdlib.h>
 #include "common.cuh"
 
+#ifndef B200REC_SPMM_SCAN
+#define B200REC_SPMM_SCAN 4
+#endif
+
 namespace b200rec {
 
 struct SpmmParams {
@@ -75,7 +79,7 @@ template <int G, int VPL>
 __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int gl, float4 (&acc)[VPL]) {
   constexpr int D = G * VPL * 4;
   float sc = p.post_scale;
-  if (p.row_scale) sc *= __ldg(p.row_scale + row);
+  if (p.row_scale) sc *= p.row_scale[row];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) {
     const size_t off = (size_t)row * D + (size_t)(gl + t * G) * 4;
@@ -109,9 +113,13 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   constexpr int D = G * VPL * 4;
   constexpr int U = 8;                    // neighbour rows in flight per lane
   constexpr int GPW = 32 / G;             // groups per warp
-  constexpr int EB = (G >= 16) ? G : 16;  // edges staged per group per block (narrow rows: several edges per lane)
-  constexpr int EPL = EB / G;             // edges loaded per lane per block
   constexpr bool COMPACT = HAS_MASK || HAS_SRCF;
+  // edges staged per group per block (narrow rows: several edges per lane).  The filtered variants scan SCAN x as many:
+  // their index / flag loads are independent and pipeline, and the survivors of the wider window fill the U-deep gather
+  // batches (a 16-edge window with ~30 % survivors issues 5 real loads and 3 pads per L2 round trip).
+  constexpr int SCAN = !COMPACT ? 1 : (G >= 4 ? B200REC_SPMM_SCAN : 2);  // G = 2: 128 groups per block, shared-memory budget
+  constexpr int EB = ((G >= 16) ? G : 16) * SCAN;
+  constexpr int EPL = EB / G;             // edges loaded per lane per block
   constexpr int CVS = (G == 32) ? EB : EB + 1;  // slot stride per group: +1 keeps the groups' broadcast reads off one bank
   __shared__ int2 s_cv[(256 / G) * CVS];
   const int lane = threadIdx.x & 31;
@@ -124,8 +132,11 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
     start = __ldg(p.item_start + item);
     end = __ldg(p.item_end + item);
     dst = __ldg(p.item_dst + item);
-    if (p.dst_flags && !__ldg(p.dst_flags + __ldg(p.item_row + item))) end = start;  // row not needed this call
   }
+  // the work plan above is static; everything below may read what the previous kernel of the step wrote
+  pdl_trigger();
+  pdl_wait();
+  if (item < p.n_items && p.dst_flags && !ldc_u8(p.dst_flags + __ldg(p.item_row + item))) end = start;  // row not needed
   const bool live = end > start;
   int maxlen = end - start;
   if (GPW > 1) {
@@ -138,7 +149,7 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   float4 acc[VPL];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* __restrict__ xg = p.x + (size_t)gl * 4;
+  const float* xg = p.x + (size_t)gl * 4;
 
   for (int base = 0; base < maxlen; base += EB) {
     int cnt = 0;  // contributing edges of this group in this block of EB; cntmax: warp-uniform loop bound
@@ -158,10 +169,10 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
         v = HAS_VALS ? ld_stream_f32(p.vals + k) : 1.f;
         if (HAS_MASK) {
           const int eidx = HAS_EID ? ld_stream_i32(p.eid + k) : k;
-          valid = ((__ldg(p.keep_bits + (eidx >> 5)) >> (eidx & 31)) & 1u) != 0u;
+          valid = ((*(p.keep_bits + (eidx >> 5)) >> (eidx & 31)) & 1u) != 0u;
         }
-        if (HAS_SRCF) valid = valid && (__ldg(p.src_flags + (c & 0x7fffffff)) != 0);
-        if (HAS_NBR && valid) v *= __ldg(p.nbr_scale + (c & 0x7fffffff));
+        if (HAS_SRCF) valid = valid && (ldc_u8(p.src_flags + (c & 0x7fffffff)) != 0);
+        if (HAS_NBR && valid) v *= p.nbr_scale[c & 0x7fffffff];
       }
       if (COMPACT) {
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
           }
         } else {
 #pragma unroll
-          for (int t = 0; t < VPL; ++t) xv[u][t] = ldg_f4(r + t * G * 4);
+          for (int t = 0; t < VPL; ++t) xv[u][t] = ldc_f4(r + t * G * 4);
         }
       }
 #pragma unroll
@@ -221,7 +232,7 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
     __syncwarp();  // slots are rewritten by the next block
   }
   if (item >= p.n_items) return;
-  if (p.dst_flags && !__ldg(p.dst_flags + __ldg(p.item_row + item))) return;
+  if (p.dst_flags && !ldc_u8(p.dst_flags + __ldg(p.item_row + item))) return;
   if (dst >= 0) {
     epilogue_row<G, VPL>(p, dst, gl, acc);
     return;
@@ -287,8 +298,7 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
     const int hint = a->col_hint;
 #define B2_SPMM_CASE_H(V, N, M, E, S, H)                                          \
   if (hv == V && hn == N && hm == M && he == E && hs == S && hint == H) {         \
-    spmm_items_kernel<G, VPL, V, N, M, E, S, H><<<grid, tpb, 0, st>>>(p);         \
-    B2_LAUNCHED();                                                                \
+    B2_LAUNCH_PDL(spmm_items_kernel<G, VPL, V, N, M, E, S, H>, grid, tpb, 0, st, p); \
   } else
 #define B2_SPMM_CASE(V, N, M, E, S) B2_SPMM_CASE_H(V, N, M, E, S, 0)
     B2_SPMM_CASE_H(true, false, false, false, false, 0)   // normalised adjacency
