@@ -31,3 +31,24 @@ for d in dims:
     torch.cuda.synchronize()
     print("%s D=%d items=%d long=%d chunk=%d: %.1f us/layer (L2-warm)" % (wl, d, op.n_items, op.n_long, op.chunk,
                                                                          a.elapsed_time(b) / iters * 1e3), flush=True)
+    if os.environ.get("MASKED", "0") == "1":
+        # the two restricted layers of a BPR step: flags from one device-sampled batch of 2048 triples
+        ptr32, idx32 = g.train_indptr.to(torch.int32), g.train_items.to(torch.int32)
+        step = torch.zeros(1, dtype=torch.int64, device="cuda")
+        batch = ops.bpr_sample(ptr32, idx32, g.n_users, g.n_items, 2021, step, 2048)
+        flags = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        ops.mark_rows(batch, g.n_users, flags)
+        gs = torch.zeros_like(x)
+        gs[flags.bool()] = torch.randn((int(flags.sum()), d), device="cuda")
+        frac = float((flags[op.colidx.long() & 0x7fffffff] != 0).float().mean())
+        for name, kw, src in (("dst-masked", dict(dst_flags=flags), x), ("src-masked", dict(src_flags=flags), gs)):
+            for _ in range(3):
+                ops.spmm(op, src, y=y, addend=acc, out=acc, **kw)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(iters):
+                ops.spmm(op, src, y=y, addend=acc, out=acc, **kw)
+            b.record()
+            torch.cuda.synchronize()
+            print("   %s: %.1f us/layer  (flagged rows %d, edges with a flagged source %.1f %%)" % (
+                name, a.elapsed_time(b) / iters * 1e3, int(flags.sum()), 100 * frac), flush=True)
