@@ -190,6 +190,20 @@ int b200rec_adam_step(float* param, const float* grad, float* exp_avg, float* ex
 int b200rec_step_advance(int64_t* step, int64_t* step_b, const float* loss, double* loss_accum /*[2]*/,
                          int32_t n_batch, void* stream);
 
+/* ---- contrastive views (SGL model.py:130-243, HALF :246-365) ----
+ * InfoNCE of the `info_nce` package as the reference calls it (cal_loss, model.py:206-214 / :322-332): 'unpaired'
+ * negatives with negative_keys == positive_key, reduction 'mean':
+ *   qn = q/max(|q|,1e-12), kn likewise; logits_i = [qn_i.kn_i, qn_i.kn_0 .. qn_i.kn_{n-1}] / temperature; CE against index 0.
+ * Forward and backward in one call; the n x n logits are never stored.
+ *   rows == NULL: q, k are [n,d]; gq, gk [n,d] are OVERWRITTEN with loss_scale * dLoss/dq, dLoss/dk.
+ *   rows != NULL: q, k are tables [*,d]; sample i is row rows[i*row_stride] of both (the users of a [B,3] BPR batch:
+ *                 rows = batch, row_stride = 3); gq, gk are tables and the gradients are ADDED at those rows.
+ * loss_out[0] += loss_scale * mean_i CE_i.  workspace: b200rec_infonce_workspace_floats(n, d) floats. */
+int64_t b200rec_infonce_workspace_floats(int32_t n, int32_t d);
+int b200rec_infonce_fwd_bwd(const float* q, const float* k, const int64_t* rows, int32_t row_stride, int32_t n, int32_t d,
+                            float temperature, float loss_scale, float* loss_out, float* gq, float* gk, float* workspace,
+                            void* stream);
+
 /* Edge-dropout keep mask of NGCF.dropout_sp_mat (model.py:4016-4021) drawn on device: bit e = floor((1-p) + r[e]),
  * r uniform [0,1) at 24-bit resolution from Philox4x32-10 (key = seed, counter = (e>>2, step_lo, step_hi, 0xD0),
  * lane e&3); restated in oracle/oracle_c.c.  keep_bits: uint32 [ceil(nnz/32)], edge order = CSR position. */

@@ -57,6 +57,8 @@ PROTOTYPES = {
     "b200rec_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
     "b200rec_step_advance": (C.c_int, [_P, _P, _P, _P, _I32, _P]),
     "b200rec_dropout_mask": (C.c_int, [_I32, _F, _U64, _P, _P, _P]),
+    "b200rec_infonce_workspace_floats": (C.c_int64, [_I32, _I32]),
+    "b200rec_infonce_fwd_bwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _F, _F, _P, _P, _P, _P, _P]),
     "b200rec_score_dense_f32": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P]),
     "b200rec_score_topk_workspace": (C.c_int64, [_I32, _I32, _I32, _I32, _I32]),
     "b200rec_score_topk": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),

@@ -25,11 +25,15 @@ def _adam_state(opt, p):
 
 class BprEngine:
     def __init__(self, model, dataset, opt, batch_size, l2_reg, aux_reg=0.0, aux_dataset=None, seed=2021,
-                 use_graph=True, partition=None, dim_shard=None):
+                 use_graph=True, partition=None, dim_shard=None, contrastive_reg=0.0):
         self.model, self.dataset, self.opt = model, dataset, opt
         self.kind = type(model).__name__
-        if self.kind not in ('LightGCN', 'IGCN', 'IMF', 'MF'):
-            raise ValueError('BprEngine supports LightGCN / IGCN / IMF / MF, got ' + self.kind)
+        if self.kind not in ('LightGCN', 'IGCN', 'IMF', 'MF', 'SGL', 'HALF'):
+            raise ValueError('BprEngine supports LightGCN / IGCN / IMF / MF / SGL / HALF, got ' + self.kind)
+        self.contrastive_reg = float(contrastive_reg)
+        if self.kind in ('SGL', 'HALF') and (partition is not None or dim_shard is not None
+                                             or getattr(model, '_dim_shard', None) is not None):
+            raise ValueError('the contrastive step is single-GPU (its B x B logits couple every column and row)')
         if type(opt).__name__ != 'Adam':
             raise ValueError('the fused step implements Adam; use the autograd path for other optimisers')
         g = opt.param_groups[0]
@@ -99,6 +103,13 @@ class BprEngine:
             else:
                 self.rep = torch.empty((n, D), **f32)
                 self.bufs = [torch.empty((n, D), **f32) if L >= 2 + i else None for i in range(2)]
+            if self.kind in ('SGL', 'HALF'):
+                nv = model.n_views
+                self.user_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+                self.view_rep = [torch.empty((n, D), **f32) for _ in range(nv)]
+                self.view_g = [torch.zeros((n, D), **f32) for _ in range(nv)]
+                self.view_grad = torch.empty((n, D), **f32)
+                self.nce_ws = ops.infonce_workspace(batch_size, D, dev)
             if self.kind in ('IGCN', 'IMF'):
                 self.x0 = torch.empty((n, D), **f32)
                 self.dx0 = torch.empty((n, D), **f32)
@@ -123,21 +134,25 @@ class BprEngine:
         self.steps_done = 0
 
     # ------------------------------------------------------------------------------------------------ one step
-    def _propagate_fwd(self, x0, join=None):
+    def _propagate_fwd(self, x0, join=None, adj=None, flags=None, rep=None):
         """L x SpMM + layer mean into self.rep.  Only the LAST layer needs the batch (it is restricted to the sampled
         rows), so `join` -- which makes the main stream wait for the side stream that draws the batch and marks its rows --
         is called right before it: sampling overlaps the first L-1 layers inside the step graph."""
         m = self.model
         L = m.n_layers
+        own = adj is None  # the model's full graph; otherwise an augmented view (SGL / HALF)
+        adj = m.norm_adj if own else adj
+        flags = self.row_flags if flags is None else flags
+        rep = self.rep if rep is None else rep
         if self.partition is not None:
             if join:
                 join()
-            self.partition.propagate_fwd(m.norm_adj, x0, L, self.bufs, self.rep, needed_rows=self.row_flags)
+            self.partition.propagate_fwd(adj, x0, L, self.bufs, rep, needed_rows=flags)
             return
         if L == 0:
             if join:
                 join()
-            ops.propagate_fwd(m.norm_adj, x0, L, self.bufs, self.rep)
+            ops.propagate_fwd(adj, x0, L, self.bufs, rep)
             return
         inv = 1.0 / (L + 1)
         src = x0
@@ -146,26 +161,30 @@ class BprEngine:
             if last and join:
                 join()
             y = None if last else self.bufs[k & 1]
-            ops.spmm(self.adj_sparse if last else m.norm_adj, src, y=y, addend=x0 if k == 0 else self.rep, out=self.rep,
-                     out_scale=inv if last else 1.0, dst_flags=self.row_flags if last else None)
+            ops.spmm(self.adj_sparse if (last and own) else adj, src, y=y, addend=x0 if k == 0 else rep, out=rep,
+                     out_scale=inv if last else 1.0, dst_flags=flags if last else None)
             src = y
 
-    def _propagate_bwd(self, out):
+    def _propagate_bwd(self, out, adj=None, flags=None, g=None):
         m = self.model
+        own = adj is None
+        adj = m.norm_adj if own else adj
+        flags = self.row_flags if flags is None else flags
+        g = self.g_rep if g is None else g
         if self.partition is not None:
-            self.partition.propagate_bwd(m.norm_adj, self.g_rep, m.n_layers, self.bufs, out)
+            self.partition.propagate_bwd(adj, g, m.n_layers, self.bufs, out)
             return
         L = m.n_layers
         if L == 0:
-            ops.propagate_bwd(m.norm_adj, self.g_rep, L, self.bufs, out)
+            ops.propagate_bwd(adj, g, L, self.bufs, out)
             return
         inv = 1.0 / (L + 1)
-        src = self.g_rep
+        src = g
         for k in range(1, L + 1):  # H_k = G + A H_{k-1}; the first hop reads only the <= 3B non-zero rows of G
             last = k == L
             dst = out if last else self.bufs[(k - 1) & 1]
-            ops.spmm(self.adj_sparse if k == 1 else m.norm_adj, src, addend=self.g_rep, out=dst, out_scale=inv if last else 1.0,
-                     src_flags=self.row_flags if k == 1 else None)
+            ops.spmm(self.adj_sparse if (k == 1 and own) else adj, src, addend=g, out=dst, out_scale=inv if last else 1.0,
+                     src_flags=flags if k == 1 else None)
             src = dst
 
     def _bpr(self, rep, batch, item_offset, l2_reg, reg_mode, g_rep, w=None, g_w=None, loss_scale=1.0):
@@ -222,6 +241,31 @@ class BprEngine:
             if self.l2_reg != 0.0:
                 ops.bpr_l2_emb0(self.table, self.batch, nu, self.l2_reg, self.grad, self.loss, self.scratch)
             self._adam(self.table, self.grad, self.m, self.v)
+        elif self.kind in ('SGL', 'HALF'):
+            # SGLTrainer / HALFTrainer.train_one_epoch (trainer.py:440-456): BPR on the full graph + contrastive_reg *
+            # InfoNCE between two views' rows of the batch users; the views need their last layer (and send gradient)
+            # only at those user rows.  Three (two) propagations forward, three (two) Horner chains backward, summed.
+            views = [m.norm_aug_adj1] + ([m.norm_aug_adj2] if m.n_views == 2 else [])
+            self.user_flags.zero_()
+            self.user_flags.index_fill_(0, self.batch[:, 0], 1)
+            self.g_rep.zero_()
+            for gv in self.view_g:
+                gv.zero_()
+            self._propagate_fwd(self.table)
+            for adj, rep in zip(views, self.view_rep):
+                self._propagate_fwd(self.table, adj=adj, flags=self.user_flags, rep=rep)
+            self._bpr(self.rep, self.batch, nu, self.l2_reg, 1 if self.l2_reg != 0.0 else 0, self.g_rep)
+            if self.kind == 'SGL':
+                q, k, gq, gk = self.view_rep[0], self.view_rep[1], self.view_g[0], self.view_g[1]
+            else:
+                q, k, gq, gk = self.rep, self.view_rep[0], self.g_rep, self.view_g[0]
+            ops.infonce_fwd_bwd(q, k, self.loss, gq, gk, self.nce_ws, temperature=m.temperature,
+                                loss_scale=self.contrastive_reg, rows=self.batch, row_stride=3, n=B)
+            self._propagate_bwd(self.grad)
+            for adj, gv in zip(views, self.view_g):
+                self._propagate_bwd(self.view_grad, adj=adj, flags=self.user_flags, g=gv)
+                self.grad.add_(self.view_grad)
+            self._adam(self.table, self.grad, self.m, self.v)
         else:  # IGCN / IMF
             p = float(m.dropout)
             keep, inv_keep = None, 1.0
@@ -249,6 +293,11 @@ class BprEngine:
         if not self.use_graph:
             self._body(sample, draw_mask)
             return
+        ver = getattr(self.model, 'aug_version', 0)  # SGL / HALF redraw their views every epoch: new operands, new graph
+        if ver != getattr(self, '_graph_ver', 0):
+            torch.cuda.synchronize()
+            self._graphs.clear()
+            self._graph_ver = ver
         g = self._graphs.get((sample, draw_mask))
         if g is None:
             # warm-up on a side stream (lazy module loading, cudaFuncSetAttribute) with state restored afterwards

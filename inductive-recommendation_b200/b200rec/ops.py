@@ -109,6 +109,25 @@ def dropout_bits(nnz, p, seed, step, out=None):
     return out
 
 
+def infonce_workspace(n, d, device):
+    return torch.empty(int(_lib().b200rec_infonce_workspace_floats(n, d)), dtype=torch.float32, device=device)
+
+
+def infonce_fwd_bwd(q, k, loss_out, gq, gk, workspace, temperature=0.1, loss_scale=1.0, rows=None, row_stride=1, n=None):
+    """InfoNCE (unpaired, negatives == positive keys) forward + backward; see include/b200rec.h.  Dense form: q, k [n,d],
+    gq / gk overwritten.  Table form (rows = int64 index tensor, e.g. a [B,3] batch with row_stride 3): gradients are added
+    into the tables gq / gk at the sampled rows."""
+    _abi.require_cuda(q, k, loss_out, gq, gk, workspace, rows)
+    d = q.shape[1]
+    if rows is None:
+        n = q.shape[0]
+        assert k.shape == q.shape == gq.shape == gk.shape
+    assert q.dtype == k.dtype == gq.dtype == gk.dtype == torch.float32
+    assert workspace.numel() >= int(_lib().b200rec_infonce_workspace_floats(n, d))
+    check(_lib().b200rec_infonce_fwd_bwd(ptr(q), ptr(k), ptr(rows), row_stride, n, d, temperature, loss_scale, ptr(loss_out),
+                                         ptr(gq), ptr(gk), ptr(workspace), stream_ptr()), "infonce_fwd_bwd")
+
+
 def score_dense(rep_users, users, rep_items):
     _abi.require_cuda(rep_users, users, rep_items)
     out = torch.empty((users.numel(), rep_items.shape[0]), dtype=torch.float32, device=rep_users.device)
@@ -238,3 +257,25 @@ class _GatherRows(torch.autograd.Function):
 def gather_rows(table, idx, offset=0):
     """table[idx + offset, :] with a scatter-add backward (the index_put_(accumulate) of autograd)"""
     return _GatherRows.apply(table, idx, offset)
+
+
+class _InfoNCE(torch.autograd.Function):
+    """loss = InfoNCE(q, k) of the reference's cal_loss (model.py:206-214); gradients are produced by the same call."""
+
+    @staticmethod
+    def forward(ctx, q, k, temperature):
+        q, k = q.contiguous(), k.contiguous()
+        loss = torch.zeros(1, dtype=torch.float32, device=q.device)
+        gq, gk = torch.empty_like(q), torch.empty_like(k)
+        infonce_fwd_bwd(q, k, loss, gq, gk, infonce_workspace(q.shape[0], q.shape[1], q.device), temperature)
+        ctx.save_for_backward(gq, gk)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        gq, gk = ctx.saved_tensors
+        return gq * g, gk * g, None
+
+
+def infonce(q, k, temperature=0.1):
+    return _InfoNCE.apply(q, k, temperature)

@@ -1,11 +1,12 @@
-"""Drop-in for the reference's model.py, hot-path classes only: MF, LightGCN, IGCN, IMF.
+"""Drop-in for the reference's model.py, hot-path classes only: MF, LightGCN, IGCN, IMF, SGL, HALF.
 
 Surface kept from /root/reference/model.py: get_model (:20-25), BasicModel (:35-53), MF (:56-76), LightGCN (:79-127),
 IGCN (:4107-4220), IMF (:4290-4297) -- same constructor config keys, attributes (embedding, w, user_map, item_map,
 norm_adj, feat_mat, alpha, row_sum), methods (get_rep, bpr_forward, predict, generate_graph, generate_feat,
 update_feat_mat, feat_mat_anneal, save, load) and state_dict keys.  The arithmetic the reference hands to DGL / ATen
 (gspmm, index gather/put, mm) runs in libb200rec's sm_100a kernels through b200rec.ops; there is no CPU path, models
-must live on a CUDA device.  Out of scope: NGCF proper, SGL/HALF, DOSE_*, ItemKNN, Popularity,
+must live on a CUDA device.  SGL / HALF (:130-365) are built on the same operators.  Out of scope
+(SURVEY.md section 2.1): NGCF proper, DOSE_*, ItemKNN, Popularity,
 MultiVAE, NeuMF, IMCGAE, IDCF.
 
 Additions: `recommend()` (fused score + mask + top-K, used by trainer.eval instead of predict + topk), an eval-mode
@@ -162,6 +163,89 @@ class LightGCN(BasicModel):
         with torch.no_grad():
             rep, items = self.score_tables()
             return ops.score_dense(rep, users.contiguous(), items)
+
+
+class SGL(LightGCN):
+    """LightGCN + self-supervised contrast between two edge-dropped views (reference model.py:130-243).
+
+    `norm_aug_adj1/2` are D^-1/2 A' D^-1/2 of a uniform sample of int(E * aug_rate) train edges each (utils.py:91-103),
+    redrawn by update_aug_adj() at every epoch end.  bpr_forward returns the reference's 5-tuple; the contrastive term is
+    InfoNCE (temperature 0.1 -- the reference never passes its `taugh` key on) between the views' rows of the batch users.
+    The reference samples the kept edges with Python's `random.sample`; here the subset comes from a seeded device
+    permutation (same distribution, different stream), or from `keep_index` when a caller supplies the subset."""
+    n_views = 2
+
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.alpha = 1.
+        self.delta = model_config.get('delta', 0.99)
+        self.taugh = model_config.get('taugh', 0.2)
+        self.aug_rate = model_config.get('aug_rate', 0.8)
+        self.temperature = 0.1  # InfoNCE() default; see class docstring
+        self.times = model_config.get('times', 0)
+        self._aug_gen = torch.Generator(device=self.device)
+        self._aug_gen.manual_seed(int(model_config.get('aug_seed', 2021)))
+        self.aug_version = 0
+        dataset = model_config['dataset']
+        self.norm_aug_adj1 = self.generate_drop_graph(dataset)
+        self.norm_aug_adj2 = self.generate_drop_graph(dataset) if self.n_views == 2 else None
+
+    def _train_pairs_dev(self, dataset):
+        if getattr(self, '_pairs_src', None) is not dataset:
+            users, items = dataset.train_pairs()
+            self._pairs = (torch.from_numpy(np.ascontiguousarray(users)).to(self.device),
+                           torch.from_numpy(np.ascontiguousarray(items)).to(self.device))
+            self._pairs_src = dataset
+        return self._pairs
+
+    def generate_drop_graph(self, dataset, keep_index=None):
+        """normalised adjacency of an edge subset: exactly int(E * aug_rate) distinct train pairs (utils.py:93-94), degrees
+        recomputed on the subset (model.py:166-176)"""
+        users, items = self._train_pairs_dev(dataset)
+        n_edges = users.numel()
+        if keep_index is None:
+            n_keep = int(n_edges * self.aug_rate)
+            keep_index = torch.randperm(n_edges, generator=self._aug_gen, device=self.device)[:n_keep]
+            keep_index = torch.sort(keep_index).values
+        else:
+            keep_index = torch.as_tensor(keep_index, dtype=torch.int64, device=self.device)
+        return b2graph.build_norm_adj(dataset.n_users, dataset.n_items, users[keep_index], items[keep_index],
+                                      device=self.device, d=self.embedding_size)
+
+    def get_aug_rep(self, norm_aug_adj):
+        return ops.propagate(norm_aug_adj, self.layer0(), self.n_layers)
+
+    def cal_loss(self, users_r, aug_users_r):
+        return ops.infonce(users_r, aug_users_r, self.temperature)
+
+    def _views(self, rep, users):
+        a1 = ops.gather_rows(self.get_aug_rep(self.norm_aug_adj1), users)
+        a2 = ops.gather_rows(self.get_aug_rep(self.norm_aug_adj2), users)
+        return a1, a2
+
+    def bpr_forward(self, users, pos_items, neg_items):
+        rep = self.get_rep()
+        users_r = ops.gather_rows(rep, users)
+        pos_items_r = ops.gather_rows(rep, pos_items, self.n_users)
+        neg_items_r = ops.gather_rows(rep, neg_items, self.n_users)
+        l2_norm_sq = (users_r * users_r).sum(1) + (pos_items_r * pos_items_r).sum(1) + (neg_items_r * neg_items_r).sum(1)
+        q, k = self._views(users_r, users)
+        return users_r, pos_items_r, neg_items_r, l2_norm_sq, self.cal_loss(q, k)
+
+    def update_aug_adj(self):
+        dataset = self.config['dataset']
+        self.norm_aug_adj1 = self.generate_drop_graph(dataset)
+        if self.n_views == 2:
+            self.norm_aug_adj2 = self.generate_drop_graph(dataset)
+        self.aug_version += 1
+
+
+class HALF(SGL):
+    """One augmented view contrasted with the full graph's representation (reference model.py:246-365)."""
+    n_views = 1
+
+    def _views(self, users_r, users):
+        return users_r, ops.gather_rows(self.get_aug_rep(self.norm_aug_adj1), users)
 
 
 class IGCN(BasicModel):

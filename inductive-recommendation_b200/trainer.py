@@ -1,4 +1,5 @@
-"""Drop-in for the reference's trainer.py, hot-path classes only: BasicTrainer, BPRTrainer, IGCNTrainer.
+"""Drop-in for the reference's trainer.py, hot-path classes only: BasicTrainer, BPRTrainer, IGCNTrainer, SGLTrainer,
+HALFTrainer.
 
 Surface kept from /root/reference/trainer.py: get_trainer (:16-22); BasicTrainer (:25-253) with train, eval,
 calculate_metrics, inductive_eval, initialize_optimizer, record and the attributes topks / epoch / best_ndcg /
@@ -6,7 +7,8 @@ save_path / opt / dataloader / test_user_loader; BPRTrainer (:403-429); IGCNTrai
 reference's (config.py); optional extras: 'fused' (default True: CUDA-graphed libb200rec step with on-device
 sampling), 'sampler' ('device' | 'host': draw triples on device, or iterate the DataLoader like the reference),
 'seed', 'eval_precision' (0 exact fp32, 1 tcgen05 bf16 candidates + exact re-score).
-Out of scope: DOSE*/SGL/HALF/IDCF/BCE/ML trainers.
+SGLTrainer (:432-459) and HALFTrainer (:460-486) ride on the same engine.
+Out of scope: DOSE*/IDCF/BCE/ML trainers.
 
 What changes underneath: one training step is a replayed CUDA graph (b200rec.engine.BprEngine); evaluation computes
 the representation once, then runs the fused score + mask + top-K kernel over large user chunks and a hit-matrix
@@ -267,7 +269,8 @@ class BPRTrainer(BasicTrainer):
         if self.engine is None:
             self.engine = BprEngine(self.model, self.dataset, self.opt, self.batch_size, self.l2_reg,
                                     aux_reg=self.aux_reg, aux_dataset=self._aux_dataset(), seed=self.seed,
-                                    partition=self.config.get('partition'))
+                                    partition=self.config.get('partition'),
+                                    contrastive_reg=getattr(self, 'contrastive_reg', 0.0))
         return self.engine
 
     def steps_per_epoch(self):
@@ -368,3 +371,29 @@ class IGCNTrainer(BPRTrainer):
             loss = eng.meter_avg()
         self.model.feat_mat_anneal()
         return loss
+
+
+class SGLTrainer(BPRTrainer):
+    """BPR + contrastive_reg * InfoNCE between two edge-dropped views; the views are redrawn after every epoch
+    (reference trainer.py:432-459)."""
+
+    def __init__(self, trainer_config):
+        super().__init__(trainer_config)
+        self.contrastive_reg = trainer_config['contrastive_reg']
+
+    def _loss(self, inputs, aux_inputs):
+        users, pos_items, neg_items = inputs[:, 0].contiguous(), inputs[:, 1].contiguous(), inputs[:, 2].contiguous()
+        users_r, pos_items_r, neg_items_r, l2_norm_sq, contrastive_loss = self.model.bpr_forward(users, pos_items, neg_items)
+        pos_scores = torch.sum(users_r * pos_items_r, dim=1)
+        neg_scores = torch.sum(users_r * neg_items_r, dim=1)
+        return (F.softplus(neg_scores - pos_scores).mean() + self.l2_reg * l2_norm_sq.mean()
+                + self.contrastive_reg * contrastive_loss.mean())
+
+    def train_one_epoch(self):
+        loss = super().train_one_epoch()
+        self.model.update_aug_adj()
+        return loss
+
+
+class HALFTrainer(SGLTrainer):
+    """one augmented view against the full graph (reference trainer.py:460-486)"""

@@ -240,9 +240,77 @@ def run_inductive_case(tag, full_graph, out_dir, seed=2021):
         print("   ", l)
 
 
+def run_contrastive_case(tag, graph, model_name, out_dir, seed=2021, batch=256):
+    """SGL (model.py:130-243, SGLTrainer trainer.py:432-459) / HALF (model.py:246-365, HALFTrainer :460-486): LightGCN
+    propagation on the full graph and on edge-dropped views + InfoNCE between the views' user rows."""
+    tmp = tempfile.mkdtemp()
+    synth.write_processed(graph, tmp)
+    ds = quiet(ref_dataset.get_dataset, {"name": "ProcessedDataset", "path": tmp, "device": CPU})
+    ref_utils.set_seed(seed)
+    mcfg = {"name": model_name, "embedding_size": 64, "n_layers": 3, "aug_rate": 0.8}
+    tcfg = {"name": model_name + "Trainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 1e-4, "contrastive_reg": 0.1}
+    model = quiet(ref_model.get_model, dict(mcfg, device=CPU), ds)
+    tr = quiet(ref_trainer.get_trainer,
+               dict(tcfg, device=CPU, dataloader_num_workers=0, topks=TOPKS, n_epochs=1, batch_size=batch,
+                    test_batch_size=128), ds, model)
+    out = {"n_users": ds.n_users, "n_items": ds.n_items, "train_indptr": graph.train_indptr.numpy(),
+           "train_items": graph.train_items.numpy(), "val_indptr": graph.val_indptr.numpy(),
+           "val_items": graph.val_items.numpy(), "test_indptr": graph.test_indptr.numpy(),
+           "test_items": graph.test_items.numpy()}
+    out["adj_idx"], out["adj_val"] = coo_of(model.norm_adj)
+    out["aug1_idx"], out["aug1_val"] = coo_of(model.norm_aug_adj1)
+    if model_name == "SGL":
+        out["aug2_idx"], out["aug2_val"] = coo_of(model.norm_aug_adj2)
+    out["emb0"] = model.embedding.weight.detach().numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        out["rep_eval"] = model.get_rep().numpy().copy()
+        out["aug1_rep"] = model.get_aug_rep(model.norm_aug_adj1).numpy().copy()
+    model.train()
+    ref_utils.set_seed(seed + 1)
+    rows = [ds[0] for _ in range(batch)]
+    b = torch.tensor(np.stack(rows)[:, 0, :], dtype=torch.int64)
+    out["batch"] = b.numpy().copy()
+    users, pos, neg = b[:, 0], b[:, 1], b[:, 2]
+    F = torch.nn.functional
+    # trainer.py:441-456 restated on the recorded batch (the reference draws its batches inside the DataLoader loop)
+    ur, pr, nr, l2, con = model.bpr_forward(users, pos, neg)
+    bpr = F.softplus((ur * nr).sum(1) - (ur * pr).sum(1)).mean()
+    loss = bpr + tcfg["l2_reg"] * l2.mean() + tcfg["contrastive_reg"] * con.mean()
+    out["users_r"], out["l2_norm_sq"] = ur.detach().numpy().copy(), l2.detach().numpy().copy()
+    out["bpr_loss"], out["contrastive_loss"], out["loss"] = float(bpr), float(con), float(loss)
+    tr.opt.zero_grad()
+    loss.backward()
+    out["grad_emb"] = model.embedding.weight.grad.numpy().copy()
+    tr.opt.step()
+    out["emb1"] = model.embedding.weight.detach().numpy().copy()
+    # a second step on the same batch pins the optimizer state hand-over
+    ur, pr, nr, l2, con = model.bpr_forward(users, pos, neg)
+    loss2 = (F.softplus((ur * nr).sum(1) - (ur * pr).sum(1)).mean() + tcfg["l2_reg"] * l2.mean()
+             + tcfg["contrastive_reg"] * con.mean())
+    tr.opt.zero_grad()
+    loss2.backward()
+    tr.opt.step()
+    out["loss2"] = float(loss2)
+    out["emb2"] = model.embedding.weight.detach().numpy().copy()
+    # epoch end: both views are redrawn (model.py:231-237); only the size contract is recorded
+    quiet(model.update_aug_adj)
+    out["aug1_nnz_after_update"] = int(model.norm_aug_adj1._nnz())
+    out["lr"], out["l2_reg"], out["contrastive_reg"] = tcfg["lr"], tcfg["l2_reg"], tcfg["contrastive_reg"]
+    out["aug_rate"], out["n_layers"], out["temperature"] = mcfg["aug_rate"], mcfg["n_layers"], 0.1
+    path = os.path.join(out_dir, tag + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def main():
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--only-contrastive" in sys.argv:
+        g = synth.generate(300, 500, 6000, seed=7)
+        run_contrastive_case("sgl_tiny", g, "SGL", out_dir)
+        run_contrastive_case("half_tiny", g, "HALF", out_dir)
+        return
     if "--only-inductive" in sys.argv:
         run_inductive_case("igcn_inductive", synth.generate(400, 600, 9000, seed=21), out_dir)
         return
@@ -261,6 +329,8 @@ def main():
     g2 = synth.generate(400, 300, 9000, seed=11, a_item=1.1)
     run_case("lightgcn_d128", g2, {"name": "LightGCN", "embedding_size": 128, "n_layers": 4}, bpr, out_dir)
     run_inductive_case("igcn_inductive", synth.generate(400, 600, 9000, seed=21), out_dir)
+    run_contrastive_case("sgl_tiny", g, "SGL", out_dir)
+    run_contrastive_case("half_tiny", g, "HALF", out_dir)
 
 
 if __name__ == "__main__":

@@ -59,6 +59,8 @@ MODEL_CFG = {
     "igcn_tiny": {"name": "IGCN", "embedding_size": 64, "n_layers": 3, "dropout": 0.3, "feature_ratio": 1.0},
     "igcn_fr_tiny": {"name": "IGCN", "embedding_size": 64, "n_layers": 2, "dropout": 0.3, "feature_ratio": 0.5},
     "imf_tiny": {"name": "IMF", "embedding_size": 64, "n_layers": 0, "dropout": 0.3, "feature_ratio": 1.0},
+    "sgl_tiny": {"name": "SGL", "embedding_size": 64, "n_layers": 3, "aug_rate": 0.8},
+    "half_tiny": {"name": "HALF", "embedding_size": 64, "n_layers": 3, "aug_rate": 0.8},
 }
 
 

@@ -132,3 +132,45 @@ def test_eval_topk_and_metrics(golden, name):
     for mname in ("Precision", "Recall", "NDCG"):
         ours = np.array([metrics[mname][k] for k in TOPKS])
         np.testing.assert_allclose(ours, g["metric_%s_test_banned" % mname], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["sgl_tiny", "half_tiny"])
+def test_contrastive_fixture_against_closed_form(golden, name):
+    """SGL / HALF (model.py:130-365): the fixtures were produced through oracle/stubs/info_nce.py (the `info_nce` package
+    is absent here).  Re-derive the recorded numbers WITHOUT that stub, in float64 numpy: views = mean_k A'^k E on the
+    recorded edge subsets, loss_i = -s_ii/T + log(exp(s_ii/T) + sum_j exp(s_ij/T)) on L2-normalised rows."""
+    import scipy.sparse as sp
+    g = golden(name)
+    n = int(g["n_users"]) + int(g["n_items"])
+    L = int(g["n_layers"])
+
+    def rep_of(key):
+        a = sp.coo_matrix((g[key + "_val"].astype(np.float64), (g[key + "_idx"][0], g[key + "_idx"][1])), shape=(n, n)).tocsr()
+        x = g["emb0"].astype(np.float64)
+        acc = x.copy()
+        for _ in range(L):
+            x = a @ x
+            acc += x
+        return acc / (L + 1)
+
+    users = g["batch"][:, 0]
+    rep = rep_of("adj")
+    np.testing.assert_allclose(rep, g["rep_eval"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(rep_of("aug1"), g["aug1_rep"], rtol=2e-5, atol=1e-7)
+    if name == "sgl_tiny":
+        q, k = rep_of("aug1")[users], rep_of("aug2")[users]
+    else:
+        q, k = rep[users], rep_of("aug1")[users]
+    qn = q / np.maximum(np.linalg.norm(q, axis=1, keepdims=True), 1e-12)
+    kn = k / np.maximum(np.linalg.norm(k, axis=1, keepdims=True), 1e-12)
+    s = qn @ kn.T / float(g["temperature"])
+    pos = np.diag(s)
+    loss = np.mean(-pos + np.log(np.exp(pos) + np.exp(s).sum(1)))
+    assert abs(loss - float(g["contrastive_loss"])) < 2e-5
+    # the view keeps exactly int(E * aug_rate) train pairs, both directions (utils.py:91-103)
+    n_edges = int(g["train_indptr"][-1])
+    assert g["aug1_idx"].shape[1] == 2 * int(n_edges * float(g["aug_rate"])) == int(g["aug1_nnz_after_update"])
+    # total loss recorded by the trainer arithmetic (trainer.py:447-452)
+    ur = g["users_r"].astype(np.float64)
+    total = float(g["bpr_loss"]) + float(g["l2_reg"]) * float(np.mean(g["l2_norm_sq"])) + float(g["contrastive_reg"]) * loss
+    assert abs(total - float(g["loss"])) < 1e-5 and ur.shape == (len(users), 64)
