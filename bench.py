@@ -158,7 +158,9 @@ def run_own(args, rank, world):
     partition = None
     model_cfg = {"lightgcn": {"name": "LightGCN", "embedding_size": d, "n_layers": n_layers},
                  "igcn": {"name": "IGCN", "embedding_size": d, "n_layers": n_layers, "dropout": 0.3, "feature_ratio": 1.0},
-                 "mf": {"name": "MF", "embedding_size": d}}[args.model]
+                 "mf": {"name": "MF", "embedding_size": d},
+                 "sgl": {"name": "SGL", "embedding_size": d, "n_layers": n_layers, "aug_rate": 0.8},
+                 "half": {"name": "HALF", "embedding_size": d, "n_layers": n_layers, "aug_rate": 0.8}}[args.model]
     m = M.get_model(dict(model_cfg, device=dev), ds)
     if world > 1:
         from b200rec.dist import DimShard, PeerRowPartition, RowPartition, shard_model_dims
@@ -169,7 +171,8 @@ def run_own(args, rank, world):
         else:
             shard_model_dims(m, DimShard(rank, world))
             d = m.embedding_size
-    tr = T.get_trainer({"name": "IGCNTrainer" if args.model == "igcn" else "BPRTrainer", "optimizer": "Adam", "lr": LR,
+    trainer_name = {"igcn": "IGCNTrainer", "sgl": "SGLTrainer", "half": "HALFTrainer"}.get(args.model, "BPRTrainer")
+    tr = T.get_trainer({"name": trainer_name, "contrastive_reg": 0.1, "optimizer": "Adam", "lr": LR,
                         "l2_reg": 0.0 if args.model == "igcn" else L2_REG, "aux_reg": 0.01, "device": dev,
                         "n_epochs": 1, "batch_size": BATCH, "dataloader_num_workers": 0, "test_batch_size": 512,
                         "topks": TOPKS, "partition": partition}, ds, m)
@@ -342,7 +345,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="lightgcn", choices=["lightgcn", "igcn", "mf"],
+    ap.add_argument("--model", default="lightgcn", choices=["lightgcn", "igcn", "mf", "sgl", "half"],
                     help="lightgcn is the headline; igcn = inductive template-feature layer + propagation (config.py:18-23)")
     ap.add_argument("--parallelism", default="dim", choices=["dim", "row", "peer"],
                     help="multi-GPU decomposition: embedding-dimension sharding (default), the row partition with NCCL "
