@@ -2,7 +2,7 @@
 // the `info_nce` package's 'unpaired' form with negative_keys == positive_key, temperature 0.1):
 //   qn = q / max(|q|, 1e-12), kn likewise;  logits_i = [qn_i.kn_i, qn_i.kn_0, ..., qn_i.kn_{n-1}] / T;  loss = mean_i CE(logits_i, 0)
 // The n x n logit matrix (2048 x 2048 per step) is never stored: a statistics pass keeps a running (max, sum) per row,
-// two gradient passes recompute the tiles and contract them with the other view on the fly (flash-attention style),
+// a gradient pass (both views in one launch) recomputes the tiles and contracts them with the other view on the fly,
 // then apply the normalisation's Jacobian row-locally.  All sums run in a fixed order (reproducible run to run; only the
 // scatter-add of rows that occur twice in `rows` depends on arrival order, like every other gradient scatter here).
 #include "common.cuh"
@@ -10,7 +10,6 @@
 namespace b200rec {
 
 constexpr int NCE_TM = 32;  // rows of the block's own view per CTA
-constexpr int NCE_TN = 32;  // rows of the other view per tile
 constexpr float NCE_EPS = 1e-12f;
 
 // one warp per sample: gather (optional), normalise both views, positive logit
@@ -59,94 +58,163 @@ __global__ void __launch_bounds__(256) infonce_prep_kernel(const float* q, const
   }
 }
 
-// MODE 0: per-row log-sum-exp over [pos_i, S_i0 .. S_i,n-1] and the row's loss term.
-// MODE 1: gradient w.r.t. the query view  (own = qn, other = kn, softmax rows indexed by the OWN row).
-// MODE 2: gradient w.r.t. the key view    (own = kn, other = qn, softmax rows indexed by the OTHER row).
+// One CTA (128 threads) = 32 rows of its OWN view against tiles of 64 rows of the OTHER view.  Both contractions are
+// register-tiled 4 x 4 per thread with 128-bit shared-memory loads (shared memory feeds 32 floats per clock per SM
+// against 128 FMAs, so every loaded value has to be used at least four times):
+//   logits  S[i][j]  = sum_c own[i][c] * other[j][c]        thread (ti, tj): rows ti+8r, columns tj+16q
+//   output  O[i][d] += sum_j P[i][j] * other[j][d]          thread (ti, td): rows ti+8r, columns td*CW .. td*CW+CW-1
+// The other view's rows are split into column parts over more CTAs (grid.y / grid.z): 64 row blocks alone would leave
+// most of the 148 SMs with one 4-warp CTA or none.
+//  MODE 0 (grid.y = column parts): running (max, sum) of exp(logit) per row over this part's columns.
+//  MODE 1 (grid.y = 0: gradient of the query view, own = qn, softmax offset = lse[own row];
+//          grid.y = 1: gradient of the key view,   own = kn, softmax offset = lse[other row]; grid.z = column parts):
+//          P tile -> shared memory -> this part's share of O -> workspace; infonce_finish_kernel completes the row.
+constexpr int NCE_TN2 = 64;
+constexpr int NCE_THREADS = 128;
+
+template <int D>
+struct NceSmem {
+  static constexpr int XS = D + 4;              // row stride of both operand tiles: 16-byte aligned, rows 4 banks apart
+  static constexpr int PS = NCE_TN2 + 4;
+  static constexpr int A_FLOATS = NCE_TM * XS;
+  static constexpr int B_FLOATS = NCE_TN2 * XS;
+  static constexpr int P_FLOATS = NCE_TM * PS;
+  static constexpr size_t BYTES = (size_t)(A_FLOATS + B_FLOATS + P_FLOATS + NCE_TN2) * sizeof(float);
+};
+
 template <int D, int MODE>
-__global__ void __launch_bounds__(256) infonce_pass_kernel(const float* own, const float* other, const float* own_den,
-                                                           const float* pos, float* lse, float* loss_part, int n, float inv_t,
-                                                           float coef, const int64_t* rows, int row_stride, float* g_out) {
+__global__ void __launch_bounds__(NCE_THREADS) infonce_pass_kernel(const float* qn, const float* kn, const float* qden,
+                                                                   const float* kden, const float* pos, const float* lse,
+                                                                   float* part_m, float* part_l, int n, float inv_t,
+                                                                   float* opart) {
+  using L = NceSmem<D>;
   extern __shared__ __align__(16) float smem[];
-  constexpr int AS = D;          // own tile: broadcast reads
-  constexpr int BS = D + 1;      // other tile: lane <-> row, padded against bank conflicts
-  float* As = smem;                       // [TM][AS]
-  float* Bs = As + NCE_TM * AS;           // [TN][BS]
-  float* Ps = Bs + NCE_TN * BS;           // [TM][TN+1]
-  float* s_lse = Ps + NCE_TM * (NCE_TN + 1);  // [TN] softmax offsets of the other rows (MODE 2)
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  float* As = smem;                    // [TM][XS]
+  float* Bs = As + L::A_FLOATS;        // [TN][XS]
+  float* Ps = Bs + L::B_FLOATS;        // [TM][PS]
+  float* s_off = Ps + L::P_FLOATS;     // [TN]
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
   const int row0 = blockIdx.x * NCE_TM;
+  const bool key_side = (MODE == 1) && blockIdx.y == 1;
+  const int part = (MODE == 0) ? blockIdx.y : blockIdx.z, n_part = (MODE == 0) ? gridDim.y : gridDim.z;
+  const float* own = key_side ? kn : qn;
+  const float* other = key_side ? qn : kn;
   pdl_trigger();
   pdl_wait();
-  for (int e = tid; e < NCE_TM * D; e += 256) {
+  for (int e = tid * 4; e < NCE_TM * D; e += NCE_THREADS * 4) {
     const int i = e / D, c = e - i * D;
-    As[i * AS + c] = (row0 + i < n) ? own[(size_t)(row0 + i) * D + c] : 0.f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + i < n) v = *reinterpret_cast<const float4*>(own + (size_t)row0 * D + e);
+    *reinterpret_cast<float4*>(As + i * L::XS + c) = v;
   }
-  // MODE 0: running (max, sum) of the 4 rows this thread shares with its warp, seeded with the positive logit
-  float m_run[4], l_run[4], own_lse[4];
+  // the other view's rows are split over n_part CTAs on tile boundaries (a 2048-sample batch has only 64 row blocks)
+  const int tiles = (n + NCE_TN2 - 1) / NCE_TN2, per = (tiles + n_part - 1) / n_part;
+  const int j_begin = min(n, part * per * NCE_TN2), j_end = min(n, (part + 1) * per * NCE_TN2);
+  float m_run[4], l_run[4], own_off[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const int i = row0 + ty * 4 + r;
-    m_run[r] = (MODE == 0 && i < n) ? pos[i] : 0.f;
-    l_run[r] = 1.f;
-    own_lse[r] = (MODE == 1 && i < n) ? lse[i] : 0.f;
+    m_run[r] = -INFINITY;
+    l_run[r] = 0.f;
+    const int i = row0 + ti + 8 * r;
+    own_off[r] = (MODE == 1 && !key_side && i < n) ? lse[i] : 0.f;
   }
-  // MODE 1/2: output accumulators, thread = (row tid/8, columns (tid%8) + 8*c)
-  constexpr int CPT = (D + 7) / 8;
-  const int orow = tid >> 3, oc0 = tid & 7;
-  float acc[CPT];
+  constexpr int CW = (D >= 16) ? D / 16 : 1;  // output columns per thread (16 threads per row; D = 8: half of them idle)
+  const int oc0 = tj * CW;
+  const bool oc_live = oc0 < D;
+  float acc[4][CW];
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < CW; ++c) acc[r][c] = 0.f;
   __syncthreads();
 
-  for (int j0 = 0; j0 < n; j0 += NCE_TN) {
-    for (int e = tid; e < NCE_TN * D; e += 256) {
+  for (int j0 = j_begin; j0 < j_end; j0 += NCE_TN2) {
+    for (int e = tid * 4; e < NCE_TN2 * D; e += NCE_THREADS * 4) {
       const int j = e / D, c = e - j * D;
-      Bs[j * BS + c] = (j0 + j < n) ? other[(size_t)(j0 + j) * D + c] : 0.f;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + j < n) v = *reinterpret_cast<const float4*>(other + (size_t)j0 * D + e);
+      *reinterpret_cast<float4*>(Bs + j * L::XS + c) = v;
     }
-    if (MODE == 2 && tid < NCE_TN) s_lse[tid] = (j0 + tid < n) ? lse[j0 + tid] : 0.f;
+    if (key_side && tid < NCE_TN2) s_off[tid] = (j0 + tid < n) ? lse[j0 + tid] : 0.f;
     __syncthreads();
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* brow = Bs + tx * BS;
+    float s[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[r][q] = 0.f;
 #pragma unroll 2
     for (int c = 0; c < D; c += 4) {
-      const float b0 = brow[c], b1 = brow[c + 1], b2 = brow[c + 2], b3 = brow[c + 3];
+      float4 a[4], b[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float4 a = *reinterpret_cast<const float4*>(As + (ty * 4 + r) * AS + c);  // broadcast LDS.128
-        s[r] = fmaf(a.x, b0, s[r]);
-        s[r] = fmaf(a.y, b1, s[r]);
-        s[r] = fmaf(a.z, b2, s[r]);
-        s[r] = fmaf(a.w, b3, s[r]);
-      }
+      for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(As + (ti + 8 * r) * L::XS + c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(Bs + (tj + 16 * q) * L::XS + c);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          s[r][q] = fmaf(a[r].x, b[q].x, s[r][q]);
+          s[r][q] = fmaf(a[r].y, b[q].y, s[r][q]);
+          s[r][q] = fmaf(a[r].z, b[q].z, s[r][q]);
+          s[r][q] = fmaf(a[r].w, b[q].w, s[r][q]);
+        }
     }
-    const bool jv = j0 + tx < n;
     if (MODE == 0) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const float z = jv ? s[r] * inv_t : -INFINITY;
-        float tm = z;
+        float tm = -INFINITY;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
-        const float m_new = fmaxf(m_run[r], tm);
-        float ex = jv ? expf(z - m_new) : 0.f;
-        ex = warp_sum(ex);
-        l_run[r] = l_run[r] * expf(m_run[r] - m_new) + ex;
-        m_run[r] = m_new;
+        for (int q = 0; q < 4; ++q)
+          if (j0 + tj + 16 * q < j_end) tm = fmaxf(tm, s[r][q] * inv_t);
+        if (tm > -INFINITY) {
+          const float m_new = fmaxf(m_run[r], tm);
+          float ex = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (j0 + tj + 16 * q < j_end) ex += expf(s[r][q] * inv_t - m_new);
+          l_run[r] = l_run[r] * expf(m_run[r] - m_new) + ex;  // exp(-inf) = 0 on the first tile
+          m_run[r] = m_new;
+        }
       }
     } else {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float off = (MODE == 1) ? own_lse[r] : s_lse[tx];
-        Ps[(ty * 4 + r) * (NCE_TN + 1) + tx] = jv ? expf(s[r] * inv_t - off) : 0.f;
-      }
-      __syncthreads();
-#pragma unroll 4
-      for (int j = 0; j < NCE_TN; ++j) {
-        const float pv = Ps[orow * (NCE_TN + 1) + j];
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          const int col = oc0 + 8 * c;
-          if (col < D) acc[c] = fmaf(pv, Bs[j * BS + col], acc[c]);
+        for (int q = 0; q < 4; ++q) {
+          const int j = tj + 16 * q;
+          const float off = key_side ? s_off[j] : own_off[r];
+          Ps[(ti + 8 * r) * L::PS + j] = (j0 + j < n) ? expf(s[r][q] * inv_t - off) : 0.f;
+        }
+      __syncthreads();
+      if (oc_live) {
+#pragma unroll 2
+        for (int j = 0; j < NCE_TN2; j += 4) {
+          float4 pv[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) pv[r] = *reinterpret_cast<const float4*>(Ps + (ti + 8 * r) * L::PS + j);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float bv[CW];
+            const float* bp = Bs + (j + jj) * L::XS + oc0;
+            if (CW % 4 == 0) {
+#pragma unroll
+              for (int c = 0; c < CW; c += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(bp + c);
+                bv[c] = t.x; bv[c + 1] = t.y; bv[c + 2] = t.z; bv[c + 3] = t.w;
+              }
+            } else if (CW == 2) {
+              const float2 t = *reinterpret_cast<const float2*>(bp);
+              bv[0] = t.x; bv[CW - 1] = t.y;
+            } else {
+              bv[0] = bp[0];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const float p = jj == 0 ? pv[r].x : jj == 1 ? pv[r].y : jj == 2 ? pv[r].z : pv[r].w;
+#pragma unroll
+              for (int c = 0; c < CW; ++c) acc[r][c] = fmaf(p, bv[c], acc[r][c]);
+            }
+          }
         }
       }
     }
@@ -154,69 +222,118 @@ __global__ void __launch_bounds__(256) infonce_pass_kernel(const float* own, con
   }
 
   if (MODE == 0) {
-    // thread tx == 0 of each warp holds the finished rows; block-ordered loss partial
-    float* s_loss = Ps;
-    if (tx == 0) {
+    // merge the (max, sum) pairs of the 16 threads that share a row: xor butterfly, the same order every run
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int i = row0 + ty * 4 + r;
-        float li = 0.f;
-        if (i < n) {
-          const float v = m_run[r] + logf(l_run[r]);
-          lse[i] = v;
-          li = v - pos[i];
-        }
-        s_loss[ty * 4 + r] = li;
+    for (int r = 0; r < 4; ++r) {
+      float m = m_run[r], l = l_run[r];
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
+        const float m_new = fmaxf(m, mo);
+        if (m_new > -INFINITY) l = l * expf(m - m_new) + lo * expf(mo - m_new);
+        m = m_new;
       }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      float t = 0.f;
-      for (int i = 0; i < NCE_TM; ++i) t += s_loss[i];
-      loss_part[blockIdx.x] = t;
+      const int i = row0 + ti + 8 * r;
+      if (tj == 0 && i < n) {
+        part_m[(size_t)blockIdx.y * n + i] = m;
+        part_l[(size_t)blockIdx.y * n + i] = l;
+      }
     }
     return;
   }
 
-  // positive-pair term, scale, and the Jacobian of x -> x / max(|x|, eps), all local to the row's 8 threads
-  const int i = row0 + orow;
-  const bool iv = i < n;
-  const float ppos = iv ? expf(pos[i] - lse[i]) - 1.f : 0.f;  // d loss_i / d pos_i (the positive sits at label 0)
-  const float den = iv ? own_den[i] : 1.f;
-  float dotp = 0.f;
+  // this part's share of O; infonce_finish_kernel adds the parts in order
+  float* obase = opart + ((size_t)(key_side ? n_part : 0) + part) * n * D;
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int col = oc0 + 8 * c;
-    if (col < D && iv) {
-      acc[c] = (acc[c] + ppos * other[(size_t)i * D + col]) * coef;
-      dotp = fmaf(As[orow * AS + col], acc[c], dotp);
-    }
-  }
-  dotp += __shfl_xor_sync(0xffffffffu, dotp, 1);
-  dotp += __shfl_xor_sync(0xffffffffu, dotp, 2);
-  dotp += __shfl_xor_sync(0xffffffffu, dotp, 4);
-  if (!iv) return;
-  const bool clamped = den <= NCE_EPS;  // F.normalize's clamp: the quotient is then linear in x
-  const int64_t r_out = rows ? rows[(size_t)i * row_stride] : i;
+  for (int r = 0; r < 4; ++r) {
+    const int i = row0 + ti + 8 * r;
+    if (i < n && oc_live) {
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int col = oc0 + 8 * c;
-    if (col < D) {
-      const float gx = clamped ? acc[c] / den : (acc[c] - As[orow * AS + col] * dotp) / den;
-      if (rows) atomicAdd(g_out + (size_t)r_out * D + col, gx);
-      else g_out[(size_t)r_out * D + col] = gx;
+      for (int c = 0; c < CW; ++c) obase[(size_t)i * D + oc0 + c] = acc[r][c];
     }
   }
 }
 
-__global__ void infonce_loss_kernel(const float* loss_part, int n_part, float scale, float* loss_out) {
+// One warp per (view, sample): O = sum of the column parts (fixed order) + the positive-pair term, scaled; then the
+// Jacobian of x -> x / max(|x|, eps) and the store / scatter-add of the gradient row.
+template <int D>
+__global__ void __launch_bounds__(256) infonce_finish_kernel(const float* qn, const float* kn, const float* qden, const float* kden,
+                                                             const float* pos, const float* lse, const float* opart, int n_part,
+                                                             int n, float coef, const int64_t* rows, int row_stride, float* gq,
+                                                             float* gk) {
+  pdl_trigger();
   pdl_wait();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < n_part; ++i) t += loss_part[i];
-    loss_out[0] += t * scale;
+  const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (wid >= 2 * n) return;
+  const bool key_side = wid >= n;
+  const int i = key_side ? wid - n : wid;
+  const float* own = (key_side ? kn : qn) + (size_t)i * D;
+  const float* other = (key_side ? qn : kn) + (size_t)i * D;
+  const float* ob = opart + (size_t)(key_side ? n_part : 0) * n * D + (size_t)i * D;
+  const float ppos = expf(pos[i] - lse[i]) - 1.f;  // d loss_i / d pos_i (the positive sits at label 0)
+  const float den = key_side ? kden[i] : qden[i];
+  constexpr int PER = (D + 31) / 32;
+  float o[PER], x[PER];
+  float dotp = 0.f;
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
+    const int c = lane + 32 * t;
+    o[t] = 0.f;
+    x[t] = 0.f;
+    if (c < D) {
+      for (int h = 0; h < n_part; ++h) o[t] += ob[(size_t)h * n * D + c];
+      o[t] = (o[t] + ppos * other[c]) * coef;
+      x[t] = own[c];
+      dotp = fmaf(x[t], o[t], dotp);
+    }
+  }
+  dotp = warp_sum(dotp);
+  const bool clamped = den <= NCE_EPS;  // F.normalize's clamp: the quotient is then linear in x
+  const int64_t r_out = rows ? rows[(size_t)i * row_stride] : i;
+  float* g_out = (key_side ? gk : gq) + (size_t)r_out * D;
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
+    const int c = lane + 32 * t;
+    if (c < D) {
+      const float gx = clamped ? o[t] / den : (o[t] - x[t] * dotp) / den;
+      if (rows) atomicAdd(g_out + c, gx);
+      else g_out[c] = gx;
+    }
   }
 }
+
+// lse_i over [pos_i, row i's logits] from the column halves' partials; loss_out[0] += scale * sum_i (lse_i - pos_i),
+// summed in a fixed order (thread-strided partials, then a shared-memory tree)
+__global__ void __launch_bounds__(256) infonce_lse_kernel(const float* part_m, const float* part_l, int n_half, const float* pos,
+                                                          int n, float scale, float* lse, float* loss_out) {
+  __shared__ float s_sum[256];
+  pdl_trigger();
+  pdl_wait();
+  float t = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    float m = pos[i], l = 1.f;
+    for (int h = 0; h < n_half; ++h) {
+      const float mh = part_m[(size_t)h * n + i], lh = part_l[(size_t)h * n + i];
+      if (mh > -INFINITY) {
+        const float m_new = fmaxf(m, mh);
+        l = l * expf(m - m_new) + lh * expf(mh - m_new);
+        m = m_new;
+      }
+    }
+    const float v = m + logf(l);
+    lse[i] = v;
+    t += v - pos[i];
+  }
+  s_sum[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] += s_sum[0] * scale;
+}
+
+constexpr int NCE_MAX_PARTS = 8;
 
 template <int D>
 static int infonce_launch(const float* q, const float* k, const int64_t* rows, int row_stride, int n, float temperature,
@@ -227,27 +344,35 @@ static int infonce_launch(const float* q, const float* k, const int64_t* rows, i
   float* kden = qden + n;
   float* pos = kden + n;
   float* lse = pos + n;
-  const int nblk = ceil_div(n, NCE_TM);
-  float* part = lse + n;
+  float* part_m = lse + n;
+  float* part_l = part_m + (size_t)NCE_MAX_PARTS * n;
+  float* opart = part_l + (size_t)NCE_MAX_PARTS * n;  // [2][parts][n][D]
+  const int nblk = ceil_div(n, NCE_TM), tiles = ceil_div(n, NCE_TN2);
+  // enough CTAs for ~3 per SM: the row blocks alone are too few (64 for a 2048-sample batch)
+  const int parts_stat = max(1, min(min(NCE_MAX_PARTS, tiles), ceil_div(444, nblk)));
+  const int parts_grad = max(1, min(min(NCE_MAX_PARTS, tiles), ceil_div(444, 2 * nblk)));
   const float inv_t = 1.f / temperature;
-  const size_t smem = (size_t)(NCE_TM * D + NCE_TN * (D + 1) + NCE_TM * (NCE_TN + 1) + NCE_TN) * sizeof(float);
+  const size_t smem = NceSmem<D>::BYTES;
   static bool attr_done = false;
   if (!attr_done) {
     B2_CUDA(cudaFuncSetAttribute(infonce_pass_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B2_CUDA(cudaFuncSetAttribute(infonce_pass_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2_CUDA(cudaFuncSetAttribute(infonce_pass_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   B2_LAUNCH_PDL(infonce_prep_kernel<D>, ceil_div((long long)n * 32, 256), 256, 0, st, q, k, rows, row_stride, n, inv_t, qn, kn,
                 qden, kden, pos);
-  B2_LAUNCH_PDL(infonce_pass_kernel<D, 0>, nblk, 256, smem, st, (const float*)qn, (const float*)kn, (const float*)qden,
-                (const float*)pos, lse, part, n, inv_t, 0.f, (const int64_t*)nullptr, 0, (float*)nullptr);
-  B2_LAUNCH_PDL(infonce_loss_kernel, 1, 32, 0, st, (const float*)part, nblk, loss_scale / (float)n, loss_out);
+  B2_LAUNCH_PDL((infonce_pass_kernel<D, 0>), dim3(nblk, parts_stat), NCE_THREADS, smem, st, (const float*)qn, (const float*)kn,
+                (const float*)qden, (const float*)kden, (const float*)pos, (const float*)lse, part_m, part_l, n, inv_t,
+                (float*)nullptr);
+  B2_LAUNCH_PDL(infonce_lse_kernel, 1, 256, 0, st, (const float*)part_m, (const float*)part_l, parts_stat, (const float*)pos, n,
+                loss_scale / (float)n, lse, loss_out);
+  B2_LAUNCH_PDL((infonce_pass_kernel<D, 1>), dim3(nblk, 2, parts_grad), NCE_THREADS, smem, st, (const float*)qn,
+                (const float*)kn, (const float*)qden, (const float*)kden, (const float*)pos, (const float*)lse, part_m, part_l, n,
+                inv_t, opart);
   const float coef = loss_scale * inv_t / (float)n;
-  B2_LAUNCH_PDL(infonce_pass_kernel<D, 1>, nblk, 256, smem, st, (const float*)qn, (const float*)kn, (const float*)qden,
-                (const float*)pos, lse, part, n, inv_t, coef, rows, row_stride, gq);
-  B2_LAUNCH_PDL(infonce_pass_kernel<D, 2>, nblk, 256, smem, st, (const float*)kn, (const float*)qn, (const float*)kden,
-                (const float*)pos, lse, part, n, inv_t, coef, rows, row_stride, gk);
+  B2_LAUNCH_PDL(infonce_finish_kernel<D>, ceil_div((long long)2 * n * 32, 256), 256, 0, st, (const float*)qn, (const float*)kn,
+                (const float*)qden, (const float*)kden, (const float*)pos, (const float*)lse, (const float*)opart, parts_grad, n,
+                coef, rows, row_stride, gq, gk);
   return 0;
 }
 
@@ -257,7 +382,7 @@ using namespace b200rec;
 
 extern "C" int64_t b200rec_infonce_workspace_floats(int32_t n, int32_t d) {
   if (n <= 0 || d <= 0) return 0;
-  return 2ll * n * d + 4ll * n + (n + NCE_TM - 1) / NCE_TM + 64;
+  return 2ll * n * d + 4ll * n + 2ll * NCE_MAX_PARTS * n + 2ll * NCE_MAX_PARTS * n * d + 64;
 }
 
 extern "C" int b200rec_infonce_fwd_bwd(const float* q, const float* k, const int64_t* rows, int32_t row_stride, int32_t n,

@@ -92,6 +92,15 @@ def test_infonce_degenerate_rows():
     assert abs(float(loss) - float(ref(q, k, k, temperature=0.1))) < 1e-5
 
 
+def _assert_adam_close(actual, desired, grad_ref, lr, atol):
+    """Adam's early updates are lr * m / (sqrt(v) + 1e-8): where |g| is within a few orders of eps the quotient amplifies the
+    last-bit differences of g (summation order), so those entries are only held to a fraction of the step size lr."""
+    solid = np.abs(grad_ref) > 1e-6
+    np.testing.assert_allclose(actual[solid], desired[solid], rtol=1e-5, atol=atol)
+    np.testing.assert_allclose(actual[~solid], desired[~solid], rtol=0, atol=0.25 * lr)
+    assert solid.mean() > 0.8
+
+
 def _keep_index(g, ds, key):
     """positions, in the dataset's train-pair order, of the edges the reference's random.sample kept for a view"""
     n_users, n_items = int(g["n_users"]), int(g["n_items"])
@@ -158,10 +167,10 @@ def test_autograd_path_two_steps(golden, name):
     loss.backward()
     np.testing.assert_allclose(_np(m.embedding.weight.grad), g["grad_emb"], rtol=1e-4, atol=2e-9)
     tr.opt.step()
-    np.testing.assert_allclose(_np(m.embedding.weight), g["emb1"], rtol=1e-5, atol=5e-6)
+    _assert_adam_close(_np(m.embedding.weight), g["emb1"], g["grad_emb"], float(g["lr"]), 5e-6)
     loss2 = tr._autograd_step(batch, None)
     assert abs(loss2 - float(g["loss2"])) < 2e-6
-    np.testing.assert_allclose(_np(m.embedding.weight), g["emb2"], rtol=1e-5, atol=1e-5)
+    _assert_adam_close(_np(m.embedding.weight), g["emb2"], g["grad_emb"], float(g["lr"]), 1e-5)
 
 
 @pytest.mark.parametrize("name", ["sgl_tiny", "half_tiny"])
@@ -176,10 +185,10 @@ def test_fused_engine_two_steps(golden, name, use_graph):
     eng.step(host_batch=hb)
     assert abs(eng.last_loss() - float(g["loss"])) < 2e-6
     np.testing.assert_allclose(_np(m.embedding.weight.grad), g["grad_emb"], rtol=1e-4, atol=2e-9)
-    np.testing.assert_allclose(_np(m.embedding.weight), g["emb1"], rtol=1e-5, atol=5e-6)
+    _assert_adam_close(_np(m.embedding.weight), g["emb1"], g["grad_emb"], float(g["lr"]), 5e-6)
     eng.step(host_batch=hb)
     assert abs(eng.last_loss() - float(g["loss2"])) < 2e-6
-    np.testing.assert_allclose(_np(m.embedding.weight), g["emb2"], rtol=1e-5, atol=1e-5)
+    _assert_adam_close(_np(m.embedding.weight), g["emb2"], g["grad_emb"], float(g["lr"]), 1e-5)
     eng.sync_optimizer_state()
     assert int(tr.opt.state[m.embedding.weight]["step"]) == 2
 
