@@ -79,3 +79,34 @@ def test_no_cpu_fallback():
     ds = dataset.get_dataset({'name': 'SyntheticDataset', 'device': 'cpu', 'graph': synth.generate(50, 60, 400, seed=1)})
     with pytest.raises(_abi.B200RecError):
         model.get_model({'name': 'LightGCN', 'embedding_size': 64, 'n_layers': 2, 'device': 'cpu'}, ds)
+
+
+def test_argument_errors_are_codes_with_messages():
+    """every entry point validates before it launches: a bad call returns a negative code and leaves a message in
+    b200rec_last_error() -- checked here without a GPU (validation comes before any CUDA call)"""
+    lib = _abi.load()
+    null = C.c_void_p(0)
+
+    def err():
+        return lib.b200rec_last_error().decode()
+
+    rc = lib.b200rec_spmm_f32(None, null, 64, null, C.c_float(1.0), null, null, null, C.c_float(1.0), null)
+    assert rc < 0 and "null operand" in err()
+    csr = _abi.CsrStruct()
+    x = np.zeros(64, dtype=np.float32)
+    rc = lib.b200rec_spmm_f32(C.byref(csr), x.ctypes.data, 64, null, C.c_float(1.0), null, null, null, C.c_float(1.0), null)
+    assert rc < 0 and "no output" in err()
+    rc = lib.b200rec_spmm_f32(C.byref(csr), x.ctypes.data, 48, null, C.c_float(1.0), x.ctypes.data, null, null, C.c_float(1.0),
+                              null)
+    assert rc < 0 and "8/16/32/64/128/256" in err()
+    rc = lib.b200rec_infonce_fwd_bwd(x.ctypes.data, x.ctypes.data, null, 1, 4, 16, C.c_float(0.0), C.c_float(1.0), x.ctypes.data,
+                                     x.ctypes.data, x.ctypes.data, x.ctypes.data, null)
+    assert rc < 0 and "temperature" in err()
+    rc = lib.b200rec_infonce_fwd_bwd(x.ctypes.data, x.ctypes.data, null, 1, 4, 24, C.c_float(0.1), C.c_float(1.0), x.ctypes.data,
+                                     x.ctypes.data, x.ctypes.data, x.ctypes.data, null)
+    assert rc < 0 and "embedding size" in err()
+    step = np.zeros(1, dtype=np.int64)
+    rc = lib.b200rec_adam_step(x.ctypes.data + 4, x.ctypes.data, x.ctypes.data, x.ctypes.data, 8, 1e-3, 0.9, 0.999, 1e-8,
+                               step.ctypes.data, null)
+    assert rc < 0 and "alignment" in err()
+    assert lib.b200rec_infonce_workspace_floats(0, 64) == 0 and lib.b200rec_infonce_workspace_floats(2048, 64) > 2 * 2048 * 64
