@@ -14,8 +14,9 @@ g = torch.Generator(device="cuda").manual_seed(0)
 rep_u = 0.1 * torch.randn((nu, d), device="cuda", generator=g)
 rep_i = 0.1 * torch.randn((ni, d), device="cuda", generator=g)
 users = torch.arange(nu, device="cuda")
-for prec in (0, 1):
-    for chunk in (16384, 65536):
+tc_only = os.environ.get("TC_ONLY", "0") == "1"  # for ncu captures: the tcgen05 path only, one chunk size
+for prec in ((1,) if tc_only else (0, 1)):
+    for chunk in ((65536,) if tc_only else (16384, 65536)):
         def run():
             for s in range(0, nu, chunk):
                 ops.score_topk(rep_u, users[s:s + chunk].contiguous(), rep_i, k, precision=prec)
