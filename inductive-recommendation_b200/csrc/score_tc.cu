@@ -77,6 +77,18 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -413,7 +425,7 @@ __global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant_
 // at the cursor.  Total work per row is O(E) for the whole sweep.  (Measured alternatives: deferring the test to the
 // re-score kernel with a K+E cut tripled the candidate volume, 8 -> 20 ms on the C2 sweep; a hash-bitmap prefilter left
 // the heavy rows at 13 ms.)
-constexpr int TC_QCAP = 64;       // records per ring (power of two); 8 rings: (quadrant, column half)
+constexpr int TC_QCAP = 128;      // records per ring (power of two); 8 rings: (quadrant, column half)
 constexpr int TC_REFINE_AT = 128; // list length that triggers a cut refinement
 struct __align__(16) HitRec {
   float v[8];
@@ -537,48 +549,98 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
       mbar_wait(tfull + as, (t >> 1) & 1);
       tc_fence_after();
       const int i0 = t * BN;
-#pragma unroll 1
-      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
-        unsigned hit4 = 0;
+      // this warp's half of the tile: all its columns go to registers with ONE wait, and the accumulator stage is handed
+      // back to the MMA warp before any of the (slow, ring-dependent) hit handling below
+      static_assert(BN == 128, "drain layout: two 32-column chunks per warp");
+      uint32_t vv[2][32];
+      const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * 64);
+      tc_ld32_nowait(tcol, vv[0]);
+      tc_ld32_nowait(tcol + 32, vv[1]);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + as);
+      // group-of-8 maxima against the row's cut: bit cc*4+g <-> columns half*64 + cc*32 + g*8 .. +7
+      unsigned hit8 = 0;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          const uint32_t* v = vv[cc];
           const float a = fmaxf(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
           const float b = fmaxf(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
           const float c2 = fmaxf(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
           const float d2 = fmaxf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
-          if (fmaxf(fmaxf(a, b), fmaxf(c2, d2)) >= cut) hit4 |= 1u << g;
+          if (fmaxf(fmaxf(a, b), fmaxf(c2, d2)) >= cut) hit8 |= 1u << (cc * 4 + g);
         }
-        if (__any_sync(0xffffffffu, hit4 != 0)) {
+      }
+      if (__any_sync(0xffffffffu, hit8 != 0)) {
+        // one batch per tile: per-lane record count -> warp prefix -> one wait for room, one fence, one publish.  A lane's
+        // records stay consecutive and ascending in item id (what the consumer's forward-only exclusion cursor relies on).
+        const int mine_n = __popc(hit8);
+        int pre = mine_n;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const bool mine = (hit4 >> g) & 1u;
-            const unsigned bal = __ballot_sync(0xffffffffu, mine);
-            if (bal == 0) continue;
-            const int n = __popc(bal);
-            // wait for room in the ring (bounded)
-            unsigned spins = 0;
-            while (tail + n - s_head[ring] > TC_QCAP) {
-              if (++spins > 200000000u) __trap();
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t2 = __shfl_up_sync(0xffffffffu, pre, o);
+          if (lane >= o) pre += t2;
+        }
+        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        pre -= mine_n;
+        if (total <= TC_QCAP) {
+          unsigned spins = 0;
+          while (tail + total - s_head[ring] > TC_QCAP) {
+            if (++spins > 200000000u) __trap();
+          }
+          int k2 = tail + pre;
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if ((hit8 >> (cc * 4 + g)) & 1u) {
+                const uint32_t* v = vv[cc];
+                HitRec* r = q + (k2 & (TC_QCAP - 1));
+                *reinterpret_cast<uint4*>(&r->v[0]) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+                *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+                r->base = i0 + half * 64 + cc * 32 + g * 8;
+                r->row = row;
+                ++k2;
+              }
             }
-            if (mine) {
-              HitRec* r = q + ((tail + __popc(bal & ((1u << lane) - 1u))) & (TC_QCAP - 1));
-              *reinterpret_cast<uint4*>(&r->v[0]) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
-              *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
-              r->base = i0 + c * 32 + g * 8;
-              r->row = row;
+          }
+          tail += total;
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) s_tail[ring] = tail;  // publish
+        } else {
+          // more records than the ring holds (the first tiles, before the rows have a cut): group by group
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t* v = vv[cc];
+              const bool mine = (hit8 >> (cc * 4 + g)) & 1u;
+              const unsigned bal = __ballot_sync(0xffffffffu, mine);
+              if (bal == 0) continue;
+              const int n = __popc(bal);
+              unsigned spins = 0;
+              while (tail + n - s_head[ring] > TC_QCAP) {
+                if (++spins > 200000000u) __trap();
+              }
+              if (mine) {
+                HitRec* r = q + ((tail + __popc(bal & ((1u << lane) - 1u))) & (TC_QCAP - 1));
+                *reinterpret_cast<uint4*>(&r->v[0]) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+                *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+                r->base = i0 + half * 64 + cc * 32 + g * 8;
+                r->row = row;
+              }
+              tail += n;
+              __threadfence_block();
+              __syncwarp();
+              if (lane == 0) s_tail[ring] = tail;  // publish
             }
-            tail += n;
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) s_tail[ring] = tail;  // publish
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + as);
     }
     __threadfence_block();
     __syncwarp();
@@ -708,7 +770,7 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
       }
       if (progressed) {
         // rows whose list grew long: tighten their cut
-        __threadfence();  // list entries written by the lanes above are visible to the whole warp
+        __threadfence_block();  // list entries written by the lanes above are visible to the whole warp (same SM)
         const int row = quad * 32 + lane;
         const int kk = s_kk[row];
         const bool need = (u0 + row) < p.n_users && s_cnt[row] >= max(TC_REFINE_AT, min(2 * kk, 3 * TC_CAP / 4));
@@ -725,7 +787,7 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
       }
     }
     // final: lower-bound pass for every row, publish counts
-    __threadfence();
+    __threadfence_block();
     for (int r = 0; r < 32; ++r) {
       const int row = quad * 32 + r;
       if ((u0 + row) >= p.n_users) continue;
