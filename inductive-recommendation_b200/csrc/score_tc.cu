@@ -425,7 +425,10 @@ __global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant_
 // at the cursor.  Total work per row is O(E) for the whole sweep.  (Measured alternatives: deferring the test to the
 // re-score kernel with a K+E cut tripled the candidate volume, 8 -> 20 ms on the C2 sweep; a hash-bitmap prefilter left
 // the heavy rows at 13 ms.)
-constexpr int TC_QCAP = 128;      // records per ring (power of two); 8 rings: (quadrant, column half)
+constexpr int TC_QCAP = 64;       // records per ring (power of two); 16 rings: (quadrant, column half, row half)
+constexpr int TC_RINGS = 16;
+constexpr int TC_CONSUMERS = 8;    // consumer warp (quadrant, row half) owns 16 rows and their two rings
+constexpr int TC2_THREADS = (2 + 8 + TC_CONSUMERS) * 32;
 constexpr int TC_REFINE_AT = 128; // list length that triggers a cut refinement
 struct __align__(16) HitRec {
   float v[8];
@@ -435,7 +438,7 @@ struct __align__(16) HitRec {
 };
 
 template <int D, int BN, int STAGES>
-__global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant__ CUtensorMap tm_users,
+__global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_constant__ CUtensorMap tm_users,
                                                                             const __grid_constant__ CUtensorMap tm_items,
                                                                             const TcParams p) {
   constexpr int KB = D / 64;
@@ -444,17 +447,17 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + A_BYTES;
-  HitRec* queues = reinterpret_cast<HitRec*>(sB + (size_t)STAGES * B_STAGE_BYTES);      // [8][TC_QCAP]
-  Cand* sort_area = reinterpret_cast<Cand*>(queues + 8 * TC_QCAP);                        // [4 consumer warps][TC_CAP]
-  float* s_cut = reinterpret_cast<float*>(sort_area + 4 * TC_CAP);                        // [128]
+  HitRec* queues = reinterpret_cast<HitRec*>(sB + (size_t)STAGES * B_STAGE_BYTES);      // [TC_RINGS][TC_QCAP]
+  Cand* sort_area = reinterpret_cast<Cand*>(queues + TC_RINGS * TC_QCAP);                 // [TC_CONSUMERS][TC_CAP]
+  float* s_cut = reinterpret_cast<float*>(sort_area + TC_CONSUMERS * TC_CAP);                        // [128]
   int* s_cnt = reinterpret_cast<int*>(s_cut + TC_M);                                      // [128]
   int* s_kk = s_cnt + TC_M;                                                               // [128] rank the cut is derived from
   int* s_xend = s_kk + TC_M;                                                              // [2 lists][128] end of the row's exclusion entries
   int* s_xcur = s_xend + 2 * TC_M;                                                        // [2 lists][2 halves][128] merge cursors
-  volatile int* s_tail = reinterpret_cast<volatile int*>(s_xcur + 4 * TC_M);              // [8] records published
-  volatile int* s_head = s_tail + 8;                                                      // [8] records consumed
-  volatile int* s_done = s_head + 8;                                                      // [8] producer finished
-  uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(s_done) + 8);
+  volatile int* s_tail = reinterpret_cast<volatile int*>(s_xcur + 4 * TC_M);              // [TC_RINGS] records published
+  volatile int* s_head = s_tail + TC_RINGS;                                               // records consumed
+  volatile int* s_done = s_head + TC_RINGS;                                               // producer finished
+  uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(s_done) + TC_RINGS);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
     }
     s_cut[threadIdx.x] = cut0; s_cnt[threadIdx.x] = 0; s_kk[threadIdx.x] = kk;
   }
-  if (threadIdx.x < 8) { s_tail[threadIdx.x] = 0; s_head[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
+  if (threadIdx.x < TC_RINGS) { s_tail[threadIdx.x] = 0; s_head[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
@@ -538,7 +541,8 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
     // tcgen05.ld / FMNMX latency.
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int ring = quad * 2 + half;
+    const int lh = lane >> 4;                          // row half: lanes 0-15 feed one consumer, 16-31 the other
+    const int ring = (quad * 2 + half) * 2 + lh;
     const int row = quad * 32 + lane;
     const bool active = (u0 + row) < p.n_users;
     HitRec* q = queues + ring * TC_QCAP;
@@ -578,17 +582,17 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
         // one batch per tile: per-lane record count -> warp prefix -> one wait for room, one fence, one publish.  A lane's
         // records stay consecutive and ascending in item id (what the consumer's forward-only exclusion cursor relies on).
         const int mine_n = __popc(hit8);
-        int pre = mine_n;
+        int pre = mine_n;  // prefix sum inside each 16-lane row half (each half has its own ring; `tail` is per half)
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t2 = __shfl_up_sync(0xffffffffu, pre, o);
-          if (lane >= o) pre += t2;
+        for (int o = 1; o < 16; o <<= 1) {
+          const int t2 = __shfl_up_sync(0xffffffffu, pre, o, 16);
+          if ((lane & 15) >= o) pre += t2;
         }
-        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        const int total = __shfl_sync(0xffffffffu, pre, 15, 16);
         pre -= mine_n;
-        if (total <= TC_QCAP) {
+        if (__all_sync(0xffffffffu, total <= TC_QCAP)) {
           unsigned spins = 0;
-          while (tail + total - s_head[ring] > TC_QCAP) {
+          while (__any_sync(0xffffffffu, tail + total - s_head[ring] > TC_QCAP)) {
             if (++spins > 200000000u) __trap();
           }
           int k2 = tail + pre;
@@ -610,7 +614,7 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
           tail += total;
           __threadfence_block();
           __syncwarp();
-          if (lane == 0) s_tail[ring] = tail;  // publish
+          if ((lane & 15) == 0) s_tail[ring] = tail;  // publish (one lane per half)
         } else {
           // more records than the ring holds (the first tiles, before the rows have a cut): group by group
 #pragma unroll
@@ -619,15 +623,16 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
             for (int g = 0; g < 4; ++g) {
               const uint32_t* v = vv[cc];
               const bool mine = (hit8 >> (cc * 4 + g)) & 1u;
-              const unsigned bal = __ballot_sync(0xffffffffu, mine);
-              if (bal == 0) continue;
+              const unsigned bal_all = __ballot_sync(0xffffffffu, mine);
+              if (bal_all == 0) continue;
+              const unsigned bal = (bal_all >> (lh * 16)) & 0xffffu;  // this row half's lanes
               const int n = __popc(bal);
               unsigned spins = 0;
-              while (tail + n - s_head[ring] > TC_QCAP) {
+              while (__any_sync(0xffffffffu, tail + n - s_head[ring] > TC_QCAP)) {
                 if (++spins > 200000000u) __trap();
               }
               if (mine) {
-                HitRec* r = q + ((tail + __popc(bal & ((1u << lane) - 1u))) & (TC_QCAP - 1));
+                HitRec* r = q + ((tail + __popc(bal & ((1u << (lane & 15)) - 1u))) & (TC_QCAP - 1));
                 *reinterpret_cast<uint4*>(&r->v[0]) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
                 *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
                 r->base = i0 + half * 64 + cc * 32 + g * 8;
@@ -636,7 +641,7 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
               tail += n;
               __threadfence_block();
               __syncwarp();
-              if (lane == 0) s_tail[ring] = tail;  // publish
+              if ((lane & 15) == 0) s_tail[ring] = tail;  // publish
             }
           }
         }
@@ -644,11 +649,13 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
     }
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) s_done[ring] = 1;
+    if ((lane & 15) == 0) s_done[ring] = 1;
   } else {
-    // ===== consumer warps: warp 10+q owns the two rings and the 32 rows of drain quadrant q =====
-    const int quad = warp - 10;
-    Cand* my_sort = sort_area + (size_t)quad * TC_CAP;
+    // ===== consumer warps: warp 10 + 2q + h owns rows 32q + 16h .. +15 and their two rings (one per column half) =====
+    const int cw = warp - 10;
+    const int quad = cw >> 1, rh = cw & 1;
+    const int row_base = quad * 32 + rh * 16;
+    Cand* my_sort = sort_area + (size_t)cw * TC_CAP;
     const float vmax = __uint_as_float(*p.vmax_bits);
     int head2[2] = {0, 0};
 
@@ -706,7 +713,7 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
       bool progressed = false, all_done = true;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const int ring = quad * 2 + hf;
+        const int ring = (quad * 2 + hf) * 2 + rh;
         HitRec* q = queues + ring * TC_QCAP;
         const int done = s_done[ring];      // read BEFORE the tail: done => the tail read below is final
         __threadfence_block();
@@ -771,14 +778,14 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
       if (progressed) {
         // rows whose list grew long: tighten their cut
         __threadfence_block();  // list entries written by the lanes above are visible to the whole warp (same SM)
-        const int row = quad * 32 + lane;
+        const int row = row_base + (lane & 15);
         const int kk = s_kk[row];
-        const bool need = (u0 + row) < p.n_users && s_cnt[row] >= max(TC_REFINE_AT, min(2 * kk, 3 * TC_CAP / 4));
+        const bool need = lane < 16 && (u0 + row) < p.n_users && s_cnt[row] >= max(TC_REFINE_AT, min(2 * kk, 3 * TC_CAP / 4));
         unsigned needm = __ballot_sync(0xffffffffu, need);
         while (needm) {
           const int r = __ffs(needm) - 1;
           needm &= needm - 1;
-          refine_row(quad * 32 + r);
+          refine_row(row_base + r);
         }
         idle = 0;
       } else {
@@ -788,8 +795,8 @@ __global__ void __launch_bounds__(448, 1) score_tc2_kernel(const __grid_constant
     }
     // final: lower-bound pass for every row, publish counts
     __threadfence_block();
-    for (int r = 0; r < 32; ++r) {
-      const int row = quad * 32 + r;
+    for (int r = 0; r < 16; ++r) {
+      const int row = row_base + r;
       if ((u0 + row) >= p.n_users) continue;
       refine_row(row);
       if (lane == 0) p.cand_cnt[u0 + row] = min(s_cnt[row], TC_CAP);
@@ -944,10 +951,10 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
     B2_LAUNCHED();
   } else {
     B2_CUDA(cudaMemsetAsync(ovf, 0, (size_t)nb * sizeof(int), st));
-    const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 8 * TC_QCAP * sizeof(HitRec) +
-                        4 * TC_CAP * sizeof(Cand) + 9 * TC_M * 4 + 512;
+    const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + TC_RINGS * TC_QCAP * sizeof(HitRec) +
+                        TC_CONSUMERS * TC_CAP * sizeof(Cand) + 9 * TC_M * 4 + 1024;
     B2_CUDA(cudaFuncSetAttribute(score_tc2_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 448, smem, st>>>(mu, mi, p);
+    score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), TC2_THREADS, smem, st>>>(mu, mi, p);
     B2_LAUNCHED();
   }
   const size_t rsmem = 4 * TC_CAP * sizeof(Cand);
