@@ -717,9 +717,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
         HitRec* q = queues + ring * TC_QCAP;
         const int done = s_done[ring];      // read BEFORE the tail: done => the tail read below is final
         __threadfence_block();
-        const int tl = s_tail[ring];
+        const int tl_all = s_tail[ring];
         __threadfence_block();              // acquire: the records below were written before the tail was published
         int head = head2[hf];
+        // at most 16 records per ring per pass: a pass appends <= 2 * 16 * 8 = 256 values to one row (all records may
+        // belong to the same row, e.g. a tile with a single live user), and the refinement check below runs before a list
+        // that was under its threshold (<= 3/4 TC_CAP) can reach TC_CAP
+        const int tl = min(tl_all, head + 16);
         const bool any = head < tl;
         while (head < tl) {
           const int nrec = min(4, tl - head);
@@ -773,7 +777,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
           if (lane == 0) s_head[ring] = head;  // free the slots
           progressed = true;
         }
-        if (!(done && head == tl)) all_done = false;
+        if (!(done && head == tl_all)) all_done = false;
       }
       if (progressed) {
         // rows whose list grew long: tighten their cut
@@ -825,6 +829,10 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(const float* __restrict
   Cand* row = buf + (size_t)warp * TC_CAP;
   const int n = cand_cnt[u];
   const float* ur = rep_users + (size_t)users[u] * D;
+  // the user's row is shared by every candidate of the warp: one copy in shared memory, read as broadcast 128-bit words
+  __shared__ __align__(16) float s_user[4][D];
+  for (int d = lane; d < D; d += 32) s_user[warp][d] = __ldg(ur + d);
+  __syncwarp();
   int np = 32;
   while (np < n) np <<= 1;
   for (int t = lane; t < np; t += 32) {
@@ -835,10 +843,21 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(const float* __restrict
       const bool masked = (id >= p.banned_lo && id < p.banned_hi) || row_has(p.excl_ptr_a, p.excl_idx_a, users[u], id) ||
                           row_has(p.excl_ptr_b, p.excl_idx_b, users[u], id);
       if (!masked) {
-        const float* vr = rep_items + (size_t)id * D;
+        // one lane per candidate (the oracle's chain runs d = 0..D-1 in order, so a row cannot be split over lanes); the row
+        // is read 16 B at a time with 8 loads in flight -- a lane consumes whole sectors while they are in flight instead of
+        // counting on L1 to keep 32 lanes x 512 B rows alive between 4-byte loads (measured: 2.67 -> see DESIGN 4.6)
+        const float4* vr = reinterpret_cast<const float4*>(rep_items + (size_t)id * D);
+        const float4* uw = reinterpret_cast<const float4*>(s_user[warp]);
         float acc = 0.f;
 #pragma unroll 8
-        for (int d = 0; d < D; ++d) acc = fmaf(__ldg(ur + d), __ldg(vr + d), acc);  // the oracle's chain, d = 0..D-1
+        for (int d4 = 0; d4 < D / 4; ++d4) {
+          const float4 v = __ldg(vr + d4);
+          const float4 w4 = uw[d4];
+          acc = fmaf(w4.x, v.x, acc);
+          acc = fmaf(w4.y, v.y, acc);
+          acc = fmaf(w4.z, v.z, acc);
+          acc = fmaf(w4.w, v.w, acc);
+        }
         c = Cand{acc, id};
       }
     }
