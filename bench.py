@@ -302,7 +302,7 @@ def run_own(args, rank, world):
                      "score_roofline": {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s",
                                         "frac": tf / tf_peak, "note": "whole recommend_all sweep (propagation + prep + "
                                         "tcgen05 score/candidates + exact re-score) per GPU; epilogue-latency-bound, see DESIGN 4.6"},
-                     "includes": "get_rep + score/mask/top-K + D2H ids + hit matrix + metrics"}
+                     "includes": "trainer.eval('test'): get_rep + score/mask/top-K + fused rank-metrics pass + D2H of the metric sums"}
 
     # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload on the host cores ----
     cpu_baseline = None

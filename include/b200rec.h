@@ -234,6 +234,13 @@ int b200rec_score_topk(const float* rep_users, const int64_t* users, int32_t n_b
                        int32_t banned_lo, int32_t banned_hi, int32_t k, int32_t precision,
                        int32_t* out_ids /*[b,K]*/, float* out_scores /*[b,K]*/, int32_t* out_overflow /*[b]*/,
                        void* workspace, void* stream);
+/* Precision / Recall / NDCG at every cut-off of `topks` (device int32 [n_topks], ascending, each <= k, n_topks <= 32) in one
+ * pass over the recommended ids (calculate_metrics, trainer.py:115-144): hit = rec[u,j] in eval row u, gains 1/log2(j+2),
+ * ideal gains over min(len, k), users without eval items excluded.  block_sums: double [ceil(n_rows/128)][3*n_topks+1],
+ * per block the sums of (precision, recall, ndcg) per cut-off and the number of counted users; the caller adds the blocks
+ * and divides.  fp64, fixed reduction order. */
+int b200rec_rank_metrics(const int32_t* rec_ids, int32_t n_rows, int32_t k, int64_t user0, const int32_t* eval_ptr,
+                         const int32_t* eval_idx, const int32_t* topks, int32_t n_topks, double* block_sums, void* stream);
 /* hit[u,j] = rec[u,j] in eval row u (trainer.py:117-121), eval rows sorted CSR. */
 int b200rec_hit_matrix(const int32_t* rec_ids, int32_t n_rows, int32_t k, int64_t user0,
                        const int32_t* eval_ptr, const int32_t* eval_idx, float* hit, void* stream);

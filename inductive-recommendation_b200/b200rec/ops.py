@@ -163,6 +163,19 @@ def score_topk(rep_users, users, rep_items, k, excl_a=None, excl_b=None, banned=
     return ids, sc
 
 
+def rank_metrics(rec_ids, user0, eval_ptr, eval_idx, topks):
+    """(precision, recall, ndcg) sums per cut-off and the number of users with eval items: float64 [3*len(topks)+1] on
+    device.  topks ascending, each <= rec_ids.shape[1]."""
+    _abi.require_cuda(rec_ids, eval_ptr, eval_idx)
+    n, k = rec_ids.shape
+    tk = torch.tensor(list(topks), dtype=torch.int32, device=rec_ids.device)
+    blocks = (n + 127) // 128
+    part = torch.empty((blocks, 3 * len(topks) + 1), dtype=torch.float64, device=rec_ids.device)
+    check(_lib().b200rec_rank_metrics(ptr(rec_ids), n, k, user0, ptr(eval_ptr), ptr(eval_idx), ptr(tk), len(topks),
+                                      ptr(part), stream_ptr()), "rank_metrics")
+    return part.sum(0)
+
+
 def hit_matrix(rec_ids, user0, eval_ptr, eval_idx):
     _abi.require_cuda(rec_ids, eval_ptr, eval_idx)
     hit = torch.empty(rec_ids.shape, dtype=torch.float32, device=rec_ids.device)

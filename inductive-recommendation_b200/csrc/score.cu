@@ -268,6 +268,57 @@ __global__ void hit_matrix_kernel(const int32_t* __restrict__ rec, int n_rows, i
   hit[t] = (id >= 0 && csr_row_has(eval_ptr, eval_idx, user0 + r, id)) ? 1.f : 0.f;
 }
 
+// Precision / Recall / NDCG @k for a list of cut-offs in one pass (trainer.py:123-143): one thread per user walks its K
+// recommended ids once, keeping the hit count and the discounted gains; at every requested k it adds its three ratios to
+// per-thread sums.  Sums are fp64 and reduced in a fixed order (warp butterfly, warps in order, one partial per block):
+// the caller adds the block partials.  Users without eval items do not count (user_masks, trainer.py:139).
+constexpr int METRIC_MAX_KS = 32;
+__global__ void __launch_bounds__(128) rank_metrics_kernel(const int32_t* __restrict__ rec, int n_rows, int k, int64_t user0,
+                                                           const int32_t* __restrict__ eval_ptr,
+                                                           const int32_t* __restrict__ eval_idx,
+                                                           const int32_t* __restrict__ topks, int nk, double* block_sums) {
+  __shared__ double s_part[4][3 * METRIC_MAX_KS + 1];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[3 * METRIC_MAX_KS + 1];
+#pragma unroll
+  for (int i = 0; i < 3 * METRIC_MAX_KS + 1; ++i) acc[i] = 0.0;
+  if (r < n_rows) {
+    const int b = eval_ptr[user0 + r], e = eval_ptr[user0 + r + 1];
+    const int n_eval = e - b;
+    if (n_eval > 0) {
+      int n_hit = 0, ti = 0;
+      double dcg = 0.0, idcg = 0.0;
+      for (int j = 0; j < k && ti < nk; ++j) {
+        const int id = rec[(size_t)r * k + j];
+        const double gain = 1.0 / log2((double)(j + 2));
+        if (id >= 0 && csr_row_has(eval_ptr, eval_idx, user0 + r, id)) {
+          ++n_hit;
+          dcg += gain;
+        }
+        if (j < n_eval) idcg += gain;
+#pragma unroll 1
+        while (ti < nk && topks[ti] == j + 1) {
+          acc[3 * ti + 0] = (double)n_hit / (double)(j + 1);
+          acc[3 * ti + 1] = (double)n_hit / (double)n_eval;
+          acc[3 * ti + 2] = dcg / idcg;
+          ++ti;
+        }
+      }
+      acc[3 * nk] = 1.0;
+    }
+  }
+  for (int i = 0; i <= 3 * nk; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[warp][i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= 3 * nk; i += blockDim.x)
+    block_sums[(size_t)blockIdx.x * (3 * nk + 1) + i] = ((s_part[0][i] + s_part[1][i]) + s_part[2][i]) + s_part[3][i];
+}
+
 static int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -374,6 +425,17 @@ extern "C" int b200rec_score_topk(const float* rep_users, const int64_t* users, 
   B2_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
   topk_merge_kernel<<<ceil_div(n_batch_users, 4), 128, msmem, st>>>(p.partial, p.n_split, n_batch_users, k, np, out_ids,
                                                                     out_scores);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_rank_metrics(const int32_t* rec_ids, int32_t n_rows, int32_t k, int64_t user0, const int32_t* eval_ptr,
+                                    const int32_t* eval_idx, const int32_t* topks, int32_t n_topks, double* block_sums,
+                                    void* stream) {
+  B2_REQUIRE(rec_ids && eval_ptr && eval_idx && topks && block_sums && n_rows > 0 && k > 0, "bad argument");
+  B2_REQUIRE(n_topks > 0 && n_topks <= METRIC_MAX_KS, "1..32 cut-offs");
+  rank_metrics_kernel<<<ceil_div(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(rec_ids, n_rows, k, user0, eval_ptr, eval_idx,
+                                                                              topks, n_topks, block_sums);
   B2_LAUNCHED();
   return 0;
 }

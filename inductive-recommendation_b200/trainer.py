@@ -121,36 +121,58 @@ class BasicTrainer:
         return self.best_ndcg
 
     # ------------------------------------------------------------------------------------------------ metrics
-    def hit_matrix(self, eval_data, rec_items):
-        """hit[u, j] = rec_items[u, j] in eval_data[u]  (device kernel; eval rows as sorted CSR)"""
+    def _eval_csr(self, eval_data):
+        """eval lists as a sorted int32 CSR on the device: (ptr, idx)"""
         dev = self.device
         for split in ('train', 'val', 'test'):  # the dataset's own lists: use its cached device CSR
             if eval_data is getattr(self.dataset, split + '_data', None):
                 ptr_d, idx_d = self.dataset.csr(split, device=dev)
-                if idx_d.numel() == 0:
-                    idx_d = torch.zeros(1, dtype=torch.int32, device=dev)
-                rec_d = rec_items if isinstance(rec_items, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rec_items))
-                rec_d = rec_d.to(device=dev, dtype=torch.int32).contiguous()
-                n_eval = (ptr_d[1:] - ptr_d[:-1]).cpu().numpy().astype(np.int32)
-                return ops.hit_matrix(rec_d, 0, ptr_d, idx_d).cpu().numpy(), n_eval
-        if hasattr(eval_data, 'ptr'):  # lazy CSR-backed lists
-            ptr, idx = np.asarray(eval_data.ptr, dtype=np.int64), np.asarray(eval_data.idx, dtype=np.int64)
+                break
         else:
-            lens = np.fromiter((len(x) for x in eval_data), dtype=np.int64, count=len(eval_data))
-            ptr = np.zeros(len(eval_data) + 1, dtype=np.int64)
-            np.cumsum(lens, out=ptr[1:])
-            idx = np.concatenate([np.asarray(x, dtype=np.int64) for x in eval_data if len(x)]) if ptr[-1] else \
-                np.zeros(0, dtype=np.int64)
-        rows = np.repeat(np.arange(len(ptr) - 1, dtype=np.int64), np.diff(ptr))
-        idx = idx[np.lexsort((idx, rows))]
-        ptr_d = torch.from_numpy(ptr.astype(np.int32)).to(dev)
-        idx_d = torch.from_numpy(idx.astype(np.int32)).to(dev) if idx.size else torch.zeros(1, dtype=torch.int32, device=dev)
+            if hasattr(eval_data, 'ptr'):  # lazy CSR-backed lists
+                ptr, idx = np.asarray(eval_data.ptr, dtype=np.int64), np.asarray(eval_data.idx, dtype=np.int64)
+            else:
+                lens = np.fromiter((len(x) for x in eval_data), dtype=np.int64, count=len(eval_data))
+                ptr = np.zeros(len(eval_data) + 1, dtype=np.int64)
+                np.cumsum(lens, out=ptr[1:])
+                idx = np.concatenate([np.asarray(x, dtype=np.int64) for x in eval_data if len(x)]) if ptr[-1] else \
+                    np.zeros(0, dtype=np.int64)
+            rows = np.repeat(np.arange(len(ptr) - 1, dtype=np.int64), np.diff(ptr))
+            idx = idx[np.lexsort((idx, rows))]
+            ptr_d = torch.from_numpy(ptr.astype(np.int32)).to(dev)
+            idx_d = torch.from_numpy(idx.astype(np.int32)).to(dev)
+        if idx_d.numel() == 0:
+            idx_d = torch.zeros(1, dtype=torch.int32, device=dev)
+        return ptr_d, idx_d
+
+    def _rec_on_device(self, rec_items):
         rec_d = rec_items if isinstance(rec_items, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rec_items))
-        rec_d = rec_d.to(device=dev, dtype=torch.int32).contiguous()
-        return ops.hit_matrix(rec_d, 0, ptr_d, idx_d).cpu().numpy(), np.diff(ptr).astype(np.int32)
+        return rec_d.to(device=self.device, dtype=torch.int32).contiguous()
+
+    def hit_matrix(self, eval_data, rec_items):
+        """hit[u, j] = rec_items[u, j] in eval_data[u]  (device kernel; eval rows as sorted CSR) and the row lengths"""
+        ptr_d, idx_d = self._eval_csr(eval_data)
+        n_eval = (ptr_d[1:] - ptr_d[:-1]).cpu().numpy().astype(np.int32)
+        return ops.hit_matrix(self._rec_on_device(rec_items), 0, ptr_d, idx_d).cpu().numpy(), n_eval
 
     def calculate_metrics(self, eval_data, rec_items):
-        """Precision / Recall / NDCG @k for every k in topks, averaged over users with at least one eval item."""
+        """Precision / Recall / NDCG @k for every k in topks, averaged over users with at least one eval item
+        (trainer.py:115-144) -- one device pass over the recommended ids, 3*len(topks)+1 doubles come back."""
+        rec_d = self._rec_on_device(rec_items)
+        ks = sorted(set(int(k) for k in self.topks))
+        if rec_d.shape[0] == 0 or len(ks) > 32 or ks[-1] > rec_d.shape[1]:
+            return self._calculate_metrics_host(eval_data, rec_items)
+        ptr_d, idx_d = self._eval_csr(eval_data)
+        sums = ops.rank_metrics(rec_d, 0, ptr_d, idx_d, ks).cpu().numpy()
+        n = sums[-1]
+        results = {'Precision': {}, 'Recall': {}, 'NDCG': {}}
+        for i, k in enumerate(ks):
+            for j, name in enumerate(('Precision', 'Recall', 'NDCG')):
+                results[name][k] = np.float32(sums[3 * i + j] / n) if n > 0 else np.float32(np.nan)
+        return results
+
+    def _calculate_metrics_host(self, eval_data, rec_items):
+        """the same arithmetic from the device hit matrix in numpy (any number of cut-offs)"""
         hit, n_eval = self.hit_matrix(eval_data, rec_items)
         results = {'Precision': {}, 'Recall': {}, 'NDCG': {}}
         has_items = n_eval > 0

@@ -222,6 +222,30 @@ def test_hit_matrix():
     assert _np(hit).tolist() == [[1, 0, 1], [0, 0, 0], [1, 0, 0]]
 
 
+@pytest.mark.parametrize("n_users,k,topks", [(1000, 20, [1, 5, 10, 15, 20]), (333, 100, list(range(5, 101, 5)) + [1]), (5, 3, [3])])
+def test_rank_metrics_kernel_matches_oracle(n_users, k, topks):
+    """fused Precision / Recall / NDCG pass vs the restated calculate_metrics (oracle/ref_port.py, trainer.py:115-144)"""
+    from b200rec import ops
+    rng = np.random.default_rng(n_users + k)
+    n_items = 400
+    lens = rng.integers(0, 30, n_users)
+    lens[:3] = [0, 1, 29][:min(3, n_users)]          # users without eval items are excluded from the means
+    eval_data = [sorted(rng.choice(n_items, l, replace=False).tolist()) for l in lens]
+    rec = np.stack([rng.permutation(n_items)[:k] for _ in range(n_users)]).astype(np.int32)
+    rec[n_users // 2, k - 1] = -1                    # an unfilled slot never hits
+    ptr = np.zeros(n_users + 1, dtype=np.int32)
+    np.cumsum(lens, out=ptr[1:])
+    idx = np.concatenate([np.asarray(x, dtype=np.int32) for x in eval_data] + [np.zeros(0, np.int32)])
+    ks = sorted(set(topks))
+    sums = _np(ops.rank_metrics(torch.from_numpy(rec).to(DEV), 0, torch.from_numpy(ptr).to(DEV),
+                                torch.from_numpy(idx if idx.size else np.zeros(1, np.int32)).to(DEV), ks))
+    ref = rp.calculate_metrics(eval_data, rec, ks)
+    assert sums[-1] == (lens > 0).sum()
+    for i, kk in enumerate(ks):
+        for j, name in enumerate(("Precision", "Recall", "NDCG")):
+            assert abs(sums[3 * i + j] / sums[-1] - float(ref[name][kk])) < 2e-6, (name, kk)
+
+
 def test_spmm_row_and_source_masks_are_bit_identical(golden):
     """dst_flags / src_flags skip work without changing a bit of the rows that are computed"""
     from b200rec import graph, ops
