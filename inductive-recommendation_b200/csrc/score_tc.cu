@@ -454,7 +454,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
   int* s_kk = s_cnt + TC_M;                                                               // [128] rank the cut is derived from
   int* s_xend = s_kk + TC_M;                                                              // [2 lists][128] end of the row's exclusion entries
   int* s_xcur = s_xend + 2 * TC_M;                                                        // [2 lists][2 halves][128] merge cursors
-  volatile int* s_tail = reinterpret_cast<volatile int*>(s_xcur + 4 * TC_M);              // [TC_RINGS] records published
+  int* s_xnext = s_xcur + 4 * TC_M;                                                       // [2 lists][2 halves][128] value at the cursor
+  volatile int* s_tail = reinterpret_cast<volatile int*>(s_xnext + 4 * TC_M);              // [TC_RINGS] records published
   volatile int* s_head = s_tail + TC_RINGS;                                               // records consumed
   volatile int* s_done = s_head + TC_RINGS;                                               // producer finished
   uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(s_done) + TC_RINGS);
@@ -475,11 +476,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
     int kk = p.k;
     for (int which = 0; which < 2; ++which) {
       const int32_t* ptr = which ? p.excl_ptr_b : p.excl_ptr_a;
+      const int32_t* xidx = which ? p.excl_idx_b : p.excl_idx_a;
       int b = 0, e = 0;
       if (ptr && u < p.n_users) { const int64_t user = p.users[u]; b = ptr[user]; e = ptr[user + 1]; }
+      const int first = (xidx && b < e) ? xidx[b] : INT32_MAX;
       s_xend[which * TC_M + threadIdx.x] = e;
       s_xcur[(which * 2 + 0) * TC_M + threadIdx.x] = b;
       s_xcur[(which * 2 + 1) * TC_M + threadIdx.x] = b;
+      s_xnext[(which * 2 + 0) * TC_M + threadIdx.x] = first;
+      s_xnext[(which * 2 + 1) * TC_M + threadIdx.x] = first;
     }
     s_cut[threadIdx.x] = cut0; s_cnt[threadIdx.x] = 0; s_kk[threadIdx.x] = kk;
   }
@@ -744,7 +749,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
           for (int which = 0; which < 2; ++which) {
             const int32_t* idx = which ? p.excl_idx_b : p.excl_idx_a;
             if (!idx) continue;
-            const bool gneed = (__ballot_sync(0xffffffffu, pass) & gmask) != 0u;  // some lane of my record still passes
+            // the value at the row's cursor is kept in shared memory: a record whose 8 items all lie below it contains no
+            // excluded item and needs no cursor move -- the common case, and it costs no global load
+            int* nxp = s_xnext + (which * 2 + hf) * TC_M + row;
+            const bool gneed = (__ballot_sync(0xffffffffu, pass) & gmask) != 0u  // some lane of my record still passes
+                               && *nxp < base + 8;
+            if (!__any_sync(0xffffffffu, gneed)) continue;
             int* curp = s_xcur + (which * 2 + hf) * TC_M + row;
             const int end = s_xend[which * TC_M + row];
             int cur = gneed ? *curp : end;
@@ -761,7 +771,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
             bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
             bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
             if ((bits >> j) & 1u) pass = false;
-            if (gneed && j == 0) atomicMax(curp, cur);
+            if (gneed && j == 0) {  // two records of one row in the same pass: the later base wins both maxima
+              atomicMax(curp, cur);
+              atomicMax(nxp, ev);
+            }
           }
           if (pass) {
             const int pos = atomicAdd(&s_cnt[row], 1);
@@ -971,7 +984,7 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
   } else {
     B2_CUDA(cudaMemsetAsync(ovf, 0, (size_t)nb * sizeof(int), st));
     const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + TC_RINGS * TC_QCAP * sizeof(HitRec) +
-                        TC_CONSUMERS * TC_CAP * sizeof(Cand) + 9 * TC_M * 4 + 1024;
+                        TC_CONSUMERS * TC_CAP * sizeof(Cand) + 13 * TC_M * 4 + 1024;
     B2_CUDA(cudaFuncSetAttribute(score_tc2_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), TC2_THREADS, smem, st>>>(mu, mi, p);
     B2_LAUNCHED();
