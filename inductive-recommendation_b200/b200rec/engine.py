@@ -227,6 +227,8 @@ class BprEngine:
                 # and the first backward hop are restricted to them (bit-identical on the rows that matter)
                 self.row_flags.zero_()
                 ops.mark_rows(self.batch, nu, self.row_flags)
+            if forked:
+                self.g_rep.zero_()  # needed only by the BPR kernel: cleared beside the first forward layers
         join = (lambda: main.wait_stream(side)) if forked else None
         self.loss.zero_()
         if self.kind == 'MF':
@@ -234,7 +236,8 @@ class BprEngine:
             self._bpr(self.table, self.batch, nu, self.l2_reg, 1, self.grad)
             self._adam(self.table, self.grad, self.m, self.v)
         elif self.kind == 'LightGCN':
-            self.g_rep.zero_()
+            if not forked:
+                self.g_rep.zero_()
             self._propagate_fwd(self.table, join)
             self._bpr(self.rep, self.batch, nu, 0.0, 0, self.g_rep)
             self._propagate_bwd(self.grad)
