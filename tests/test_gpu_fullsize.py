@@ -192,3 +192,45 @@ def test_c3_inductive_protocol():
     assert int(rec_new_items[rec_new_items >= 0].min()) >= n_old_i
     tr2.eval_precision = 0
     assert torch.equal(tr2.recommend_all("test", banned_items=np.arange(n_old_i)), rec_new_items)  # exact == tcgen05
+
+
+@pytest.mark.parametrize("name", ["SGL", "HALF"])
+def test_c2_contrastive_step_full_size(name):
+    """SGL / HALF at the headline shape (batch 2048, D 64): the graphed step agrees with the autograd path on the same
+    batch, the views keep exactly int(E * aug_rate) pairs, and a redraw re-captures the step."""
+    import dataset as D
+    import model as M
+    import trainer as T
+    from b200rec import synth
+    g = synth.generate_named("c2", seed=0, device=DEV)
+    ds = D.get_dataset({"name": "SyntheticDataset", "device": DEV, "graph": g})
+    cfg = {"name": name + "Trainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 1e-4, "contrastive_reg": 0.1, "device": DEV,
+           "n_epochs": 1, "batch_size": 2048, "dataloader_num_workers": 0, "test_batch_size": 512, "topks": [1, 5, 10, 15, 20]}
+    torch.manual_seed(1)
+    m = M.get_model({"name": name, "embedding_size": 64, "n_layers": 3, "aug_rate": 0.8, "device": DEV}, ds)
+    n_edges = len(ds)
+    assert m.norm_aug_adj1.nnz == 2 * int(n_edges * 0.8)
+    tr = T.get_trainer(cfg, ds, m)
+    m.train()
+    eng = tr._engine()
+    eng.step()                                                   # device-sampled batch
+    torch.cuda.synchronize()
+    batch = eng.batch.clone()
+    loss_fused = eng.last_loss()
+    w_fused = m.embedding.weight.detach().clone()
+    # the same step through autograd + torch.optim.Adam from the same start
+    torch.manual_seed(1)
+    m2 = M.get_model({"name": name, "embedding_size": 64, "n_layers": 3, "aug_rate": 0.8, "device": DEV}, ds)
+    m2.norm_aug_adj1, m2.norm_aug_adj2 = m.norm_aug_adj1, m.norm_aug_adj2
+    tr2 = T.get_trainer(dict(cfg, fused=False), ds, m2)
+    m2.train()
+    loss_ref = tr2._autograd_step(batch, None)
+    assert abs(loss_fused - loss_ref) < 5e-6 * max(1.0, abs(loss_ref))
+    diff = (w_fused - m2.embedding.weight.detach()).abs()
+    assert float(diff.max()) <= 2.5e-4 and float((diff > 1e-5).float().mean()) < 0.02   # Adam's first step, see _assert_adam_close
+    v0 = m.aug_version
+    m.update_aug_adj()
+    assert m.aug_version == v0 + 1 and m.norm_aug_adj1.nnz == 2 * int(n_edges * 0.8)
+    for _ in range(3):
+        eng.step()                                               # new operands -> the step graph is captured again
+    assert np.isfinite(eng.last_loss())
