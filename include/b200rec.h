@@ -135,6 +135,16 @@ int b200rec_bpr_sample(const int32_t* user_ptr, const int32_t* user_items, int32
                        uint64_t seed, const int64_t* step /*device scalar*/, int32_t batch,
                        int64_t* out_batch, void* stream);
 
+/* Row-restricted SpMM through a compacted work list (the last forward layer of a BPR step, which is needed only at the
+ * <= 3B sampled rows): b200rec_live_items writes the plan items whose row has a non-zero flag to live_items (int32
+ * [n_items], any order) and their number to *live_count (device scalar); b200rec_spmm_f32_live runs exactly those items
+ * with a grid sized for max_live (an upper bound of the count known to the caller, e.g. 3B + the number of hub pieces).
+ * Rows outside the list are left untouched; the rows computed are bit-identical to b200rec_spmm_f32. */
+int b200rec_live_items(const b200rec_csr* a, const uint8_t* row_flags, int32_t* live_items, int32_t* live_count, void* stream);
+int b200rec_spmm_f32_live(const b200rec_csr* a, const float* x, int32_t d, float post_scale, float* y, const float* addend,
+                          float* out, float out_scale, const int32_t* live_items, const int32_t* live_count,
+                          int32_t max_live, void* stream);
+
 /* Byte mask of the table rows a batch touches: flags[user] = flags[item_offset+pos] = flags[item_offset+neg] = 1.
  * flags [n_rows] must be zeroed by the caller first.  Feeds needed_rows / nonzero_rows of the propagation calls. */
 int b200rec_mark_rows(const int64_t* batch /*[B,3]*/, int32_t n_batch, int64_t item_offset, uint8_t* flags, void* stream);

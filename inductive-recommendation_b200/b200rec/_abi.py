@@ -44,6 +44,8 @@ PROTOTYPES = {
     "b200rec_adj_normalize": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P]),
     "b200rec_spmm_f32": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P]),
     "b200rec_spmm_f32_ex": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P, _P, _P]),
+    "b200rec_live_items": (C.c_int, [_CSRP, _P, _P, _P, _P]),
+    "b200rec_spmm_f32_live": (C.c_int, [_CSRP, _P, _I32, _F, _P, _P, _P, _F, _P, _P, _I32, _P]),
     "b200rec_propagate_fwd": (C.c_int, [_CSRP, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "b200rec_propagate_bwd": (C.c_int, [_CSRP, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "b200rec_bpr_sample": (C.c_int, [_P, _P, _I32, _I32, _U64, _P, _I32, _P, _P]),

@@ -98,6 +98,14 @@ class BprEngine:
             self.adj_sparse = model.norm_adj.replan(sc) if (partition is None and sc > 0 and sc != model.norm_adj.chunk) \
                 else model.norm_adj
             L = model.n_layers
+            # compacted work list of the last forward layer (only the sampled rows are needed): built beside the first layers
+            self.live = None
+            if partition is None and self.shard is None and self.kind == 'LightGCN' and L >= 2 \
+                    and os.environ.get('B200REC_NO_LIVE_LIST', '0') != '1':
+                op = self.adj_sparse
+                n_hub_items = int((op.item_dst[:op.n_items] < 0).sum())
+                self.live = (torch.empty(max(op.n_items, 1), dtype=torch.int32, device=dev),
+                             torch.zeros(1, dtype=torch.int32, device=dev), min(op.n_items, 3 * batch_size + n_hub_items))
             if partition is not None and hasattr(partition, 'rep'):
                 self.rep, self.bufs = partition.rep, [partition.buf0, partition.buf1]
             else:
@@ -161,8 +169,12 @@ class BprEngine:
             if last and join:
                 join()
             y = None if last else self.bufs[k & 1]
-            ops.spmm(self.adj_sparse if (last and own) else adj, src, y=y, addend=x0 if k == 0 else rep, out=rep,
-                     out_scale=inv if last else 1.0, dst_flags=flags if last else None)
+            if last and own and join is not None and self.live is not None and flags is self.row_flags:
+                ops.spmm_live(self.adj_sparse, src, self.live[0], self.live[1], self.live[2], addend=x0 if k == 0 else rep,
+                              out=rep, out_scale=inv)
+            else:
+                ops.spmm(self.adj_sparse if (last and own) else adj, src, y=y, addend=x0 if k == 0 else rep, out=rep,
+                         out_scale=inv if last else 1.0, dst_flags=flags if last else None)
             src = y
 
     def _propagate_bwd(self, out, adj=None, flags=None, g=None):
@@ -227,6 +239,8 @@ class BprEngine:
                 # and the first backward hop are restricted to them (bit-identical on the rows that matter)
                 self.row_flags.zero_()
                 ops.mark_rows(self.batch, nu, self.row_flags)
+                if forked and self.live is not None:
+                    ops.live_items(self.adj_sparse, self.row_flags, self.live[0], self.live[1])
             if forked:
                 self.g_rep.zero_()  # needed only by the BPR kernel: cleared beside the first forward layers
         join = (lambda: main.wait_stream(side)) if forked else None

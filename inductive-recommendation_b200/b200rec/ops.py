@@ -34,6 +34,21 @@ def spmm(op, x, keep_bits=None, post_scale=1.0, y=None, addend=None, out=None, o
                                          stream_ptr()), "spmm_f32_ex")
 
 
+def live_items(op, row_flags, live_list, live_count):
+    """compacted list of the plan items whose row is flagged (for spmm_live)"""
+    _abi.require_cuda(row_flags, live_list, live_count)
+    check(_lib().b200rec_live_items(C.byref(op.struct()), ptr(row_flags), ptr(live_list), ptr(live_count), stream_ptr()),
+          "live_items")
+
+
+def spmm_live(op, x, live_list, live_count, max_live, post_scale=1.0, y=None, addend=None, out=None, out_scale=1.0):
+    _abi.require_cuda(x, y, addend, out, live_list, live_count)
+    d = x.shape[1]
+    assert x.dtype == torch.float32 and x.shape[0] >= op.n_cols
+    check(_lib().b200rec_spmm_f32_live(C.byref(op.struct()), ptr(x), d, post_scale, ptr(y), ptr(addend), ptr(out), out_scale,
+                                       ptr(live_list), ptr(live_count), int(max_live), stream_ptr()), "spmm_f32_live")
+
+
 def propagate_fwd(op, x0, n_layers, bufs, mean_out, needed_rows=None):
     _abi.require_cuda(x0, mean_out, needed_rows)
     check(_lib().b200rec_propagate_fwd(C.byref(op.struct()), ptr(x0), x0.shape[1], n_layers, ptr(bufs[0]), ptr(bufs[1]),

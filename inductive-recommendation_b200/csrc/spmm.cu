@@ -23,6 +23,8 @@ struct SpmmParams {
   const uint32_t* keep_bits;
   const uint8_t* dst_flags;  // optional: only rows with a non-zero flag are computed (others left untouched)
   const uint8_t* src_flags;  // optional: gathered rows with a zero flag are known to be all-zero and are skipped
+  const int32_t* live_items; // optional: compacted list of the work items to run (b200rec_live_items), instead of all of them
+  const int32_t* live_count; // device scalar: entries in live_items
   const int32_t* item_start;
   const int32_t* item_end;
   const int32_t* item_dst;
@@ -125,10 +127,10 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-  const int item = warp * GPW + lane / G;
+  int item = warp * GPW + lane / G;
   int2* my_cv = s_cv + (threadIdx.x / G) * CVS;  // this group's EB slots
   int start = 0, end = 0, dst = 0;
-  if (item < p.n_items) {
+  if (!p.live_items && item < p.n_items) {
     start = __ldg(p.item_start + item);
     end = __ldg(p.item_end + item);
     dst = __ldg(p.item_dst + item);
@@ -136,6 +138,14 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   // the work plan above is static; everything below may read what the previous kernel of the step wrote
   pdl_trigger();
   pdl_wait();
+  if (p.live_items) {  // row-restricted call: the grid covers an upper bound of the list, most of it a few blocks
+    item = (item < *p.live_count) ? p.live_items[item] : p.n_items;
+    if (item < p.n_items) {
+      start = __ldg(p.item_start + item);
+      end = __ldg(p.item_end + item);
+      dst = __ldg(p.item_dst + item);
+    }
+  }
   if (item < p.n_items && p.dst_flags && !ldc_u8(p.dst_flags + __ldg(p.item_row + item))) end = start;  // row not needed
   const bool live = end > start;
   int maxlen = end - start;
@@ -280,7 +290,7 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
 }
 
 template <int G, int VPL>
-static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t st) {
+static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t st, int max_live) {
   constexpr int GPW = 32 / G;
   // threads per block: 256 measured best or equal on every shape (C2: 57-58 us at 32/64/256 for D=64; C4 D=16:
   // 1.86 ms at 256 vs 4.9 ms at 32); B200REC_SPMM_TPB overrides for experiments
@@ -292,7 +302,7 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
   }
   const int items_per_block = (tpb / 32) * GPW;
   if (a->n_items > 0) {
-    const int grid = ceil_div(a->n_items, items_per_block);
+    const int grid = ceil_div(p.live_items ? min(max_live, a->n_items) : a->n_items, items_per_block);
     const bool hv = p.vals != nullptr, hn = p.nbr_scale != nullptr, hm = p.keep_bits != nullptr, he = p.eid != nullptr && hm;
     const bool hs = p.src_flags != nullptr;
     const int hint = a->col_hint;
@@ -323,7 +333,8 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
 static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint32_t* keep_bits, float post_scale,
                          float* y, const float* addend, float* out, float out_scale, const uint8_t* dst_flags,
                          const uint8_t* src_flags, cudaStream_t st, int n_peer = 0, float* const* peer_y = nullptr,
-                         float* const* peer_out = nullptr) {
+                         float* const* peer_out = nullptr, const int32_t* live_items = nullptr,
+                         const int32_t* live_count = nullptr, int max_live = 0) {
   B2_REQUIRE(a && x, "null operand");
   B2_REQUIRE(y || out, "no output");
   B2_REQUIRE(a->n_items == 0 || (a->item_start && a->item_end && a->item_dst && a->colidx), "csr plan missing");
@@ -335,6 +346,8 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
   SpmmParams p;
   p.colidx = a->colidx; p.vals = a->vals; p.nbr_scale = a->nbr_scale; p.row_scale = a->row_scale; p.eid = a->eid;
   p.keep_bits = keep_bits; p.dst_flags = dst_flags; p.src_flags = src_flags;
+  p.live_items = live_items; p.live_count = live_count;
+  B2_REQUIRE(!live_items || (live_count && max_live > 0), "live_items needs live_count and max_live");
   p.item_start = a->item_start; p.item_end = a->item_end; p.item_dst = a->item_dst; p.item_row = a->item_row;
   p.n_items = a->n_items;
   p.n_peer = n_peer;
@@ -346,14 +359,31 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
   p.partial = a->partial; p.slot_long = a->slot_long; p.long_row = a->long_row; p.long_slot0 = a->long_slot0;
   p.long_nslot = a->long_nslot; p.long_cnt = a->long_cnt;
   switch (d) {
-    case 8: return launch_spmm<2, 1>(a, p, st);
-    case 16: return launch_spmm<4, 1>(a, p, st);
-    case 32: return launch_spmm<8, 1>(a, p, st);
-    case 64: return launch_spmm<16, 1>(a, p, st);
-    case 128: return launch_spmm<32, 1>(a, p, st);
-    case 256: return launch_spmm<32, 2>(a, p, st);
+    case 8: return launch_spmm<2, 1>(a, p, st, max_live);
+    case 16: return launch_spmm<4, 1>(a, p, st, max_live);
+    case 32: return launch_spmm<8, 1>(a, p, st, max_live);
+    case 64: return launch_spmm<16, 1>(a, p, st, max_live);
+    case 128: return launch_spmm<32, 1>(a, p, st, max_live);
+    case 256: return launch_spmm<32, 2>(a, p, st, max_live);
     default: return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "embedding size must be 8/16/32/64/128/256");
   }
+}
+
+// ---- compacted work list for a row-restricted call -----------------------------------------------------------------
+// A BPR step needs its last forward layer only at the <= 3B sampled rows: of the 72 103 work items of the C2 plan ~8 000
+// are live, and 4 507 blocks that mostly load three plan entries and a flag and exit cost ~15 us.  The list is built
+// beside the first forward layers (side stream); the order of its entries only changes the schedule, never a sum.
+__global__ void live_items_kernel(const int32_t* __restrict__ item_row, int n_items, const uint8_t* row_flags,
+                                  int32_t* __restrict__ live_items, int32_t* live_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n_items && ldc_u8(row_flags + __ldg(item_row + i)) != 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, live);
+  if (bal == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(live_count, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (live) live_items[base + __popc(bal & ((1u << lane) - 1u))] = i;
 }
 
 // ---- adjacency normalisation (model.py:89-98) ----------------------------------------------------------
@@ -422,6 +452,26 @@ extern "C" int b200rec_spmm_f32_peer(const b200rec_csr* a, const float* x, int32
   B2_REQUIRE(n_peers >= 0 && n_peers <= 8, "at most 8 peers");
   return spmm_dispatch(a, x, d, keep_bits, post_scale, y, addend, out, out_scale, dst_flags, src_flags, (cudaStream_t)stream,
                        n_peers, peer_y, peer_out);
+}
+
+extern "C" int b200rec_live_items(const b200rec_csr* a, const uint8_t* row_flags, int32_t* live_items, int32_t* live_count,
+                                  void* stream) {
+  B2_REQUIRE(a && row_flags && live_items && live_count && a->item_row, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  B2_CUDA(cudaMemsetAsync(live_count, 0, sizeof(int32_t), st));
+  if (a->n_items > 0) {
+    live_items_kernel<<<ceil_div(a->n_items, 256), 256, 0, st>>>(a->item_row, a->n_items, row_flags, live_items, live_count);
+    B2_LAUNCHED();
+  }
+  return 0;
+}
+
+extern "C" int b200rec_spmm_f32_live(const b200rec_csr* a, const float* x, int32_t d, float post_scale, float* y,
+                                     const float* addend, float* out, float out_scale, const int32_t* live_items,
+                                     const int32_t* live_count, int32_t max_live, void* stream) {
+  B2_REQUIRE(live_items && live_count && max_live > 0, "live list missing");
+  return spmm_dispatch(a, x, d, nullptr, post_scale, y, addend, out, out_scale, nullptr, nullptr, (cudaStream_t)stream, 0,
+                       nullptr, nullptr, live_items, live_count, max_live);
 }
 
 extern "C" int b200rec_propagate_fwd(const b200rec_csr* a, const float* x0, int32_t d, int32_t n_layers, float* buf0,

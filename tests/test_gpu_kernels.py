@@ -222,6 +222,39 @@ def test_hit_matrix():
     assert _np(hit).tolist() == [[1, 0, 1], [0, 0, 0], [1, 0, 0]]
 
 
+def test_spmm_live_list_is_bit_identical(golden):
+    """the compacted work list runs exactly the flagged rows' items: same bits on those rows, other rows untouched"""
+    from b200rec import graph, ops
+    g = golden("lightgcn_tiny")
+    users, items = rp.pairs_from_csr(g["train_indptr"], g["train_items"])
+    op = graph.build_norm_adj(int(g["n_users"]), int(g["n_items"]), torch.from_numpy(users), torch.from_numpy(items), DEV,
+                              chunk=64)   # hub rows split: their pieces must all make the list
+    assert op.n_long > 0
+    n, d = op.n_rows, 64
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn((n, d), device=DEV, generator=gen)
+    acc = torch.randn((n, d), device=DEV, generator=gen)
+    flags = (torch.rand(n, device=DEV, generator=gen) < 0.2).to(torch.uint8)
+    flags[op.long_row[:op.n_long].long()] = 1
+    full = torch.empty_like(x)
+    ops.spmm(op, x, addend=acc, out=full, out_scale=0.25)
+    live = torch.empty(op.n_items, dtype=torch.int32, device=DEV)
+    cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.live_items(op, flags, live, cnt)
+    n_live = int(cnt)
+    want = flags[op.item_row[:op.n_items].long()].bool()
+    assert n_live == int(want.sum())
+    assert sorted(_np(live[:n_live]).tolist()) == torch.nonzero(want).flatten().tolist()
+    out = torch.full_like(x, 7.0)
+    ops.spmm_live(op, x, live, cnt, n_live + 5, addend=acc, out=out, out_scale=0.25)
+    sel = flags.bool()
+    assert torch.equal(out[sel], full[sel]) and bool((out[~sel] == 7.0).all())
+    cnt.zero_()                                         # empty list: nothing is written
+    out.fill_(7.0)
+    ops.spmm_live(op, x, live, cnt, 16, addend=acc, out=out, out_scale=0.25)
+    assert bool((out == 7.0).all())
+
+
 @pytest.mark.parametrize("n_users,k,topks", [(1000, 20, [1, 5, 10, 15, 20]), (333, 100, list(range(5, 101, 5)) + [1]), (5, 3, [3])])
 def test_rank_metrics_kernel_matches_oracle(n_users, k, topks):
     """fused Precision / Recall / NDCG pass vs the restated calculate_metrics (oracle/ref_port.py, trainer.py:115-144)"""
