@@ -2,13 +2,13 @@
 // a TMA-fed tcgen05 bf16 user x item score GEMM whose epilogue never writes the score matrix.
 //
 //   prep kernel     : gather the user rows, convert users / items to bf16 (K-major), row norms, max item norm
-//   score_tc_kernel : one CTA per 128 users; warp 0 = TMA producer (item tiles, ring of STAGES), warp 1 = tcgen05.mma
-//                     issuer (128 x BN x 16 UMMAs, fp32 accumulators in TMEM, two accumulator stages), warps 2-5 =
-//                     epilogue: tcgen05.ld 32 columns at a time, running max, and only values above the row's cut-off
-//                     are looked at individually, tested against the user's sorted train / val rows and the banned
-//                     range, and appended to the row's candidate list.  The cut-off is (K-th best approximate score so
-//                     far) - 2 eps; it is re-derived by a warp-cooperative sort of the row's list at a few scheduled
-//                     tile indices (the list then holds a superset of the K best seen so far).
+//   score_tc2_kernel: one CTA per 128 users, 18 warps; warp 0 = TMA producer (item tiles, ring of STAGES), warp 1 =
+//                     tcgen05.mma issuer (128 x BN x 16 UMMAs, fp32 accumulators in TMEM, two accumulator stages),
+//                     warps 2-9 = drain (TMEM -> registers, group-of-8 maxima against the row's cut, hit groups pushed
+//                     into shared-memory rings), warps 10-17 = consumers (per-value cut / banned-range / exclusion
+//                     tests, append to the row's candidate list, re-derive the row's cut when the list grows long).
+//                     The cut-off is (K-th best approximate score so far) - 2 eps.  score_tc_kernel is the first
+//                     generation (four warps doing drain + per-hit work), kept behind B200REC_TC_V1 for A/B runs.
 //   rescore kernel  : exact fp32 scores (the same fmaf chain in d-order as the precision-0 path and the C oracle) for the
 //                     candidates, final (score desc, id asc) top-K.
 // Exactness: |approx - exact| <= eps_u = 1.05 * 2^-7 * ||u|| * max_i ||v_i|| (two bf16 roundings, Cauchy-Schwarz; fp32
@@ -417,11 +417,13 @@ __global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------------ main kernel, v2
 // Same pipeline, different epilogue: ncu on v1 showed the tensor pipe 3 % busy with the MMA warp spinning on `tempty` --
 // four latency-exposed warps both drained TMEM and ran the branchy per-hit work (range / exclusion tests, list appends,
-// cut refinement).  Here the four DRAIN warps (2-5) only load 32 columns, reduce them to four group maxima, compare
-// with the row's cut and push the rare hit groups (row, first item, 8 scores) into a per-warp single-producer /
-// single-consumer ring in shared memory; two CONSUMER warps (6-7), each owning the rows of two drain warps, pop the
-// records, do the per-value tests, append to the row lists, and re-derive a row's cut when its list grows long.
-// No locks: a row is touched by exactly one consumer (one consumer warp per drain warp); a stale cut only costs extra
+// cut refinement).  Here eight DRAIN warps (2-9: two per TMEM lane quadrant, each half of a tile's columns) load their
+// 64 columns with one wait, hand the accumulator stage back, reduce to eight group maxima, compare with the row's cut
+// and push the hit groups (row, first item, 8 scores) of the tile as one batch into single-producer / single-consumer
+// rings in shared memory (ring = quadrant x column half x row half); eight CONSUMER warps (10-17), each owning 16 rows
+// and their two rings, pop the records, do the per-value tests, append to the row lists, and re-derive a row's cut when
+// its list grows long.
+// No locks: a row is touched by exactly one consumer; a stale cut only costs extra
 // records.  The train / val exclusion test must not be a binary search per candidate: a heavy user's thousands of train
 // items all score above its cut, never raise it (they are excluded) and would each cost a chain of dependent global
 // loads in the one warp that owns the row.  Instead the test is a MERGE: the records of one (row, column half) arrive in
