@@ -2,9 +2,11 @@
 //
 // Mapping: one group of G = D/4 lanes owns one work item (a row, or a chunk of a hub row).  Each lane keeps a
 // float4 slice of the row sum, so a gathered neighbour row is one 128-bit load per lane, 256 B (D=64, two rows per
-// warp) or 512 B (D=128) fully coalesced.  Column ids / values are loaded G at a time, coalesced, and broadcast
-// with width-G shuffles; U neighbour rows are in flight per lane before the FMAs retire them.  The sum runs in CSR
-// order, so results do not depend on the grid, the item order or (multi-GPU) the row partition.
+// warp) or 512 B (D=128) fully coalesced.  (Column id, value) pairs are loaded >= 16 at a time, coalesced, parked in
+// shared memory and re-read with one broadcast LDS.64 per neighbour; U neighbour rows are in flight per lane before
+// the FMAs retire them.  The sum runs in CSR order, so results do not depend on the grid, the item order or
+// (multi-GPU) the row partition.  Launched with programmatic stream serialisation: the work-plan loads run while the
+// previous kernel of the step drains (common.cuh).
 #include <stdlib.h>
 #include "common.cuh"
 
