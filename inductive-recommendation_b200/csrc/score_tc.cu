@@ -436,7 +436,10 @@ constexpr int TC_QCAP = 64;       // records per ring (power of two); 16 rings: 
 constexpr int TC_RINGS = 16;
 constexpr int TC_CONSUMERS = 8;    // consumer warp (quadrant, row half) owns 16 rows and their two rings
 constexpr int TC2_THREADS = (2 + 8 + TC_CONSUMERS) * 32;
-constexpr int TC_REFINE_AT = 128; // list length that triggers a cut refinement
+#ifndef B200REC_TC_REFINE_AT
+#define B200REC_TC_REFINE_AT 128
+#endif
+constexpr int TC_REFINE_AT = B200REC_TC_REFINE_AT; // list length that triggers a cut refinement
 struct __align__(16) HitRec {
   float v[8];
   int base;   // item id of v[0]
