@@ -981,11 +981,10 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
   p.users = users; p.n_users = nb; p.n_items = ni; p.k = k;
   p.excl_ptr_a = ea_ptr; p.excl_idx_a = ea_idx; p.excl_ptr_b = eb_ptr; p.excl_idx_b = eb_idx;
   p.banned_lo = blo; p.banned_hi = bhi; p.unorm = unorm; p.vmax_bits = vmax; p.cand = cand; p.cand_cnt = cnt; p.overflow = ovf;
-  static int use_v1 = -1;
-  if (use_v1 < 0) {
+  static const bool use_v1 = [] {
     const char* e = getenv("B200REC_TC_V1");
-    use_v1 = (e && e[0] == '1') ? 1 : 0;
-  }
+    return e && e[0] == '1';
+  }();
   if (use_v1) {
     const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 4 * TC_CAP * sizeof(Cand) + 256;
     B2_CUDA(cudaFuncSetAttribute(score_tc_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

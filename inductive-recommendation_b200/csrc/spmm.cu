@@ -296,12 +296,11 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
   constexpr int GPW = 32 / G;
   // threads per block: 256 measured best or equal on every shape (C2: 57-58 us at 32/64/256 for D=64; C4 D=16:
   // 1.86 ms at 256 vs 4.9 ms at 32); B200REC_SPMM_TPB overrides for experiments
-  static int tpb = 0;
-  if (!tpb) {
+  static const int tpb = [] {
     const char* e = getenv("B200REC_SPMM_TPB");
-    tpb = e ? atoi(e) : 256;
-    if (tpb != 32 && tpb != 64 && tpb != 128 && tpb != 256) tpb = 256;
-  }
+    const int v = e ? atoi(e) : 256;
+    return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 256;
+  }();
   const int items_per_block = (tpb / 32) * GPW;
   if (a->n_items > 0) {
     const int grid = ceil_div(p.live_items ? min(max_live, a->n_items) : a->n_items, items_per_block);
