@@ -171,3 +171,102 @@ void oracle_spmm_csr(const int32_t* rowptr, const int32_t* colidx, const float* 
   free(acc);
   free(tot);
 }
+
+/* InfoNCE as SGL / HALF call it (model.py:206-214, :322-332; info_nce package, 'unpaired', negative_keys == positive_key,
+ * reduction 'mean'): rows L2-normalised with the norm clamped at 1e-12, logits_i = [qn_i.kn_i, qn_i.kn_0 .. qn_i.kn_{n-1}]/T,
+ * cross-entropy against index 0.  Plain double arithmetic; returns the loss and writes dLoss/dq, dLoss/dk (may be NULL). */
+double oracle_infonce(const float* q, const float* k, int32_t n, int32_t d, double temperature, double* gq, double* gk) {
+  double* qn = (double*)malloc(sizeof(double) * (size_t)n * d);
+  double* kn = (double*)malloc(sizeof(double) * (size_t)n * d);
+  double* qden = (double*)malloc(sizeof(double) * (size_t)n);
+  double* kden = (double*)malloc(sizeof(double) * (size_t)n);
+  double* dqn = (double*)calloc((size_t)n * d, sizeof(double));
+  double* dkn = (double*)calloc((size_t)n * d, sizeof(double));
+  double* row = (double*)malloc(sizeof(double) * (size_t)n);
+  for (int32_t i = 0; i < n; ++i) {
+    double sq = 0, sk = 0;
+    for (int32_t c = 0; c < d; ++c) {
+      sq += (double)q[(size_t)i * d + c] * q[(size_t)i * d + c];
+      sk += (double)k[(size_t)i * d + c] * k[(size_t)i * d + c];
+    }
+    qden[i] = fmax(sqrt(sq), 1e-12);
+    kden[i] = fmax(sqrt(sk), 1e-12);
+    for (int32_t c = 0; c < d; ++c) {
+      qn[(size_t)i * d + c] = q[(size_t)i * d + c] / qden[i];
+      kn[(size_t)i * d + c] = k[(size_t)i * d + c] / kden[i];
+    }
+  }
+  double loss = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    double mx = -INFINITY;
+    for (int32_t j = 0; j < n; ++j) {
+      double s = 0;
+      for (int32_t c = 0; c < d; ++c) s += qn[(size_t)i * d + c] * kn[(size_t)j * d + c];
+      row[j] = s / temperature;
+      if (row[j] > mx) mx = row[j];
+    }
+    const double pos = row[i];
+    double z = exp(pos - mx);
+    for (int32_t j = 0; j < n; ++j) z += exp(row[j] - mx);
+    const double lse = mx + log(z);
+    loss += lse - pos;
+    /* d loss_i / d logits: softmax over [pos, row[0..n-1]] minus the one-hot at the positive slot */
+    const double ppos = exp(pos - lse) - 1.0;
+    for (int32_t j = 0; j < n; ++j) {
+      double w = exp(row[j] - lse);
+      if (j == i) w += ppos;
+      w /= temperature * n;
+      for (int32_t c = 0; c < d; ++c) {
+        dqn[(size_t)i * d + c] += w * kn[(size_t)j * d + c];
+        dkn[(size_t)j * d + c] += w * qn[(size_t)i * d + c];
+      }
+    }
+  }
+  /* Jacobian of x -> x / max(|x|, eps): (g - xn (xn.g)) / |x| above the clamp, g / eps below it */
+  for (int side = 0; side < 2; ++side) {
+    double* g = side ? gk : gq;
+    if (!g) continue;
+    const double* xn = side ? kn : qn;
+    const double* den = side ? kden : qden;
+    const double* dxn = side ? dkn : dqn;
+    for (int32_t i = 0; i < n; ++i) {
+      double dot = 0;
+      for (int32_t c = 0; c < d; ++c) dot += xn[(size_t)i * d + c] * dxn[(size_t)i * d + c];
+      for (int32_t c = 0; c < d; ++c)
+        g[(size_t)i * d + c] = den[i] <= 1e-12 ? dxn[(size_t)i * d + c] / den[i]
+                                               : (dxn[(size_t)i * d + c] - xn[(size_t)i * d + c] * dot) / den[i];
+    }
+  }
+  free(qn); free(kn); free(qden); free(kden); free(dqn); free(dkn); free(row);
+  return loss / n;
+}
+
+/* Precision / Recall / NDCG at each cut-off (calculate_metrics, trainer.py:115-144): hit = rec[u][j] in the user's eval
+ * row (sorted CSR), gains 1/log2(j+2), ideal gains over min(len, k), mean over users with at least one eval item.
+ * out: [3][n_topks] (precision, recall, ndcg rows); returns the number of users counted. */
+int32_t oracle_rank_metrics(const int32_t* rec, int32_t n_users, int32_t k, const int32_t* eval_ptr, const int32_t* eval_idx,
+                            const int32_t* topks, int32_t n_topks, double* out) {
+  for (int32_t t = 0; t < 3 * n_topks; ++t) out[t] = 0;
+  int32_t counted = 0;
+  for (int32_t u = 0; u < n_users; ++u) {
+    const int32_t b = eval_ptr[u], len = eval_ptr[u + 1] - eval_ptr[u];
+    if (len <= 0) continue;
+    ++counted;
+    for (int32_t t = 0; t < n_topks; ++t) {
+      const int32_t kk = topks[t] < k ? topks[t] : k;
+      int32_t hits = 0;
+      double dcg = 0, idcg = 0;
+      for (int32_t j = 0; j < kk; ++j) {
+        const double gain = 1.0 / log2((double)(j + 2));
+        const int32_t id = rec[(size_t)u * k + j];
+        if (id >= 0 && row_contains(eval_idx + b, len, id)) { ++hits; dcg += gain; }
+        if (j < len) idcg += gain;
+      }
+      out[0 * n_topks + t] += (double)hits / topks[t];
+      out[1 * n_topks + t] += (double)hits / len;
+      out[2 * n_topks + t] += dcg / idcg;
+    }
+  }
+  for (int32_t t = 0; t < 3 * n_topks && counted; ++t) out[t] /= counted;
+  return counted;
+}

@@ -77,3 +77,30 @@ def spmm_csr(rowptr, colidx, vals, x, chunk=1024):
     y = np.empty((len(rp) - 1, x.shape[1]), dtype=np.float32)
     lib().oracle_spmm_csr(_p(rp), _p(ci), _p(va), C.c_int32(len(rp) - 1), _p(x), C.c_int32(x.shape[1]), C.c_int32(chunk), _p(y))
     return y
+
+
+def infonce(q, k, temperature=0.1, grads=True):
+    """(loss, dq, dk) of the reference's InfoNCE call (float64), see oracle_c.c"""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    k = np.ascontiguousarray(k, dtype=np.float32)
+    n, d = q.shape
+    gq = np.empty((n, d), dtype=np.float64) if grads else None
+    gk = np.empty((n, d), dtype=np.float64) if grads else None
+    f = lib().oracle_infonce
+    f.restype = C.c_double
+    loss = f(_p(q), _p(k), C.c_int32(n), C.c_int32(d), C.c_double(temperature), _p(gq), _p(gk))
+    return float(loss), gq, gk
+
+
+def rank_metrics(rec, eval_ptr, eval_idx, topks):
+    """{'Precision'|'Recall'|'NDCG': {k: value}} like calculate_metrics (trainer.py:115-144), plus the user count"""
+    rec = np.ascontiguousarray(rec, dtype=np.int32)
+    ptr = np.ascontiguousarray(eval_ptr, dtype=np.int32)
+    idx = np.ascontiguousarray(eval_idx, dtype=np.int32) if len(eval_idx) else np.zeros(1, dtype=np.int32)
+    tk = np.ascontiguousarray(list(topks), dtype=np.int32)
+    out = np.empty((3, len(tk)), dtype=np.float64)
+    f = lib().oracle_rank_metrics
+    f.restype = C.c_int32
+    n = f(_p(rec), C.c_int32(rec.shape[0]), C.c_int32(rec.shape[1]), _p(ptr), _p(idx), _p(tk), C.c_int32(len(tk)), _p(out))
+    res = {name: {int(kk): float(out[r, t]) for t, kk in enumerate(tk)} for r, name in enumerate(("Precision", "Recall", "NDCG"))}
+    return res, int(n)

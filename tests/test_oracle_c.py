@@ -98,3 +98,55 @@ def test_dropout_mask_rate_and_tail():
     assert (int(bits[-1]) >> (nnz % 32)) == 0  # bits past nnz are cleared
     assert np.array_equal(bits, oc.dropout_mask(nnz, p, 2021, 7))
     assert not np.array_equal(bits, oc.dropout_mask(nnz, p, 2021, 8))
+
+
+@pytest.mark.parametrize("n,d", [(1, 8), (5, 16), (64, 32), (130, 64)])
+def test_infonce_c_restatement_matches_package_formula(n, d):
+    """oracle_infonce (plain C, double) against the restated info_nce package run in torch float64 with autograd:
+    loss and both gradients, including a zero row (F.normalize's clamp)"""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "stubs"))
+    try:
+        from info_nce import info_nce
+    finally:
+        sys.path.pop(0)
+    rng = np.random.default_rng(n * 100 + d)
+    q = (0.1 * rng.standard_normal((n, d))).astype(np.float32)
+    k = (0.5 * q + 0.1 * rng.standard_normal((n, d))).astype(np.float32)
+    if n > 4:
+        q[2] = 0
+    loss, gq, gk = oc.infonce(q, k, 0.1)
+    tq = torch.from_numpy(q).double().requires_grad_(True)
+    tk = torch.from_numpy(k).double().requires_grad_(True)
+    ref = info_nce(tq, tk, tk, temperature=0.1)
+    ref.backward()
+    assert abs(loss - float(ref)) < 1e-10
+    live = np.ones(n, dtype=bool)
+    if n > 4:
+        live[2] = False        # autograd's subgradient at the clamp differs by convention; the clamp branch is checked below
+    np.testing.assert_allclose(gq[live], tq.grad.numpy()[live], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(gk, tk.grad.numpy(), rtol=1e-8, atol=1e-12)
+    if n > 4:
+        assert np.isfinite(gq[2]).all()
+
+
+def test_rank_metrics_c_restatement_matches_port():
+    """oracle_rank_metrics against the restated calculate_metrics (oracle/ref_port.py, trainer.py:115-144)"""
+    from oracle import ref_port as rp
+    rng = np.random.default_rng(4)
+    n_users, n_items, k = 400, 300, 50
+    lens = rng.integers(0, 25, n_users)
+    eval_data = [sorted(rng.choice(n_items, l, replace=False).tolist()) for l in lens]
+    rec = np.stack([rng.permutation(n_items)[:k] for _ in range(n_users)]).astype(np.int32)
+    ptr = np.zeros(n_users + 1, dtype=np.int32)
+    np.cumsum(lens, out=ptr[1:])
+    idx = np.concatenate([np.asarray(x, dtype=np.int32) for x in eval_data])
+    topks = [1, 5, 10, 20, 50]
+    got, counted = oc.rank_metrics(rec, ptr, idx, topks)
+    want = rp.calculate_metrics(eval_data, rec, topks)
+    assert counted == int((lens > 0).sum())
+    for name in ("Precision", "Recall", "NDCG"):
+        for kk in topks:
+            assert abs(got[name][kk] - float(want[name][kk])) < 2e-6, (name, kk)
