@@ -157,39 +157,24 @@ class BasicTrainer:
 
     def calculate_metrics(self, eval_data, rec_items):
         """Precision / Recall / NDCG @k for every k in topks, averaged over users with at least one eval item
-        (trainer.py:115-144) -- one device pass over the recommended ids, 3*len(topks)+1 doubles come back."""
+        (trainer.py:115-144) -- one device pass over the recommended ids per 32 cut-offs, 3*len(topks)+1 doubles come back."""
         rec_d = self._rec_on_device(rec_items)
         ks = sorted(set(int(k) for k in self.topks))
-        if rec_d.shape[0] == 0 or len(ks) > 32 or ks[-1] > rec_d.shape[1]:
-            return self._calculate_metrics_host(eval_data, rec_items)
+        if rec_d.dim() != 2 or ks[0] < 1 or ks[-1] > rec_d.shape[1]:
+            raise ValueError('calculate_metrics needs rec_items [n_users, K] with K >= max(topks)')
+        results = {'Precision': {}, 'Recall': {}, 'NDCG': {}}
+        if rec_d.shape[0] == 0:
+            for name in results:
+                results[name] = {k: np.float32(np.nan) for k in ks}
+            return results
         ptr_d, idx_d = self._eval_csr(eval_data)
-        sums = ops.rank_metrics(rec_d, 0, ptr_d, idx_d, ks).cpu().numpy()
-        n = sums[-1]
-        results = {'Precision': {}, 'Recall': {}, 'NDCG': {}}
-        for i, k in enumerate(ks):
-            for j, name in enumerate(('Precision', 'Recall', 'NDCG')):
-                results[name][k] = np.float32(sums[3 * i + j] / n) if n > 0 else np.float32(np.nan)
-        return results
-
-    def _calculate_metrics_host(self, eval_data, rec_items):
-        """the same arithmetic from the device hit matrix in numpy (any number of cut-offs)"""
-        hit, n_eval = self.hit_matrix(eval_data, rec_items)
-        results = {'Precision': {}, 'Recall': {}, 'NDCG': {}}
-        has_items = n_eval > 0
-        for k in self.topks:
-            h = hit[:, :k]
-            n_hit = h.sum(axis=1)
-            with np.errstate(invalid='ignore', divide='ignore'):
-                recall = n_hit / n_eval
-            discount = np.log2(np.arange(2, k + 2, dtype=np.float32))[None, :]
-            dcg = (h / discount).sum(axis=1)
-            ideal = (np.arange(k)[None, :] < np.minimum(n_eval, k)[:, None]).astype(np.float32)
-            idcg = (ideal / discount).sum(axis=1)
-            with np.errstate(invalid='ignore', divide='ignore'):
-                ndcg = dcg / idcg
-            results['Precision'][k] = (n_hit / k)[has_items].mean()
-            results['Recall'][k] = recall[has_items].mean()
-            results['NDCG'][k] = ndcg[has_items].mean()
+        for c0 in range(0, len(ks), 32):  # the kernel takes up to 32 cut-offs per pass
+            part = ks[c0:c0 + 32]
+            sums = ops.rank_metrics(rec_d, 0, ptr_d, idx_d, part).cpu().numpy()
+            n = sums[-1]
+            for i, k in enumerate(part):
+                for j, name in enumerate(('Precision', 'Recall', 'NDCG')):
+                    results[name][k] = np.float32(sums[3 * i + j] / n) if n > 0 else np.float32(np.nan)
         return results
 
     def recommend_all(self, val_or_test, banned_items=None):
