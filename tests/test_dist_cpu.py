@@ -43,6 +43,13 @@ def test_dim_shard_ranges():
     s = DimShard(5, 8, min_cols=8)
     s.configure(64)
     assert (s.world, s.rank) == (8, 5)
+    # default narrowest shard by table residency: 32 columns for an L2-resident table, 16 for one that streams from HBM
+    small = DimShard(1, 2).configure(64, n_rows=69716)             # C2: 17.8 MB table
+    assert (small.min_cols, small.world, small.rank) == (32, 2, 1)
+    big = DimShard(3, 8).configure(128, n_rows=3_000_000)          # C4: 1.5 GB table -> 8 x 16 columns
+    assert (big.min_cols, big.world, big.rank) == (16, 8, 3)
+    legacy = DimShard(0, 2).configure(64)                          # no size given: the HBM rule
+    assert legacy.min_cols == 16
 
 
 def _worker(rank, world, port, out):
