@@ -107,3 +107,39 @@ def test_world_size_2_gloo_collectives():
         p.join(120)
         assert p.exitcode == 0
     assert sorted(out.get(timeout=5) for _ in range(2)) == [0, 1]
+
+
+def _worker_replicas(rank, world, port, out):
+    """4 ranks, D = 8, narrowest shard 4 columns -> two 2-way shard groups (replicas): the bench layout on 4 / 8 GPUs"""
+    sys.path[:0] = [PKG, REPO]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200rec.dist import DimShard
+    s = DimShard(rank, world, min_cols=4).configure(8)
+    assert (s.world, s.rank, s.replica) == (2, rank % 2, rank // 2) and s.cols(8) == ((rank % 2) * 4, (rank % 2) * 4 + 4)
+    # the per-step all-reduce stays inside the replica's shard group ...
+    t = s.all_reduce_sum(torch.tensor([float(rank)]))
+    assert float(t) == float(4 * (rank // 2) + 1)          # ranks {0,1} -> 1, ranks {2,3} -> 5
+    # ... the column gather too, while evaluation rows are sharded over the whole world
+    full = torch.arange(3 * 8, dtype=torch.float32).reshape(3, 8)
+    lo, hi = s.cols(8)
+    assert torch.equal(s.gather_cols(full[:, lo:hi].contiguous()), full)
+    ids = torch.arange(10 * 2, dtype=torch.int32).reshape(10, 2)
+    a, b = s.user_range(10)
+    assert (a, b) == (min(10, rank * 3), min(10, rank * 3 + 3))
+    assert torch.equal(s.gather_user_rows(ids[a:b].contiguous(), 10), ids)
+    out.put(rank)
+    dist.destroy_process_group()
+
+
+def test_world_size_4_gloo_replicated_shard_groups():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_replicas, args=(r, 4, port, out)) for r in range(4)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert sorted(out.get(timeout=5) for _ in range(4)) == [0, 1, 2, 3]
