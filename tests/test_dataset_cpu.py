@@ -92,3 +92,22 @@ def test_output_dataset_round_trip(tmp_path, lists):
     ds.output_dataset(q)
     ds2 = D.get_dataset({"name": "ProcessedDataset", "path": q, "device": "cpu"})
     assert ds2.train_data == ds.train_data and ds2.test_data == ds.test_data and ds2.n_items == ds.n_items
+
+
+def test_parser_property_random_files(tmp_path):
+    """the vectorised parser against the reference's line-by-line parse on random files (users without items, single
+    items, large ids)"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.lists(st.integers(0, 10 ** 6), max_size=12), min_size=1, max_size=40))
+    def check(rows):
+        path = str(tmp_path / "f.txt")
+        with open(path, "w") as f:
+            for u, items in enumerate(rows):
+                f.write(" ".join([str(u)] + [str(i) for i in items]) + "\n")
+        ptr, idx = D._parse_lists(path)
+        got = [idx[ptr[u]:ptr[u + 1]].tolist() for u in range(len(ptr) - 1)]
+        assert got == _naive(path) == rows
+
+    check()
