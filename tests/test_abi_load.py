@@ -169,3 +169,19 @@ def test_plan_build_host_invariants_random():
             assert (np.diff((end - start)[ph]) <= 0).all()                          # longest first inside a phase
 
     check()
+
+
+def test_library_is_sm100a_and_carries_tensor_core_code():
+    """the built library holds sm_100a cubins only, and the evaluation kernel really is tcgen05 / TMA / TMEM code
+    (SASS: UTCHMMA = tcgen05.mma, UTMALDG = TMA tile load, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit)"""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run([cuobjdump, "-lelf", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    cubins = [line.split()[-1] for line in elf.splitlines() if "cubin" in line]
+    assert cubins and all(".sm_100a." in c for c in cubins), cubins
+    sass = subprocess.run([cuobjdump, "-sass", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
+        assert mnemonic in sass, mnemonic
