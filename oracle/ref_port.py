@@ -169,6 +169,55 @@ class LightGCNPort(torch.nn.Module):
         return torch.mm(rep[users, :], rep[self.n_users:, :].t())
 
 
+def infonce(query, positive_key, temperature=0.1):
+    """The `info_nce` package as SGL / HALF call it (model.py:206-214): InfoNCE(negative_mode='unpaired')(q, k, k) --
+    rows L2-normalised (F.normalize), logits [q.k_i (positive) | q.K^T] / T, cross-entropy against index 0, mean."""
+    q = F.normalize(query, dim=-1)
+    k = F.normalize(positive_key, dim=-1)
+    logits = torch.cat([torch.sum(q * k, dim=1, keepdim=True), q @ k.t()], dim=1) / temperature
+    return F.cross_entropy(logits, torch.zeros(len(logits), dtype=torch.long), reduction='mean')
+
+
+class SGLPort(LightGCNPort):
+    """SGL (model.py:130-243) / HALF (:246-365): LightGCN propagation on the full graph plus one or two edge-dropped views
+    (utils.py:91-103: a uniform sample of int(E * aug_rate) train pairs, degrees recomputed), contrasted with InfoNCE at
+    the batch users.  `views`: list of (users, items) pair arrays of the kept edges (two for SGL, one for HALF)."""
+
+    def __init__(self, n_users, n_items, users, items, emb0, n_layers, views, half=False):
+        super().__init__(n_users, n_items, users, items, emb0, n_layers)
+        self.half = half
+        self.views = [torch_csr(norm_adjacency(n_users, n_items, vu, vi)) for vu, vi in views]
+        assert len(self.views) == (1 if half else 2)
+
+    def get_aug_rep(self, a):  # model.py:189-200
+        x = self.layer0()
+        reps = [x]
+        for _ in range(self.n_layers):
+            x = spmm(a, a, x)
+            reps.append(x)
+        return torch.stack(reps, dim=0).mean(dim=0)
+
+    def bpr_forward(self, users, pos, neg):  # model.py:216-229 / :334-349: l2 on the FINAL representations
+        rep = self.get_rep()
+        ur, pr, nr = rep[users, :], rep[self.n_users + pos, :], rep[self.n_users + neg, :]
+        l2 = torch.norm(ur, p=2, dim=1) ** 2 + torch.norm(pr, p=2, dim=1) ** 2 + torch.norm(nr, p=2, dim=1) ** 2
+        a1 = self.get_aug_rep(self.views[0])[users, :]
+        con = infonce(ur, a1) if self.half else infonce(a1, self.get_aug_rep(self.views[1])[users, :])
+        return ur, pr, nr, l2, con
+
+
+def contrastive_train_step(model, opt, batch, l2_reg, contrastive_reg):
+    """One iteration of SGLTrainer / HALFTrainer.train_one_epoch (trainer.py:440-456)."""
+    users, pos, neg = batch[:, 0], batch[:, 1], batch[:, 2]
+    ur, pr, nr, l2, con = model.bpr_forward(users, pos, neg)
+    bpr = F.softplus(torch.sum(ur * nr, dim=1) - torch.sum(ur * pr, dim=1)).mean()
+    loss = bpr + l2_reg * l2.mean() + contrastive_reg * con.mean()
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return loss.item(), float(con.detach())
+
+
 class MFPort(torch.nn.Module):
     """model.py:56-76."""
 

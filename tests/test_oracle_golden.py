@@ -174,3 +174,30 @@ def test_contrastive_fixture_against_closed_form(golden, name):
     ur = g["users_r"].astype(np.float64)
     total = float(g["bpr_loss"]) + float(g["l2_reg"]) * float(np.mean(g["l2_norm_sq"])) + float(g["contrastive_reg"]) * loss
     assert abs(total - float(g["loss"])) < 1e-5 and ur.shape == (len(users), 64)
+
+
+@pytest.mark.parametrize("name", ["sgl_tiny", "half_tiny"])
+def test_contrastive_port_matches_reference_steps(golden, name):
+    """oracle/ref_port.py SGLPort + contrastive_train_step against the unmodified reference's two recorded steps"""
+    g = golden(name)
+    nu, ni = int(g["n_users"]), int(g["n_items"])
+    users, items = _pairs(g)
+
+    def view(key):
+        idx = g[key + "_idx"]
+        sel = idx[0] < nu
+        return idx[0][sel].astype(np.int64), idx[1][sel].astype(np.int64) - nu
+
+    views = [view("aug1")] + ([view("aug2")] if name == "sgl_tiny" else [])
+    port = rp.SGLPort(nu, ni, users, items, g["emb0"], int(g["n_layers"]), views, half=(name == "half_tiny")).train()
+    a = port.views[0].to_sparse_coo().coalesce()
+    assert np.array_equal(a.indices().numpy(), g["aug1_idx"]) and np.array_equal(a.values().numpy(), g["aug1_val"])
+    opt = torch.optim.Adam(port.parameters(), lr=float(g["lr"]))
+    batch = torch.from_numpy(g["batch"])
+    loss, con = rp.contrastive_train_step(port, opt, batch, float(g["l2_reg"]), float(g["contrastive_reg"]))
+    assert abs(loss - float(g["loss"])) < 1e-6 and abs(con - float(g["contrastive_loss"])) < 1e-6
+    np.testing.assert_allclose(port.embedding.weight.grad.numpy(), g["grad_emb"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(port.embedding.weight.detach().numpy(), g["emb1"], rtol=1e-5, atol=2e-6)
+    loss2, _ = rp.contrastive_train_step(port, opt, batch, float(g["l2_reg"]), float(g["contrastive_reg"]))
+    assert abs(loss2 - float(g["loss2"])) < 1e-6
+    np.testing.assert_allclose(port.embedding.weight.detach().numpy(), g["emb2"], rtol=1e-5, atol=4e-6)
