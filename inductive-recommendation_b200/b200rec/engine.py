@@ -136,6 +136,7 @@ class BprEngine:
                     self.aux_ptr, self.aux_items = aux_dataset.csr('train', device=dev)
         import os
         self.use_graph = use_graph and os.environ.get('B200REC_NO_GRAPH', '0') != '1'
+        self._adj_ref = getattr(model, 'norm_adj', None)  # the step (and its captured graph) is built on THIS operand
         self._side_stream = torch.cuda.Stream(device=dev)
         self._graphs = {}
         self._kernels = {}
@@ -307,6 +308,8 @@ class BprEngine:
         ops.step_advance(self.adam_step, self.sample_step, self.loss, self.loss_accum, B)
 
     def _run(self, sample, draw_mask=True):
+        if getattr(self.model, 'norm_adj', None) is not self._adj_ref:
+            raise RuntimeError('model.norm_adj was replaced after the training engine was built: create a new trainer')
         if not self.use_graph:
             self._body(sample, draw_mask)
             return
