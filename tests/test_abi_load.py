@@ -185,3 +185,19 @@ def test_library_is_sm100a_and_carries_tensor_core_code():
     sass = subprocess.run([cuobjdump, "-sass", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
         assert mnemonic in sass, mnemonic
+
+
+def test_csr_struct_mirror_matches_header_and_integration_doc():
+    """b200rec_csr: field names, order and C types in include/b200rec.h == the ctypes mirror in b200rec/_abi.py == the stub
+    shown in INTEGRATION.md (a reordered field would silently shift every pointer)"""
+    text = open(os.path.join(REPO, "include", "b200rec.h")).read()
+    body = text[text.index("typedef struct {"):text.index("} b200rec_csr;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"^\s*(const\s+)?(int32_t|float)\s*(\*?)\s*([a-z0-9_]+);", body, flags=re.M)
+    header = [(name, "ptr" if star else ctype) for _, ctype, star, name in fields]
+    mirror = [(n, "ptr" if t is C.c_void_p else {C.c_int32: "int32_t"}[t]) for n, t in _abi.CsrStruct._fields_]
+    assert header == mirror and len(header) >= 20
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    stub = doc[doc.index("class b200rec_csr(ctypes.Structure)"):doc.index("def get_rep(self):")]
+    doc_fields = re.findall(r'\("([a-z0-9_]+)", ctypes\.(c_int32|c_void_p)\)', stub)
+    assert [(n, "ptr" if t == "c_void_p" else "int32_t") for n, t in doc_fields] == mirror
