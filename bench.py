@@ -114,7 +114,18 @@ def cpu_port_step_time(graph, workload, n_steps, warmup, seed=2021):
     t0 = time.perf_counter()
     for b in batches[warmup:]:
         rp.train_step(port, opt, b, L2_REG)
-    return (time.perf_counter() - t0) / max(n_steps, 1), threads
+    return (time.perf_counter() - t0) / max(n_steps, 1), threads, port
+
+
+def cpu_port_eval_rate(graph, port, n_users=1024):
+    """full-rank evaluation of the first `n_users` users by the oracle port, the way the reference does it (trainer.py:
+    146-170: every 512-user batch re-propagates, dense scores, Python exclusion lists, topk): users/s on the host cores"""
+    from oracle import ref_port as rp
+    n = min(n_users, graph.n_users)
+    train, val, test = graph.lists("train")[:n], graph.lists("val")[:n], graph.lists("test")[:n]
+    t0 = time.perf_counter()
+    rp.evaluate(port, train, val, test, "test", TOPKS, test_batch_size=512, n_users=n)
+    return n / (time.perf_counter() - t0), n
 
 
 def run_reference(args, rank):
@@ -124,8 +135,9 @@ def run_reference(args, rank):
     graph = build_graph(workload, "cpu")
     n_train = int(graph.train_items.numel())
     steps_per_epoch = (n_train + BATCH - 1) // BATCH
-    s_per_step, threads = cpu_port_step_time(graph, workload, args.steps, args.warmup)
+    s_per_step, threads, port = cpu_port_step_time(graph, workload, args.steps, args.warmup)
     value = 1.0 / (steps_per_epoch * s_per_step)
+    eval_rate, eval_n = cpu_port_eval_rate(graph, port)
     sample = "%d timed train steps (batch %d) of %d per epoch, extrapolated" % (args.steps, BATCH, steps_per_epoch)
     line = {"impl": "reference", "metric": "bpr_epochs_per_sec", "value": value, "unit": "epochs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True,
@@ -133,7 +145,8 @@ def run_reference(args, rank):
             "config": {"workload": workload + ": " + WORKLOAD_DOC[workload], "batch": BATCH,
                        "steps_per_epoch": steps_per_epoch},
             "cpu_baseline": {"value": value, "unit": "epochs/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "eval": {"users_per_s_e2e": eval_rate, "sample": "first %d users, test split, K=%d, 512-user batches" % (eval_n, max(TOPKS))}}
     print(json.dumps(line), flush=True)
 
 
@@ -308,7 +321,7 @@ def run_own(args, rank, world):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "lightgcn":
         n_cpu = 3 if workload != "c4" else 1
-        s_cpu, threads = cpu_port_step_time(graph, workload, n_cpu, 1)
+        s_cpu, threads, _ = cpu_port_step_time(graph, workload, n_cpu, 1)
         cpu_baseline = {"value": 1.0 / (steps_per_epoch * s_cpu), "unit": "epochs/s", "cores": threads, "kind": "port",
                         "sample": "%d timed train steps (batch %d) of %d per epoch on torch-CPU CSR/MKL, extrapolated"
                                   % (n_cpu, BATCH, steps_per_epoch), "ms_per_step": 1e3 * s_cpu}
