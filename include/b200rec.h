@@ -46,15 +46,20 @@ uint64_t b200rec_launch_count(void);
  * is ~slot (negative) -- they write a partial row into `partial[slot]`, and whichever lane group parks the last
  * chunk of a row adds that row's slots in slot order (deterministic) and writes the row.  Items are sorted by length, longest first.
  * The decomposition is built once per graph by b200rec_plan_build().
+ *
+ * Column-blocked plans (tables larger than L2, e.g. 3M x 128 fp32): the source rows are cut into blocks that fit L2 and
+ * the items into one PASS per block -- a pass holds, for every row (or hub piece) with entries in that block, the slice
+ * of its entries that falls into it.  CSR columns ascend inside a row, so the slices of a row are consecutive; each
+ * continues the row's running fmaf chain (bit 29 of the item code = "reload the running sum", bit 30 = "park it again
+ * instead of finishing", the low 29 bits = row id or slot) -- same chain, same bits as the single-pass kernel.
+ * b200rec_spmm_f32_blocked launches the passes back to back; the other entry points take single-pass plans only.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
   int32_t n_rows;            /* output rows */
   int32_t n_cols;            /* rows of the gathered table */
   int32_t nnz;
   const int32_t* rowptr;     /* [n_rows+1] */
-  const int32_t* colidx;     /* [nnz] ascending inside a row; with col_hint != 0 bit 31 marks a "hot" column */
-  int32_t col_hint;          /* 0: plain ids; 1: hot rows allocate in L1, others L1::no_allocate;
-                                2: hot rows L2::evict_last, others L2::evict_first (table larger than L2) */
+  const int32_t* colidx;     /* [nnz] ascending inside a row */
   const float* vals;         /* [nnz] per-edge value, or NULL (all ones) */
   const float* nbr_scale;    /* [n_cols] multiplies each gathered row, or NULL */
   const float* row_scale;    /* [n_rows] multiplies the finished row sum, or NULL */
@@ -63,7 +68,7 @@ typedef struct {
   int32_t n_items;
   const int32_t* item_start; /* [n_items] */
   const int32_t* item_end;   /* [n_items] */
-  const int32_t* item_dst;   /* [n_items] row id, or ~slot for a piece of a long row */
+  const int32_t* item_dst;   /* [n_items] row id, or ~slot for a piece of a long row (column-blocked plans: | bits 29/30) */
   const int32_t* item_row;   /* [n_items] the row the item belongs to (needed only with dst_flags) */
   int32_t n_long;            /* rows that were split */
   const int32_t* long_row;   /* [n_long] */
@@ -73,15 +78,37 @@ typedef struct {
   int32_t n_slots;
   const int32_t* slot_long;  /* [n_slots] index (into long_*) of the split row a slot belongs to */
   float* partial;            /* [n_slots, D] scratch for split rows (caller-owned, D = largest D used) */
+  int32_t n_passes;          /* 1 (or 0) = single-pass plan; > 1 = column-blocked plan */
+  const int32_t* pass_ptr;   /* HOST [n_passes+1]: items [pass_ptr[b], pass_ptr[b+1]) form pass b (NULL for single-pass plans) */
 } b200rec_csr;
 
-/* Build the decomposition on the HOST (one-time, per graph).  All pointers here are HOST pointers.
- * Call once with the output arrays NULL to get the sizes, allocate, call again to fill. */
-int b200rec_plan_build_host(const int32_t* rowptr /*HOST [n_rows+1]*/, int32_t n_rows, int32_t chunk,
-                            int32_t phase_split /*rows < this are scheduled first (n_users), 0 = one phase*/,
-                            int32_t* n_items, int32_t* n_long, int32_t* n_slots,
-                            int32_t* item_start, int32_t* item_end, int32_t* item_dst, int32_t* item_row,
-                            int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot, int32_t* slot_long);
+/* COO -> coalesced int32 CSR on the device (utils.py:42-50 generate_daj_mat: scipy COO->CSR sums duplicates;
+ * utils.py:33-39 get_sparse_tensor: coalesced, row-major, columns ascending).  Entry i is (rows[i] + row_offset,
+ * cols[i] + col_offset); int64 ids like the reference's train_array.  Outputs (caller-allocated): rowptr [n_rows+1],
+ * colidx [n] and mult [n] (capacity n = the upper bound; *nnz_out (HOST) entries are valid; mult = multiplicity of each
+ * entry as fp32, may be NULL), first_pos [n] (optional: list position of the first entry merged into each output
+ * entry -- a transposed operand uses it as its edge-id map).  *has_dup_out (HOST) = 1 if any pair repeated.
+ * Setup-time call: allocates scratch and synchronises `stream`. */
+int b200rec_csr_build(const int64_t* rows, const int64_t* cols, int64_t n, int64_t row_offset, int64_t col_offset,
+                      int32_t n_rows, int32_t n_cols, int32_t* rowptr, int32_t* colidx, float* mult,
+                      int32_t* first_pos, int32_t* nnz_out /*HOST*/, int32_t* has_dup_out /*HOST*/, void* stream);
+/* The symmetric bipartite adjacency of the E train pairs (utils.py:42-50): rows/cols [users | items + n_users],
+ * both directions, duplicates summed.  colidx / mult capacity 2E. */
+int b200rec_adj_build(const int64_t* users, const int64_t* items, int64_t n_pairs, int32_t n_users, int32_t n_items,
+                      int32_t* rowptr, int32_t* colidx, float* mult, int32_t* nnz_out /*HOST*/,
+                      int32_t* has_dup_out /*HOST*/, void* stream);
+/* Build the work decomposition on the device (one-time, per graph and -- for column-blocked plans -- per table width).
+ * order_split: rows >= it are scheduled after the others (n_users: each side of the bipartite graph gathers from the
+ * other side only, so each phase has the caches to itself); 0 = one phase.
+ * col_bounds (HOST [n_blocks+1], ascending from 0 to n_cols) cuts the source rows into n_blocks L2-sized blocks;
+ * n_blocks = 1 (col_bounds may be NULL) builds a single-pass plan.
+ * Call once with item_start == NULL to get sizes[3] (HOST) = {n_items, n_long, n_slots}, allocate, call again.
+ * pass_ptr: HOST out [max(n_blocks,1)+1].  Allocates scratch and synchronises `stream`. */
+int b200rec_plan_build(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows, int32_t chunk, int32_t order_split,
+                       const int32_t* col_bounds /*HOST*/, int32_t n_blocks, int32_t* sizes /*HOST out [3]*/,
+                       int32_t* item_start, int32_t* item_end, int32_t* item_dst, int32_t* item_row,
+                       int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot, int32_t* slot_long,
+                       int32_t* pass_ptr /*HOST out*/, void* stream);
 
 /* Symmetric-normalised adjacency values (model.py:89-98 LightGCN.generate_graph; utils.py:42-50).
  * deg[r] = max(1, sum of multiplicities in row r); dinv = deg^-1/2 (fp32, correctly rounded);
@@ -107,6 +134,14 @@ int b200rec_spmm_f32(const b200rec_csr* a /*HOST struct of device pointers*/, co
 int b200rec_spmm_f32_ex(const b200rec_csr* a, const float* x, int32_t d, const uint32_t* keep_bits, float post_scale,
                         float* y, const float* addend, float* out, float out_scale,
                         const uint8_t* dst_flags, const uint8_t* src_flags, void* stream);
+
+/* The same sum through a column-blocked plan (a->n_passes > 1): one launch per block of source rows, running sums carried
+ * in `carry` ([n_rows, ld] fp32 scratch).  Plain valued operand only (no masks / scales).  `ld` is the row stride in
+ * floats of x, y, addend, out and carry (>= d): with ld > d the call works on d columns of wider tables -- a D = 128
+ * table can be swept as two independent 64-column halves, each with half as many passes.  Bit-identical to
+ * b200rec_spmm_f32 on a single-pass plan with the same chunk. */
+int b200rec_spmm_f32_blocked(const b200rec_csr* a, const float* x, int32_t d, int32_t ld, float post_scale,
+                             float* y, const float* addend, float* out, float out_scale, float* carry, void* stream);
 
 /* L-layer propagation + layer mean (model.py:100-110 LightGCN.get_rep; :4193-4199 IGCN.get_rep):
  *   X_{k+1} = A X_k,  mean_out = (X_0 + ... + X_L) / (L+1).  buf0/buf1: [n_rows, D] scratch (L >= 2 needs both).

@@ -21,7 +21,7 @@ class CsrStruct(C.Structure):
     """mirror of `b200rec_csr` (include/b200rec.h)"""
     _fields_ = [
         ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int32),
-        ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("col_hint", C.c_int32), ("vals", C.c_void_p),
+        ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("vals", C.c_void_p),
         ("nbr_scale", C.c_void_p), ("row_scale", C.c_void_p), ("eid", C.c_void_p),
         ("n_items", C.c_int32),
         ("item_start", C.c_void_p), ("item_end", C.c_void_p), ("item_dst", C.c_void_p), ("item_row", C.c_void_p),
@@ -29,6 +29,7 @@ class CsrStruct(C.Structure):
         ("long_row", C.c_void_p), ("long_slot0", C.c_void_p), ("long_nslot", C.c_void_p), ("long_cnt", C.c_void_p),
         ("n_slots", C.c_int32), ("slot_long", C.c_void_p),
         ("partial", C.c_void_p),
+        ("n_passes", C.c_int32), ("pass_ptr", C.c_void_p),
     ]
 
 
@@ -40,10 +41,13 @@ PROTOTYPES = {
     "b200rec_last_error": (C.c_char_p, []),
     "b200rec_version": (C.c_int, []),
     "b200rec_launch_count": (C.c_uint64, []),
-    "b200rec_plan_build_host": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200rec_csr_build": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "b200rec_adj_build": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "b200rec_plan_build": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200rec_adj_normalize": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P]),
     "b200rec_spmm_f32": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P]),
     "b200rec_spmm_f32_ex": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P, _P, _P]),
+    "b200rec_spmm_f32_blocked": (C.c_int, [_CSRP, _P, _I32, _I32, _F, _P, _P, _P, _F, _P, _P]),
     "b200rec_live_items": (C.c_int, [_CSRP, _P, _P, _P, _P]),
     "b200rec_spmm_f32_live": (C.c_int, [_CSRP, _P, _I32, _F, _P, _P, _P, _F, _P, _P, _I32, _P]),
     "b200rec_propagate_fwd": (C.c_int, [_CSRP, _P, _I32, _I32, _P, _P, _P, _P, _P]),

@@ -116,8 +116,6 @@ def shard_model_dims(model, shard):
             model.w = nn.Parameter(model.w.data[lo:hi].contiguous())
     model.full_embedding_size = d
     model.embedding_size = hi - lo
-    if hasattr(model, 'norm_adj'):
-        model.norm_adj.apply_cache_hints(hi - lo, model.n_users)  # row bytes changed: re-rank what fits the caches
     model._dim_shard = shard
     model._rep_cache = None
     return model

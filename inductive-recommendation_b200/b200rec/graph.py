@@ -34,9 +34,31 @@ def auto_chunk(nnz, d=None):
     return c
 
 
+def blocking_policy(n_cols, d):
+    """(sweep width, source rows per block) for a gathered table [n_cols, d] fp32, or None when the table is left to the
+    cache as it is.  A table much larger than L2 (C4: 3M x 128 x 4 B = 1.5 GB against 126 MB) is gathered at a few
+    percent L2 hit rate and the SpMM runs at the HBM ceiling moving ~16x its algorithmic bytes; cutting the source rows
+    into L2-sized blocks (one pass each, b200rec_spmm_f32_blocked) turns those gathers into L2 hits.  Wide tables are
+    swept in column slices of `sweep` floats: half the width = half as many passes = half the carried-sum traffic, for a
+    second read of the 8 B/edge index stream.  Environment overrides for experiments: B200REC_BLOCK_MB (0 = never block),
+    B200REC_SWEEP_D."""
+    import os
+    block_mb = float(os.environ.get("B200REC_BLOCK_MB", "48"))
+    if block_mb <= 0:
+        return None
+    sweep = int(os.environ.get("B200REC_SWEEP_D", "64"))
+    sweep = min(d, max(8, sweep))
+    if d % sweep:
+        sweep = d
+    block_bytes = block_mb * (1 << 20)
+    if n_cols * sweep * 4 <= 1.5 * block_bytes:
+        return None
+    return sweep, max(1024, int(block_bytes // (sweep * 4)))
+
+
 class CsrOperand:
     def __init__(self, rowptr, colidx, n_cols, vals=None, nbr_scale=None, row_scale=None, eid=None, chunk=None,
-                 max_d=256, phase_split=0, d=None):
+                 max_d=256, phase_split=0, d=None, col_bounds=None):
         _abi.require_cuda(rowptr, colidx, vals, nbr_scale, row_scale, eid)
         assert rowptr.dtype == torch.int32 and colidx.dtype == torch.int32
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
@@ -47,34 +69,37 @@ class CsrOperand:
         self.device = rowptr.device
         self.chunk = chunk if chunk is not None else auto_chunk(self.nnz, d)
         self.phase_split = int(phase_split)
-        self.col_hint = 0
+        self.col_bounds = None if col_bounds is None else np.ascontiguousarray(col_bounds, dtype=np.int32)
         self._build_plan(max_d)
         self._struct = None
+        self._blocked = {}   # sweep width -> column-blocked twin of this operand (shared CSR arrays, own plan)
+        self._carry = {}     # row stride -> carried-sum scratch [n_rows, ld]
 
     def _build_plan(self, max_d):
+        """b200rec_plan_build on the device: sizes first, then the arrays"""
         lib = _abi.load()
-        rp = self.rowptr.cpu().numpy()
-        n_items, n_long, n_slots = C.c_int32(0), C.c_int32(0), C.c_int32(0)
-        null = C.c_void_p(0)
-        _abi.check(lib.b200rec_plan_build_host(rp.ctypes.data, self.n_rows, self.chunk, self.phase_split,
-                                               C.addressof(n_items),
-                                               C.addressof(n_long), C.addressof(n_slots), null, null, null, null, null,
-                                               null, null, null), "plan_build_host(size)")
-        ni, nl, ns = n_items.value, n_long.value, n_slots.value
-        a = [np.empty(max(ni, 1), dtype=np.int32) for _ in range(4)]
-        b = [np.empty(max(nl, 1), dtype=np.int32) for _ in range(3)]
-        sl = np.zeros(max(ns, 1), dtype=np.int32)
-        _abi.check(lib.b200rec_plan_build_host(rp.ctypes.data, self.n_rows, self.chunk, self.phase_split,
-                                               C.addressof(n_items),
-                                               C.addressof(n_long), C.addressof(n_slots),
-                                               a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
-                                               b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, sl.ctypes.data),
-                   "plan_build_host")
         dev = self.device
+        nb = 1 if self.col_bounds is None else len(self.col_bounds) - 1
+        bounds = C.c_void_p(0) if self.col_bounds is None else C.c_void_p(self.col_bounds.ctypes.data)
+        sizes = (C.c_int32 * 3)()
+        null = C.c_void_p(0)
+        with torch.cuda.device(dev):
+            _abi.check(lib.b200rec_plan_build(_abi.ptr(self.rowptr), _abi.ptr(self.colidx), self.n_rows, self.chunk,
+                                              self.phase_split, bounds, nb, sizes, null, null, null, null, null, null,
+                                              null, null, null, _abi.stream_ptr()), "plan_build(size)")
+            ni, nl, ns = sizes[0], sizes[1], sizes[2]
+            i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=dev)  # noqa: E731
+            self.item_start, self.item_end, self.item_dst, self.item_row = i32(ni), i32(ni), i32(ni), i32(ni)
+            self.long_row, self.long_slot0, self.long_nslot, self.slot_long = i32(nl), i32(nl), i32(nl), i32(ns)
+            self.pass_ptr = np.zeros(nb + 1, dtype=np.int32)
+            _abi.check(lib.b200rec_plan_build(_abi.ptr(self.rowptr), _abi.ptr(self.colidx), self.n_rows, self.chunk,
+                                              self.phase_split, bounds, nb, sizes, _abi.ptr(self.item_start),
+                                              _abi.ptr(self.item_end), _abi.ptr(self.item_dst), _abi.ptr(self.item_row),
+                                              _abi.ptr(self.long_row), _abi.ptr(self.long_slot0), _abi.ptr(self.long_nslot),
+                                              _abi.ptr(self.slot_long), C.c_void_p(self.pass_ptr.ctypes.data),
+                                              _abi.stream_ptr()), "plan_build")
         self.n_items, self.n_long, self.n_slots = ni, nl, ns
-        self.item_start, self.item_end, self.item_dst, self.item_row = (torch.from_numpy(x[:max(ni, 1)]).to(dev) for x in a)
-        self.long_row, self.long_slot0, self.long_nslot = (torch.from_numpy(x[:max(nl, 1)]).to(dev) for x in b)
-        self.slot_long = torch.from_numpy(sl).to(dev)
+        self.n_passes = nb
         self.long_cnt = torch.zeros(max(nl, 1), dtype=torch.int32, device=dev)
         self.partial = torch.empty((max(ns, 1), max_d), dtype=torch.float32, device=dev) if ns else None
         self.max_d = max_d
@@ -84,9 +109,7 @@ class CsrOperand:
             s = _abi.CsrStruct()
             s.n_rows, s.n_cols, s.nnz = self.n_rows, self.n_cols, self.nnz
             p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
-            s.rowptr, s.vals = p(self.rowptr), p(self.vals)
-            s.colidx = p(self.colidx_enc if self.col_hint else self.colidx)
-            s.col_hint = self.col_hint
+            s.rowptr, s.vals, s.colidx = p(self.rowptr), p(self.vals), p(self.colidx)
             s.nbr_scale, s.row_scale, s.eid = p(self.nbr_scale), p(self.row_scale), p(self.eid)
             s.n_items = self.n_items
             s.item_start, s.item_end, s.item_dst = p(self.item_start), p(self.item_end), p(self.item_dst)
@@ -96,54 +119,49 @@ class CsrOperand:
             s.n_slots = self.n_slots
             s.slot_long, s.long_cnt = p(self.slot_long), p(self.long_cnt)
             s.partial = p(self.partial)
+            s.n_passes = self.n_passes
+            s.pass_ptr = self.pass_ptr.ctypes.data if self.n_passes > 1 else None
             self._struct = s
         return self._struct
 
-    def apply_cache_hints(self, d, n_users=None):
-        """Flag the hottest gathered rows (bit 31 of a private copy of colidx) for the kernel's cache-policy loads.
-        Table larger than L2 -> hint 2: the top rows that fit ~half of L2 are kept with L2::evict_last while every other
-        row streams through evict_first.  Table L2-resident -> hint 1: the top rows that fit L1 allocate there, the
-        rest bypass L1.  Users and items are ranked separately: a row gathers only from the other side, and the
-        plan runs the two sides as two phases."""
-        if self.n_rows != self.n_cols or self.nnz == 0:
-            return self
-        l2 = torch.cuda.get_device_properties(self.device).L2_cache_size
-        row_bytes = d * 4
-        import os
-        frac = float(os.environ.get("B200REC_HOT_FRAC", "0"))  # measured on C4: hints 11.8-12.1 ms/layer vs 11.6 without -> off
-        if self.n_cols * row_bytes > 0.6 * l2 and frac > 0:
-            hint, k = 2, int(frac * l2 / row_bytes)
-        elif os.environ.get("B200REC_L1_HINT", "0") == "1":
-            hint, k = 1, int(160 * 1024 / row_bytes)
-        else:
-            # L2-resident table: measured on the C2 shape, bypassing L1 for cold rows is a loss (0.372 -> 0.507 ms/step)
-            self.col_hint, self._struct = 0, None
-            return self
-        deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
-        hot = torch.zeros(self.n_cols, dtype=torch.bool, device=self.device)
-        sides = [(0, self.n_cols)] if not n_users else [(0, n_users), (n_users, self.n_cols)]
-        for lo, hi in sides:
-            kk = min(k, hi - lo)
-            if kk > 0:
-                hot[lo + torch.topk(deg[lo:hi], kk).indices] = True
-        enc = self.colidx.clone()
-        enc[hot[self.colidx.long()]] |= -2 ** 31
-        self.colidx_enc, self.col_hint, self.hot_rows, self._struct = enc, hint, int(hot.sum()), None
-        return self
+    # ---- column-blocked execution for tables that do not fit L2 ----
+    def blocked_for(self, d):
+        """(twin operand with a column-blocked plan, sweep width) for a gathered table of width d, or None"""
+        if self.vals is None or self.nbr_scale is not None or self.eid is not None or self.n_passes > 1:
+            return None
+        pol = blocking_policy(self.n_cols, d)
+        if pol is None:
+            return None
+        sweep, block_rows = pol
+        key = (sweep, block_rows)
+        if key not in self._blocked:
+            split = self.phase_split if 0 < self.phase_split < self.n_cols and self.n_rows == self.n_cols else 0
+            sides = [(0, self.n_cols)] if not split else [(0, split), (split, self.n_cols)]
+            bounds = [0]
+            for lo, hi in sides:  # a block never straddles the user | item boundary: each side is gathered by the other
+                nblk = max(1, -(-(hi - lo) // block_rows))
+                step = -(-(hi - lo) // nblk)
+                bounds += [min(hi, lo + (k + 1) * step) for k in range(nblk)]
+            self._blocked[key] = CsrOperand(self.rowptr, self.colidx, self.n_cols, vals=self.vals, chunk=self.chunk,
+                                            max_d=self.max_d, phase_split=self.phase_split, col_bounds=bounds)
+        return self._blocked[key], sweep
+
+    def carry(self, ld):
+        if ld not in self._carry:
+            self._carry[ld] = torch.empty((self.n_rows, ld), dtype=torch.float32, device=self.device)
+        return self._carry[ld]
 
     def replan(self, chunk):
         """the same matrix with a different hub-row chunk (own work plan and scratch, shared CSR arrays)"""
-        o = CsrOperand(self.rowptr, self.colidx, self.n_cols, vals=self.vals, nbr_scale=self.nbr_scale,
-                       row_scale=self.row_scale, eid=self.eid, chunk=chunk, max_d=self.max_d, phase_split=self.phase_split)
-        if self.col_hint:
-            o.colidx_enc, o.col_hint = self.colidx_enc, self.col_hint
-        return o
+        return CsrOperand(self.rowptr, self.colidx, self.n_cols, vals=self.vals, nbr_scale=self.nbr_scale,
+                          row_scale=self.row_scale, eid=self.eid, chunk=chunk, max_d=self.max_d, phase_split=self.phase_split)
 
     def with_scales(self, nbr_scale=None, row_scale=None):
         """same structure/plan, different per-node scale vectors (IGCN anneal: F's values change every epoch)"""
         o = object.__new__(CsrOperand)
         o.__dict__.update(self.__dict__)
         o.nbr_scale, o.row_scale, o._struct = nbr_scale, row_scale, None
+        o._blocked, o._carry = {}, {}
         return o
 
     def row_slice(self, lo, hi=None):
@@ -153,6 +171,8 @@ class CsrOperand:
         o = object.__new__(CsrOperand)
         o.__dict__.update(self.__dict__)
         o._struct = None
+        o._blocked, o._carry = {}, {}
+        assert self.n_passes <= 1, "row_slice of a column-blocked plan"
         row = self.item_row[:self.n_items]
         keep = torch.zeros_like(row, dtype=torch.bool)
         for a, b in ranges:
@@ -191,48 +211,56 @@ class CsrOperand:
         return rows, self.colidx.long(), self.vals
 
 
-def _rowptr_from_sorted_rows(rows, n_rows):
-    counts = torch.bincount(rows, minlength=n_rows)
-    rp = torch.zeros(n_rows + 1, dtype=torch.int64, device=rows.device)
-    torch.cumsum(counts, 0, out=rp[1:])
-    return rp
-
-
-def _coalesce(rows, cols, n_rows, n_cols):
-    """sort by (row, col), merge duplicates -> (rowptr int32, colidx int32, mult fp32 or None)"""
-    key = rows * n_cols + cols
-    key, _ = torch.sort(key)
-    uniq, counts = torch.unique_consecutive(key, return_counts=True)
-    r = torch.div(uniq, n_cols, rounding_mode="floor")
-    c = uniq - r * n_cols
-    mult = None
-    if uniq.numel() != key.numel():
-        mult = counts.to(torch.float32)
-    rp = _rowptr_from_sorted_rows(r, n_rows)
-    assert int(rp[-1]) < 2 ** 31, "nnz must fit int32"
-    return rp.to(torch.int32), c.to(torch.int32), mult
+def csr_from_coo(rows, cols, n_rows, n_cols, want_first_pos=False):
+    """b200rec_csr_build: coalesced int32 CSR of the (row, col) entry list -> (rowptr, colidx, mult or None[, first_pos])"""
+    lib = _abi.load()
+    rows, cols = rows.contiguous(), cols.contiguous()
+    _abi.require_cuda(rows, cols)
+    assert rows.dtype == torch.int64 and cols.dtype == torch.int64
+    dev = rows.device
+    n = rows.numel()
+    rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    colidx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    mult = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    first = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_first_pos else None
+    nnz, dup = C.c_int32(0), C.c_int32(0)
+    with torch.cuda.device(dev):
+        _abi.check(lib.b200rec_csr_build(_abi.ptr(rows), _abi.ptr(cols), n, 0, 0, n_rows, n_cols, _abi.ptr(rowptr),
+                                         _abi.ptr(colidx), _abi.ptr(mult), _abi.ptr(first), C.byref(nnz), C.byref(dup),
+                                         _abi.stream_ptr()), "csr_build")
+    k = nnz.value
+    out = (rowptr, colidx[:k].clone() if k < n else colidx[:k], mult[:k].clone() if dup.value else None)
+    return out + (first[:k],) if want_first_pos else out
 
 
 def build_norm_adj(n_users, n_items, users, items, device=None, chunk=None, d=None):
     """users/items: int64 tensors of the E train pairs (train_array, dataset.py:149-151), any order, duplicates allowed
-    (they are summed, like scipy's COO->CSR in utils.py:47-49).  Returns (CsrOperand with .vals/.dinv, mult)."""
+    (they are summed, like scipy's COO->CSR in utils.py:47-49).  Returns a CsrOperand with .vals / .dinv / .mult.
+    Built behind the C ABI: b200rec_adj_build (CSR), b200rec_adj_normalize (values), b200rec_plan_build (work plan)."""
     device = torch.device(device) if device is not None else users.device
-    users, items = users.to(device, torch.int64), items.to(device, torch.int64)
+    users, items = users.to(device, torch.int64).contiguous(), items.to(device, torch.int64).contiguous()
     n = n_users + n_items
-    rows = torch.cat([users, items + n_users])
-    cols = torch.cat([items + n_users, users])
-    rowptr, colidx, mult = _coalesce(rows, cols, n, n)
-    dinv = torch.empty(n, dtype=torch.float32, device=device)
-    vals = torch.empty(colidx.numel(), dtype=torch.float32, device=device)
+    e = users.numel()
     lib = _abi.load()
-    _abi.require_cuda(rowptr)
-    _abi.check(lib.b200rec_adj_normalize(_abi.ptr(rowptr), _abi.ptr(colidx), _abi.ptr(mult), n, _abi.ptr(dinv),
-                                         _abi.ptr(vals), _abi.stream_ptr()), "adj_normalize")
+    _abi.require_cuda(users, items)
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=device)
+    colidx = torch.empty(max(2 * e, 1), dtype=torch.int32, device=device)
+    mult = torch.empty(max(2 * e, 1), dtype=torch.float32, device=device)
+    nnz, dup = C.c_int32(0), C.c_int32(0)
+    with torch.cuda.device(device):
+        _abi.check(lib.b200rec_adj_build(_abi.ptr(users), _abi.ptr(items), e, n_users, n_items, _abi.ptr(rowptr),
+                                         _abi.ptr(colidx), _abi.ptr(mult), C.byref(nnz), C.byref(dup), _abi.stream_ptr()),
+                   "adj_build")
+        k = nnz.value
+        colidx = colidx[:k].clone() if k < 2 * e else colidx
+        mult = mult[:k].clone() if dup.value else None
+        dinv = torch.empty(n, dtype=torch.float32, device=device)
+        vals = torch.empty(colidx.numel(), dtype=torch.float32, device=device)
+        _abi.check(lib.b200rec_adj_normalize(_abi.ptr(rowptr), _abi.ptr(colidx), _abi.ptr(mult), n, _abi.ptr(dinv),
+                                             _abi.ptr(vals), _abi.stream_ptr()), "adj_normalize")
     import os
     op = CsrOperand(rowptr, colidx, n, vals=vals, chunk=chunk, d=d,
                     phase_split=0 if os.environ.get("B200REC_NO_PHASE", "0") == "1" else n_users)
-    if d is not None:
-        op.apply_cache_hints(d, n_users)
     op.dinv = dinv
     op.mult = mult
     return op
@@ -267,21 +295,17 @@ def build_feat(n_users, n_items, users, items, user_tmpl, item_tmpl, device=None
     rows = torch.cat([users[mi], n_users + items[mu], ar_u, n_users + ar_i])
     cols = torch.cat([tu + item_tmpl[items[mi]], user_tmpl[users[mu]],
                       torch.full_like(ar_u, tu + ti), torch.full_like(ar_i, tu + ti + 1)])
-    rowptr, colidx, mult = _coalesce(rows, cols, n, t)
+    rowptr, colidx, mult = csr_from_coo(rows, cols, n, t)
     if mult is None:
         row_sum = (rowptr[1:] - rowptr[:-1]).to(torch.float32)
     else:  # np.sum(feat, axis=1) counts duplicates
         r = torch.repeat_interleave(torch.arange(n, device=device), (rowptr[1:] - rowptr[:-1]).long())
         row_sum = torch.zeros(n, dtype=torch.float32, device=device).index_add_(0, r, mult)
     fwd = CsrOperand(rowptr, colidx, t)
-    # transpose: sort edges by (col, row); remember the forward position of every edge
+    # transpose: the forward entries re-sorted by (col, row); first_pos = the forward position of every entry
     nnz = colidx.numel()
     r = torch.repeat_interleave(torch.arange(n, device=device), (rowptr[1:] - rowptr[:-1]).long())
-    key = colidx.long() * n + r
-    key, eid = torch.sort(key)
-    tc = torch.div(key, n, rounding_mode="floor")
-    tr = key - tc * n
-    trp = _rowptr_from_sorted_rows(tc, t).to(torch.int32)
-    bwd = CsrOperand(trp, tr.to(torch.int32), n, eid=eid.to(torch.int32))
+    trp, tr, _, eid = csr_from_coo(colidx.long(), r, t, n, want_first_pos=True)
+    bwd = CsrOperand(trp, tr, n, eid=eid)
     assert nnz == bwd.nnz
     return FeatOperand(fwd, bwd, row_sum), tu, ti

@@ -25,6 +25,12 @@ def spmm(op, x, keep_bits=None, post_scale=1.0, y=None, addend=None, out=None, o
     d = x.shape[1]
     assert x.dtype == torch.float32 and x.shape[0] >= op.n_cols
     assert op.partial is None or d <= op.max_d
+    if keep_bits is None and dst_flags is None and src_flags is None and op.row_scale is None:
+        blk = op.blocked_for(d)
+        if blk is not None:  # table larger than L2
+            spmm_blocked(blk[0], x, blk[1], op.carry(d), post_scale=post_scale, y=y, addend=addend, out=out,
+                         out_scale=out_scale)
+            return
     if dst_flags is None and src_flags is None:
         check(_lib().b200rec_spmm_f32(C.byref(op.struct()), ptr(x), d, ptr(keep_bits), post_scale, ptr(y), ptr(addend),
                                       ptr(out), out_scale, stream_ptr()), "spmm_f32")
@@ -32,6 +38,19 @@ def spmm(op, x, keep_bits=None, post_scale=1.0, y=None, addend=None, out=None, o
         check(_lib().b200rec_spmm_f32_ex(C.byref(op.struct()), ptr(x), d, ptr(keep_bits), post_scale, ptr(y),
                                          ptr(addend), ptr(out), out_scale, ptr(dst_flags), ptr(src_flags),
                                          stream_ptr()), "spmm_f32_ex")
+
+
+def spmm_blocked(bop, x, sweep, carry, post_scale=1.0, y=None, addend=None, out=None, out_scale=1.0):
+    """The same product through a column-blocked plan (CsrOperand built with col_bounds): one pass per L2-sized block of
+    source rows, per column slice of `sweep` floats of the [*, d] tables (row stride d); carry: [n_rows, d] scratch."""
+    _abi.require_cuda(x, y, addend, out, carry)
+    d = x.shape[1]
+    assert d % sweep == 0 and carry.shape[1] == d and x.dtype == torch.float32
+    off = lambda t, c0: C.c_void_p(t.data_ptr() + 4 * c0) if t is not None else C.c_void_p(0)  # noqa: E731
+    for c0 in range(0, d, sweep):
+        check(_lib().b200rec_spmm_f32_blocked(C.byref(bop.struct()), off(x, c0), sweep, d, post_scale, off(y, c0),
+                                              off(addend, c0), off(out, c0), out_scale, off(carry, c0), stream_ptr()),
+              "spmm_f32_blocked")
 
 
 def live_items(op, row_flags, live_list, live_count):
@@ -51,12 +70,29 @@ def spmm_live(op, x, live_list, live_count, max_live, post_scale=1.0, y=None, ad
 
 def propagate_fwd(op, x0, n_layers, bufs, mean_out, needed_rows=None):
     _abi.require_cuda(x0, mean_out, needed_rows)
+    if n_layers > 0 and op.blocked_for(x0.shape[1]) is not None:  # the layer loop of b200rec_propagate_fwd over spmm()
+        inv, src = 1.0 / (n_layers + 1), x0
+        for k in range(n_layers):
+            last = k == n_layers - 1
+            y = None if last else bufs[k & 1]
+            spmm(op, src, y=y, addend=x0 if k == 0 else mean_out, out=mean_out, out_scale=inv if last else 1.0,
+                 dst_flags=needed_rows if last else None)
+            src = y
+        return
     check(_lib().b200rec_propagate_fwd(C.byref(op.struct()), ptr(x0), x0.shape[1], n_layers, ptr(bufs[0]), ptr(bufs[1]),
                                        ptr(mean_out), ptr(needed_rows), stream_ptr()), "propagate_fwd")
 
 
 def propagate_bwd(op, g, n_layers, bufs, dx0, nonzero_rows=None):
     _abi.require_cuda(g, dx0, nonzero_rows)
+    if n_layers > 0 and op.blocked_for(g.shape[1]) is not None:
+        inv, src = 1.0 / (n_layers + 1), g
+        for k in range(1, n_layers + 1):
+            last = k == n_layers
+            dst = dx0 if last else bufs[(k - 1) & 1]
+            spmm(op, src, addend=g, out=dst, out_scale=inv if last else 1.0, src_flags=nonzero_rows if k == 1 else None)
+            src = dst
+        return
     check(_lib().b200rec_propagate_bwd(C.byref(op.struct()), ptr(g), g.shape[1], n_layers, ptr(bufs[0]), ptr(bufs[1]),
                                        ptr(dx0), ptr(nonzero_rows), stream_ptr()), "propagate_bwd")
 

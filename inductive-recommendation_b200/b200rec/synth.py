@@ -7,8 +7,10 @@ bipartite graphs of the same shape: item popularity ~ r
 item-list form the reference's ProcessedDataset parses (dataset.py:140-164); `write_processed`
 emits the same `user item item ...` text files.
 
-The generator is torch code so the 100 M-edge shapes can be produced on the GPU in about a second;
-for a given (seed, device type) it is deterministic.
+The generator is torch code so the 100 M-edge shapes can be produced on the GPU in about a second.  Its
+randomness is integer-only (splitmix64 of a counter against integer CDF thresholds) and its set operations are
+order-free, so a (shape, seed) pair names ONE graph whether it is built on the CPU or on a GPU: bench.py's own arm
+and its CPU reference arm time the same graph.
 """
 import os
 from dataclasses import dataclass
@@ -45,16 +47,49 @@ class SynthGraph:
         return [idx[ptr[u]:ptr[u + 1]].tolist() for u in range(self.n_users)]
 
 
-def _powerlaw_cdf(n, a, gen, device):
-    w = torch.arange(1, n + 1, dtype=torch.float64, device=device).pow_(-a)
-    perm = torch.randperm(n, generator=gen, device=device)
-    cdf = torch.cumsum(w, 0)
-    cdf /= cdf[-1].clone()
-    return cdf, perm
+_MASK63 = (1 << 63) - 1
 
 
-def _draw(cdf, perm, m, gen, device):
-    r = torch.rand(m, generator=gen, device=device, dtype=torch.float64)
+def _c64(v):
+    """a 64-bit constant as the signed value torch's int64 arithmetic (wrapping, two's complement) takes"""
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _lsr(x, s):
+    """logical shift right of an int64 tensor (torch's >> is arithmetic)"""
+    return (x >> s) & ((1 << (64 - s)) - 1)
+
+
+def _mix64(x):
+    """splitmix64 finaliser (Steele et al. 2014) on int64 tensors: integer-only, so identical on every device"""
+    x = x + _c64(0x9E3779B97F4A7C15)
+    x = (x ^ _lsr(x, 30)) * _c64(0xBF58476D1CE4E5B9)
+    x = (x ^ _lsr(x, 27)) * _c64(0x94D049BB133111EB)
+    return x ^ _lsr(x, 31)
+
+
+def _stream(seed, stream, start, count, device):
+    """`count` 62-bit uniform integers of stream (seed, stream), positions start .. start+count-1"""
+    base = _c64((seed * 0xD1342543DE82EF95 + stream * 0x2545F4914F6CDD1D) & ((1 << 64) - 1))
+    idx = torch.arange(start, start + count, dtype=torch.int64, device=device)
+    return _lsr(_mix64(_mix64(idx + base) ^ base), 2)
+
+
+def _powerlaw_cdf(n, a, seed, stream, device):
+    """integer CDF thresholds (62-bit) of weights rank^-a, and a hash-ordered permutation of the ids.  The CDF is formed
+    on the host in float64 (numpy cumsum: sequential, deterministic) and only compared as integers afterwards."""
+    w = np.arange(1, n + 1, dtype=np.float64) ** (-a)
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    cdf_int = np.minimum(np.floor(cdf * float(1 << 62)), float((1 << 62) - 1)).astype(np.int64)
+    cdf_int[-1] = (1 << 62) - 1
+    h = _stream(seed, stream, 0, n, "cpu")
+    perm = torch.sort(h, stable=True).indices
+    return torch.from_numpy(cdf_int).to(device), perm.to(device)
+
+
+def _draw(cdf, perm, r):
     k = torch.searchsorted(cdf, r).clamp_(max=cdf.numel() - 1)
     return perm[k]
 
@@ -70,15 +105,16 @@ def _to_csr(keys, n_users, n_items):
 
 
 def generate(n_users, n_items, n_train, seed=0, a_item=0.8, a_user=0.6, heldout=True, device="cpu"):
-    """Return a SynthGraph with exactly `n_train` unique train pairs."""
+    """Return a SynthGraph with exactly `n_train` unique train pairs.  Every random choice is a splitmix64 hash of a
+    counter compared against integer thresholds, and every set operation (unique, sort) is order-free, so the graph is a
+    function of (shape, seed) alone: the CUDA build of it and the CPU build of it are the same graph."""
     device = torch.device(device)
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
     assert n_train >= n_users and n_train < n_users * n_items // 2
-    ucdf, uperm = _powerlaw_cdf(n_users, a_user, gen, device)
-    icdf, iperm = _powerlaw_cdf(n_items, a_item, gen, device)
+    ucdf, uperm = _powerlaw_cdf(n_users, a_user, seed, 1, device)
+    icdf, iperm = _powerlaw_cdf(n_items, a_item, seed, 2, device)
     # one guaranteed interaction per user
-    first = torch.arange(n_users, device=device, dtype=torch.int64) * n_items + _draw(icdf, iperm, n_users, gen, device)
+    first = torch.arange(n_users, device=device, dtype=torch.int64) * n_items \
+        + _draw(icdf, iperm, _stream(seed, 3, 0, n_users, device))
     keys = first
     target_total = n_train
     n_val = n_test = 0
@@ -86,14 +122,18 @@ def generate(n_users, n_items, n_train, seed=0, a_item=0.8, a_user=0.6, heldout=
         n_val = n_train // 7
         n_test = 2 * n_train // 7
         target_total = n_train + n_val + n_test
+    pos = 0
     while keys.numel() < target_total:
         m = int((target_total - keys.numel()) * 1.25) + 1024
-        new = _draw(ucdf, uperm, m, gen, device) * n_items + _draw(icdf, iperm, m, gen, device)
+        new = _draw(ucdf, uperm, _stream(seed, 4, pos, m, device)) * n_items \
+            + _draw(icdf, iperm, _stream(seed, 5, pos, m, device))
+        pos += m
         keys = torch.unique(torch.cat([keys, new]))
-    # `first` must stay in train: pick the rest at random
+    # `first` must stay in train: the rest is ordered by a hash of the pair (a random order that needs no generator)
     is_first = torch.isin(keys, first)
     rest = keys[~is_first]
-    rest = rest[torch.randperm(rest.numel(), generator=gen, device=device)]
+    order = torch.sort(_mix64(rest ^ _c64(seed * 0x9E3779B97F4A7C15 + 0x51ED270B)), stable=True).indices
+    rest = rest[order]
     n_rest_train = n_train - first.numel()
     train = torch.cat([first, rest[:n_rest_train]])
     val = rest[n_rest_train:n_rest_train + n_val]
@@ -108,6 +148,19 @@ def generate(n_users, n_items, n_train, seed=0, a_item=0.8, a_user=0.6, heldout=
         u = int(torch.argmax(deg))
         ti[tp[u + 1] - 1] = n_items - 1
     return SynthGraph(n_users, n_items, tp, ti, vp, vi, sp, si)
+
+
+def fingerprint(graph):
+    """order-sensitive 64-bit digest of the three CSRs (fixtures store it: a fixture built on one box must meet the same
+    graph on another)"""
+    acc = 0
+    for name in ("train", "val", "test"):
+        for t in (getattr(graph, name + "_indptr"), getattr(graph, name + "_items")):
+            t = t.to(torch.int64)
+            idx = torch.arange(t.numel(), dtype=torch.int64, device=t.device)
+            h = int(_mix64(t * _c64(0x9E3779B97F4A7C15) + idx).sum().item()) & ((1 << 64) - 1)
+            acc = (acc * 0x100000001B3 + h) & ((1 << 64) - 1)
+    return acc
 
 
 def generate_named(name, seed=0, device="cpu", heldout=True):

@@ -28,46 +28,6 @@ def test_library_exports_every_declared_symbol():
     assert lib.b200rec_version() >= 100
 
 
-def test_plan_build_host_long_rows_and_order():
-    lib = _abi.load()
-    lens = np.array([3, 0, 2500, 1, 70, 1024, 1025], dtype=np.int32)
-    rp = np.zeros(len(lens) + 1, dtype=np.int32)
-    np.cumsum(lens, out=rp[1:])
-    ni, nl, ns = C.c_int32(), C.c_int32(), C.c_int32()
-    null = C.c_void_p(0)
-    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, 0, C.addressof(ni), C.addressof(nl), C.addressof(ns),
-                                       null, null, null, null, null, null, null, null) == 0
-    assert (ni.value, nl.value, ns.value) == (5 + 3 + 2, 2, 5)
-    a = [np.empty(ni.value, dtype=np.int32) for _ in range(4)]
-    b = [np.empty(nl.value, dtype=np.int32) for _ in range(3)]
-    sl = np.empty(ns.value, dtype=np.int32)
-    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, 0, C.addressof(ni), C.addressof(nl), C.addressof(ns),
-                                       a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
-                                       b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, sl.ctypes.data) == 0
-    assert sl.tolist() == [0, 0, 0, 1, 1]
-    start, end, dst, row = a
-    assert np.array_equal(row[dst >= 0], dst[dst >= 0]) and set(row[dst < 0].tolist()) == {2, 6}
-    ln = end - start
-    assert (np.diff(ln) <= 0).all()                      # longest first
-    assert ln.sum() == lens.sum()
-    assert sorted(dst[dst >= 0].tolist()) == [0, 1, 3, 4, 5]
-    assert sorted((~dst[dst < 0]).tolist()) == [0, 1, 2, 3, 4]
-    assert b[0].tolist() == [2, 6] and b[1].tolist() == [0, 3] and b[2].tolist() == [3, 2]
-    # two phases: rows < 4 first, each phase longest-first
-    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), 1024, 4, C.addressof(ni), C.addressof(nl), C.addressof(ns),
-                                       a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
-                                       b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, sl.ctypes.data) == 0
-    first = row < 4
-    assert first[:first.sum()].all() and not first[first.sum():].any()
-    for ph in (first, ~first):
-        assert (np.diff((end - start)[ph]) <= 0).all()
-    # every nnz covered exactly once
-    cover = np.zeros(lens.sum(), dtype=np.int32)
-    for s, e in zip(start, end):
-        cover[s:e] += 1
-    assert (cover == 1).all()
-
-
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     from b200rec import ops
@@ -110,65 +70,6 @@ def test_argument_errors_are_codes_with_messages():
                                step.ctypes.data, null)
     assert rc < 0 and "alignment" in err()
     assert lib.b200rec_infonce_workspace_floats(0, 64) == 0 and lib.b200rec_infonce_workspace_floats(2048, 64) > 2 * 2048 * 64
-
-
-def _plan(lib, lens, chunk, split):
-    rp = np.zeros(len(lens) + 1, dtype=np.int32)
-    np.cumsum(lens, out=rp[1:])
-    ni, nl, ns = C.c_int32(), C.c_int32(), C.c_int32()
-    null = C.c_void_p(0)
-    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), chunk, split, C.addressof(ni), C.addressof(nl),
-                                       C.addressof(ns), null, null, null, null, null, null, null, null) == 0
-    a = [np.full(max(ni.value, 1), -7, dtype=np.int32) for _ in range(4)]
-    b = [np.full(max(nl.value, 1), -7, dtype=np.int32) for _ in range(3)]
-    sl = np.full(max(ns.value, 1), -7, dtype=np.int32)
-    assert lib.b200rec_plan_build_host(rp.ctypes.data, len(lens), chunk, split, C.addressof(ni), C.addressof(nl),
-                                       C.addressof(ns), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
-                                       a[3].ctypes.data, b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data,
-                                       sl.ctypes.data) == 0
-    return rp, ni.value, nl.value, ns.value, [x[:ni.value] for x in a], [x[:nl.value] for x in b], sl[:ns.value]
-
-
-def test_plan_build_host_invariants_random():
-    """the work plan on random degree sequences (power-law tails, empty rows, any chunk, one or two phases): every edge
-    is covered exactly once, every row (empty ones included) is produced, pieces stay inside their row and within `chunk`, split rows own consecutive slots in piece
-    order, and each phase is sorted longest first"""
-    from hypothesis import given, settings, strategies as st
-    lib = _abi.load()
-
-    @settings(max_examples=60, deadline=None)
-    @given(st.lists(st.one_of(st.integers(0, 40), st.integers(0, 3000)), min_size=1, max_size=60),
-           st.sampled_from([32, 64, 256, 1024]), st.integers(0, 60))
-    def check(lens, chunk, split):
-        lens = np.asarray(lens, dtype=np.int32)
-        split = min(split, len(lens))
-        rp, ni, nl, ns, (start, end, dst, row), (lrow, lslot0, lnslot), slot_long = _plan(lib, lens, chunk, split)
-        cover = np.zeros(int(lens.sum()), dtype=np.int32)
-        for s, e, r in zip(start, end, row):
-            assert rp[r] <= s <= e <= rp[r + 1] and e - s <= chunk
-            cover[s:e] += 1
-        assert (cover == 1).all()
-        long_rows = np.nonzero(lens > chunk)[0]
-        assert sorted(lrow.tolist()) == long_rows.tolist() and nl == len(long_rows)
-        assert ns == int(sum(-(-int(lens[r]) // chunk) for r in long_rows))
-        for li, r in enumerate(lrow):
-            pieces = np.nonzero(row == r)[0]
-            assert len(pieces) == lnslot[li] == -(-int(lens[r]) // chunk)
-            slots = sorted((~dst[pieces]).tolist())
-            assert slots == list(range(lslot0[li], lslot0[li] + lnslot[li]))       # consecutive slots
-            order = np.argsort(~dst[pieces])
-            assert (np.diff(start[pieces][order]) > 0).all()                        # slot order = position in the row
-            assert (slot_long[lslot0[li]:lslot0[li] + lnslot[li]] == li).all()
-        whole = dst >= 0
-        assert np.array_equal(dst[whole], row[whole]) and not np.isin(row[whole], long_rows).any()
-        assert sorted(row[whole].tolist()) == np.nonzero(lens <= chunk)[0].tolist()   # empty rows too: their output is written
-        first = row < split if split > 0 else np.zeros(ni, dtype=bool)
-        if split > 0:
-            assert first[:first.sum()].all() and not first[first.sum():].any()      # phase 0 (rows < split) comes first
-        for ph in ((first, ~first) if split > 0 else (np.ones(ni, dtype=bool),)):
-            assert (np.diff((end - start)[ph]) <= 0).all()                          # longest first inside a phase
-
-    check()
 
 
 def test_library_is_sm100a_and_carries_tensor_core_code():
