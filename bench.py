@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 hot path (BASELINE.json: BPR epochs/s, SpMM HBM GB/s, eval users/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl reference]
 
 A "step" is one BPR training iteration (batch 2048: sample -> L x SpMM + layer mean -> BPR loss/grad -> L x SpMM
-backward -> Adam) on a synthetic graph of a BASELINE.json shape; default workload c2 (Yelp2018-shaped, LightGCN,
-3 layers, dim 64).  `value` = epochs/s = 1 / (steps_per_epoch * s_per_step) with all inputs resident in HBM
-(device sampler).  `e2e` = the same metric through the trainer-facing engine call with HOST batches: every step
-copies a pinned int64 [B,3] batch host->device and reads the loss back.  One JSON line on stdout (rank 0).
+backward -> Adam) on a synthetic graph of a BASELINE.json shape.  Default workload: c4, the largest configuration that
+fits one GPU (2M x 1M power-law graph, 100M train edges, LightGCN L=4 D=128); its full-rank evaluation is BASELINE's
+config 5 (2M x 1M score sweep + masked top-20).  `value` = epochs/s = 1 / (steps_per_epoch * s_per_step) with all
+inputs resident in HBM (device sampler).  `e2e` = the same metric through the trainer-facing engine call with HOST
+batches: every step copies a pinned int64 [B,3] batch host->device and reads the loss back.  One JSON line on stdout
+(rank 0).  `--workload c5` times the evaluation sweep alone (metric eval_users_per_sec).
 
 `--impl reference` times the oracle port (oracle/ref_port.py: the reference's algorithm restated on torch-CPU with
-an MKL CSR SpMM, all host threads) on the same workload; the reference itself is pure Python + DGL and cannot be
-installed or shipped to the GPU box (no DGL wheel, /root/reference is not present there).
+an MKL CSR SpMM, all host threads) on the same graph (the generator is device-independent); the reference itself is
+pure Python + DGL and cannot be installed or shipped to the GPU box (no DGL wheel, /root/reference is not present
+there).  On c4 one CPU step is tens of seconds, so a reference "step" is a bounded sample of it (see cpu_port_sample).
 """
 import argparse
 import json
@@ -33,20 +36,23 @@ import torch  # noqa: E402
 BATCH = 2048
 LR, L2_REG = 1e-3, 1e-4  # config.py:13-14 (LightGCN + BPRTrainer)
 TOPKS = [1, 5, 10, 15, 20]
+DEFAULT_WORKLOAD = "c4"
 WORKLOAD_DOC = {
     "c1": "LightGCN L=3 D=64, synthetic Gowalla-shaped graph 29858x40981, 1027370 train edges",
     "c2": "LightGCN L=3 D=64, synthetic Yelp2018-shaped graph 31668x38048, 1561406 train edges",
     "c3": "LightGCN L=3 D=64, synthetic Amazon-book-shaped graph 52643x91599, 2984108 train edges",
-    "c4": "LightGCN L=4 D=128, synthetic power-law graph 2000000x1000000, 100000000 train edges",
+    "c4": "LightGCN L=4 D=128, synthetic power-law graph 2000000x1000000, 100000000 train edges (BASELINE configs 4+5)",
+    "c5": "full-rank evaluation sweep 2000000 users x 1000000 items, D=128, train+val masked top-20 (BASELINE config 5, graph of c4)",
 }
+BIG = ("c4", "c5")
 
 
 def peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -66,7 +72,7 @@ class ClockSampler:
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def __enter__(self):
         self.t.start()
@@ -85,69 +91,141 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def graph_name(workload):
+    return "c4" if workload == "c5" else workload
+
+
 def build_graph(workload, device):
+    """the same graph whichever device builds it (b200rec.synth is integer-only); both arms use the GPU when there is one"""
     from b200rec import synth
-    return synth.generate_named(workload, seed=0, device=device)
+    return synth.generate_named(graph_name(workload), seed=0, device=device)
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
-def cpu_port_step_time(graph, workload, n_steps, warmup, seed=2021):
-    """oracle port: LightGCN train step on torch-CPU (CSR/MKL), all host threads.  Returns (s_per_step, threads)."""
-    from b200rec import synth
-    from oracle import oracle_c as oc
-    from oracle import ref_port as rp
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    _, _, _, d, n_layers = synth.SHAPES[workload]
-    ptr = graph.train_indptr.cpu().numpy()
-    items = graph.train_items.cpu().numpy()
-    users, items64 = rp.pairs_from_csr(ptr, items)
-    torch.manual_seed(seed)
-    emb0 = (0.1 * torch.randn(graph.n_users + graph.n_items, d)).numpy()
-    port = rp.LightGCNPort(graph.n_users, graph.n_items, users, items64, emb0, n_layers).train()
-    opt = torch.optim.Adam(port.parameters(), lr=LR)
-    p32, i32 = ptr.astype(np.int32), items.astype(np.int32)
-    batches = [torch.from_numpy(oc.bpr_sample(p32, i32, graph.n_users, graph.n_items, seed, s, BATCH))
-               for s in range(n_steps + warmup)]
-    for b in batches[:warmup]:
-        rp.train_step(port, opt, b, L2_REG)
-    t0 = time.perf_counter()
-    for b in batches[warmup:]:
-        rp.train_step(port, opt, b, L2_REG)
-    return (time.perf_counter() - t0) / max(n_steps, 1), threads, port
+class CpuPort:
+    """oracle port of the LightGCN training step on torch-CPU (CSR/MKL), all host threads.
+
+    Small workloads: a timed step is one full train step (trainer.py:412-429).  c4: a full step is 8 SpMM layers over
+    200M entries (tens of seconds), so a timed step is a BOUNDED SAMPLE -- the complete train step of a ONE-layer port
+    (1 forward + 1 backward SpMM over the whole graph, the batch gathers, loss, backward, dense Adam over the 3M x 128
+    table), and the full step is estimated as  t_L1 + (L-1) * t_pair  with t_pair = one forward + one backward SpMM
+    timed alone.  The estimate leaves out the (L+1)-way stack/mean of the deeper model, i.e. it favours the CPU."""
+
+    def __init__(self, graph, workload, seed=2021):
+        from b200rec import synth
+        from oracle import oracle_c as oc
+        from oracle import ref_port as rp
+        self.rp, self.oc = rp, oc
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        _, _, _, d, n_layers = synth.SHAPES[graph_name(workload)]
+        self.n_layers, self.sampled = n_layers, workload in BIG
+        self.graph = graph
+        self.ptr = graph.train_indptr.cpu().numpy()
+        self.items = graph.train_items.cpu().numpy()
+        users, items64 = rp.pairs_from_csr(self.ptr, self.items)
+        torch.manual_seed(seed)
+        emb0 = (0.1 * torch.randn(graph.n_users + graph.n_items, d)).numpy()
+        self.port = rp.LightGCNPort(graph.n_users, graph.n_items, users, items64, emb0, 1 if self.sampled else n_layers).train()
+        self.opt = torch.optim.Adam(self.port.parameters(), lr=LR)
+        self.p32, self.i32 = self.ptr.astype(np.int32), self.items.astype(np.int32)
+        self.seed, self.step_no = seed, 0
+        self.t_pair = None
+
+    def _batch(self):
+        g = self.graph
+        b = torch.from_numpy(self.oc.bpr_sample(self.p32, self.i32, g.n_users, g.n_items, self.seed, self.step_no, BATCH))
+        self.step_no += 1
+        return b
+
+    def measure_pair(self, reps=2):
+        a = self.port.a
+        x = self.port.embedding.weight.detach()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            y = torch.sparse.mm(a, x)
+            torch.sparse.mm(a, y)
+            ts.append(time.perf_counter() - t0)
+        self.t_pair = float(np.median(ts))
+
+    def step(self):
+        """seconds of one (estimated) full train step"""
+        b = self._batch()
+        t0 = time.perf_counter()
+        self.rp.train_step(self.port, self.opt, b, L2_REG)
+        t = time.perf_counter() - t0
+        if self.sampled:
+            if self.t_pair is None:
+                self.measure_pair()
+            t += (self.n_layers - 1) * self.t_pair
+        return t
+
+    def sample_doc(self, n_steps, steps_per_epoch):
+        if self.sampled:
+            return ("%d timed samples; each = the complete train step of a 1-layer port (1 fwd + 1 bwd SpMM over all %d "
+                    "entries, batch %d, dense Adam) + (L-1) x one fwd+bwd SpMM pair timed alone (%.2f s); extrapolated to "
+                    "%d steps per epoch" % (n_steps, 2 * self.items.size, BATCH, self.t_pair or 0.0, steps_per_epoch))
+        return "%d timed train steps (batch %d) of %d per epoch on torch-CPU CSR/MKL, extrapolated" % (n_steps, BATCH, steps_per_epoch)
+
+    def eval_rate(self, n_users):
+        """full-rank evaluation of the first `n_users` users the way the reference does it (trainer.py:146-170: every
+        512-user batch re-propagates, dense scores, Python exclusion lists, topk): users/s on the host cores"""
+        g = self.graph
+        n = min(n_users, g.n_users)
+        lists = lambda which: _head_lists(getattr(g, which + "_indptr"), getattr(g, which + "_items"), n)  # noqa: E731
+        full_layers = self.port.n_layers
+        self.port.n_layers = self.n_layers  # evaluation always runs the real depth
+        t0 = time.perf_counter()
+        self.rp.evaluate(self.port, lists("train"), lists("val"), lists("test"), "test", TOPKS, test_batch_size=512, n_users=n)
+        dt = time.perf_counter() - t0
+        self.port.n_layers = full_layers
+        return n / dt, n
 
 
-def cpu_port_eval_rate(graph, port, n_users=1024):
-    """full-rank evaluation of the first `n_users` users by the oracle port, the way the reference does it (trainer.py:
-    146-170: every 512-user batch re-propagates, dense scores, Python exclusion lists, topk): users/s on the host cores"""
-    from oracle import ref_port as rp
-    n = min(n_users, graph.n_users)
-    train, val, test = graph.lists("train")[:n], graph.lists("val")[:n], graph.lists("test")[:n]
-    t0 = time.perf_counter()
-    rp.evaluate(port, train, val, test, "test", TOPKS, test_batch_size=512, n_users=n)
-    return n / (time.perf_counter() - t0), n
+def _head_lists(indptr, items, n):
+    ptr = indptr[: n + 1].cpu().numpy()
+    idx = items[: int(ptr[-1])].cpu().numpy()
+    return [idx[ptr[u]:ptr[u + 1]].tolist() for u in range(n)]
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    workload = args.workload or "c2"
-    graph = build_graph(workload, "cpu")
+    workload = args.workload or DEFAULT_WORKLOAD
+    dev = "cuda" if torch.cuda.is_available() else "cpu"  # input generation only; everything timed below is CPU work
+    graph = build_graph(workload, dev)
     n_train = int(graph.train_items.numel())
     steps_per_epoch = (n_train + BATCH - 1) // BATCH
-    s_per_step, threads, port = cpu_port_step_time(graph, workload, args.steps, args.warmup)
+    port = CpuPort(graph, workload)
+    for _ in range(args.warmup):
+        port.step()
+    times = [port.step() for _ in range(args.steps)]
+    s_per_step = float(np.mean(times)) if times else float("nan")
     value = 1.0 / (steps_per_epoch * s_per_step)
-    eval_rate, eval_n = cpu_port_eval_rate(graph, port)
-    sample = "%d timed train steps (batch %d) of %d per epoch, extrapolated" % (args.steps, BATCH, steps_per_epoch)
-    line = {"impl": "reference", "metric": "bpr_epochs_per_sec", "value": value, "unit": "epochs/s", "n_gpus": args.gpus,
+    eval_rate, eval_n = port.eval_rate(256 if workload in BIG else 1024)
+    if workload == "c5":
+        metric, unit, value_out = "eval_users_per_sec", "users/s", eval_rate
+    else:
+        metric, unit, value_out = "bpr_epochs_per_sec", "epochs/s", value
+    line = {"impl": "reference", "metric": metric, "value": value_out, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload + ": " + WORKLOAD_DOC[workload], "batch": BATCH,
-                       "steps_per_epoch": steps_per_epoch},
-            "cpu_baseline": {"value": value, "unit": "epochs/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "eval": {"users_per_s_e2e": eval_rate, "sample": "first %d users, test split, K=%d, 512-user batches" % (eval_n, max(TOPKS))}}
+                       "steps_per_epoch": steps_per_epoch, "graph_fingerprint": "%016x" % _fingerprint(graph)},
+            "cpu_baseline": {"value": value_out, "unit": unit, "cores": port.threads, "kind": "port",
+                             "sample": port.sample_doc(args.steps, steps_per_epoch) if workload != "c5" else
+                             "first %d users, test split, K=%d" % (eval_n, max(TOPKS))},
+            "e2e": {"value": value_out, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "train": {"epochs_per_s": value, "ms_per_step": 1e3 * s_per_step},
+            "eval": {"users_per_s_e2e": eval_rate, "sample": "first %d users, test split, K=%d, 512-user batches, re-propagation "
+                     "per batch like trainer.py:150-170" % (eval_n, max(TOPKS))}}
     print(json.dumps(line), flush=True)
+
+
+def _fingerprint(graph):
+    from b200rec import synth
+    return synth.fingerprint(graph)
 
 
 # ---------------------------------------------------------------------------------------------------- own arm
@@ -163,8 +241,9 @@ def run_own(args, rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    workload = args.workload or "c2"
-    _, _, _, d, n_layers = synth.SHAPES[workload]
+    workload = args.workload or DEFAULT_WORKLOAD
+    big = workload in BIG
+    _, _, _, d, n_layers = synth.SHAPES[graph_name(workload)]
     graph = build_graph(workload, dev)
     ds = D.get_dataset({"name": "SyntheticDataset", "device": dev, "graph": graph})
     torch.manual_seed(2021)  # same seed on every rank: the shards are slices of one initialisation
@@ -194,156 +273,186 @@ def run_own(args, rank, world):
     steps_per_epoch = tr.steps_per_epoch()
     K, W = args.steps, max(args.warmup, 3)
     l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
-    flush_buf = torch.empty(max(2 * l2_bytes, 256 << 20), dtype=torch.uint8, device=dev)
+    # small shapes are L2-resident: flush between timed steps.  c4's tables (1.5 GB each) are 12x the L2: no flush needed.
+    flush_buf = None if big else torch.empty(max(2 * l2_bytes, 256 << 20), dtype=torch.uint8, device=dev)
+
+    def flush():
+        if flush_buf is not None:
+            flush_buf.fill_(1)
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(fn, n, flush):
+    def timed_steps(fn, n, do_flush):
         """device time of n calls of fn, CUDA events on the launching stream; L2 flushed (untimed) between calls"""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         for a, b in ev:
-            if flush:
-                flush_buf.fill_(1)
+            if do_flush:
+                flush()
             a.record()
             fn()
             b.record()
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in ev]
 
-    for _ in range(W):
-        eng.step()
-    barrier()
-    launches0 = _abi.launch_count()
-    graph_replays0 = eng.steps_done
-    with ClockSampler(local) as clocks:
-        times = timed_steps(eng.step, K, flush=True)
-        barrier()
-        # the same K steps back to back (L2 warm: the steady state of a real epoch), one event pair
-        t_warm = timed_steps(lambda: [eng.step() for _ in range(K)], 1, flush=False)[0] / K
-    total_ms = float(sum(times))
-    if world > 1:
-        t = torch.tensor([total_ms, t_warm], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        total_ms, t_warm = float(t[0]), float(t[1])
-    ms_per_step = total_ms / K
-    value = 1e3 / (ms_per_step * steps_per_epoch)
-    kernels_per_step = eng.kernels_per_step()
-    gpu_launches = kernels_per_step * K
-    assert _abi.launch_count() >= launches0  # replays do not pass through the host counter
-
-    # ---- e2e: host batches through the engine's public step(), H2D of the batch + D2H of the loss every step ----
-    host_batches = []
-    st = torch.zeros(1, dtype=torch.int64, device=dev)
-    for s in range(K + W):
-        st.fill_(10_000_000 + s)
-        host_batches.append(ops.bpr_sample(eng.user_ptr, eng.user_items, ds.n_users, ds.n_items, 2021, st, BATCH)
-                            .cpu().pin_memory())
-    for b in host_batches[:W]:
-        eng.step(host_batch=b)
-        eng.last_loss()
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    t0.record()
-    for b in host_batches[W:]:
-        flush_buf.fill_(1)
-        eng.step(host_batch=b)
-        loss = eng.last_loss()  # device->host read of the step's loss (the reference's loss.item(), trainer.py:428)
-    t1.record()
-    torch.cuda.synchronize()
-    e2e_ms = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0)) / K
-    # the flush is inside this region (it cannot be hoisted out of a host-synchronous loop): subtract its measured cost
-    flush_ms = float(np.median(timed_steps(lambda: flush_buf.fill_(1), 10, flush=False)))
-    e2e_ms_net = max(e2e_ms - flush_ms, 1e-6)
-    if world > 1:
-        t = torch.tensor([e2e_ms_net], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        e2e_ms_net = float(t[0])
-    e2e_value = 1e3 / (e2e_ms_net * steps_per_epoch)
-
-    # ---- roofline of the dominant kernel: one SpMM layer (propagation forward layer k: Y = A X, acc += Y) ----
-    n = ds.n_users + ds.n_items
-    adj = m.norm_adj if partition is None else partition.local_op
-    nnz_local = int(adj.item_end[:adj.n_items].sum() - adj.item_start[:adj.n_items].sum()) if partition is not None else adj.nnz
-    rows_local = n if partition is None else partition.n_local_rows
-    x = torch.randn((n, d), device=dev)
-    y = torch.empty_like(x)
-    acc = torch.zeros_like(x)
-    spmm_call = lambda: ops.spmm(adj, x, y=y, addend=acc, out=acc)  # noqa: E731
-    for _ in range(3):
-        spmm_call()
-    spmm_ms = float(np.median(timed_steps(spmm_call, 30, flush=True)))
-    spmm_ms_warm = timed_steps(lambda: [spmm_call() for _ in range(30)], 1, flush=False)[0] / 30
-    # algorithmic bytes per launch (SURVEY 8d): nnz*(4+4) + (N+1)*4 + 2*N*D*4 ; + N*D*4 for the fused layer-sum read+write/2
-    bytes_min = nnz_local * 8 + (rows_local + 1) * 4 + (n + rows_local) * d * 4
-    bytes_gather = nnz_local * 8 + nnz_local * d * 4 + rows_local * d * 4
     peak, peak_src = peaks()
-    achieved = bytes_min / (spmm_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(REPO, "profiles", "spmm_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(workload)
-    roofline = {"bound": "hbm", "kernel": "spmm_items_kernel (one propagation layer, D=%d)" % d, "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_min": bytes_min, "launch_ms": spmm_ms, "launch_ms_l2_warm": spmm_ms_warm,
-                "effective_gather_gbs": bytes_gather / (spmm_ms * 1e-3) / 1e9,
-                "effective_gather_gbs_l2_warm": bytes_gather / (spmm_ms_warm * 1e-3) / 1e9}
+    hbm_peak = float(peak["hbm_gbs"])
+    n = ds.n_users + ds.n_items
+    line = {}
+    with ClockSampler(local) as clocks:
+        if workload != "c5":
+            for _ in range(W):
+                eng.step()
+            barrier()
+            launches0 = _abi.launch_count()
+            times = timed_steps(eng.step, K, True)
+            barrier()
+            # the same K steps back to back (L2 warm: the steady state of a real epoch), one event pair
+            t_warm = timed_steps(lambda: [eng.step() for _ in range(K)], 1, False)[0] / K
+            total_ms = float(sum(times))
+            if world > 1:
+                t = torch.tensor([total_ms, t_warm], device=dev, dtype=torch.float64)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                total_ms, t_warm = float(t[0]), float(t[1])
+            ms_per_step = total_ms / K
+            value = 1e3 / (ms_per_step * steps_per_epoch)
+            kernels_per_step = eng.kernels_per_step()
+            assert _abi.launch_count() >= launches0  # replays do not pass through the host counter
 
-    # ---- full-rank evaluation (users/s): representation + fused score/mask/top-20 + metrics ----
-    eval_info = None
-    if workload != "c4":  # every rank takes part: the sweep is user-sharded and gathers the columns collectively
-        m.eval()
-        tr.eval("test")
-        torch.cuda.synchronize()
-        w0 = time.perf_counter()
-        _, metrics, _ = tr.eval("test")
-        torch.cuda.synchronize()
-        eval_s = time.perf_counter() - w0
-        ke = timed_steps(lambda: tr.recommend_all("test"), 3, flush=True)
-        d_full = getattr(m, "full_embedding_size", m.embedding_size)
-        score_flops = 2.0 * ds.n_users * ds.n_items * d_full
-        pk = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
-        tf_peak = float(pk.get("bf16_tflops", 1590.0))
-        tf = score_flops / (min(ke) * 1e-3) / 1e12 * (1.0 / world)  # per GPU: the sweep is user-sharded
-        eval_info = {"users_per_s_e2e": ds.n_users / eval_s, "users_per_s_kernels": ds.n_users / (min(ke) * 1e-3),
-                     "k": max(TOPKS), "recall@20": float(metrics["Recall"][20]), "ndcg@20": float(metrics["NDCG"][20]),
-                     "precision": tr.eval_precision,
-                     "score_roofline": {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s",
-                                        "frac": tf / tf_peak, "note": "whole recommend_all sweep (propagation + prep + "
-                                        "tcgen05 score/candidates + exact re-score) per GPU; epilogue-latency-bound, see DESIGN 4.6"},
-                     "includes": "trainer.eval('test'): get_rep + score/mask/top-K + fused rank-metrics pass + D2H of the metric sums"}
+            # ---- e2e: host batches through the engine's public step(), H2D of the batch + D2H of the loss every step ----
+            host_batches = []
+            st = torch.zeros(1, dtype=torch.int64, device=dev)
+            for s in range(K + W):
+                st.fill_(10_000_000 + s)
+                host_batches.append(ops.bpr_sample(eng.user_ptr, eng.user_items, ds.n_users, ds.n_items, 2021, st, BATCH)
+                                    .cpu().pin_memory())
+            for b in host_batches[:W]:
+                eng.step(host_batch=b)
+                eng.last_loss()
+            barrier()
+            t0 = torch.cuda.Event(enable_timing=True)
+            t1 = torch.cuda.Event(enable_timing=True)
+            wall0 = time.perf_counter()
+            t0.record()
+            for b in host_batches[W:]:
+                flush()
+                eng.step(host_batch=b)
+                loss = eng.last_loss()  # device->host read of the step's loss (the reference's loss.item(), trainer.py:428)
+            t1.record()
+            torch.cuda.synchronize()
+            e2e_ms = max(t0.elapsed_time(t1), 1e3 * (time.perf_counter() - wall0)) / K
+            # a flush inside this region cannot be hoisted out of a host-synchronous loop: subtract its measured cost
+            flush_ms = float(np.median(timed_steps(flush, 10, False))) if flush_buf is not None else 0.0
+            e2e_ms_net = max(e2e_ms - flush_ms, 1e-6)
+            if world > 1:
+                t = torch.tensor([e2e_ms_net], device=dev, dtype=torch.float64)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                e2e_ms_net = float(t[0])
+            e2e_value = 1e3 / (e2e_ms_net * steps_per_epoch)
+
+            # ---- roofline of the dominant kernel: one SpMM layer as the step runs it (Y = A X, acc += Y) ----
+            adj = m.norm_adj if partition is None else partition.local_op
+            nnz_local = int(adj.item_end[:adj.n_items].sum() - adj.item_start[:adj.n_items].sum()) if partition is not None else adj.nnz
+            rows_local = n if partition is None else partition.n_local_rows
+            x = torch.randn((n, d), device=dev)
+            y = torch.empty_like(x)
+            acc = torch.zeros_like(x)
+            spmm_call = lambda: ops.spmm(adj, x, y=y, addend=acc, out=acc)  # noqa: E731
+            l0 = _abi.launch_count()
+            spmm_call()
+            launches_per_layer = _abi.launch_count() - l0
+            for _ in range(2):
+                spmm_call()
+            reps = 10 if big else 30
+            spmm_ms = float(np.median(timed_steps(spmm_call, reps, True)))
+            spmm_ms_warm = timed_steps(lambda: [spmm_call() for _ in range(reps)], 1, False)[0] / reps
+            del x, y, acc
+            # algorithmic bytes per layer (SURVEY 8d): nnz*(4+4) + (N+1)*4 + 2*N*D*4
+            bytes_min = nnz_local * 8 + (rows_local + 1) * 4 + (n + rows_local) * d * 4
+            bytes_gather = nnz_local * 8 + nnz_local * d * 4 + rows_local * d * 4
+            achieved = bytes_min / (spmm_ms * 1e-3) / 1e9
+            blk = adj.blocked_for(d) if partition is None else None
+            roofline = {"bound": "hbm", "kernel": "spmm_items_kernel (one propagation layer, D=%d%s)" % (
+                            d, "" if blk is None else ", column-blocked: %d passes x %d-column sweeps" % (blk[0].n_passes, blk[1])),
+                        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                        "traffic": None, "traffic_note": "not measurable inside the run; ncu dram__bytes per layer are in profiles/",
+                        "peak_source": peak_src, "bytes_min": bytes_min, "launch_ms": spmm_ms,
+                        "launches_per_layer": launches_per_layer, "launch_ms_l2_warm": spmm_ms_warm,
+                        "effective_gather_gbs": bytes_gather / (spmm_ms * 1e-3) / 1e9,
+                        "effective_gather_note": "nnz*D*4 gathered bytes / t: the rate the rows come out of L2 at (the bound "
+                                                 "that actually binds: ~10 TB/s L2 fabric, see DESIGN 4.1)"}
+            line.update({"metric": "bpr_epochs_per_sec", "value": value, "unit": "epochs/s", "ms_per_step": ms_per_step,
+                         "ms_per_step_l2_warm": t_warm, "epochs_per_sec_l2_warm": 1e3 / (t_warm * steps_per_epoch),
+                         "e2e": {"value": e2e_value, "unit": "epochs/s", "h2d_bytes_per_step": BATCH * 3 * 8,
+                                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_net, "last_loss": loss},
+                         "gpu_launches": kernels_per_step * K, "kernels_per_step": kernels_per_step, "roofline": roofline})
+
+        # ---- full-rank evaluation (users/s): representation + fused score/mask/top-20 + metrics ----
+        eval_info = None
+        if not args.no_eval:  # every rank takes part: the sweep is user-sharded and gathers the columns collectively
+            m.eval()
+            n_eval = 1 if big else 2
+            tr.eval("test")
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(n_eval):
+                _, metrics, _ = tr.eval("test")
+            barrier()
+            eval_s = (time.perf_counter() - w0) / n_eval
+            ke = timed_steps(lambda: tr.recommend_all("test"), 2 if big else 3, not big)
+            ke_ms = float(min(ke))
+            if world > 1:
+                t = torch.tensor([eval_s, ke_ms], device=dev, dtype=torch.float64)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                eval_s, ke_ms = float(t[0]), float(t[1])
+            d_full = getattr(m, "full_embedding_size", m.embedding_size)
+            score_flops = 2.0 * ds.n_users * ds.n_items * d_full
+            tf_peak = float(peak.get("bf16_tflops_sustained" if big else "bf16_tflops", 1590.0))
+            tf = score_flops / (ke_ms * 1e-3) / 1e12 / world  # per GPU: the sweep is user-sharded
+            eval_info = {"users_per_s_e2e": ds.n_users / eval_s, "users_per_s_kernels": ds.n_users / (ke_ms * 1e-3),
+                         "sweep_ms": ke_ms, "k": max(TOPKS), "recall@20": float(metrics["Recall"][20]),
+                         "ndcg@20": float(metrics["NDCG"][20]), "precision": tr.eval_precision,
+                         "trained_steps": eng.steps_done,
+                         "score_roofline": {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s",
+                                            "frac": tf / tf_peak, "note": "whole recommend_all sweep (propagation + prep + "
+                                            "tcgen05 score/candidates + exact re-score) per GPU; see DESIGN 4.6"},
+                         "includes": "trainer.eval('test'): get_rep + score/mask/top-K + fused rank-metrics pass + D2H of the metric sums"}
+            if workload == "c5":
+                line.update({"metric": "eval_users_per_sec", "value": ds.n_users / (ke_ms * 1e-3), "unit": "users/s",
+                             "ms_per_step": ke_ms, "e2e": {"value": ds.n_users / eval_s, "unit": "users/s",
+                                                           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": (3 * len(TOPKS) + 1) * 8,
+                                                           "note": "trainer.eval('test') end to end; inputs are the resident model"},
+                             "gpu_launches": None, "roofline": eval_info["score_roofline"]})
 
     # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload on the host cores ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "lightgcn":
-        n_cpu = 3 if workload != "c4" else 1
-        s_cpu, threads, _ = cpu_port_step_time(graph, workload, n_cpu, 1)
-        cpu_baseline = {"value": 1.0 / (steps_per_epoch * s_cpu), "unit": "epochs/s", "cores": threads, "kind": "port",
-                        "sample": "%d timed train steps (batch %d) of %d per epoch on torch-CPU CSR/MKL, extrapolated"
-                                  % (n_cpu, BATCH, steps_per_epoch), "ms_per_step": 1e3 * s_cpu}
+        port = CpuPort(graph, workload)
+        n_cpu = 1 if big else 3
+        if not big:
+            port.step()
+        s_cpu = float(np.mean([port.step() for _ in range(n_cpu)]))
+        cpu_baseline = {"value": 1.0 / (steps_per_epoch * s_cpu), "unit": "epochs/s", "cores": port.threads, "kind": "port",
+                        "sample": port.sample_doc(n_cpu, steps_per_epoch), "ms_per_step": 1e3 * s_cpu}
     if rank == 0:
-        line = {"metric": "bpr_epochs_per_sec", "value": value, "unit": "epochs/s", "n_gpus": world, "steps": K,
-                "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload + ": " + WORKLOAD_DOC[workload].replace("LightGCN", model_cfg["name"]), "batch": BATCH,
-                           "steps_per_epoch": steps_per_epoch, "optimizer": "Adam", "sampler": "device (Philox)",
-                           "l2": "flushed between timed steps (write of %d MiB)" % (flush_buf.numel() >> 20),
-                           "parallelism": "single GPU" if world == 1 else (
-                               ("row-partitioned graph x%d, exchange fused into the SpMM / Adam epilogues (NVLink peer stores) "
-                                "+ signal/wait hand-shake" % world) if args.parallelism == "peer" else
-                               "row-partitioned graph x%d, per-layer NCCL block exchange" % world if partition is not None else
-                               "embedding dimension sharded x%d (%d columns per GPU) x %d replicas, one [B,3] all-reduce per "
-                               "step; evaluation user-sharded x%d" % (m._dim_shard.world, d, world // m._dim_shard.world, world))},
-                "ms_per_step_l2_warm": t_warm, "epochs_per_sec_l2_warm": 1e3 / (t_warm * steps_per_epoch),
-                "e2e": {"value": e2e_value, "unit": "epochs/s", "h2d_bytes_per_step": BATCH * 3 * 8,
-                        "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_net, "last_loss": loss},
-                "gpu_launches": gpu_launches, "kernels_per_step": kernels_per_step,
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "eval": eval_info, "clocks": clocks.summary()}
-        print(json.dumps(line), flush=True)
+        out = {"metric": None, "value": None, "unit": None, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": None,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": workload + ": " + WORKLOAD_DOC[workload].replace("LightGCN", model_cfg["name"]), "batch": BATCH,
+                          "steps_per_epoch": steps_per_epoch, "optimizer": "Adam", "sampler": "device (Philox)",
+                          "graph_fingerprint": "%016x" % _fingerprint(graph),
+                          "l2": ("inputs larger than L2 (tables of %d MB against %d MB of L2): no flush" % ((n * d * 4) >> 20, l2_bytes >> 20))
+                          if big else "flushed between timed steps (write of %d MiB)" % (flush_buf.numel() >> 20),
+                          "parallelism": "single GPU" if world == 1 else (
+                              ("row-partitioned graph x%d, exchange fused into the SpMM / Adam epilogues (NVLink peer stores) "
+                               "+ signal/wait hand-shake" % world) if args.parallelism == "peer" else
+                              "row-partitioned graph x%d, per-layer NCCL block exchange" % world if partition is not None else
+                              "embedding dimension sharded x%d (%d columns per GPU) x %d replicas, one [B,3] all-reduce per "
+                              "step; evaluation user-sharded x%d" % (m._dim_shard.world, d, world // m._dim_shard.world, world))}}
+        out.update(line)
+        out.update({"cpu_baseline": cpu_baseline, "eval": eval_info, "clocks": clocks.summary()})
+        print(json.dumps(out), flush=True)
     if world > 1:
         eng.close()
         torch.distributed.barrier()
@@ -353,11 +462,12 @@ def run_own(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--model", default="lightgcn", choices=["lightgcn", "igcn", "mf", "sgl", "half"],
                     help="lightgcn is the headline; igcn = inductive template-feature layer + propagation (config.py:18-23)")
     ap.add_argument("--parallelism", default="dim", choices=["dim", "row", "peer"],

@@ -36,20 +36,27 @@ def auto_chunk(nnz, d=None):
 
 def blocking_policy(n_cols, d):
     """(sweep width, source rows per block) for a gathered table [n_cols, d] fp32, or None when the table is left to the
-    cache as it is.  A table much larger than L2 (C4: 3M x 128 x 4 B = 1.5 GB against 126 MB) is gathered at a few
-    percent L2 hit rate and the SpMM runs at the HBM ceiling moving ~16x its algorithmic bytes; cutting the source rows
-    into L2-sized blocks (one pass each, b200rec_spmm_f32_blocked) turns those gathers into L2 hits.  Wide tables are
-    swept in column slices of `sweep` floats: half the width = half as many passes = half the carried-sum traffic, for a
-    second read of the 8 B/edge index stream.  Environment overrides for experiments: B200REC_BLOCK_MB (0 = never block),
-    B200REC_SWEEP_D."""
+    cache as it is.  A table much larger than L2 (C4: 3M x 128 x 4 B = 1.5 GB against 126 MB) is gathered at ~24 % L2 hit
+    rate and the SpMM moves ~16x its algorithmic bytes over HBM; cutting the source rows into L2-sized blocks (one pass
+    each, b200rec_spmm_f32_blocked) turns those gathers into L2 hits.  Wide tables can be swept in column slices of
+    `sweep` floats (fewer passes per slice, one more read of the 8 B/edge index stream).
+
+    Measured on C4 (profiles/r02_spmm_block_sweep.txt, ms per layer): D=128 single pass 11.9; blocked 96 MB x 32-column
+    sweeps 12.5, 64 MB x 64 13.8-15.6, 48 MB x 128 27.7 -- every pass cuts rows into ~6-edge items and the gathered bytes
+    still cross the L2 fabric at ~8-9 TB/s, which is where the single-pass kernel already is (104 GB in 11.9 ms), so the
+    HBM saving buys nothing at 512 B rows.  D=16 (the 8-GPU shard of C4): 1.94 single pass, 1.76 with 64 MB blocks --
+    eight items per warp hide the per-item latency.  Default therefore: block only tables of rows <= 64 B that exceed
+    1.5 blocks.  Overrides for experiments: B200REC_BLOCK_MB (0 = never block), B200REC_BLOCK_MAX_D, B200REC_SWEEP_D."""
     import os
-    block_mb = float(os.environ.get("B200REC_BLOCK_MB", "48"))
+    block_mb = float(os.environ.get("B200REC_BLOCK_MB", "64"))
     if block_mb <= 0:
         return None
-    sweep = int(os.environ.get("B200REC_SWEEP_D", "64"))
+    sweep = int(os.environ.get("B200REC_SWEEP_D", "0")) or d
     sweep = min(d, max(8, sweep))
     if d % sweep:
         sweep = d
+    if sweep > int(os.environ.get("B200REC_BLOCK_MAX_D", "16")):
+        return None
     block_bytes = block_mb * (1 << 20)
     if n_cols * sweep * 4 <= 1.5 * block_bytes:
         return None
@@ -127,7 +134,8 @@ class CsrOperand:
     # ---- column-blocked execution for tables that do not fit L2 ----
     def blocked_for(self, d):
         """(twin operand with a column-blocked plan, sweep width) for a gathered table of width d, or None"""
-        if self.vals is None or self.nbr_scale is not None or self.eid is not None or self.n_passes > 1:
+        if self.vals is None or self.nbr_scale is not None or self.eid is not None or self.n_passes > 1 \
+                or getattr(self, "_row_sliced", False):
             return None
         pol = blocking_policy(self.n_cols, d)
         if pol is None:
@@ -171,7 +179,7 @@ class CsrOperand:
         o = object.__new__(CsrOperand)
         o.__dict__.update(self.__dict__)
         o._struct = None
-        o._blocked, o._carry = {}, {}
+        o._blocked, o._carry, o._row_sliced = {}, {}, True
         assert self.n_passes <= 1, "row_slice of a column-blocked plan"
         row = self.item_row[:self.n_items]
         keep = torch.zeros_like(row, dtype=torch.bool)

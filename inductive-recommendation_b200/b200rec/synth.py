@@ -163,6 +163,23 @@ def fingerprint(graph):
     return acc
 
 
+def hashed_embedding(graph, d, seed=2021, std=0.1, popularity=0.02):
+    """Deterministic layer-0 table [n_users + n_items, d] fp32 for fixtures that cannot store one (C1: 18 MB): uniform
+    values of standard deviation `std` from a splitmix64 hash of the element index, plus a popularity direction on
+    column 0 (users +1, items + popularity * sqrt(train degree)) so that full-rank metrics sit at the popularity
+    baseline instead of at chance.  Integer hash -> exact fp32 conversion, IEEE sqrt and one rounded multiply-add: the
+    same bits on every machine.  numpy [N, d]."""
+    n = graph.n_users + graph.n_items
+    idx = torch.arange(n * d, dtype=torch.int64)
+    h = _lsr(_mix64(idx + _c64(seed * 0x9E3779B97F4A7C15)), 40)             # 24 bits
+    u = (h.to(torch.float32) - 8388608.0) * (1.0 / 8388608.0)                # exact: [-1, 1)
+    emb = (u * np.float32(std * 3 ** 0.5)).view(n, d).numpy().copy()
+    deg = torch.bincount(graph.train_items.cpu(), minlength=graph.n_items).to(torch.float32)
+    emb[:graph.n_users, 0] += np.float32(1.0)
+    emb[graph.n_users:, 0] += (np.float32(popularity) * torch.sqrt(deg)).numpy()
+    return emb
+
+
 def generate_named(name, seed=0, device="cpu", heldout=True):
     u, i, e, _, _ = SHAPES[name]
     return generate(u, i, e, seed=seed, heldout=heldout, device=device)

@@ -4,6 +4,10 @@ TEST INFRASTRUCTURE ONLY.  Runs in the build container (where /root/reference is
 fixtures it writes are committed so they travel to the GPU box, which has no /root/reference.
 
     python oracle/make_golden.py            # rewrites tests/golden/{lightgcn,igcn,igcn_fr,imf,mf}_tiny.npz
+    python oracle/make_golden.py --only-c1  # the BASELINE-sized case c1_ref.npz (about 3 minutes of CPU)
+
+The tiny fixtures carry their graph inside the file (they were drawn with the round-1 generator); c1_ref names its
+graph by (shape, seed) and stores the generator's fingerprint.
 
 The three third-party leaves the reference imports but this image lacks (dgl, info_nce,
 torchmetrics) are satisfied by oracle/stubs (contract: SURVEY.md Appendix B).  Everything recorded
@@ -303,9 +307,92 @@ def run_contrastive_case(tag, graph, model_name, out_dir, seed=2021, batch=256):
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def run_baseline_case(tag, shape, out_dir, n_rows_kept=2048, n_users_kept=1024, batch=2048, seed=2021):
+    """A BASELINE.json-sized case (C1: 29 858 x 40 981, 1 027 370 edges, LightGCN L=3 D=64, batch 2048): the unmodified
+    reference's normalised adjacency, eval-mode representation, one recorded training step and eval('val'/'test') with
+    Recall/NDCG@20.  The inputs are regenerated by the tests (synth.generate_named + synth.hashed_embedding are
+    deterministic; the fixture stores the graph's fingerprint), the outputs are kept at `n_rows_kept` sampled table rows
+    and `n_users_kept` users so that the file stays at a few MB."""
+    graph = synth.generate_named(shape, seed=0)
+    tmp = tempfile.mkdtemp()
+    synth.write_processed(graph, tmp)
+    ds = quiet(ref_dataset.get_dataset, {"name": "ProcessedDataset", "path": tmp, "device": CPU})
+    ref_utils.set_seed(seed)
+    _, _, _, d, n_layers = synth.SHAPES[shape]
+    model = quiet(ref_model.get_model, {"name": "LightGCN", "embedding_size": d, "n_layers": n_layers, "device": CPU}, ds)
+    tcfg = {"name": "BPRTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 1e-4}
+    tr = quiet(ref_trainer.get_trainer, dict(tcfg, device=CPU, dataloader_num_workers=0, topks=TOPKS, n_epochs=1,
+                                             batch_size=batch, test_batch_size=512), ds, model)
+    emb0 = synth.hashed_embedding(graph, d)
+    with torch.no_grad():
+        model.embedding.weight.copy_(torch.from_numpy(emb0))     # an input, like the graph
+    n = ds.n_users + ds.n_items
+    out = {"shape": shape, "fingerprint": np.uint64(synth.fingerprint(graph)), "n_users": ds.n_users, "n_items": ds.n_items,
+           "emb0_checksum": np.float64(np.abs(emb0.astype(np.float64)).sum())}
+    idx, val = coo_of(model.norm_adj)
+    rng = np.random.default_rng(seed)
+    pos = np.sort(rng.choice(val.shape[0], size=8192, replace=False))
+    out["adj_nnz"], out["adj_pos"], out["adj_idx_at"], out["adj_val_at"] = val.shape[0], pos, idx[:, pos], val[pos]
+    model.eval()
+    with torch.no_grad():
+        rep = model.get_rep().numpy()
+    # ---- one training step on a batch drawn by the reference's own sampler ----
+    model.train()
+    ref_utils.set_seed(seed + 1)
+    rows = [ds[0] for _ in range(batch)]
+    b = torch.tensor(np.stack(rows)[:, 0, :], dtype=torch.int64)
+    out["batch"] = b.numpy().copy()
+    touched = np.unique(np.concatenate([b[:, 0].numpy(), ds.n_users + b[:, 1].numpy(), ds.n_users + b[:, 2].numpy()]))
+    keep = np.unique(np.concatenate([rng.choice(touched, size=n_rows_kept // 2, replace=False),
+                                     rng.choice(n, size=n_rows_kept // 2, replace=False)]))
+    out["rows_kept"] = keep
+    out["rep_eval_rows"] = rep[keep].copy()
+    out["rep_eval_abs_sum"] = np.float64(np.abs(rep.astype(np.float64)).sum())
+    users, p_, n_ = b[:, 0], b[:, 1], b[:, 2]
+    ur, pr, nr, l2 = model.bpr_forward(users, p_, n_)
+    F = torch.nn.functional
+    bpr = F.softplus((ur * nr).sum(1) - (ur * pr).sum(1)).mean()
+    loss = bpr + tcfg["l2_reg"] * l2.mean()
+    out["bpr_loss"], out["loss"] = float(bpr), float(loss)
+    tr.opt.zero_grad()
+    loss.backward()
+    g = model.embedding.weight.grad.numpy()
+    out["grad_rows"] = g[keep].copy()
+    out["grad_abs_sum"] = np.float64(np.abs(g.astype(np.float64)).sum())
+    tr.opt.step()
+    out["emb1_rows"] = model.embedding.weight.detach().numpy()[keep].copy()
+    with torch.no_grad():
+        model.embedding.weight.copy_(torch.from_numpy(emb0))     # evaluate the recorded input, not the stepped one
+    # ---- full-rank evaluation (trainer.py:146-210) ----
+    model.eval()
+    for split in ("val", "test"):
+        _, metrics, _ = tr.eval(split)
+        for m in ("Precision", "Recall", "NDCG"):
+            out["metric_%s_%s" % (m, split)] = np.array([metrics[m][k] for k in TOPKS], dtype=np.float64)
+    with torch.no_grad():
+        us = torch.arange(n_users_kept, dtype=torch.int64)
+        scores = model.predict(us)
+        ex_u, ex_i = [], []
+        for ui, u in enumerate(us.tolist()):
+            items = ds.train_data[u] + ds.val_data[u]
+            ex_u.extend([ui] * len(items))
+            ex_i.extend(items)
+        scores[ex_u, ex_i] = -np.inf
+        v, it = torch.topk(scores, k=max(TOPKS))
+    out["topk_ids_test"], out["topk_val_test"] = it.numpy(), v.numpy()
+    out["lr"], out["l2_reg"], out["n_layers"], out["topks"] = tcfg["lr"], tcfg["l2_reg"], n_layers, np.array(TOPKS)
+    path = os.path.join(out_dir, tag + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+    print("   recall@20 test", out["metric_Recall_test"][-1], "ndcg@20", out["metric_NDCG_test"][-1], "loss", out["loss"])
+
+
 def main():
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--only-c1" in sys.argv:
+        run_baseline_case("c1_ref", "c1", out_dir)
+        return
     if "--only-contrastive" in sys.argv:
         g = synth.generate(300, 500, 6000, seed=7)
         run_contrastive_case("sgl_tiny", g, "SGL", out_dir)

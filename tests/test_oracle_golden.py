@@ -201,3 +201,56 @@ def test_contrastive_port_matches_reference_steps(golden, name):
     loss2, _ = rp.contrastive_train_step(port, opt, batch, float(g["l2_reg"]), float(g["contrastive_reg"]))
     assert abs(loss2 - float(g["loss2"])) < 1e-6
     np.testing.assert_allclose(port.embedding.weight.detach().numpy(), g["emb2"], rtol=1e-5, atol=4e-6)
+
+
+def test_port_matches_reference_at_c1_size():
+    """the port against the BASELINE-sized fixture c1_ref (29 858 x 40 981, 1 027 370 edges, D=64, L=3, batch 2048) that
+    oracle/make_golden.py --only-c1 recorded from the unmodified reference: representation, one training step, and the
+    full Recall/NDCG@20 of eval('test') (trainer.py:115-210).  The inputs are regenerated: the generator and the hashed
+    layer-0 table are deterministic, the fixture stores the graph's fingerprint."""
+    from conftest import load_golden
+    from b200rec import synth
+    f = load_golden("c1_ref")
+    g = synth.generate_named("c1", seed=0)
+    assert synth.fingerprint(g) == int(f["fingerprint"])
+    emb0 = synth.hashed_embedding(g, 64)
+    assert abs(float(np.abs(emb0.astype(np.float64)).sum()) - float(f["emb0_checksum"])) < 1e-6
+    ptr, idx = g.train_indptr.numpy(), g.train_items.numpy()
+    users, items = rp.pairs_from_csr(ptr, idx)
+    m = rp.LightGCNPort(g.n_users, g.n_items, users, items, emb0, 3).eval()
+    coo = m.adj_sp.tocoo()
+    assert coo.nnz == int(f["adj_nnz"])
+    pos = f["adj_pos"]
+    assert np.array_equal(np.stack([coo.row[pos], coo.col[pos]]), f["adj_idx_at"])
+    np.testing.assert_allclose(coo.data[pos], f["adj_val_at"], rtol=3e-7)
+    with torch.no_grad():
+        rep = m.get_rep().numpy()
+    np.testing.assert_allclose(rep[f["rows_kept"]], f["rep_eval_rows"], rtol=1e-5, atol=1e-7)
+    # full-rank evaluation from the cached representation (the reference re-propagates per batch; same numbers)
+    n_u = g.n_users
+    rec = np.empty((n_u, 20), dtype=np.int64)
+    vptr, vidx = g.val_indptr.numpy(), g.val_items.numpy()
+    for s in range(0, n_u, 2048):
+        e = min(n_u, s + 2048)
+        sc = rep[s:e] @ rep[n_u:].T
+        for u in range(s, e):
+            sc[u - s, idx[ptr[u]:ptr[u + 1]]] = -np.inf
+            sc[u - s, vidx[vptr[u]:vptr[u + 1]]] = -np.inf
+        rec[s:e] = rp.topk_tiebreak(sc, 20)[0]
+    metrics = rp.calculate_metrics(g.lists("test"), rec, TOPKS)
+    for name in ("Precision", "Recall", "NDCG"):
+        ours = np.array([metrics[name][k] for k in TOPKS])
+        np.testing.assert_allclose(ours, f["metric_%s_test" % name], rtol=1e-5, atol=1e-7)
+    ref_ids, ref_val = f["topk_ids_test"], f["topk_val_test"]
+    d = np.abs(np.diff(ref_val, axis=1)) > 1e-6
+    sep = np.ones_like(ref_ids, dtype=bool)
+    sep[:, 1:] &= d
+    sep[:, :-1] &= d
+    assert sep.mean() > 0.97 and np.array_equal(rec[: ref_ids.shape[0]][sep], ref_ids[sep])
+    # one training step on the reference's recorded batch
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=float(f["lr"]))
+    loss = rp.train_step(m, opt, torch.from_numpy(f["batch"]), float(f["l2_reg"]))
+    assert abs(loss - float(f["loss"])) < 1e-6
+    np.testing.assert_allclose(m.embedding.weight.grad.numpy()[f["rows_kept"]], f["grad_rows"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(m.embedding.weight.detach().numpy()[f["rows_kept"]], f["emb1_rows"], rtol=1e-5, atol=2e-6)
