@@ -47,6 +47,15 @@ WORKLOAD_DOC = {
 BIG = ("c4", "c5")
 
 
+_T0 = time.time()
+
+
+def _log(msg):
+    """progress on stderr (stdout carries the one JSON line)"""
+    if int(os.environ.get("RANK", 0)) == 0:
+        print("[bench %7.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -197,13 +206,19 @@ def run_reference(args, rank):
     graph = build_graph(workload, dev)
     n_train = int(graph.train_items.numel())
     steps_per_epoch = (n_train + BATCH - 1) // BATCH
+    _log("reference arm: graph ready, building the CPU port")
     port = CpuPort(graph, workload)
+    _log("CPU port built (%d threads)" % port.threads)
     for _ in range(args.warmup):
         port.step()
-    times = [port.step() for _ in range(args.steps)]
+    times = []
+    for i in range(args.steps):
+        times.append(port.step())
+        _log("reference step %d: %.2f s" % (i, times[-1]))
     s_per_step = float(np.mean(times)) if times else float("nan")
     value = 1.0 / (steps_per_epoch * s_per_step)
     eval_rate, eval_n = port.eval_rate(256 if workload in BIG else 1024)
+    _log("reference evaluation sample: %.1f users/s" % eval_rate)
     if workload == "c5":
         metric, unit, value_out = "eval_users_per_sec", "users/s", eval_rate
     else:
@@ -244,8 +259,10 @@ def run_own(args, rank, world):
     workload = args.workload or DEFAULT_WORKLOAD
     big = workload in BIG
     _, _, _, d, n_layers = synth.SHAPES[graph_name(workload)]
+    _log("building the %s graph on %s" % (workload, dev))
     graph = build_graph(workload, dev)
     ds = D.get_dataset({"name": "SyntheticDataset", "device": dev, "graph": graph})
+    _log("graph ready: %d users x %d items, %d train pairs" % (ds.n_users, ds.n_items, len(ds)))
     torch.manual_seed(2021)  # same seed on every rank: the shards are slices of one initialisation
     partition = None
     model_cfg = {"lightgcn": {"name": "LightGCN", "embedding_size": d, "n_layers": n_layers},
@@ -269,6 +286,7 @@ def run_own(args, rank, world):
                         "n_epochs": 1, "batch_size": BATCH, "dataloader_num_workers": 0, "test_batch_size": 512,
                         "topks": TOPKS, "partition": partition}, ds, m)
     m.train()
+    _log("model + trainer ready")
     eng = tr._engine()
     steps_per_epoch = tr.steps_per_epoch()
     K, W = args.steps, max(args.warmup, 3)
@@ -306,6 +324,7 @@ def run_own(args, rank, world):
             for _ in range(W):
                 eng.step()
             barrier()
+            _log("warm-up done (%d steps), timing %d steps" % (W, K))
             launches0 = _abi.launch_count()
             times = timed_steps(eng.step, K, True)
             barrier()
@@ -321,6 +340,7 @@ def run_own(args, rank, world):
             kernels_per_step = eng.kernels_per_step()
             assert _abi.launch_count() >= launches0  # replays do not pass through the host counter
 
+            _log("device-timed: %.3f ms/step" % ms_per_step)
             # ---- e2e: host batches through the engine's public step(), H2D of the batch + D2H of the loss every step ----
             host_batches = []
             st = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -352,6 +372,7 @@ def run_own(args, rank, world):
                 e2e_ms_net = float(t[0])
             e2e_value = 1e3 / (e2e_ms_net * steps_per_epoch)
 
+            _log("e2e: %.3f ms/step" % e2e_ms_net)
             # ---- roofline of the dominant kernel: one SpMM layer as the step runs it (Y = A X, acc += Y) ----
             adj = m.norm_adj if partition is None else partition.local_op
             nnz_local = int(adj.item_end[:adj.n_items].sum() - adj.item_start[:adj.n_items].sum()) if partition is not None else adj.nnz
@@ -390,12 +411,15 @@ def run_own(args, rank, world):
                          "gpu_launches": kernels_per_step * K, "kernels_per_step": kernels_per_step, "roofline": roofline})
 
         # ---- full-rank evaluation (users/s): representation + fused score/mask/top-20 + metrics ----
+        if workload != "c5":
+            _log("SpMM layer: %.3f ms" % spmm_ms)
         eval_info = None
         if not args.no_eval:  # every rank takes part: the sweep is user-sharded and gathers the columns collectively
             m.eval()
             n_eval = 1 if big else 2
             tr.eval("test")
             barrier()
+            _log("first evaluation pass done")
             w0 = time.perf_counter()
             for _ in range(n_eval):
                 _, metrics, _ = tr.eval("test")
@@ -427,9 +451,11 @@ def run_own(args, rank, world):
                              "gpu_launches": None, "roofline": eval_info["score_roofline"]})
 
     # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload on the host cores ----
+    _log("GPU legs done")
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "lightgcn":
         port = CpuPort(graph, workload)
+        _log("CPU port built (%d threads)" % port.threads)
         n_cpu = 1 if big else 3
         if not big:
             port.step()

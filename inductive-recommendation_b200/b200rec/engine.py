@@ -59,6 +59,11 @@ class BprEngine:
         self.loss_accum = torch.zeros(2, dtype=torch.float64, device=dev)
         self.scratch = ops.bpr_scratch(batch_size, D, dev)
         self.dots = torch.zeros((batch_size, 3), **f32)  # per-sample (pos, neg, l2) partials when the dimension is sharded
+        # ordered scatter (b200rec_bpr_group_rows): one store per distinct row, contributions summed in slot order
+        import os
+        self.ordered = 3 * batch_size <= ops.GROUP_CAP and os.environ.get('B200REC_ATOMIC_SCATTER', '0') != '1'
+        self.grouping = ops.bpr_grouping(batch_size, dev) if self.ordered else None
+        self.aux_grouping = None
         self.user_ptr, self.user_items = dataset.csr('train', device=dev)
         n = model.n_users + model.n_items
         self.n = n
@@ -134,6 +139,7 @@ class BprEngine:
                 self.aux = aux_dataset
                 if aux_dataset is not None:
                     self.aux_ptr, self.aux_items = aux_dataset.csr('train', device=dev)
+                    self.aux_grouping = ops.bpr_grouping(batch_size, dev) if self.ordered else None
         import os
         self.use_graph = use_graph and os.environ.get('B200REC_NO_GRAPH', '0') != '1'
         self._adj_ref = getattr(model, 'norm_adj', None)  # the step (and its captured graph) is built on THIS operand
@@ -200,7 +206,22 @@ class BprEngine:
                      src_flags=flags if k == 1 else None)
             src = dst
 
-    def _bpr(self, rep, batch, item_offset, l2_reg, reg_mode, g_rep, w=None, g_w=None, loss_scale=1.0):
+    def _bpr(self, rep, batch, item_offset, l2_reg, reg_mode, g_rep, w=None, g_w=None, loss_scale=1.0, grouping=None,
+             accumulate=False):
+        """grouping: the batch's (order, seg_start, n_seg, coef) from ops.bpr_group_rows -> deterministic aggregated
+        scatter (g_rep rows are STORED unless accumulate); None -> one 128-bit red per sample and role"""
+        if grouping is not None:
+            if self.shard is None:
+                ops.bpr_fwd_bwd_ordered(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, grouping,
+                                        w=w, g_w=g_w, loss_scale=loss_scale, accumulate=accumulate)
+                return
+            ops.bpr_fwd_bwd_ordered(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, grouping,
+                                    dots=self.dots, phase=1, w=w, g_w=g_w, loss_scale=loss_scale)
+            self.shard.all_reduce_sum(self.dots)
+            ops.bpr_fwd_bwd_ordered(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, grouping,
+                                    dots=self.dots, phase=2, loss_weight=1.0 if self.shard.rank == 0 else 0.0, w=w, g_w=g_w,
+                                    loss_scale=loss_scale, accumulate=accumulate)
+            return
         if self.shard is None:
             ops.bpr_fwd_bwd(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, w=w, g_w=g_w,
                             loss_scale=loss_scale)
@@ -229,12 +250,18 @@ class BprEngine:
         main = torch.cuda.current_stream()
         forked = self.kind == 'LightGCN' and self.partition is None and m.n_layers >= 2
         side = self._side_stream if forked else main
+        grp = self.grouping
+        # g_rep is all-zero between steps: with the ordered scatter the BPR kernel STORES the touched rows and they are
+        # cleared again once the backward chain has consumed them (no [N, D] memset per step: 1.5 GB on C4)
+        lazy_clear = grp is not None and self.kind in ('LightGCN', 'IGCN', 'IMF')
         if forked:
             side.wait_stream(main)
         with torch.cuda.stream(side):
             if sample:
                 ops.bpr_sample(self.user_ptr, self.user_items, self.dataset.n_users, self.dataset.n_items, self.seed,
                                self.sample_step, B, out=self.batch)
+            if grp is not None:
+                ops.bpr_group_rows(self.batch, nu, grp)
             if self.kind != 'MF':
                 # the step reads rep only at the <= 3B sampled rows, and G is non-zero only there: the last forward layer
                 # and the first backward hop are restricted to them (bit-identical on the rows that matter)
@@ -242,22 +269,27 @@ class BprEngine:
                 ops.mark_rows(self.batch, nu, self.row_flags)
                 if forked and self.live is not None:
                     ops.live_items(self.adj_sparse, self.row_flags, self.live[0], self.live[1])
-            if forked:
+            if forked and not lazy_clear:
                 self.g_rep.zero_()  # needed only by the BPR kernel: cleared beside the first forward layers
         join = (lambda: main.wait_stream(side)) if forked else None
         self.loss.zero_()
         if self.kind == 'MF':
             self.grad.zero_()
-            self._bpr(self.table, self.batch, nu, self.l2_reg, 1, self.grad)
+            self._bpr(self.table, self.batch, nu, self.l2_reg, 1, self.grad, grouping=grp)
             self._adam(self.table, self.grad, self.m, self.v)
         elif self.kind == 'LightGCN':
-            if not forked:
+            if not forked and not lazy_clear:
                 self.g_rep.zero_()
             self._propagate_fwd(self.table, join)
-            self._bpr(self.rep, self.batch, nu, 0.0, 0, self.g_rep)
+            self._bpr(self.rep, self.batch, nu, 0.0, 0, self.g_rep, grouping=grp)
             self._propagate_bwd(self.grad)
+            if lazy_clear:
+                ops.clear_rows(self.batch, nu, self.g_rep)
             if self.l2_reg != 0.0:
-                ops.bpr_l2_emb0(self.table, self.batch, nu, self.l2_reg, self.grad, self.loss, self.scratch)
+                if grp is not None:
+                    ops.bpr_l2_emb0_ordered(self.table, self.batch, nu, self.l2_reg, self.grad, self.loss, self.scratch, grp)
+                else:
+                    ops.bpr_l2_emb0(self.table, self.batch, nu, self.l2_reg, self.grad, self.loss, self.scratch)
             self._adam(self.table, self.grad, self.m, self.v)
         elif self.kind in ('SGL', 'HALF'):
             # SGLTrainer / HALFTrainer.train_one_epoch (trainer.py:440-456): BPR on the full graph + contrastive_reg *
@@ -272,7 +304,7 @@ class BprEngine:
             self._propagate_fwd(self.table)
             for adj, rep in zip(views, self.view_rep):
                 self._propagate_fwd(self.table, adj=adj, flags=self.user_flags, rep=rep)
-            self._bpr(self.rep, self.batch, nu, self.l2_reg, 1 if self.l2_reg != 0.0 else 0, self.g_rep)
+            self._bpr(self.rep, self.batch, nu, self.l2_reg, 1 if self.l2_reg != 0.0 else 0, self.g_rep, grouping=grp)
             if self.kind == 'SGL':
                 q, k, gq, gk = self.view_rep[0], self.view_rep[1], self.view_g[0], self.view_g[1]
             else:
@@ -294,15 +326,21 @@ class BprEngine:
             if self.aux is not None and sample:
                 ops.bpr_sample(self.aux_ptr, self.aux_items, self.aux.n_users, self.aux.n_items, self.seed + 1,
                                self.sample_step, B, out=self.aux_batch)
-            self.g_rep.zero_()
+            if not lazy_clear:
+                self.g_rep.zero_()
             ops.spmm(self.feat_fwd, self.table, keep_bits=keep, post_scale=inv_keep, y=self.x0)
             self._propagate_fwd(self.x0)
-            self._bpr(self.rep, self.batch, nu, self.l2_reg, 1 if self.l2_reg != 0.0 else 0, self.g_rep)
+            self._bpr(self.rep, self.batch, nu, self.l2_reg, 1 if self.l2_reg != 0.0 else 0, self.g_rep, grouping=grp)
             self._propagate_bwd(self.dx0)
+            if lazy_clear:
+                ops.clear_rows(self.batch, nu, self.g_rep)
             ops.spmm(self.feat_bwd, self.dx0, keep_bits=keep, post_scale=inv_keep, y=self.grad)
             if self.aux is not None:
-                self._bpr(self.table, self.aux_batch, len(m.user_map), 0.0, 0, self.grad, w=m.w.data, g_w=self.g_w,
-                          loss_scale=self.aux_reg)
+                tu = len(m.user_map)
+                if self.aux_grouping is not None:
+                    ops.bpr_group_rows(self.aux_batch, tu, self.aux_grouping)
+                self._bpr(self.table, self.aux_batch, tu, 0.0, 0, self.grad, w=m.w.data, g_w=self.g_w,
+                          loss_scale=self.aux_reg, grouping=self.aux_grouping, accumulate=True)
                 self._adam(m.w.data, self.g_w, self.m_w, self.v_w)
             self._adam(self.table, self.grad, self.m, self.v)
         ops.step_advance(self.adam_step, self.sample_step, self.loss, self.loss_accum, B)
@@ -398,6 +436,13 @@ class BprEngine:
         if self.shard is not None:
             return float(self.shard.all_reduce_sum(self.loss.clone()).item())
         return float(self.loss.item())
+
+    def note_external_step(self, loss, n_batch):
+        """an optimiser step was taken outside the engine (eager autograd + torch.optim.Adam on the shared moments):
+        advance the device step count and the loss meter as a replay would have"""
+        self.adam_step += 1
+        self.loss_accum += torch.tensor([float(loss) * n_batch, float(n_batch)], dtype=torch.float64, device=self.dev)
+        self.model._rep_cache = None
 
     def sync_optimizer_state(self):
         """write the step count back into torch.optim.Adam's state (it keeps `step` as a CPU scalar tensor)"""

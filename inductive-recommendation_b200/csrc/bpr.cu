@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* rep, const 
                                                         const float* __restrict__ w, float loss_scale,
                                                         float* __restrict__ g_rep, float* __restrict__ g_w,
                                                         float* __restrict__ loss_out, float* scratch,
-                                                        float* __restrict__ dots, int dots_mode, float loss_weight) {
+                                                        float* __restrict__ dots, int dots_mode, float loss_weight,
+                                                        float* __restrict__ coef_out) {
+  // coef_out != NULL (ordered mode): the per-sample score derivative is stored and NO gradient row is scattered here;
+  // bpr_grad_rows_kernel then forms every touched row's gradient once, in sample order (deterministic, no atomics).
   // dots_mode 0: everything in one launch.  Embedding-dimension sharding (each rank holds D/P columns) splits it:
   // 1 = write this rank's partial (pos, neg, l2) per sample to dots[B,3] and stop; after the caller's all-reduce,
   // 2 = take the full (pos, neg, l2) from dots and produce this rank's columns of the gradient.
@@ -182,9 +185,9 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* rep, const 
     u[t] = p[t] = n[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     wv[t] = make_float4(1.f, 1.f, 1.f, 1.f);
     if (active) {
-      u[t] = ldg_f4(rep + (size_t)ru * D + c);
-      p[t] = ldg_f4(rep + (size_t)rp * D + c);
-      n[t] = ldg_f4(rep + (size_t)rn * D + c);
+      u[t] = ldc_f4(rep + (size_t)ru * D + c);  // coherent loads: rep is the output of the kernel this one overlaps (PDL)
+      p[t] = ldc_f4(rep + (size_t)rp * D + c);
+      n[t] = ldc_f4(rep + (size_t)rn * D + c);
       if constexpr (HAS_W) wv[t] = ldg_f4(w + c);
     }
     pos += u[t].x * p[t].x * wv[t].x + u[t].y * p[t].y * wv[t].y + u[t].z * p[t].z * wv[t].z + u[t].w * p[t].w * wv[t].w;
@@ -212,11 +215,13 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* rep, const 
   loss *= loss_weight;
   const float coef = loss_scale * inv_b * sigmoid_t(x);
   const float rc = (reg_mode == 1) ? 2.f * l2_reg * loss_scale * inv_b : 0.f;
+  if (coef_out && active && gl == 0) coef_out[smp] = coef;
   if (active) {
 #pragma unroll
     for (int t = 0; t < VPL; ++t) {
       const int c = (gl + t * G) * 4;
       const float4 cw = make_float4(coef * wv[t].x, coef * wv[t].y, coef * wv[t].z, coef * wv[t].w);
+      if (!coef_out) {
       float4 gu = make_float4(cw.x * (n[t].x - p[t].x) + rc * u[t].x, cw.y * (n[t].y - p[t].y) + rc * u[t].y,
                               cw.z * (n[t].z - p[t].z) + rc * u[t].z, cw.w * (n[t].w - p[t].w) + rc * u[t].w);
       float4 gp = make_float4(-cw.x * u[t].x + rc * p[t].x, -cw.y * u[t].y + rc * p[t].y, -cw.z * u[t].z + rc * p[t].z,
@@ -226,6 +231,7 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* rep, const 
       red_add_f4(g_rep + (size_t)ru * D + c, gu);
       red_add_f4(g_rep + (size_t)rp * D + c, gp);
       red_add_f4(g_rep + (size_t)rn * D + c, gn);
+      }
       if constexpr (HAS_W) {  // d(score)/dw = u * (n - p)
         s_w[gib][c + 0] = coef * u[t].x * (n[t].x - p[t].x);
         s_w[gib][c + 1] = coef * u[t].y * (n[t].y - p[t].y);
@@ -272,12 +278,177 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* rep, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- ordered scatter
+// Duplicate ids inside a batch are the rule (popular items; a user drawn twice), and a red.global.add per sample sums
+// them in arrival order -- different bits from run to run.  Instead the 3B (row, slot) pairs of the batch are sorted once
+// (one block, bitonic sort in shared memory, beside the forward layers on the side stream) and every DISTINCT row gets its
+// gradient from one lane group that adds the contributions of its slots in slot order and issues one plain store: the
+// aggregation north_star asks of the scatter (one write per distinct row instead of one atomic per sample), with a
+// fixed summation order on top.
+constexpr int GROUP_CAP = 8192;  // slots (3 * batch) the single-block sort holds: batches up to 2730 samples
+__global__ void __launch_bounds__(1024, 1) bpr_group_rows_kernel(const int64_t* __restrict__ batch, int n_slots, int64_t item_offset,
+                                                                 int32_t* __restrict__ order, int32_t* __restrict__ seg_start,
+                                                                 int32_t* __restrict__ n_seg) {
+  extern __shared__ unsigned long long s_key[];  // [GROUP_CAP] (row << 13) | slot
+  __shared__ int s_warp[32];
+  for (int i = threadIdx.x; i < GROUP_CAP; i += 1024) {
+    unsigned long long k = ~0ull;
+    if (i < n_slots) {
+      const int64_t r = batch[i] + ((i % 3) ? item_offset : 0);
+      k = ((unsigned long long)r << 13) | (unsigned)i;
+    }
+    s_key[i] = k;
+  }
+  __syncthreads();
+  for (int size = 2; size <= GROUP_CAP; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < GROUP_CAP / 2; t += 1024) {
+        const int lo = 2 * t - (t & (stride - 1));   // index of the lower element of pair t
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = s_key[lo], b = s_key[hi];
+        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  // segment heads: 8 consecutive sorted slots per thread, block-wide exclusive scan of the head counts
+  const int base = threadIdx.x * 8;
+  int heads = 0;
+  unsigned flags = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = base + j;
+    const bool h = i < n_slots && (i == 0 || (s_key[i] >> 13) != (s_key[i - 1] >> 13));
+    if (h) { flags |= 1u << j; ++heads; }
+  }
+  int incl = heads;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)(threadIdx.x & 31) >= o) incl += v;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = s_warp[threadIdx.x];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if ((int)threadIdx.x >= o) w += v;
+    }
+    s_warp[threadIdx.x] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  int pos = incl - heads + ((threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = base + j;
+    if (i < n_slots) {
+      order[i] = (int32_t)(s_key[i] & 8191ull);
+      if ((flags >> j) & 1u) seg_start[pos++] = i;
+    }
+  }
+  if (threadIdx.x == 1023) {
+    const int total = s_warp[31];
+    *n_seg = total;
+    seg_start[total] = n_slots;
+  }
+}
+
+// gradient of the BPR terms w.r.t. one touched row = sum over the row's slots, in slot order, of
+//   user slot:  coef * w * (n - p) + rc * u      pos slot:  -coef * w * u + rc * p      neg slot:  coef * w * u + rc * n
+// (the per-sample values bpr_fused_kernel scatters in its atomic mode).  L2ROWS: the contribution is rc * e[row] per slot
+// instead (LightGCN's layer-0 regulariser).  ACCUM: add the sum to what the row holds (a term on top of a propagated
+// gradient), else overwrite (g_rep is zero everywhere else).
+template <int G, int VPL, bool HAS_W, bool L2ROWS, bool ACCUM>
+__global__ void __launch_bounds__(256) bpr_grad_rows_kernel(const float* rep, const int64_t* __restrict__ batch, int64_t item_offset,
+                                                            const float* __restrict__ coef, const float* __restrict__ w,
+                                                            float rc, const int32_t* __restrict__ order,
+                                                            const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_seg,
+                                                            float* __restrict__ g_out) {
+  constexpr int D = G * VPL * 4;
+  const int seg = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G), gl = threadIdx.x & (G - 1);
+  pdl_trigger();
+  pdl_wait();
+  if (seg >= *n_seg) return;
+  const int b = seg_start[seg], e = seg_start[seg + 1];
+  float4 acc[VPL], wv[VPL];
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wv[t] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if constexpr (HAS_W) wv[t] = ldg_f4(w + (gl + t * G) * 4);
+  }
+  int64_t row = 0;
+  for (int k = b; k < e; ++k) {
+    const int slot = order[k];
+    const int smp = slot / 3, role = slot - 3 * smp;
+    const int64_t ru = batch[3 * (size_t)smp];
+    const int64_t rp = batch[3 * (size_t)smp + 1] + item_offset;
+    const int64_t rn = batch[3 * (size_t)smp + 2] + item_offset;
+    row = role == 0 ? ru : (role == 1 ? rp : rn);
+    if (L2ROWS) {  // layer-0 L2: rc * e[row] per slot
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) {
+        const float4 ev = ldc_f4(rep + (size_t)row * D + (gl + t * G) * 4);
+        acc[t].x += rc * ev.x; acc[t].y += rc * ev.y; acc[t].z += rc * ev.z; acc[t].w += rc * ev.w;
+      }
+      continue;
+    }
+    const float cf = coef[smp];
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int c = (gl + t * G) * 4;
+      const float4 cw = make_float4(cf * wv[t].x, cf * wv[t].y, cf * wv[t].z, cf * wv[t].w);
+      const float4 u = ldc_f4(rep + (size_t)ru * D + c);
+      float4 g;
+      if (role == 0) {
+        const float4 p = ldc_f4(rep + (size_t)rp * D + c), n = ldc_f4(rep + (size_t)rn * D + c);
+        g = make_float4(cw.x * (n.x - p.x) + rc * u.x, cw.y * (n.y - p.y) + rc * u.y, cw.z * (n.z - p.z) + rc * u.z,
+                        cw.w * (n.w - p.w) + rc * u.w);
+      } else if (role == 1) {
+        const float4 p = (rc != 0.f) ? ldc_f4(rep + (size_t)rp * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g = make_float4(-cw.x * u.x + rc * p.x, -cw.y * u.y + rc * p.y, -cw.z * u.z + rc * p.z, -cw.w * u.w + rc * p.w);
+      } else {
+        const float4 n = (rc != 0.f) ? ldc_f4(rep + (size_t)rn * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g = make_float4(cw.x * u.x + rc * n.x, cw.y * u.y + rc * n.y, cw.z * u.z + rc * n.z, cw.w * u.w + rc * n.w);
+      }
+      acc[t].x += g.x; acc[t].y += g.y; acc[t].z += g.z; acc[t].w += g.w;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    float* dst = g_out + (size_t)row * D + (gl + t * G) * 4;
+    if (ACCUM) {
+      const float4 old = ld_f4(dst);
+      st_f4(dst, make_float4(old.x + acc[t].x, old.y + acc[t].y, old.z + acc[t].z, old.w + acc[t].w));
+    } else {
+      st_f4(dst, acc[t]);
+    }
+  }
+}
+
+// zero the rows a batch touched (g_rep is kept all-zero between steps instead of being memset whole every step)
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) clear_rows_kernel(const int64_t* __restrict__ batch, int n_slots, int64_t item_offset,
+                                                         float* __restrict__ table) {
+  constexpr int D = G * VPL * 4;
+  const int slot = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G), gl = threadIdx.x & (G - 1);
+  pdl_trigger();
+  pdl_wait();
+  if (slot >= n_slots) return;
+  const int64_t row = batch[slot] + ((slot % 3) ? item_offset : 0);
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) st_f4(table + (size_t)row * D + (gl + t * G) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
 // LightGCN regulariser on layer-0 rows (model.py:114-117)
 template <int G, int VPL>
 __global__ void __launch_bounds__(256) bpr_l2_emb0_kernel(const float* __restrict__ emb0, const int64_t* batch,
                                                           int n_batch, int64_t item_offset, float l2_reg,
                                                           float* __restrict__ g_emb0, float* __restrict__ loss_out,
-                                                          float* scratch) {
+                                                          float* scratch) {  // g_emb0 == NULL: loss term only
   constexpr int D = G * VPL * 4;
   constexpr int SPB = 256 / G;
   __shared__ float s_loss[SPB];
@@ -297,9 +468,9 @@ __global__ void __launch_bounds__(256) bpr_l2_emb0_kernel(const float* __restric
 #pragma unroll
       for (int t = 0; t < VPL; ++t) {
         const int c = (gl + t * G) * 4;
-        const float4 e = ldg_f4(emb0 + (size_t)rows[q] * D + c);
+        const float4 e = ldc_f4(emb0 + (size_t)rows[q] * D + c);
         l2 += e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
-        red_add_f4(g_emb0 + (size_t)rows[q] * D + c, make_float4(rc * e.x, rc * e.y, rc * e.z, rc * e.w));
+        if (g_emb0) red_add_f4(g_emb0 + (size_t)rows[q] * D + c, make_float4(rc * e.x, rc * e.y, rc * e.z, rc * e.w));
       }
     }
   }
@@ -382,10 +553,20 @@ __global__ void step_advance_kernel(int64_t* step, int64_t* step_b, const float*
 template <int G, int VPL>
 static int launch_bpr(const float* rep, const int64_t* batch, int nb, int64_t off, float l2_reg, int reg_mode,
                       const float* w, float loss_scale, float* g_rep, float* g_w, float* loss_out, float* scratch,
-                      float* dots, int dots_mode, float loss_weight, cudaStream_t st) {
+                      float* dots, int dots_mode, float loss_weight, cudaStream_t st, float* coef = nullptr,
+                      const int32_t* order = nullptr, const int32_t* seg_start = nullptr, const int32_t* n_seg = nullptr,
+                      bool accumulate = false) {
   const int grid = ceil_div(nb, 256 / G);
-  if (w) B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, true>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight);
-  else B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, false>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight);
+  if (w) B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, true>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight, coef);
+  else B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, false>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight, coef);
+  if (coef && dots_mode != 1) {  // ordered mode: one lane group per distinct row
+    const float rc = (reg_mode == 1) ? 2.f * l2_reg * loss_scale / (float)nb : 0.f;
+    const int grid2 = ceil_div(3 * nb, 256 / G);
+#define B2_GRAD_ROWS(W, A) B2_LAUNCH_PDL(bpr_grad_rows_kernel<G, VPL, W, false, A>, grid2, 256, 0, st, rep, batch, off, (const float*)coef, w, rc, order, seg_start, n_seg, g_rep)
+    if (w) { if (accumulate) B2_GRAD_ROWS(true, true); else B2_GRAD_ROWS(true, false); }
+    else { if (accumulate) B2_GRAD_ROWS(false, true); else B2_GRAD_ROWS(false, false); }
+#undef B2_GRAD_ROWS
+  }
   return 0;
 }
 
@@ -467,6 +648,54 @@ extern "C" int b200rec_bpr_fwd_bwd_sharded(const float* rep, int32_t d, const in
   B2_REQUIRE(reg_mode == 0 || reg_mode == 1, "reg_mode must be 0 or 1");
   B2_REQUIRE(!w || g_w || phase == 1, "g_w required with w");
   B2_DISPATCH_D(d, { int rc = launch_bpr<G, VPL>(rep, batch, n_batch, item_offset, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, block_scratch, dots, phase, loss_weight, (cudaStream_t)stream); if (rc) return rc; });
+  return 0;
+}
+
+extern "C" int b200rec_bpr_group_rows(const int64_t* batch, int32_t n_batch, int64_t item_offset, int32_t* order,
+                                      int32_t* seg_start, int32_t* n_seg, void* stream) {
+  B2_REQUIRE(batch && order && seg_start && n_seg && n_batch > 0, "bad argument");
+  if (3 * (int64_t)n_batch > GROUP_CAP)
+    return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", __func__, "batch too large for the single-block grouping (3 * n_batch <= 8192)");
+  const size_t smem = (size_t)GROUP_CAP * sizeof(unsigned long long);
+  B2_CUDA(cudaFuncSetAttribute(bpr_group_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bpr_group_rows_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(batch, 3 * n_batch, item_offset, order, seg_start, n_seg);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_bpr_fwd_bwd_ordered(const float* rep, int32_t d, const int64_t* batch, int32_t n_batch,
+                                           int64_t item_offset, float l2_reg, int32_t reg_mode, const float* w,
+                                           float loss_scale, float* g_rep, float* g_w, float* loss_out,
+                                           float* block_scratch, float* dots, int32_t phase, float loss_weight,
+                                           float* coef, const int32_t* order, const int32_t* seg_start,
+                                           const int32_t* n_seg, int32_t accumulate, void* stream) {
+  B2_REQUIRE(rep && batch && block_scratch && n_batch > 0, "bad argument");
+  B2_REQUIRE(phase >= 0 && phase <= 2, "phase must be 0 (one GPU), 1 (partial dots) or 2 (gradients from reduced dots)");
+  B2_REQUIRE(phase == 0 || dots, "dots required when the dimension is sharded");
+  B2_REQUIRE(phase == 1 || (g_rep && loss_out && coef && order && seg_start && n_seg), "null output / grouping");
+  B2_REQUIRE(reg_mode == 0 || reg_mode == 1, "reg_mode must be 0 or 1");
+  B2_REQUIRE(!w || g_w || phase == 1, "g_w required with w");
+  B2_DISPATCH_D(d, { int rc = launch_bpr<G, VPL>(rep, batch, n_batch, item_offset, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, block_scratch, dots, phase, loss_weight, (cudaStream_t)stream, phase == 1 ? nullptr : coef, order, seg_start, n_seg, accumulate != 0); if (rc) return rc; });
+  return 0;
+}
+
+extern "C" int b200rec_bpr_l2_emb0_ordered(const float* emb0, int32_t d, const int64_t* batch, int32_t n_batch,
+                                           int64_t item_offset, float l2_reg, float* g_emb0, float* loss_out,
+                                           float* block_scratch, const int32_t* order, const int32_t* seg_start,
+                                           const int32_t* n_seg, void* stream) {
+  B2_REQUIRE(emb0 && batch && g_emb0 && loss_out && block_scratch && order && seg_start && n_seg && n_batch > 0, "bad argument");
+  const float rc = 2.f * l2_reg / (float)n_batch;
+  B2_DISPATCH_D(d, {
+    B2_LAUNCH_PDL(bpr_l2_emb0_kernel<G, VPL>, ceil_div(n_batch, 256 / G), 256, 0, (cudaStream_t)stream, emb0, batch, n_batch, item_offset, l2_reg, (float*)nullptr, loss_out, block_scratch);
+    B2_LAUNCH_PDL(bpr_grad_rows_kernel<G, VPL, false, true, true>, ceil_div(3 * n_batch, 256 / G), 256, 0, (cudaStream_t)stream, emb0, batch, item_offset, (const float*)nullptr, (const float*)nullptr, rc, order, seg_start, n_seg, g_emb0);
+  });
+  return 0;
+}
+
+extern "C" int b200rec_clear_rows(const int64_t* batch, int32_t n_batch, int64_t item_offset, float* table, int32_t d,
+                                  void* stream) {
+  B2_REQUIRE(batch && table && n_batch > 0, "bad argument");
+  B2_DISPATCH_D(d, { B2_LAUNCH_PDL(clear_rows_kernel<G, VPL>, ceil_div(3 * n_batch, 256 / G), 256, 0, (cudaStream_t)stream, batch, 3 * n_batch, item_offset, table); });
   return 0;
 }
 

@@ -353,13 +353,10 @@ static int infonce_launch(const float* q, const float* k, const int64_t* rows, i
   const int parts_grad = max(1, min(min(NCE_MAX_PARTS, tiles), ceil_div(444, 2 * nblk)));
   const float inv_t = 1.f / temperature;
   const size_t smem = NceSmem<D>::BYTES;
-  // opt in to > 48 KB of dynamic shared memory once per instantiation (magic static: thread-safe, per D)
-  static const cudaError_t attr_rc = [smem] {
-    cudaError_t e = cudaFuncSetAttribute(infonce_pass_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(infonce_pass_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }();
-  B2_CUDA(attr_rc);
+  // opt in to > 48 KB of dynamic shared memory: the attribute is per DEVICE, so it is set on every call (cheap) rather
+  // than once per process -- a process that later runs on another GPU would otherwise fail to launch
+  B2_CUDA(cudaFuncSetAttribute(infonce_pass_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2_CUDA(cudaFuncSetAttribute(infonce_pass_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B2_LAUNCH_PDL(infonce_prep_kernel<D>, ceil_div((long long)n * 32, 256), 256, 0, st, q, k, rows, row_stride, n, inv_t, qn, kn,
                 qden, kden, pos);
   B2_LAUNCH_PDL((infonce_pass_kernel<D, 0>), dim3(nblk, parts_stat), NCE_THREADS, smem, st, (const float*)qn, (const float*)kn,

@@ -7,15 +7,19 @@
 //                     warps 2-9 = drain (TMEM -> registers, group-of-8 maxima against the row's cut, hit groups pushed
 //                     into shared-memory rings), warps 10-17 = consumers (per-value cut / banned-range / exclusion
 //                     tests, append to the row's candidate list, re-derive the row's cut when the list grows long).
-//                     The cut-off is (K-th best approximate score so far) - 2 eps.  score_tc_kernel is the first
-//                     generation (four warps doing drain + per-hit work), kept behind B200REC_TC_V1 for A/B runs.
+//                     The cut-off is a lower bound of the K-th best exact score (below).
 //   rescore kernel  : exact fp32 scores (the same fmaf chain in d-order as the precision-0 path and the C oracle) for the
 //                     candidates, final (score desc, id asc) top-K.
-// Exactness: |approx - exact| <= eps_u = 1.05 * 2^-7 * ||u|| * max_i ||v_i|| (two bf16 roundings, Cauchy-Schwarz; fp32
-// accumulation error is three orders smaller).  If T is the exact K-th best score, every true top-K item has
-// approx >= T - eps and the K-th best approx is <= T + eps, so "approx >= K-th best approx - 2 eps" keeps all of them.
-// The ids and scores returned are therefore identical to the exact path by construction; a row whose candidate list
-// overflows is flagged and must be redone by the caller with precision 0.
+// Exactness: |approx_i - exact_i| <= eps_i = c_u * ||v_i||, c_u = 1.05 * 2^-7 * ||u|| (two bf16 roundings, Cauchy-Schwarz;
+// fp32 accumulation error is three orders smaller); the kernels use eps_t = c_u * max ||v|| over the item's 128-item TILE
+// (>= eps_i; one scalar per tile, so the test stays one compare per group of 8 scores).  L_i = approx_i - eps_t is a
+// lower bound of the exact score and U_i = approx_i + eps_t an upper bound.  If T is the exact K-th best score, the K-th
+// largest L over any subset of the items is <= T (those K items all have exact >= it), and every true top-K item has
+// U >= T.  So with cutL = K-th largest L over the candidates kept so far, "U_i >= cutL" keeps every true top-K item:
+// the ids and scores returned are identical to the exact path by construction.  The band is 2 * eps_t wide, i.e. it
+// follows the norms of the items actually in the tile rather than the largest norm of the catalogue (round 1), which made
+// the candidate volume -- hence the sweep time -- depend on the training state.  A row whose candidate list overflows is
+// flagged and must be redone by the caller with precision 0.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -118,11 +122,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ prep
-// rows -> bf16 (row-major, D contiguous = K-major), ||row||_2, optional gather, optional global max of the norms
+// rows -> bf16 (row-major, D contiguous = K-major), ||row||_2, optional gather, optional max of the norms per tile of
+// `tile_rows` rows (items: the band of the candidate test is scaled by the tile's largest norm)
 template <int D>
 __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ table, const int64_t* __restrict__ gather,
                                                       int n_rows, __nv_bfloat16* __restrict__ out, float* __restrict__ norms,
-                                                      unsigned* __restrict__ max_norm_bits) {
+                                                      unsigned* __restrict__ tile_max_bits, int tile_rows) {
   constexpr int G = D / 4;  // lanes per row (D = 64 -> 16, 128 -> 32)
   const int gi = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G), gl = threadIdx.x & (G - 1);
   float ss = 0.f;
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
   if (gi < n_rows && gl == 0) {
     const float nrm = sqrtf(ss);
     norms[gi] = nrm;
-    if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nrm));  // non-negative floats order like their bits
+    if (tile_max_bits) atomicMax(tile_max_bits + gi / tile_rows, __float_as_uint(nrm));  // non-negative floats order like their bits
   }
 }
 
@@ -151,7 +156,7 @@ struct TcParams {
   const int32_t *excl_ptr_a, *excl_idx_a, *excl_ptr_b, *excl_idx_b;
   int banned_lo, banned_hi;
   const float* unorm;        // [b]
-  const unsigned* vmax_bits; // max item norm
+  const unsigned* tile_vmax_bits; // [n_tiles] largest item norm of each BN-item tile (float bits)
   Cand* cand;                // [b, TC_CAP]
   int* cand_cnt;             // [b]
   int* overflow;             // [b]
@@ -184,238 +189,8 @@ __device__ __forceinline__ bool row_has(const int32_t* __restrict__ ptr, const i
   return lo < end && __ldg(idx + lo) == key;
 }
 
-// Rare path of the epilogue, kept out of line so the unrolled scan stays a compare + predicated call per value
-// (the scan is latency-exposed: 6-12 warps per SM, every branch costs a pipeline bubble).
-__device__ __noinline__ void tc_append_candidate(const TcParams& p, int64_t user, float sc, int item, Cand* list, int& cnt,
-                                                 bool& ovf) {
-  if (item >= p.n_items) return;
-  if (item >= p.banned_lo && item < p.banned_hi) return;
-  if (row_has(p.excl_ptr_a, p.excl_idx_a, user, item)) return;
-  if (row_has(p.excl_ptr_b, p.excl_idx_b, user, item)) return;
-  if (cnt < TC_CAP) list[cnt++] = Cand{sc, item};
-  else ovf = true;
-}
-
-template <int D, int BN, int STAGES>
-__global__ void __launch_bounds__(192, 2) score_tc_kernel(const __grid_constant__ CUtensorMap tm_users,
-                                                          const __grid_constant__ CUtensorMap tm_items, const TcParams p) {
-  constexpr int KB = D / 64;                        // 128-byte K blocks
-  constexpr uint32_t A_BYTES = TC_M * D * 2, B_STAGE_BYTES = BN * D * 2;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B atoms need 1024 B alignment
-  uint8_t* sA = smem;                               // [KB][128 rows][128 B]
-  uint8_t* sB = smem + A_BYTES;                     // [STAGES][KB][BN rows][128 B]
-  Cand* sort_area = reinterpret_cast<Cand*>(sB + (size_t)STAGES * B_STAGE_BYTES);  // [4 warps][TC_CAP]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sort_area + 4 * TC_CAP);
-  uint64_t* full = bars;                  // [STAGES]
-  uint64_t* empty = bars + STAGES;        // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;    // [2]
-  uint64_t* tempty = tfull + 2;           // [2]
-  uint64_t* afull = tempty + 2;           // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u0 = blockIdx.x * TC_M;
-  const int n_tiles = (p.n_items + BN - 1) / BN;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
-    mbar_init(afull, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {  // TMEM: 2 accumulator stages x BN fp32 columns = 512 columns, allocated and freed by this warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      mbar_expect_tx(afull, A_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + (size_t)kb * TC_M * 128, &tm_users, kb * 64, u0, afull);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % STAGES;
-        mbar_wait(empty + s, ((t / STAGES) & 1) ^ 1);
-        mbar_expect_tx(full + s, B_STAGE_BYTES);
-        uint8_t* dst = sB + (size_t)s * B_STAGE_BYTES;
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(dst + (size_t)kb * BN * 128, &tm_items, kb * 64, t * BN, full + s);
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (one elected lane) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_M, BN);
-      mbar_wait(afull, 0);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % STAGES, as = t & 1;
-        mbar_wait(tempty + as, ((t >> 1) & 1) ^ 1);  // epilogue drained this accumulator stage
-        mbar_wait(full + s, (t / STAGES) & 1);       // item tile landed
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K=16 per 64-wide K block; +32 B inside the swizzle atom per step
-            const uint64_t ad = umma_desc_sw128(a0 + kb * TC_M * 128 + k * 32);
-            const uint64_t bd = umma_desc_sw128(b0 + kb * BN * 128 + k * 32);
-            tc_mma_bf16(tmem_base + as * BN, ad, bd, idesc, (kb | k) ? 1u : 0u);
-          }
-        }
-        tc_commit(empty + s);    // smem stage free when these MMAs retire
-        tc_commit(tfull + as);   // accumulator ready
-      }
-    }
-  } else {
-    // ===== epilogue: thread <-> TMEM lane <-> user row =====
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;
-    const int u = u0 + row;
-    const bool active = u < p.n_users;
-    const int64_t user = active ? p.users[u] : 0;
-    Cand* my_list = p.cand + (size_t)(active ? u : 0) * TC_CAP;
-    Cand* my_sort = sort_area + (size_t)(warp - 2) * TC_CAP;
-    const float vmax = __uint_as_float(*p.vmax_bits);
-    const float margin = active ? 2.f * 1.05f * 0.0078125f * p.unorm[u] * vmax : 0.f;
-    float cut = -INFINITY;  // candidates need approx >= cut = (K-th best approx so far) - margin
-    int cnt = 0;
-    bool ovf = false;
-    const int K = p.k;
-    // refinement schedule (same recurrence in every thread): after tile 0, then whenever the expected number of new
-    // candidates since the last refinement reaches TC_CAP/8
-    float expect_acc = 0.f, seen_at_refine = 0.f;
-
-    auto refine = [&]() {
-      // Warp-cooperative, row by row.  Only a LOWER bound of the K-th best approximate score is needed (a lower cut
-      // just admits a few more candidates), so instead of sorting the list a value bisection finds a pivot with
-      // K <= #(entries >= pivot) <= 2K in a handful of counting passes over a shared-memory copy, and the band above
-      // (pivot - margin) is kept by a ballot compaction.  (A full bitonic sort here cost 13.5 M of the 20 M warp
-      // instructions of a CTA sweep.)
-      for (int r = 0; r < 32; ++r) {
-        const int rc = __shfl_sync(0xffffffffu, cnt, r);
-        const bool ract = __shfl_sync(0xffffffffu, (int)active, r) != 0;
-        if (!ract || rc < K) continue;  // fewer than K so far: keep everything, no cut yet
-        Cand* list = reinterpret_cast<Cand*>(__shfl_sync(0xffffffffu, (unsigned long long)my_list, r));
-        const float rmargin = __shfl_sync(0xffffffffu, margin, r);
-        const float rcut = __shfl_sync(0xffffffffu, cut, r);
-        float mx = -INFINITY, mn = INFINITY;
-        for (int t = lane; t < rc; t += 32) {
-          const Cand c = list[t];
-          my_sort[t] = c;
-          mx = fmaxf(mx, c.s);
-          mn = fminf(mn, c.s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        }
-        __syncwarp();
-        // invariant: #(entries >= lo) >= K  (the previous K-th best is still in the list; or lo = min and rc >= K)
-        float lo = (rcut > -INFINITY) ? rcut + rmargin : mn;
-        lo = fminf(lo, mx);
-        float hi = mx;
-        for (int itn = 0; itn < 14; ++itn) {
-          const float pv = 0.5f * (lo + hi);
-          if (!(pv > lo && pv < hi)) break;
-          int c = 0;
-          for (int t = lane; t < rc; t += 32) c += (my_sort[t].s >= pv) ? 1 : 0;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-          if (c >= K) {
-            lo = pv;
-            if (c <= 2 * K) break;
-          } else {
-            hi = pv;
-          }
-        }
-        const float ncut = lo - rmargin;
-        int base = 0;
-        for (int t0 = 0; t0 < rc; t0 += 32) {
-          const int t = t0 + lane;
-          const bool kp = t < rc && my_sort[t].s >= ncut;
-          const unsigned bal = __ballot_sync(0xffffffffu, kp);
-          if (kp) list[base + __popc(bal & ((1u << lane) - 1u))] = my_sort[t];
-          base += __popc(bal);
-        }
-        __syncwarp();
-        if (lane == r) { cnt = base; cut = ncut; }
-      }
-    };
-
-    for (int t = 0; t < n_tiles; ++t) {
-      const int as = t & 1;
-      mbar_wait(tfull + as, (t >> 1) & 1);
-      tc_fence_after();
-      const int i0 = t * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
-        // maxima of the four groups of 8, then of the whole chunk: a group is scanned value by value only when its
-        // maximum reaches the cut (with 6-12 warps per SM every instruction's latency is exposed, so the common path
-        // must stay short and branch-free)
-        float gm[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float a = fmaxf(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-          float b = fmaxf(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-          float c2 = fmaxf(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-          float d2 = fmaxf(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
-          gm[q] = fmaxf(fmaxf(a, b), fmaxf(c2, d2));
-        }
-        const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-        if (active && m >= cut) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (gm[q] < cut) continue;
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const int j = q * 8 + jj;
-              const float sc = __uint_as_float(v[j]);
-              if (sc >= cut) tc_append_candidate(p, user, sc, i0 + c * 32 + j, my_list, cnt, ovf);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + as);  // 4 epilogue warps -> barrier count 4
-      // scheduled refinement
-      bool do_refine = false;
-      if (t == 0) do_refine = true;
-      else {
-        expect_acc += (float)BN * (float)K / seen_at_refine;
-        if (expect_acc >= (float)(TC_CAP / 8)) do_refine = true;
-      }
-      if (t == n_tiles - 1) do_refine = true;
-      if (do_refine) {
-        __syncwarp();
-        refine();
-        seen_at_refine = (float)(t + 1) * (float)BN;
-        expect_acc = 0.f;
-      }
-    }
-    if (active) {
-      p.cand_cnt[u] = cnt;
-      p.overflow[u] = ovf ? 1 : 0;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ main kernel, v2
-// Same pipeline, different epilogue: ncu on v1 showed the tensor pipe 3 % busy with the MMA warp spinning on `tempty` --
+// ------------------------------------------------------------------------------------------------ main kernel
+// History: ncu on the first generation (four warps doing drain + per-hit work, deleted in round 2) showed the tensor pipe 3 % busy with the MMA warp spinning on `tempty` --
 // four latency-exposed warps both drained TMEM and ran the branchy per-hit work (range / exclusion tests, list appends,
 // cut refinement).  Here eight DRAIN warps (2-9: two per TMEM lane quadrant, each half of a tile's columns) load their
 // 64 columns with one wait, hand the accumulator stage back, reduce to eight group maxima, compare with the row's cut
@@ -461,7 +236,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
   Cand* sort_area = reinterpret_cast<Cand*>(queues + TC_RINGS * TC_QCAP);                 // [TC_CONSUMERS][TC_CAP]
   float* s_cut = reinterpret_cast<float*>(sort_area + TC_CONSUMERS * TC_CAP);                        // [128]
   int* s_cnt = reinterpret_cast<int*>(s_cut + TC_M);                                      // [128]
-  int* s_kk = s_cnt + TC_M;                                                               // [128] rank the cut is derived from
+  float* s_cu = reinterpret_cast<float*>(s_cnt + TC_M);                                   // [128] c_u = 1.05 * 2^-7 * ||u||
+  int* s_kk = reinterpret_cast<int*>(s_cu + TC_M);                                        // [128] rank the cut is derived from
   int* s_xend = s_kk + TC_M;                                                              // [2 lists][128] end of the row's exclusion entries
   int* s_xcur = s_xend + 2 * TC_M;                                                        // [2 lists][2 halves][128] merge cursors
   int* s_xnext = s_xcur + 4 * TC_M;                                                       // [2 lists][2 halves][128] value at the cursor
@@ -497,6 +273,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
       s_xnext[(which * 2 + 1) * TC_M + threadIdx.x] = first;
     }
     s_cut[threadIdx.x] = cut0; s_cnt[threadIdx.x] = 0; s_kk[threadIdx.x] = kk;
+    s_cu[threadIdx.x] = (u < p.n_users) ? 1.05f * 0.0078125f * __ldg(p.unorm + u) : 0.f;
   }
   if (threadIdx.x < TC_RINGS) { s_tail[threadIdx.x] = 0; s_head[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
   if (warp == 0 && lane == 0) {
@@ -562,9 +339,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
     const bool active = (u0 + row) < p.n_users;
     HitRec* q = queues + ring * TC_QCAP;
     int tail = 0;
+    const float cu = s_cu[row];
     for (int t = 0; t < n_tiles; ++t) {
       const int as = t & 1;
-      const float cut = active ? s_cut[row] : INFINITY;  // refreshed once per tile (the consumer may have raised it)
+      // hit test "U_i >= cutL": approx_i >= cutL - c_u * (largest norm in this tile).  cutL is refreshed once per tile
+      // (the consumer may have raised it); the tile's norm is one broadcast load
+      const float cut = active ? s_cut[row] - cu * __uint_as_float(__ldg(p.tile_vmax_bits + t)) : INFINITY;
       mbar_wait(tfull + as, (t >> 1) & 1);
       tc_fence_after();
       const int i0 = t * BN;
@@ -671,7 +451,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
     const int quad = cw >> 1, rh = cw & 1;
     const int row_base = quad * 32 + rh * 16;
     Cand* my_sort = sort_area + (size_t)cw * TC_CAP;
-    const float vmax = __uint_as_float(*p.vmax_bits);
     int head2[2] = {0, 0};
 
     auto refine_row = [&](int row) {
@@ -682,7 +461,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
       const int kk = s_kk[row];
       if (rc < kk) return;
       Cand* list = p.cand + (size_t)u * TC_CAP;
-      const float margin = 2.f * 1.05f * 0.0078125f * __ldg(p.unorm + u) * vmax;
+      const float cu2 = 2.f * s_cu[row];  // an entry holds L = approx - eps_t; its upper bound is U = L + 2 * eps_t
       const float rcut = s_cut[row];
       float mx = -INFINITY, mn = INFINITY;
       for (int t = lane; t < rc; t += 32) {
@@ -697,7 +476,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
       }
       __syncwarp();
-      float lo = (rcut > -INFINITY) ? rcut + margin : mn;  // #(entries >= lo) >= K' always holds
+      float lo = (rcut > -INFINITY) ? rcut : mn;  // #(entries with L >= lo) >= K' always holds
       lo = fminf(lo, mx);
       float hi = mx;
       for (int itn = 0; itn < 14; ++itn) {
@@ -709,11 +488,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (c >= kk) { lo = pv; if (c <= kk + kk / 2 + 8) break; } else { hi = pv; }
       }
-      const float ncut = lo - margin;
+      const float ncut = lo;  // lower bound of the K'-th largest L: the new cutL
       int base = 0;
       for (int t0 = 0; t0 < rc; t0 += 32) {
         const int t = t0 + lane;
-        const bool kp = t < rc && my_sort[t].s >= ncut;
+        bool kp = false;
+        if (t < rc) {
+          const Cand c = my_sort[t];
+          kp = c.s + cu2 * __uint_as_float(__ldg(p.tile_vmax_bits + c.id / BN)) >= ncut;  // U_i >= cutL
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, kp);
         if (kp) list[base + __popc(bal & ((1u << lane) - 1u))] = my_sort[t];
         base += __popc(bal);
@@ -753,7 +536,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
             base = r->base;
           }
           const int item = base + j;
-          bool pass = ri < nrec && sc >= s_cut[row] && item < p.n_items && !(item >= p.banned_lo && item < p.banned_hi);
+          // records carry approx; the list keeps L = approx - eps_t, the test is U = approx + eps_t >= cutL
+          const float eps_t = (ri < nrec) ? s_cu[row] * __uint_as_float(__ldg(p.tile_vmax_bits + base / BN)) : 0.f;
+          bool pass = ri < nrec && sc + eps_t >= s_cut[row] && item < p.n_items && !(item >= p.banned_lo && item < p.banned_hi);
           // merge test against the row's sorted exclusion lists (group-cooperative, warp-uniform control flow)
 #pragma unroll
           for (int which = 0; which < 2; ++which) {
@@ -788,7 +573,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
           }
           if (pass) {
             const int pos = atomicAdd(&s_cnt[row], 1);
-            if (pos < TC_CAP) p.cand[(size_t)(u0 + row) * TC_CAP + pos] = Cand{sc, item};
+            if (pos < TC_CAP) p.cand[(size_t)(u0 + row) * TC_CAP + pos] = Cand{sc - eps_t, item};
             else p.overflow[u0 + row] = 1;
           }
           head += nrec;
@@ -941,7 +726,7 @@ static TcWorkspace tc_layout(int nb, int ni, int d) {
   w.items_bf16 = o; o = align_up(o + (size_t)ni * d * 2, 1024);
   w.unorm = o; o = align_up(o + (size_t)nb * 4, 256);
   w.vnorm = o; o = align_up(o + (size_t)ni * 4, 256);
-  w.vmax = o; o = align_up(o + 4, 256);
+  w.vmax = o; o = align_up(o + ((size_t)ni / 128 + 2) * 4, 256);  // per-tile max item norm (BN = 128)
   w.cand = o; o = align_up(o + (size_t)nb * TC_CAP * sizeof(Cand), 256);
   w.cnt = o; o = align_up(o + (size_t)nb * 4, 256);
   w.ovf = o; o = align_up(o + (size_t)nb * 4, 256);
@@ -966,11 +751,12 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
   Cand* cand = reinterpret_cast<Cand*>(ws + w.cand);
   int* cnt = reinterpret_cast<int*>(ws + w.cnt);
   int* ovf = out_overflow ? out_overflow : reinterpret_cast<int*>(ws + w.ovf);
-  B2_CUDA(cudaMemsetAsync(vmax, 0, 4, st));
+  B2_CUDA(cudaMemsetAsync(vmax, 0, ((size_t)ni / BN + 2) * 4, st));
+  static_assert(BN == 128, "workspace layout assumes 128-item tiles");
   constexpr int G = D / 4;
-  tc_prep_kernel<D><<<ceil_div((long long)nb * G, 256), 256, 0, st>>>(rep_users, users, nb, ub, unorm, nullptr);
+  tc_prep_kernel<D><<<ceil_div((long long)nb * G, 256), 256, 0, st>>>(rep_users, users, nb, ub, unorm, nullptr, 1);
   B2_LAUNCHED();
-  tc_prep_kernel<D><<<ceil_div((long long)ni * G, 256), 256, 0, st>>>(rep_items, nullptr, ni, ib, vnorm, vmax);
+  tc_prep_kernel<D><<<ceil_div((long long)ni * G, 256), 256, 0, st>>>(rep_items, nullptr, ni, ib, vnorm, vmax, BN);
   B2_LAUNCHED();
   CUtensorMap mu, mi;
   int rc = make_map(&mu, ub, nb, D, TC_M);
@@ -980,24 +766,13 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
   TcParams p;
   p.users = users; p.n_users = nb; p.n_items = ni; p.k = k;
   p.excl_ptr_a = ea_ptr; p.excl_idx_a = ea_idx; p.excl_ptr_b = eb_ptr; p.excl_idx_b = eb_idx;
-  p.banned_lo = blo; p.banned_hi = bhi; p.unorm = unorm; p.vmax_bits = vmax; p.cand = cand; p.cand_cnt = cnt; p.overflow = ovf;
-  static const bool use_v1 = [] {
-    const char* e = getenv("B200REC_TC_V1");
-    return e && e[0] == '1';
-  }();
-  if (use_v1) {
-    const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + 4 * TC_CAP * sizeof(Cand) + 256;
-    B2_CUDA(cudaFuncSetAttribute(score_tc_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    score_tc_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), 192, smem, st>>>(mu, mi, p);
-    B2_LAUNCHED();
-  } else {
-    B2_CUDA(cudaMemsetAsync(ovf, 0, (size_t)nb * sizeof(int), st));
-    const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + TC_RINGS * TC_QCAP * sizeof(HitRec) +
-                        TC_CONSUMERS * TC_CAP * sizeof(Cand) + 13 * TC_M * 4 + 1024;
-    B2_CUDA(cudaFuncSetAttribute(score_tc2_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), TC2_THREADS, smem, st>>>(mu, mi, p);
-    B2_LAUNCHED();
-  }
+  p.banned_lo = blo; p.banned_hi = bhi; p.unorm = unorm; p.tile_vmax_bits = vmax; p.cand = cand; p.cand_cnt = cnt; p.overflow = ovf;
+  B2_CUDA(cudaMemsetAsync(ovf, 0, (size_t)nb * sizeof(int), st));
+  const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + TC_RINGS * TC_QCAP * sizeof(HitRec) +
+                      TC_CONSUMERS * TC_CAP * sizeof(Cand) + 14 * TC_M * 4 + 1024;
+  B2_CUDA(cudaFuncSetAttribute(score_tc2_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), TC2_THREADS, smem, st>>>(mu, mi, p);
+  B2_LAUNCHED();
   const size_t rsmem = 4 * TC_CAP * sizeof(Cand);
   tc_rescore_kernel<D><<<ceil_div(nb, 4), 128, rsmem, st>>>(rep_users, users, nb, rep_items, cand, cnt, k, out_ids, out_scores, p);
   B2_LAUNCHED();

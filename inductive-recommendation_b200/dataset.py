@@ -77,7 +77,11 @@ class BasicDataset(Dataset):
         lists = getattr(self, split + '_data')
         key = (split, str(device))
         hit = self._csr_cache.get(key)
-        if hit is not None and hit[0] is lists:  # the entry keeps `lists` alive, so identity cannot be a recycled id
+        # valid while it is the same outer list AND the same row objects of the same lengths: the reference's
+        # inductive_eval idiom `dataset.test_data[u] = []` (trainer.py:219-227) mutates the outer list in place, which
+        # identity of the outer list alone would miss.  (Editing the items INSIDE a row list in place is not detected:
+        # call invalidate_csr(split) after such an edit.)
+        if hit is not None and hit[0] is lists and hit[2] == self._rows_fingerprint(lists):
             return hit[1]
         ptr, idx = _lists_to_csr(lists)
         if sort and idx.size:
@@ -87,8 +91,19 @@ class BasicDataset(Dataset):
         out = (torch.from_numpy(ptr.astype(np.int32)), torch.from_numpy(idx.astype(np.int32)))
         if device is not None:
             out = tuple(t.to(device) for t in out)
-        self._csr_cache[key] = (lists, out)
+        self._csr_cache[key] = (lists, out, self._rows_fingerprint(lists))
         return out
+
+    @staticmethod
+    def _rows_fingerprint(lists):
+        if hasattr(lists, 'ptr'):  # CSR-backed lazy lists are immutable
+            return None
+        return hash(tuple(map(id, lists))) ^ hash(tuple(map(len, lists)))
+
+    def invalidate_csr(self, split=None):
+        """drop the cached device CSR of a split (all splits if None) after its lists were edited in place"""
+        for key in [k for k in self._csr_cache if split is None or k[0] == split]:
+            del self._csr_cache[key]
 
     def train_pairs(self):
         arr = np.asarray(self.train_array, dtype=np.int64).reshape(-1, 2)
@@ -212,6 +227,7 @@ class SyntheticDataset(BasicDataset):
         else:
             self.train_data, self.val_data, self.test_data = (_LazyLists(*self._np[s]) for s in ('train', 'val', 'test'))
         self._orig = {'train': self.train_data, 'val': self.val_data, 'test': self.test_data}
+        self._orig_fp = {k: self._rows_fingerprint(v) for k, v in self._orig.items()}
         self._np_csr_cache = {}
         self.train_array = None  # use train_pairs()
 
@@ -224,7 +240,8 @@ class SyntheticDataset(BasicDataset):
 
     def csr(self, split='train', device=None, sort=True):
         lists = getattr(self, split + '_data')
-        if lists is not self._orig[split]:  # e.g. inductive_eval temporarily replaces test_data
+        # inductive_eval replaces test_data (or, written the reference's way, edits its rows in place)
+        if lists is not self._orig[split] or self._rows_fingerprint(lists) != self._orig_fp[split]:
             return super().csr(split, device, sort)
         key = (split, str(device), 'np')
         hit = self._np_csr_cache.get(key)

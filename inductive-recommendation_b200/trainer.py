@@ -56,7 +56,10 @@ class BasicTrainer:
         self.opt = None
         # 1 = tcgen05 bf16 candidate pass + exact fp32 re-score (identical ids/scores, D = 64 / 128; falls back to 0 otherwise)
         self.eval_precision = trainer_config.get('eval_precision', 1)
-        self.eval_chunk = max(int(trainer_config['test_batch_size']), 16384)
+        # users per fused score/top-K call: whole waves of the 128-user CTAs of the tcgen05 kernel (one CTA per SM), so a
+        # 2M-user sweep does not run 128 CTAs on 148 SMs chunk after chunk
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == 'cuda' else 128
+        self.eval_chunk = max(int(trainer_config['test_batch_size']), 2 * 128 * sms)
         test_user = TensorDataset(torch.arange(self.dataset.n_users, dtype=torch.int64, device=self.device))
         self.test_user_loader = DataLoader(test_user, batch_size=trainer_config['test_batch_size'])
         self.engine = None
@@ -186,29 +189,73 @@ class BasicTrainer:
             excl_a = self.dataset.csr('train', device=dev)
             if val_or_test == 'test':
                 excl_b = self.dataset.csr('val', device=dev)
-        banned = None
+        banned, kept = None, None
         if banned_items is not None:
-            b = np.asarray(banned_items)
+            b = np.unique(np.asarray(banned_items).astype(np.int64).ravel())
             if b.size:
-                lo, hi = int(b.min()), int(b.max()) + 1
-                if hi - lo != b.size or np.unique(b).size != b.size:
-                    raise NotImplementedError('banned_items must be a contiguous id range (inductive_eval passes np.arange)')
-                banned = (lo, hi)
+                lo, hi = int(b[0]), int(b[-1]) + 1
+                if hi - lo == b.size:
+                    banned = (lo, hi)  # a contiguous id range (what inductive_eval passes): masked inside the kernel
+                else:
+                    kept = self._without_items(b, excl_a, excl_b)  # arbitrary index array (trainer.py:166-167)
         k = max(self.topks)
         n_users = self.dataset.n_users
         shard = getattr(self.model, '_dim_shard', None)
         u_lo, u_hi = (0, n_users) if shard is None else shard.user_range(n_users)
         out = []
         with torch.no_grad():
-            self.model.score_tables()  # collective (column all-gather) when sharded: every rank takes part
+            table_u, table_i = self.model.score_tables()  # collective (column all-gather) when sharded: every rank takes part
+            # The fused kernel only emits items that beat a running threshold, so a NaN / -inf score is never returned and
+            # such rows come back padded with id -1 (torch.topk would rank NaN first, trainer.py:169).  A diverged model
+            # must not pass as "all metrics zero": fail loudly instead.
+            if not bool(torch.isfinite(table_u).all()) or not bool(torch.isfinite(table_i).all()):
+                raise FloatingPointError('non-finite values in the representation: the model has diverged')
+            if kept is not None:
+                kept_ids, excl_a, excl_b = kept
+                table_i = table_i[kept_ids].contiguous()
             for s in range(u_lo, u_hi, self.eval_chunk):  # multi-GPU: each rank scores its own block of users
                 users = torch.arange(s, min(u_hi, s + self.eval_chunk), dtype=torch.int64, device=dev)
-                ids, _ = self.model.recommend(users, k, excl_a, excl_b, banned, precision=self.eval_precision)
+                if kept is None:
+                    ids, _ = self.model.recommend(users, k, excl_a, excl_b, banned, precision=self.eval_precision)
+                else:
+                    kk = min(k, int(kept_ids.numel()))
+                    ids_c, _ = ops.score_topk(table_u, users, table_i, kk, excl_a, excl_b, None, self.eval_precision)
+                    ids = torch.full((users.numel(), k), -1, dtype=torch.int32, device=dev)
+                    ids[:, :kk] = torch.where(ids_c >= 0, kept_ids[ids_c.clamp(min=0).long()].to(torch.int32), ids_c)
                 out.append(ids)
         ids = torch.cat(out, dim=0) if out else torch.zeros((0, k), dtype=torch.int32, device=dev)
         if shard is not None:
             ids = shard.gather_user_rows(ids, n_users)
         return ids
+
+    def _without_items(self, banned_sorted, excl_a, excl_b):
+        """Arbitrary banned ids: score against the item table with those rows REMOVED and map the ids back.  The compact
+        ids ascend with the original ones, so the (score desc, id asc) order is unchanged; the exclusion CSRs are
+        rewritten into compact ids (banned entries dropped).  Returns (kept original ids int64, excl_a', excl_b')."""
+        dev = self.device
+        n_items = self.dataset.n_items
+        keep = torch.ones(n_items, dtype=torch.bool, device=dev)
+        keep[torch.from_numpy(banned_sorted).to(dev)] = False
+        kept_ids = torch.nonzero(keep).flatten()
+        new_id = (torch.cumsum(keep, 0) - 1).to(torch.int32)
+
+        def remap(excl):
+            if excl is None:
+                return None
+            ptr, idx = excl
+            n_u = ptr.numel() - 1
+            rows = torch.repeat_interleave(torch.arange(n_u, device=dev), (ptr[1:] - ptr[:-1]).long())
+            idx = idx[: rows.numel()].long()
+            m = keep[idx]
+            counts = torch.bincount(rows[m], minlength=n_u)
+            ptr2 = torch.zeros(n_u + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(counts, 0, out=ptr2[1:])
+            idx2 = new_id[idx[m]].contiguous()
+            if idx2.numel() == 0:
+                idx2 = torch.zeros(1, dtype=torch.int32, device=dev)
+            return ptr2.to(torch.int32), idx2
+
+        return kept_ids, remap(excl_a), remap(excl_b)
 
     def eval(self, val_or_test, banned_items=None):
         eval_data = getattr(self.dataset, val_or_test + '_data')
@@ -295,7 +342,7 @@ class BPRTrainer(BasicTrainer):
         if self.sampler == 'host':
             for inputs in self._host_batches():
                 if inputs.shape[0] != self.batch_size:  # ragged last batch: one eager step through autograd
-                    self._autograd_step(inputs.to(self.device), None)
+                    self._eager_step_in_fused_epoch(eng, inputs.to(self.device), None)
                     continue
                 eng.step(host_batch=inputs.pin_memory())
         else:
@@ -303,6 +350,15 @@ class BPRTrainer(BasicTrainer):
                 eng.step()
         eng.sync_optimizer_state()
         return eng.meter_avg()
+
+    def _eager_step_in_fused_epoch(self, eng, inputs, aux_inputs):
+        """A batch the captured step cannot take (the ragged tail of a DataLoader epoch) goes through autograd and
+        torch.optim.Adam.  The engine keeps the real step count on the device and Adam keeps its own on the host, so the
+        count is handed over before the step (bias correction) and the engine's counter and loss meter are advanced
+        after it -- the epoch's loss average includes this batch like the reference's AverageMeter (trainer.py:428)."""
+        eng.sync_optimizer_state()
+        loss = self._autograd_step(inputs, aux_inputs)
+        eng.note_external_step(loss, inputs.shape[0])
 
     # ---- reference-shaped loop through autograd (any optimiser; also the parity path for bpr_forward) ----
     def _loss(self, inputs, aux_inputs):
@@ -368,7 +424,7 @@ class IGCNTrainer(BPRTrainer):
                     inputs = batch_data[:, 0, :].to(dtype=torch.int64)
                     aux = a_batch_data[:, 0, :].to(dtype=torch.int64)
                     if inputs.shape[0] != self.batch_size:
-                        self._autograd_step(inputs.to(self.device), aux.to(self.device))
+                        self._eager_step_in_fused_epoch(eng, inputs.to(self.device), aux.to(self.device))
                         continue
                     eng.step(host_batch=inputs.pin_memory(), host_aux_batch=aux.pin_memory())
             else:

@@ -390,6 +390,16 @@ def run_baseline_case(tag, shape, out_dir, n_rows_kept=2048, n_users_kept=1024, 
 def main():
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--only-config" in sys.argv:  # the reference's config lists (positions + hyper-parameters), device = "DEV"
+        import importlib.util
+        import json
+        spec = importlib.util.spec_from_file_location("ref_config", "/root/reference/config.py")
+        cfg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(cfg)
+        names = ["get_gowalla_config", "get_yelp_config", "get_amazon_config", "get_alibaba_config", "get_ml_config"]
+        json.dump({n: [list(t) for t in getattr(cfg, n)("DEV")] for n in names},
+                  open(os.path.join(out_dir, "config_ref.json"), "w"), indent=0)
+        return
     if "--only-c1" in sys.argv:
         run_baseline_case("c1_ref", "c1", out_dir)
         return

@@ -111,3 +111,25 @@ def test_parser_property_random_files(tmp_path):
         assert got == _naive(path) == rows
 
     check()
+
+
+def test_csr_cache_follows_in_place_row_edits():
+    """the reference's inductive_eval idiom `dataset.test_data[u] = []` (trainer.py:219-227) edits the outer list in
+    place: the cached CSR must not survive it"""
+    import dataset as D
+    from b200rec import synth
+    ds = D.get_dataset({"name": "SyntheticDataset", "device": "cpu", "graph": synth.generate(40, 50, 400, seed=2)})
+    ptr0, idx0 = ds.csr("test")
+    u = int(np.argmax(np.diff(ptr0.numpy())))
+    n_u = int(ptr0[u + 1] - ptr0[u])
+    assert n_u > 0
+    keep = list(ds.test_data[u])
+    ds.test_data[u] = []
+    ptr1, idx1 = ds.csr("test")
+    assert int(ptr1[-1]) == int(ptr0[-1]) - n_u and int(ptr1[u + 1] - ptr1[u]) == 0
+    ds.test_data[u] = keep
+    ptr2, idx2 = ds.csr("test")
+    assert np.array_equal(ptr2.numpy(), ptr0.numpy()) and np.array_equal(idx2.numpy(), idx0.numpy())
+    ds.test_data[u].append(int(idx0.max()))      # an edit INSIDE a row needs the explicit invalidation
+    ds.invalidate_csr("test")
+    assert int(ds.csr("test")[0][-1]) == int(ptr0[-1]) + 1

@@ -312,3 +312,69 @@ def test_spmm_row_and_source_masks_are_bit_identical(golden):
     ops.propagate_bwd(op, xs, L, bufs, d_full)
     ops.propagate_bwd(op, xs, L, bufs, d_part, nonzero_rows=flags)
     assert torch.equal(d_part, d_full)
+
+
+@pytest.mark.parametrize("d", [16, 64, 128])
+def test_bpr_ordered_scatter_is_deterministic_and_matches_atomic(d):
+    """heavy duplicate ids (popular items): the ordered scatter forms each touched row once, in slot order -> the same bits
+    on every run, and the same values as the per-sample atomic scatter / a float64 restatement"""
+    from b200rec import ops
+    rng = np.random.default_rng(d)
+    nu, ni, b = 50, 40, 2048
+    rep = torch.from_numpy(rng.standard_normal((nu + ni, d)).astype(np.float32)).to(DEV)
+    batch_np = np.stack([rng.integers(0, nu, b), rng.integers(0, 7, b), rng.integers(0, ni, b)], 1).astype(np.int64)
+    batch = torch.from_numpy(batch_np).to(DEV)
+    scratch = ops.bpr_scratch(b, d, DEV)
+    loss_a = torch.zeros(1, device=DEV)
+    g_atomic = torch.zeros_like(rep)
+    ops.bpr_fwd_bwd(rep, batch, nu, 1e-3, 1, g_atomic, loss_a, scratch)
+    grp = ops.bpr_grouping(b, DEV)
+    ops.bpr_group_rows(batch, nu, grp)
+    rows = np.concatenate([batch_np[:, :1], batch_np[:, 1:] + nu], 1).reshape(-1)
+    order, seg, nseg = grp[0].cpu().numpy(), grp[1].cpu().numpy(), int(grp[2])
+    assert nseg == np.unique(rows).size and seg[nseg] == 3 * b
+    for j in range(nseg):
+        sl = order[seg[j]:seg[j + 1]]
+        assert (np.diff(sl) > 0).all() and np.unique(rows[sl]).size == 1
+    assert (np.diff(rows[order[seg[:nseg]]]) > 0).all()
+    outs = []
+    for _ in range(3):
+        g = torch.zeros_like(rep)
+        loss_o = torch.zeros(1, device=DEV)
+        ops.bpr_fwd_bwd_ordered(rep, batch, nu, 1e-3, 1, g, loss_o, scratch, grp)
+        outs.append(g)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert float(loss_o) == float(loss_a)
+    torch.testing.assert_close(outs[0], g_atomic, rtol=2e-5, atol=1e-6)
+    # float64 restatement (trainer.py:414-424 + its autograd)
+    r64 = rep.double().cpu().numpy()
+    u, p, n = r64[batch_np[:, 0]], r64[nu + batch_np[:, 1]], r64[nu + batch_np[:, 2]]
+    x = (u * n).sum(1) - (u * p).sum(1)
+    coef = (1 / (1 + np.exp(-x)) / b)[:, None]
+    rc = 2 * 1e-3 / b
+    ref = np.zeros_like(r64)
+    np.add.at(ref, batch_np[:, 0], coef * (n - p) + rc * u)
+    np.add.at(ref, nu + batch_np[:, 1], -coef * u + rc * p)
+    np.add.at(ref, nu + batch_np[:, 2], coef * u + rc * n)
+    np.testing.assert_allclose(outs[0].cpu().numpy(), ref, rtol=1e-4, atol=1e-6)
+    # accumulate mode + weighted scores (IGCN auxiliary loss): added on top of what the table holds
+    w = torch.from_numpy(rng.standard_normal(d).astype(np.float32)).to(DEV)
+    base = torch.from_numpy(rng.standard_normal((nu + ni, d)).astype(np.float32)).to(DEV)
+    ga, gw_a = base.clone(), torch.zeros(d, device=DEV)
+    ops.bpr_fwd_bwd(rep, batch, nu, 0.0, 0, ga, loss_a, scratch, w=w, g_w=gw_a, loss_scale=0.3)
+    go, gw_o = base.clone(), torch.zeros(d, device=DEV)
+    ops.bpr_fwd_bwd_ordered(rep, batch, nu, 0.0, 0, go, loss_o, scratch, grp, w=w, g_w=gw_o, loss_scale=0.3, accumulate=True)
+    torch.testing.assert_close(go, ga, rtol=2e-5, atol=2e-6)
+    assert torch.equal(gw_a, gw_o)
+    # layer-0 regulariser and the row clear
+    e1, e2 = base.clone(), base.clone()
+    ops.bpr_l2_emb0(rep, batch, nu, 1e-2, e1, loss_a, scratch)
+    ops.bpr_l2_emb0_ordered(rep, batch, nu, 1e-2, e2, loss_o, scratch, grp)
+    torch.testing.assert_close(e1, e2, rtol=2e-5, atol=2e-6)
+    ops.clear_rows(batch, nu, e2)
+    touched = torch.zeros(nu + ni, dtype=torch.bool, device=DEV)
+    touched[torch.from_numpy(rows).to(DEV)] = True
+    assert bool((e2[touched] == 0).all()) and torch.equal(e2[~touched], base[~touched])
+    from b200rec import _abi
+    with pytest.raises(_abi.B200RecError):
+        ops.bpr_group_rows(torch.zeros((3000, 3), dtype=torch.int64, device=DEV), nu, ops.bpr_grouping(3000, DEV))

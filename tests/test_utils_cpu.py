@@ -54,8 +54,24 @@ def test_average_meter_and_configs():
     for getter in (config.get_gowalla_config, config.get_yelp_config, config.get_amazon_config):
         triples = getter("cuda")
         names = [t[1]["name"] for t in triples]
-        assert names == ["MF", "LightGCN", "IGCN", "IMF"]
-        for ds_cfg, model_cfg, trainer_cfg in triples:
+        assert names[:3] == ["MF", "LightGCN", "IGCN"]          # the reference's list positions
+        for ds_cfg, model_cfg, trainer_cfg in triples[:3]:
             assert ds_cfg["name"] == "ProcessedDataset" and trainer_cfg["batch_size"] == 2048 and trainer_cfg["topks"][-1] == 100
     c4 = config.get_synthetic_config("cuda", "c4")
     assert c4[1][1]["embedding_size"] == 128 and c4[1][1]["n_layers"] == 4
+
+
+def test_config_lists_equal_the_reference():
+    """every get_*_config list: same length, same positions, same keys and values as /root/reference/config.py
+    (tests/golden/config_ref.json, written by oracle/make_golden.py --only-config)"""
+    import json
+    import os
+    import config
+    from conftest import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "config_ref.json")))
+    assert set(ref) == {"get_gowalla_config", "get_yelp_config", "get_amazon_config", "get_alibaba_config", "get_ml_config"}
+    for name, triples in ref.items():
+        ours = [list(t) for t in getattr(config, name)("DEV")]
+        assert ours == triples, name
+    syn = config.get_synthetic_config("DEV", "c4")
+    assert [m["name"] for _, m, _ in syn] == ["MF", "LightGCN", "IGCN", "IMF"] and syn[1][1]["embedding_size"] == 128
