@@ -132,10 +132,11 @@ class CpuPort:
         self.graph = graph
         self.ptr = graph.train_indptr.cpu().numpy()
         self.items = graph.train_items.cpu().numpy()
-        users, items64 = rp.pairs_from_csr(self.ptr, self.items)
         torch.manual_seed(seed)
         emb0 = (0.1 * torch.randn(graph.n_users + graph.n_items, d)).numpy()
-        self.port = rp.LightGCNPort(graph.n_users, graph.n_items, users, items64, emb0, 1 if self.sampled else n_layers).train()
+        adj = rp.norm_adjacency_from_csr(graph.n_users, graph.n_items, self.ptr, self.items)  # == norm_adjacency, no COO sort
+        self.port = rp.LightGCNPort(graph.n_users, graph.n_items, None, None, emb0, 1 if self.sampled else n_layers,
+                                    adj_sp=adj).train()
         self.opt = torch.optim.Adam(self.port.parameters(), lr=LR)
         self.p32, self.i32 = self.ptr.astype(np.int32), self.items.astype(np.int32)
         self.seed, self.step_no = seed, 0

@@ -52,7 +52,10 @@ uint64_t b200rec_launch_count(void);
  * of its entries that falls into it.  CSR columns ascend inside a row, so the slices of a row are consecutive; each
  * continues the row's running fmaf chain (bit 29 of the item code = "reload the running sum", bit 30 = "park it again
  * instead of finishing", the low 29 bits = row id or slot) -- same chain, same bits as the single-pass kernel.
- * b200rec_spmm_f32_blocked launches the passes back to back; the other entry points take single-pass plans only.
+ * b200rec_stream_build re-lays such an operand out pass-major as one 8-byte record stream
+ *   [carry-in row, 1.0] [col, val] ... [end of segment: park / finish row]      record.x = type<<30 | hub<<29 | id
+ * cut into windows of equal record count that hold whole segments; b200rec_spmm_f32_blocked gives one lane group per
+ * window and launches the passes back to back.  The other entry points take single-pass plans only.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
   int32_t n_rows;            /* output rows */
@@ -80,6 +83,10 @@ typedef struct {
   float* partial;            /* [n_slots, D] scratch for split rows (caller-owned, D = largest D used) */
   int32_t n_passes;          /* 1 (or 0) = single-pass plan; > 1 = column-blocked plan */
   const int32_t* pass_ptr;   /* HOST [n_passes+1]: items [pass_ptr[b], pass_ptr[b+1]) form pass b (NULL for single-pass plans) */
+  /* record stream of a column-blocked operand (b200rec_stream_build), what b200rec_spmm_f32_blocked walks */
+  const void* records;       /* [n_records] 8-byte records, pass-major */
+  const int32_t* win_start;  /* [n_windows+1] record offset of every window */
+  const int32_t* pass_win_ptr; /* HOST [n_passes+1]: windows [pass_win_ptr[b], pass_win_ptr[b+1]) form pass b */
 } b200rec_csr;
 
 /* COO -> coalesced int32 CSR on the device (utils.py:42-50 generate_daj_mat: scipy COO->CSR sums duplicates;
@@ -102,10 +109,13 @@ int b200rec_adj_build(const int64_t* users, const int64_t* items, int64_t n_pair
  * other side only, so each phase has the caches to itself); 0 = one phase.
  * col_bounds (HOST [n_blocks+1], ascending from 0 to n_cols) cuts the source rows into n_blocks L2-sized blocks;
  * n_blocks = 1 (col_bounds may be NULL) builds a single-pass plan.
+ * row_order: 0 = items of a pass sorted longest first (work items of the single-pass kernel); 1 = rows ascending
+ * (input of b200rec_stream_build: carried sums and outputs then stream through memory in order).
  * Call once with item_start == NULL to get sizes[3] (HOST) = {n_items, n_long, n_slots}, allocate, call again.
  * pass_ptr: HOST out [max(n_blocks,1)+1].  Allocates scratch and synchronises `stream`. */
 int b200rec_plan_build(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows, int32_t chunk, int32_t order_split,
-                       const int32_t* col_bounds /*HOST*/, int32_t n_blocks, int32_t* sizes /*HOST out [3]*/,
+                       const int32_t* col_bounds /*HOST*/, int32_t n_blocks, int32_t row_order,
+                       int32_t* sizes /*HOST out [3]*/,
                        int32_t* item_start, int32_t* item_end, int32_t* item_dst, int32_t* item_row,
                        int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot, int32_t* slot_long,
                        int32_t* pass_ptr /*HOST out*/, void* stream);
@@ -135,7 +145,14 @@ int b200rec_spmm_f32_ex(const b200rec_csr* a, const float* x, int32_t d, const u
                         float* y, const float* addend, float* out, float out_scale,
                         const uint8_t* dst_flags, const uint8_t* src_flags, void* stream);
 
-/* The same sum through a column-blocked plan (a->n_passes > 1): one launch per block of source rows, running sums carried
+/* Record stream of a column-blocked plan (items sorted by pass, row_order = 1).  window: records per window (>= 32; 128).
+ * Call with records == NULL for *n_records_out / *n_windows_out (HOST), allocate records [n_records] x 8 B and win_start
+ * [n_windows + 1], call again; pass_win_ptr: HOST out [n_passes+1].  Allocates scratch, synchronises `stream`. */
+int b200rec_stream_build(const int32_t* colidx, const float* vals, int32_t n_items, const int32_t* item_start,
+                         const int32_t* item_end, const int32_t* item_dst, const int32_t* pass_ptr /*HOST*/,
+                         int32_t n_passes, int32_t window, int64_t* n_records_out /*HOST*/, int32_t* n_windows_out /*HOST*/,
+                         void* records, int32_t* win_start, int32_t* pass_win_ptr /*HOST out*/, void* stream);
+/* The same sum through a column-blocked operand (a->records): one launch per block of source rows, running sums carried
  * in `carry` ([n_rows, ld] fp32 scratch).  Plain valued operand only (no masks / scales).  `ld` is the row stride in
  * floats of x, y, addend, out and carry (>= d): with ld > d the call works on d columns of wider tables -- a D = 128
  * table can be swept as two independent 64-column halves, each with half as many passes.  Bit-identical to

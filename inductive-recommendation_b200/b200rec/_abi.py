@@ -30,6 +30,7 @@ class CsrStruct(C.Structure):
         ("n_slots", C.c_int32), ("slot_long", C.c_void_p),
         ("partial", C.c_void_p),
         ("n_passes", C.c_int32), ("pass_ptr", C.c_void_p),
+        ("records", C.c_void_p), ("win_start", C.c_void_p), ("pass_win_ptr", C.c_void_p),
     ]
 
 
@@ -43,7 +44,8 @@ PROTOTYPES = {
     "b200rec_launch_count": (C.c_uint64, []),
     "b200rec_csr_build": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "b200rec_adj_build": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
-    "b200rec_plan_build": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200rec_plan_build": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200rec_stream_build": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "b200rec_adj_normalize": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P]),
     "b200rec_spmm_f32": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P]),
     "b200rec_spmm_f32_ex": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P, _P, _P]),

@@ -65,7 +65,7 @@ def blocking_policy(n_cols, d):
 
 class CsrOperand:
     def __init__(self, rowptr, colidx, n_cols, vals=None, nbr_scale=None, row_scale=None, eid=None, chunk=None,
-                 max_d=256, phase_split=0, d=None, col_bounds=None):
+                 max_d=256, phase_split=0, d=None, col_bounds=None, row_order=None, window=None):
         _abi.require_cuda(rowptr, colidx, vals, nbr_scale, row_scale, eid)
         assert rowptr.dtype == torch.int32 and colidx.dtype == torch.int32
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
@@ -77,7 +77,13 @@ class CsrOperand:
         self.chunk = chunk if chunk is not None else auto_chunk(self.nnz, d)
         self.phase_split = int(phase_split)
         self.col_bounds = None if col_bounds is None else np.ascontiguousarray(col_bounds, dtype=np.int32)
+        # a column-blocked operand (col_bounds) is executed from its record stream: its plan is built in row order
+        self.row_order = int(col_bounds is not None) if row_order is None else int(row_order)
+        self.records = self.win_start = self.pass_win_ptr = None
         self._build_plan(max_d)
+        if self.col_bounds is not None and self.vals is not None and self.row_order:
+            import os
+            self._build_stream(int(window if window is not None else os.environ.get("B200REC_STREAM_WINDOW", "128")))
         self._struct = None
         self._blocked = {}   # sweep width -> column-blocked twin of this operand (shared CSR arrays, own plan)
         self._carry = {}     # row stride -> carried-sum scratch [n_rows, ld]
@@ -92,15 +98,15 @@ class CsrOperand:
         null = C.c_void_p(0)
         with torch.cuda.device(dev):
             _abi.check(lib.b200rec_plan_build(_abi.ptr(self.rowptr), _abi.ptr(self.colidx), self.n_rows, self.chunk,
-                                              self.phase_split, bounds, nb, sizes, null, null, null, null, null, null,
-                                              null, null, null, _abi.stream_ptr()), "plan_build(size)")
+                                              self.phase_split, bounds, nb, self.row_order, sizes, null, null, null, null,
+                                              null, null, null, null, null, _abi.stream_ptr()), "plan_build(size)")
             ni, nl, ns = sizes[0], sizes[1], sizes[2]
             i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=dev)  # noqa: E731
             self.item_start, self.item_end, self.item_dst, self.item_row = i32(ni), i32(ni), i32(ni), i32(ni)
             self.long_row, self.long_slot0, self.long_nslot, self.slot_long = i32(nl), i32(nl), i32(nl), i32(ns)
             self.pass_ptr = np.zeros(nb + 1, dtype=np.int32)
             _abi.check(lib.b200rec_plan_build(_abi.ptr(self.rowptr), _abi.ptr(self.colidx), self.n_rows, self.chunk,
-                                              self.phase_split, bounds, nb, sizes, _abi.ptr(self.item_start),
+                                              self.phase_split, bounds, nb, self.row_order, sizes, _abi.ptr(self.item_start),
                                               _abi.ptr(self.item_end), _abi.ptr(self.item_dst), _abi.ptr(self.item_row),
                                               _abi.ptr(self.long_row), _abi.ptr(self.long_slot0), _abi.ptr(self.long_nslot),
                                               _abi.ptr(self.slot_long), C.c_void_p(self.pass_ptr.ctypes.data),
@@ -110,6 +116,31 @@ class CsrOperand:
         self.long_cnt = torch.zeros(max(nl, 1), dtype=torch.int32, device=dev)
         self.partial = torch.empty((max(ns, 1), max_d), dtype=torch.float32, device=dev) if ns else None
         self.max_d = max_d
+
+    def _build_stream(self, window):
+        """b200rec_stream_build: the pass-major record stream + windows b200rec_spmm_f32_blocked walks"""
+        lib = _abi.load()
+        dev = self.device
+        n_rec, n_win = C.c_int64(0), C.c_int32(0)
+        null = C.c_void_p(0)
+        args = (_abi.ptr(self.colidx), _abi.ptr(self.vals), self.n_items, _abi.ptr(self.item_start), _abi.ptr(self.item_end),
+                _abi.ptr(self.item_dst), C.c_void_p(self.pass_ptr.ctypes.data), self.n_passes, window, C.byref(n_rec),
+                C.byref(n_win))
+        with torch.cuda.device(dev):
+            _abi.check(lib.b200rec_stream_build(*args, null, null, null, _abi.stream_ptr()), "stream_build(size)")
+            self.records = torch.empty((max(n_rec.value, 1), 2), dtype=torch.int32, device=dev)
+            self.win_start = torch.empty(n_win.value + 1, dtype=torch.int32, device=dev)
+            self.pass_win_ptr = np.zeros(self.n_passes + 1, dtype=np.int32)
+            _abi.check(lib.b200rec_stream_build(*args, _abi.ptr(self.records), _abi.ptr(self.win_start),
+                                                C.c_void_p(self.pass_win_ptr.ctypes.data), _abi.stream_ptr()), "stream_build")
+        self.n_records, self.n_windows, self.window = n_rec.value, n_win.value, window
+
+    def drop_items(self):
+        """the per-segment item arrays of a streamed operand are only needed to build the stream"""
+        dev = self.device
+        for name in ("item_start", "item_end", "item_dst", "item_row"):
+            setattr(self, name, torch.zeros(1, dtype=torch.int32, device=dev))
+        self._struct = None
 
     def struct(self):
         if self._struct is None:
@@ -128,6 +159,9 @@ class CsrOperand:
             s.partial = p(self.partial)
             s.n_passes = self.n_passes
             s.pass_ptr = self.pass_ptr.ctypes.data if self.n_passes > 1 else None
+            s.records = p(self.records)
+            s.win_start = p(self.win_start)
+            s.pass_win_ptr = self.pass_win_ptr.ctypes.data if self.pass_win_ptr is not None else None
             self._struct = s
         return self._struct
 
@@ -150,8 +184,10 @@ class CsrOperand:
                 nblk = max(1, -(-(hi - lo) // block_rows))
                 step = -(-(hi - lo) // nblk)
                 bounds += [min(hi, lo + (k + 1) * step) for k in range(nblk)]
-            self._blocked[key] = CsrOperand(self.rowptr, self.colidx, self.n_cols, vals=self.vals, chunk=self.chunk,
-                                            max_d=self.max_d, phase_split=self.phase_split, col_bounds=bounds)
+            bop = CsrOperand(self.rowptr, self.colidx, self.n_cols, vals=self.vals, chunk=self.chunk,
+                             max_d=self.max_d, phase_split=self.phase_split, col_bounds=bounds)
+            bop.drop_items()
+            self._blocked[key] = bop
         return self._blocked[key], sweep
 
     def carry(self, ld):

@@ -89,6 +89,17 @@ __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<fl
 __device__ __forceinline__ int ld_stream_i32(const int32_t* p) { return __ldcs(p); }
 __device__ __forceinline__ float ld_stream_f32(const float* p) { return __ldcs(p); }
 
+// streaming (evict-first) 128-bit accesses for rows that are touched once per launch (carried sums and outputs of a
+// column-blocked pass): they must not push the pass's source block out of L2
+__device__ __forceinline__ float4 ld_cs_f4(const float* ptr) {
+  float4 v;
+  asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ void st_cs_f4(float* ptr, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // 128-bit fire-and-forget reduction (sm_90+): 4 fp32 adds in one L2 atomic transaction
 __device__ __forceinline__ void red_add_f4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

@@ -123,7 +123,7 @@ static int csr_from_keys(Scratch& sc, uint64_t* keys, int32_t* pos, int64_t n, i
 struct PlanIn {
   const int32_t* rowptr;
   const int32_t* colidx;
-  int n_rows, chunk, order_split, n_blocks;
+  int n_rows, chunk, order_split, n_blocks, row_order;
   const int32_t* bounds;  // device [n_blocks + 1]
 };
 
@@ -166,7 +166,7 @@ __device__ __forceinline__ void walk_row(const PlanIn& in, int r, int& n_items, 
         item_start[k] = vs; item_end[k] = ve;
         item_dst[k] = is_long ? (int32_t)~idcode : (int32_t)idcode;
         item_row[k] = r;
-        item_key[k] = (order_hi << 32) | (uint32_t)(0x7fffffff - (ve - vs));
+        item_key[k] = (order_hi << 32) | (in.row_order ? 0u : (uint32_t)(0x7fffffff - (ve - vs)));
       }
       ++ni;
       continue;
@@ -186,7 +186,9 @@ __device__ __forceinline__ void walk_row(const PlanIn& in, int r, int& n_items, 
           item_start[k] = pos; item_end[k] = nxt;
           item_dst[k] = is_long ? (int32_t)~code : (int32_t)code;
           item_row[k] = r;
-          item_key[k] = ((uint64_t)b << 32) | (uint32_t)(0x7fffffff - (nxt - pos));
+          // inside a pass: longest first (one work item per launch slot), or -- for the record stream -- the emission
+          // order itself (rows ascending: the stable sort keeps it), so that carried sums and outputs stream through DRAM
+          item_key[k] = ((uint64_t)b << 32) | (in.row_order ? 0u : (uint32_t)(0x7fffffff - (nxt - pos)));
         }
         ++ni;
         first = false;
@@ -292,7 +294,8 @@ extern "C" int b200rec_adj_build(const int64_t* users, const int64_t* items, int
 }
 
 extern "C" int b200rec_plan_build(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows, int32_t chunk,
-                                  int32_t order_split, const int32_t* col_bounds, int32_t n_blocks, int32_t* sizes,
+                                  int32_t order_split, const int32_t* col_bounds, int32_t n_blocks, int32_t row_order,
+                                  int32_t* sizes,
                                   int32_t* item_start, int32_t* item_end, int32_t* item_dst, int32_t* item_row,
                                   int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot, int32_t* slot_long,
                                   int32_t* pass_ptr, void* stream) {
@@ -303,7 +306,7 @@ extern "C" int b200rec_plan_build(const int32_t* rowptr, const int32_t* colidx, 
   Scratch sc;
   PlanIn in;
   in.rowptr = rowptr; in.colidx = colidx; in.n_rows = n_rows; in.chunk = chunk; in.order_split = order_split;
-  in.n_blocks = n_blocks; in.bounds = nullptr;
+  in.n_blocks = n_blocks; in.bounds = nullptr; in.row_order = row_order;
   if (n_blocks > 1) {
     for (int b = 0; b < n_blocks; ++b) B2_REQUIRE(col_bounds[b] <= col_bounds[b + 1], "col_bounds must ascend");
     int32_t* dbounds = nullptr;

@@ -48,43 +48,28 @@ struct SpmmParams {
   int n_peer;
   float* peer_y[8];
   float* peer_out[8];
-  // column-blocked plans (b200rec_spmm_f32_blocked): the launch covers plan items [item_base, item_base + n_items); an item
-  // whose row continues from an earlier pass reloads its running sum from `carry` (hub pieces: from `partial`)
-  int item_base;
-  float* carry;
-  int ld;  // row stride (floats) of x, y, addend, out and carry; the kernel's D columns start at the given pointers
 };
 
-// streaming (evict-first) 128-bit accesses for rows that are touched once per launch (carried sums, outputs of a
-// column-blocked pass): they must not push the pass's source block out of L2
-__device__ __forceinline__ float4 ld_cs_f4(const float* ptr) {
-  float4 v;
-  asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
-  return v;
-}
-__device__ __forceinline__ void st_cs_f4(float* ptr, float4 v) {
-  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-template <int G, int VPL, bool STREAM>
+template <int G, int VPL>
 __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int gl, float4 (&acc)[VPL]) {
+  constexpr int D = G * VPL * 4;
   float sc = p.post_scale;
   if (p.row_scale) sc *= p.row_scale[row];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) {
-    const size_t off = (size_t)row * (size_t)p.ld + (size_t)(gl + t * G) * 4;
+    const size_t off = (size_t)row * D + (size_t)(gl + t * G) * 4;
     float4 s = make_float4(acc[t].x * sc, acc[t].y * sc, acc[t].z * sc, acc[t].w * sc);
     if (p.y) {
-      if (STREAM) st_cs_f4(p.y + off, s); else st_f4(p.y + off, s);
+      st_f4(p.y + off, s);
       for (int q = 0; q < p.n_peer; ++q)
         if (p.peer_y[q]) st_f4(p.peer_y[q] + off, s);  // NVLink store into the peer's table, overlapped with the gathers
     }
     if (p.out) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.addend) a = STREAM ? ld_cs_f4(p.addend + off) : ld_f4(p.addend + off);
+      if (p.addend) a = ld_f4(p.addend + off);
       const float os = p.out_scale;
       const float4 o4 = make_float4((a.x + s.x) * os, (a.y + s.y) * os, (a.z + s.z) * os, (a.w + s.w) * os);
-      if (STREAM) st_cs_f4(p.out + off, o4); else st_f4(p.out + off, o4);
+      st_f4(p.out + off, o4);
       for (int q = 0; q < p.n_peer; ++q)
         if (p.peer_out[q]) st_f4(p.peer_out[q] + off, o4);
     }
@@ -98,13 +83,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int g
 //  * edges that contribute nothing (past the row end, dropped by the edge-dropout mask, or whose source row is
 //    flagged all-zero) are squeezed out with a ballot/popc compaction before the gather loop; the slack of the last
 //    sub-block is padded with (first column of the row, weight 0), so the loop body carries no predicates or selects.
-//
-// CARRY (column-blocked plans, tables larger than L2): one launch per block of SOURCE rows that fits L2.  CSR columns
-// ascend inside a row, so a pass owns one contiguous slice of every row it touches; the slice continues the row's fmaf
-// chain from the running sum the previous pass left in `carry` (bit 29 of the item code: reload; bit 30: park again
-// instead of finishing) -- the chain, hence every bit of the result, is the one the single-pass kernel computes.
-// Carried sums and outputs move with evict-first accesses so that only the gathered block stays in L2.
-template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID, bool HAS_SRCF, bool CARRY>
+template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID, bool HAS_SRCF>
 __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(const SpmmParams p) {
   constexpr int D = G * VPL * 4;
   constexpr int U = 8;                    // neighbour rows in flight per lane
@@ -121,8 +100,8 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-  int item = warp * GPW + lane / G;       // position inside this launch's slice of the plan (or of the live list)
-  int it = item + p.item_base;            // plan index
+  int item = warp * GPW + lane / G;       // position in the plan (or in the live list)
+  int it = item;                          // plan index
   int2* my_cv = s_cv + (threadIdx.x / G) * CVS;  // this group's EB slots
   int start = 0, end = 0, dst = 0;
   if (!p.live_items && item < p.n_items) {
@@ -145,10 +124,7 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   }
   if (item < p.n_items && p.dst_flags && !ldc_u8(p.dst_flags + __ldg(p.item_row + it))) end = start;  // row not needed
   const bool hub = dst < 0;
-  const unsigned code = hub ? ~(unsigned)dst : (unsigned)dst;
-  const bool not_first = CARRY && ((code >> 29) & 1u) != 0u;
-  const bool not_last = CARRY && ((code >> 30) & 1u) != 0u;
-  const int id = CARRY ? (int)(code & 0x1fffffffu) : (int)code;  // row, or slot of a hub piece
+  const int id = hub ? ~dst : dst;  // row, or slot of a hub piece
   const bool live = end > start;
   int maxlen = end - start;
   if (GPW > 1) {
@@ -159,16 +135,7 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   float4 acc[VPL];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float* cptr = nullptr;  // where this item's running sum is parked between passes
-  if (CARRY) {
-    cptr = (hub ? p.partial + (size_t)id * D : p.carry + (size_t)id * (size_t)p.ld) + (size_t)gl * 4;
-    if (not_first) {
-#pragma unroll
-      for (int t = 0; t < VPL; ++t) acc[t] = ld_cs_f4(cptr + t * G * 4);
-    }
-  }
   const float* xg = p.x + (size_t)gl * 4;
-  const unsigned ld = (unsigned)p.ld;
 
   for (int base = 0; base < maxlen; base += EB) {
     int cnt = 0;  // contributing edges of this group in this block of EB; cntmax: warp-uniform loop bound
@@ -219,7 +186,7 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
       for (int u = 0; u < U; ++u) {
         const int2 cv = my_cv[j0 + u];  // broadcast LDS.64
         vv[u] = __int_as_float(cv.y);
-        const float* r = xg + (size_t)((unsigned)cv.x * ld);
+        const float* r = xg + (size_t)((unsigned)cv.x * (unsigned)D);
 #pragma unroll
         for (int t = 0; t < VPL; ++t) xv[u][t] = ldc_f4(r + t * G * 4);
       }
@@ -238,13 +205,8 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   }
   if (item >= p.n_items) return;
   if (p.dst_flags && !ldc_u8(p.dst_flags + __ldg(p.item_row + it))) return;
-  if (CARRY && not_last) {  // the row (or hub piece) continues in a later pass
-#pragma unroll
-    for (int t = 0; t < VPL; ++t) st_cs_f4(cptr + t * G * 4, acc[t]);
-    return;
-  }
   if (!hub) {
-    epilogue_row<G, VPL, CARRY>(p, id, gl, acc);
+    epilogue_row<G, VPL>(p, id, gl, acc);
     return;
   }
   // A chunk of a split (hub) row: park the raw partial sum; the group that parks the LAST chunk of the row adds all
@@ -286,11 +248,11 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
       acc[t].x += v1.x; acc[t].y += v1.y; acc[t].z += v1.z; acc[t].w += v1.w;
     }
   }
-  epilogue_row<G, VPL, CARRY>(p, __ldg(p.long_row + li), gl, acc);
+  epilogue_row<G, VPL>(p, __ldg(p.long_row + li), gl, acc);
 }
 
 template <int G, int VPL>
-static int launch_spmm(const b200rec_csr* a, SpmmParams p, cudaStream_t st, int max_live, bool blocked) {
+static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t st, int max_live) {
   constexpr int GPW = 32 / G;
   // threads per block: 256 measured best or equal on every shape (C2: 57-58 us at 32/64/256 for D=64; C4 D=16:
   // 1.86 ms at 256 vs 4.9 ms at 32); B200REC_SPMM_TPB overrides for experiments
@@ -300,23 +262,13 @@ static int launch_spmm(const b200rec_csr* a, SpmmParams p, cudaStream_t st, int 
     return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 256;
   }();
   const int items_per_block = (tpb / 32) * GPW;
-  if (blocked) {  // one launch per block of source rows; a pass only starts when the previous one has finished
-    for (int pass = 0; pass < a->n_passes; ++pass) {
-      p.item_base = a->pass_ptr[pass];
-      p.n_items = a->pass_ptr[pass + 1] - a->pass_ptr[pass];
-      if (p.n_items <= 0) continue;
-      B2_LAUNCH_PDL(spmm_items_kernel<G, VPL, true, false, false, false, false, true>, ceil_div(p.n_items, items_per_block), tpb,
-                    0, st, p);
-    }
-    return 0;
-  }
   if (a->n_items > 0) {
     const int grid = ceil_div(p.live_items ? min(max_live, a->n_items) : a->n_items, items_per_block);
     const bool hv = p.vals != nullptr, hn = p.nbr_scale != nullptr, hm = p.keep_bits != nullptr, he = p.eid != nullptr && hm;
     const bool hs = p.src_flags != nullptr;
 #define B2_SPMM_CASE(V, N, M, E, S)                                                      \
   if (hv == V && hn == N && hm == M && he == E && hs == S) {                             \
-    B2_LAUNCH_PDL(spmm_items_kernel<G, VPL, V, N, M, E, S, false>, grid, tpb, 0, st, p); \
+    B2_LAUNCH_PDL(spmm_items_kernel<G, VPL, V, N, M, E, S>, grid, tpb, 0, st, p);       \
   } else
     B2_SPMM_CASE(true, false, false, false, false)   // normalised adjacency
     B2_SPMM_CASE(true, false, false, false, true)    // normalised adjacency, sparse source (first backward hop)
@@ -336,25 +288,15 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
                          float* y, const float* addend, float* out, float out_scale, const uint8_t* dst_flags,
                          const uint8_t* src_flags, cudaStream_t st, int n_peer = 0, float* const* peer_y = nullptr,
                          float* const* peer_out = nullptr, const int32_t* live_items = nullptr,
-                         const int32_t* live_count = nullptr, int max_live = 0, int ld = 0, float* carry = nullptr,
-                         bool blocked = false) {
+                         const int32_t* live_count = nullptr, int max_live = 0) {
   B2_REQUIRE(a && x, "null operand");
   B2_REQUIRE(y || out, "no output");
   B2_REQUIRE(a->n_items == 0 || (a->item_start && a->item_end && a->item_dst && a->colidx), "csr plan missing");
   B2_REQUIRE(a->n_long == 0 || (a->partial && a->long_row && a->long_slot0 && a->long_nslot && a->slot_long && a->long_cnt),
              "long-row plan missing");
   B2_REQUIRE(!dst_flags || a->item_row, "dst_flags needs item_row in the plan");
-  if (ld == 0) ld = d;
-  B2_REQUIRE(ld >= d && (ld % 4) == 0, "row stride must be >= d and a multiple of 4 floats");
-  B2_REQUIRE((long long)a->n_cols * ld < (1ll << 32) && (long long)a->n_rows * ld < (1ll << 32), "tables must have < 2^32 elements");
-  if (blocked) {
-    B2_REQUIRE(a->n_passes >= 1 && a->pass_ptr, "operand has no column-blocked plan (b200rec_plan_build with col_bounds)");
-    B2_REQUIRE(carry, "carry buffer missing");
-    B2_REQUIRE(a->vals && !a->nbr_scale && !a->eid && !keep_bits && !dst_flags && !src_flags && !live_items && n_peer == 0,
-               "the column-blocked path takes a plain valued operand (no masks, scales or peers)");
-  } else {
-    B2_REQUIRE(a->n_passes <= 1, "column-blocked plan: call b200rec_spmm_f32_blocked");
-  }
+  B2_REQUIRE((long long)a->n_cols * d < (1ll << 32), "gathered table must have < 2^32 elements");
+  B2_REQUIRE(a->n_passes <= 1, "column-blocked operand: call b200rec_spmm_f32_blocked");
   SpmmParams p;
   p.colidx = a->colidx; p.vals = a->vals; p.nbr_scale = a->nbr_scale; p.row_scale = a->row_scale; p.eid = a->eid;
   p.keep_bits = keep_bits; p.dst_flags = dst_flags; p.src_flags = src_flags;
@@ -370,14 +312,13 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
   p.x = x; p.y = y; p.addend = addend; p.out = out; p.out_scale = out_scale; p.post_scale = post_scale;
   p.partial = a->partial; p.slot_long = a->slot_long; p.long_row = a->long_row; p.long_slot0 = a->long_slot0;
   p.long_nslot = a->long_nslot; p.long_cnt = a->long_cnt;
-  p.item_base = 0; p.carry = carry; p.ld = ld;
   switch (d) {
-    case 8: return launch_spmm<2, 1>(a, p, st, max_live, blocked);
-    case 16: return launch_spmm<4, 1>(a, p, st, max_live, blocked);
-    case 32: return launch_spmm<8, 1>(a, p, st, max_live, blocked);
-    case 64: return launch_spmm<16, 1>(a, p, st, max_live, blocked);
-    case 128: return launch_spmm<32, 1>(a, p, st, max_live, blocked);
-    case 256: return launch_spmm<32, 2>(a, p, st, max_live, blocked);
+    case 8: return launch_spmm<2, 1>(a, p, st, max_live);
+    case 16: return launch_spmm<4, 1>(a, p, st, max_live);
+    case 32: return launch_spmm<8, 1>(a, p, st, max_live);
+    case 64: return launch_spmm<16, 1>(a, p, st, max_live);
+    case 128: return launch_spmm<32, 1>(a, p, st, max_live);
+    case 256: return launch_spmm<32, 2>(a, p, st, max_live);
     default: return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "embedding size must be 8/16/32/64/128/256");
   }
 }
@@ -465,12 +406,6 @@ extern "C" int b200rec_spmm_f32_peer(const b200rec_csr* a, const float* x, int32
   B2_REQUIRE(n_peers >= 0 && n_peers <= 8, "at most 8 peers");
   return spmm_dispatch(a, x, d, keep_bits, post_scale, y, addend, out, out_scale, dst_flags, src_flags, (cudaStream_t)stream,
                        n_peers, peer_y, peer_out);
-}
-
-extern "C" int b200rec_spmm_f32_blocked(const b200rec_csr* a, const float* x, int32_t d, int32_t ld, float post_scale, float* y,
-                                        const float* addend, float* out, float out_scale, float* carry, void* stream) {
-  return spmm_dispatch(a, x, d, nullptr, post_scale, y, addend, out, out_scale, nullptr, nullptr, (cudaStream_t)stream, 0,
-                       nullptr, nullptr, nullptr, nullptr, 0, ld, carry, true);
 }
 
 extern "C" int b200rec_live_items(const b200rec_csr* a, const uint8_t* row_flags, int32_t* live_items, int32_t* live_count,

@@ -50,6 +50,25 @@ def norm_adjacency(n_users, n_items, users, items):
     return out
 
 
+def norm_adjacency_from_csr(n_users, n_items, indptr, items):
+    """norm_adjacency for a user-major, per-user sorted, duplicate-free pair list given as CSR (the 100M-edge bench graph):
+    the same matrix -- structure from the user-item CSR and its transpose instead of a 200M-entry COO sort, values
+    fl(fl(d_r * 1) * d_c) formed elementwise in float32, which is what d_mat.dot(adj).dot(d_mat) computes entry by entry.
+    tests/test_oracle_golden.py checks it bit for bit against norm_adjacency."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    items = np.asarray(items, dtype=np.int64)
+    r = sp.csr_matrix((np.ones(items.size, dtype=np.float32), items, indptr), shape=(n_users, n_items))
+    rt = r.T.tocsr()
+    rt.sort_indices()
+    n = n_users + n_items
+    ptr = np.concatenate([indptr, indptr[-1] + rt.indptr[1:].astype(np.int64)])
+    idx = np.concatenate([items + n_users, rt.indices.astype(np.int64)])
+    degree = np.maximum(1., np.diff(ptr).astype(np.float32))
+    d_inv = np.power(degree, -0.5)
+    data = np.multiply(np.multiply(np.repeat(d_inv, np.diff(ptr)), np.float32(1.)), d_inv[idx])
+    return sp.csr_matrix((data, idx, ptr), shape=(n, n))
+
+
 def torch_csr(mat):
     mat = mat.tocsr()
     return torch.sparse_csr_tensor(torch.from_numpy(mat.indptr.astype(np.int64)),
@@ -137,10 +156,10 @@ def dropout_keep(nnz, p, generator=None):
 class LightGCNPort(torch.nn.Module):
     """model.py:79-127."""
 
-    def __init__(self, n_users, n_items, users, items, emb0, n_layers):
+    def __init__(self, n_users, n_items, users, items, emb0, n_layers, adj_sp=None):
         super().__init__()
         self.n_users, self.n_items, self.n_layers = n_users, n_items, n_layers
-        self.adj_sp = norm_adjacency(n_users, n_items, users, items)
+        self.adj_sp = adj_sp if adj_sp is not None else norm_adjacency(n_users, n_items, users, items)
         self.a = torch_csr(self.adj_sp)          # bit-wise symmetric: a^T == a (SURVEY 8c)
         self.embedding = torch.nn.Embedding(n_users + n_items, emb0.shape[1])
         with torch.no_grad():

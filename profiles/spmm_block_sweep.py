@@ -47,9 +47,10 @@ for d in dims:
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / iters
             bytes_min = op.nnz * 8 + (n + 1) * 4 + 2 * n * d * 4
-            print("D=%3d block=%5.1f MB sweep=%3d passes=%3d items=%9d : %8.3f ms/layer  bytes_min/t = %6.0f GB/s" % (
-                d, mb, sw, 0 if blk is None else blk[0].n_passes * (d // blk[1]), op.n_items if blk is None else blk[0].n_items,
-                ms, bytes_min / ms / 1e6), flush=True)
+            print("D=%3d block=%5.1f MB sweep=%3d passes=%3d records=%10d window=%4d : %8.3f ms/layer  bytes_min/t = %6.0f GB/s  "
+                  "gathered %6.0f GB/s" % (
+                      d, mb, sw, 0 if blk is None else blk[0].n_passes * (d // blk[1]), op.nnz if blk is None else blk[0].n_records,
+                      0 if blk is None else blk[0].window, ms, bytes_min / ms / 1e6, op.nnz * d * 4 / ms / 1e6), flush=True)
             if blk is not None:
                 op._blocked.clear()  # free the plan before building the next one
             del y, acc

@@ -94,7 +94,7 @@ def test_csr_struct_mirror_matches_header_and_integration_doc():
     text = open(os.path.join(REPO, "include", "b200rec.h")).read()
     body = text[text.index("typedef struct {"):text.index("} b200rec_csr;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    fields = re.findall(r"^\s*(const\s+)?(int32_t|float)\s*(\*?)\s*([a-z0-9_]+);", body, flags=re.M)
+    fields = re.findall(r"^\s*(const\s+)?(int32_t|float|void)\s*(\*?)\s*([a-z0-9_]+);", body, flags=re.M)
     header = [(name, "ptr" if star else ctype) for _, ctype, star, name in fields]
     mirror = [(n, "ptr" if t is C.c_void_p else {C.c_int32: "int32_t"}[t]) for n, t in _abi.CsrStruct._fields_]
     assert header == mirror and len(header) >= 20

@@ -186,8 +186,8 @@ def test_ragged_last_batch_in_fused_epoch(golden, name):
     res = []
     for fused in (True, False):
         ds, m = golden_model(g, name, dropout=0.0) if name.startswith("igcn") else golden_model(g, name)
-        tr = _trainer(g, name, ds, m, fused=fused, sampler="host", batch_size=250)
-        assert len(ds) % 250 != 0
+        tr = _trainer(g, name, ds, m, fused=fused, sampler="host", batch_size=256)
+        assert len(ds) % 256 != 0
         m.train()
         losses = []
         for ep in range(2):
@@ -196,7 +196,7 @@ def test_ragged_last_batch_in_fused_epoch(golden, name):
         steps = int(tr.opt.state[m.embedding.weight]["step"])
         res.append((losses, steps, _np(m.embedding.weight).copy()))
     (l_f, s_f, w_f), (l_a, s_a, w_a) = res
-    assert s_f == s_a == 2 * -(-len(ds) // 250)
+    assert s_f == s_a == 2 * -(-len(ds) // 256)
     np.testing.assert_allclose(l_f, l_a, rtol=2e-6)
     np.testing.assert_allclose(w_f, w_a, rtol=1e-4, atol=3e-5)   # a stale bias correction moves the tail step by ~1e-2
 

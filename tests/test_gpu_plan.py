@@ -60,7 +60,7 @@ def test_csr_build_rejects_out_of_range():
         graph.csr_from_coo(torch.tensor([0, 5], device=DEV), torch.tensor([0, 1], device=DEV), 5, 4)
 
 
-def _check_plan(op, rp, cols, chunk, bounds):
+def _check_plan(op, rp, cols, chunk, bounds, row_order=False):
     n_rows = len(rp) - 1
     ni = op.n_items
     start, end, dst, row = (t[:ni].cpu().numpy() for t in (op.item_start, op.item_end, op.item_dst, op.item_row))
@@ -103,7 +103,10 @@ def _check_plan(op, rp, cols, chunk, bounds):
             for k in range(pp[b], pp[b + 1]):
                 c = cols[start[k]:end[k]]
                 assert c.size == 0 or (c.min() >= bounds[b] and c.max() < bounds[b + 1])
-            assert (np.diff((end - start)[pp[b]:pp[b + 1]]) <= 0).all()   # longest first inside a pass
+            if row_order:
+                assert (np.diff(start[pp[b]:pp[b + 1]]) > 0).all()          # CSR order = rows ascending inside a pass
+            else:
+                assert (np.diff((end - start)[pp[b]:pp[b + 1]]) <= 0).all()   # longest first inside a pass
 
 
 @pytest.mark.parametrize("chunk", [32, 256])
@@ -113,8 +116,13 @@ def test_plan_build_invariants(chunk, nblocks):
     n_rows, n_cols = 400, 3500
     rp, cols = _random_csr(rng, n_rows, n_cols)
     bounds = None if nblocks == 1 else np.linspace(0, n_cols, nblocks + 1).astype(np.int32)
-    op = graph.CsrOperand(torch.from_numpy(rp).to(DEV), torch.from_numpy(cols).to(DEV), n_cols, chunk=chunk, col_bounds=bounds)
+    op = graph.CsrOperand(torch.from_numpy(rp).to(DEV), torch.from_numpy(cols).to(DEV), n_cols, chunk=chunk, col_bounds=bounds,
+                          row_order=0)
     _check_plan(op, rp, cols, chunk, bounds)
+    if bounds is not None:  # row order (the record stream's input): same items, rows ascending inside a pass
+        op1 = graph.CsrOperand(torch.from_numpy(rp).to(DEV), torch.from_numpy(cols).to(DEV), n_cols, chunk=chunk,
+                               col_bounds=bounds, row_order=1)
+        _check_plan(op1, rp, cols, chunk, bounds, row_order=True)
     if nblocks == 1:  # two scheduling phases of a single-pass plan
         op2 = graph.CsrOperand(torch.from_numpy(rp).to(DEV), torch.from_numpy(cols).to(DEV), n_cols, chunk=chunk, phase_split=150)
         row = op2.item_row[:op2.n_items].cpu().numpy()
@@ -124,6 +132,43 @@ def test_plan_build_invariants(chunk, nblocks):
         for ph in (first, ~first):
             assert (np.diff(ln[ph]) <= 0).all()
         _check_plan(op2, rp, cols, chunk, None)
+
+
+def test_record_stream_structure():
+    """the pass-major stream: per item [carry-in?] edges [end], windows hold whole items and cover every record once"""
+    rng = np.random.default_rng(3)
+    n = 700
+    rp, cols = _random_csr(rng, n, n, hubs=4)
+    vals = rng.standard_normal(cols.size).astype(np.float32)
+    bounds = np.array([0, 90, 300, 301, 650, n], dtype=np.int32)
+    t = lambda a: torch.from_numpy(a).to(DEV)  # noqa: E731
+    op = graph.CsrOperand(t(rp), t(cols), n, vals=t(vals), chunk=64, col_bounds=bounds, window=32)
+    rec = op.records.cpu().numpy()
+    x, w = rec[:, 0].view(np.uint32), rec[:, 1].view(np.float32)
+    typ, hub, ident = x >> 30, (x >> 29) & 1, x & 0x1fffffff
+    ni = op.n_items
+    start, end, dst = (a[:ni].cpu().numpy() for a in (op.item_start, op.item_end, op.item_dst))
+    code = np.where(dst < 0, ~dst, dst).astype(np.int64)
+    nf, nl = (code >> 29) & 1, (code >> 30) & 1
+    assert op.n_records == int((end - start).sum() + nf.sum() + ni) == rec.shape[0]
+    o = 0
+    for i in range(ni):
+        if nf[i]:
+            assert typ[o] == 1 and w[o] == 1.0 and ident[o] == (code[i] & 0x1fffffff) and hub[o] == (dst[i] < 0)
+            o += 1
+        k = end[i] - start[i]
+        assert (typ[o:o + k] == 0).all() and np.array_equal(ident[o:o + k], cols[start[i]:end[i]])
+        assert np.array_equal(w[o:o + k], vals[start[i]:end[i]])
+        o += k
+        assert typ[o] == (2 if nl[i] else 3) and ident[o] == (code[i] & 0x1fffffff) and hub[o] == (dst[i] < 0)
+        o += 1
+    assert o == rec.shape[0]
+    ws, pw = op.win_start.cpu().numpy(), op.pass_win_ptr
+    assert ws[0] == 0 and ws[-1] == rec.shape[0] and (np.diff(ws) >= 0).all() and pw[-1] == len(ws) - 1
+    item_first = np.concatenate([[0], np.cumsum((end - start) + nf + 1)])
+    assert np.isin(ws, item_first).all()                      # windows start at item boundaries
+    for b in range(op.n_passes):                               # and never straddle a pass
+        assert ws[pw[b]] == item_first[op.pass_ptr[b]] and ws[pw[b + 1]] == item_first[op.pass_ptr[b + 1]]
 
 
 @pytest.mark.parametrize("d,sweep", [(16, 16), (64, 64), (128, 64), (128, 32), (256, 256)])
@@ -138,7 +183,7 @@ def test_blocked_spmm_bit_identical_to_single_pass_and_oracle(d, sweep):
     t = lambda a: torch.from_numpy(a).to(DEV)  # noqa: E731
     op = graph.CsrOperand(t(rp), t(cols), n, vals=t(vals), chunk=chunk)
     bounds = np.array([0, 100, 130, 131, 500, 500, 777, n], dtype=np.int32)   # uneven, one empty, one single-row block
-    bop = graph.CsrOperand(t(rp), t(cols), n, vals=t(vals), chunk=chunk, col_bounds=bounds)
+    bop = graph.CsrOperand(t(rp), t(cols), n, vals=t(vals), chunk=chunk, col_bounds=bounds, window=32 + 32 * (d % 3))
     xd, addd = t(x), t(add)
     y1, o1 = torch.empty_like(xd), torch.empty_like(xd)
     ops.spmm(op, xd, y=y1, addend=addd, out=o1, out_scale=0.2)

@@ -254,3 +254,15 @@ def test_port_matches_reference_at_c1_size():
     assert abs(loss - float(f["loss"])) < 1e-6
     np.testing.assert_allclose(m.embedding.weight.grad.numpy()[f["rows_kept"]], f["grad_rows"], rtol=1e-4, atol=1e-9)
     np.testing.assert_allclose(m.embedding.weight.detach().numpy()[f["rows_kept"]], f["emb1_rows"], rtol=1e-5, atol=2e-6)
+
+
+def test_fast_adjacency_builder_equals_the_scipy_one():
+    """bench.py's CPU arm builds the 100M-edge adjacency with norm_adjacency_from_csr: bit-identical to norm_adjacency"""
+    from b200rec import synth
+    for g in (synth.generate(300, 500, 6000, seed=7), synth.generate_named("c1", seed=0)):
+        ptr, idx = g.train_indptr.numpy(), g.train_items.numpy()
+        users, items = rp.pairs_from_csr(ptr, idx)
+        a = rp.norm_adjacency(g.n_users, g.n_items, users, items)
+        b = rp.norm_adjacency_from_csr(g.n_users, g.n_items, ptr, idx)
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+        assert a.data.dtype == b.data.dtype == np.float32 and np.array_equal(a.data, b.data)
