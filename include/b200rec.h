@@ -87,6 +87,7 @@ typedef struct {
   const void* records;       /* [n_records] 8-byte records, pass-major */
   const int32_t* win_start;  /* [n_windows+1] record offset of every window */
   const int32_t* pass_win_ptr; /* HOST [n_passes+1]: windows [pass_win_ptr[b], pass_win_ptr[b+1]) form pass b */
+  int32_t* win_counter;      /* [n_passes] device scratch: the passes' "next window" counters (zeroed by every call) */
 } b200rec_csr;
 
 /* COO -> coalesced int32 CSR on the device (utils.py:42-50 generate_daj_mat: scipy COO->CSR sums duplicates;

@@ -30,7 +30,7 @@ class CsrStruct(C.Structure):
         ("n_slots", C.c_int32), ("slot_long", C.c_void_p),
         ("partial", C.c_void_p),
         ("n_passes", C.c_int32), ("pass_ptr", C.c_void_p),
-        ("records", C.c_void_p), ("win_start", C.c_void_p), ("pass_win_ptr", C.c_void_p),
+        ("records", C.c_void_p), ("win_start", C.c_void_p), ("pass_win_ptr", C.c_void_p), ("win_counter", C.c_void_p),
     ]
 
 

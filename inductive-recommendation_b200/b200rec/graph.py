@@ -36,26 +36,30 @@ def auto_chunk(nnz, d=None):
 
 def blocking_policy(n_cols, d):
     """(sweep width, source rows per block) for a gathered table [n_cols, d] fp32, or None when the table is left to the
-    cache as it is.  A table much larger than L2 (C4: 3M x 128 x 4 B = 1.5 GB against 126 MB) is gathered at ~24 % L2 hit
-    rate and the SpMM moves ~16x its algorithmic bytes over HBM; cutting the source rows into L2-sized blocks (one pass
-    each, b200rec_spmm_f32_blocked) turns those gathers into L2 hits.  Wide tables can be swept in column slices of
-    `sweep` floats (fewer passes per slice, one more read of the 8 B/edge index stream).
+    cache as it is -- the default.
 
-    Measured on C4 (profiles/r02_spmm_block_sweep.txt, ms per layer): D=128 single pass 11.9; blocked 96 MB x 32-column
-    sweeps 12.5, 64 MB x 64 13.8-15.6, 48 MB x 128 27.7 -- every pass cuts rows into ~6-edge items and the gathered bytes
-    still cross the L2 fabric at ~8-9 TB/s, which is where the single-pass kernel already is (104 GB in 11.9 ms), so the
-    HBM saving buys nothing at 512 B rows.  D=16 (the 8-GPU shard of C4): 1.94 single pass, 1.76 with 64 MB blocks --
-    eight items per warp hide the per-item latency.  Default therefore: block only tables of rows <= 64 B that exceed
-    1.5 blocks.  Overrides for experiments: B200REC_BLOCK_MB (0 = never block), B200REC_BLOCK_MAX_D, B200REC_SWEEP_D."""
+    A table much larger than L2 (C4: 3M x 128 x 4 B = 1.5 GB against 126 MB) is gathered at ~24 % L2 hit rate and the
+    single-pass SpMM moves ~16x its algorithmic bytes over HBM.  Cutting the source rows into L2-sized blocks (one pass
+    each, b200rec_spmm_f32_blocked; wide tables optionally swept in column slices of `sweep` floats) turns those gathers
+    into L2 hits -- random 512 B rows come out of a <= 80 MB table at 17.5 TB/s against 7.5 TB/s out of 1.5 GB
+    (profiles/r02_l2_gather_ceiling.txt) -- but every pass cuts the rows into ~5-edge segments, and three builds of the
+    blocked kernel (profiles/r02_spmm_block_sweep.txt) all lost to the single-pass kernel on C4, ms per layer:
+        D=128  single pass 11.1-11.9 | one work item per segment 12.5-34 | record stream, static windows 22.8-24.2 |
+               record stream, dynamic windows + DRAM-row prefetch 17.9-19.7
+        D=16   single pass 1.86      | one work item per segment 1.76    | record stream 8.8 -> 3.6
+    The single-pass kernel already runs at the HBM ceiling (81 % of peak DRAM throughput, and FASTER than a pure random
+    gather of the same footprint thanks to the power-law reuse), so the blocked form has to beat it on issue slots and
+    latency as well, and with one carried-sum round trip per ~5 edges it does not.  Blocking therefore stays opt-in
+    (B200REC_BLOCK_MB=<MB per block>, B200REC_BLOCK_MAX_D, B200REC_SWEEP_D) for experiments and is exercised by the tests."""
     import os
-    block_mb = float(os.environ.get("B200REC_BLOCK_MB", "64"))
+    block_mb = float(os.environ.get("B200REC_BLOCK_MB", "0"))
     if block_mb <= 0:
         return None
     sweep = int(os.environ.get("B200REC_SWEEP_D", "0")) or d
     sweep = min(d, max(8, sweep))
     if d % sweep:
         sweep = d
-    if sweep > int(os.environ.get("B200REC_BLOCK_MAX_D", "16")):
+    if sweep > int(os.environ.get("B200REC_BLOCK_MAX_D", "256")):
         return None
     block_bytes = block_mb * (1 << 20)
     if n_cols * sweep * 4 <= 1.5 * block_bytes:
@@ -79,7 +83,7 @@ class CsrOperand:
         self.col_bounds = None if col_bounds is None else np.ascontiguousarray(col_bounds, dtype=np.int32)
         # a column-blocked operand (col_bounds) is executed from its record stream: its plan is built in row order
         self.row_order = int(col_bounds is not None) if row_order is None else int(row_order)
-        self.records = self.win_start = self.pass_win_ptr = None
+        self.records = self.win_start = self.pass_win_ptr = self.win_counter = None
         self._build_plan(max_d)
         if self.col_bounds is not None and self.vals is not None and self.row_order:
             import os
@@ -133,6 +137,7 @@ class CsrOperand:
             self.pass_win_ptr = np.zeros(self.n_passes + 1, dtype=np.int32)
             _abi.check(lib.b200rec_stream_build(*args, _abi.ptr(self.records), _abi.ptr(self.win_start),
                                                 C.c_void_p(self.pass_win_ptr.ctypes.data), _abi.stream_ptr()), "stream_build")
+        self.win_counter = torch.zeros(self.n_passes, dtype=torch.int32, device=dev)
         self.n_records, self.n_windows, self.window = n_rec.value, n_win.value, window
 
     def drop_items(self):
@@ -162,6 +167,7 @@ class CsrOperand:
             s.records = p(self.records)
             s.win_start = p(self.win_start)
             s.pass_win_ptr = self.pass_win_ptr.ctypes.data if self.pass_win_ptr is not None else None
+            s.win_counter = p(self.win_counter)
             self._struct = s
         return self._struct
 

@@ -36,6 +36,7 @@ struct StreamParams {
   const int2* rec;
   const int32_t* win_start;  // [n_windows_total + 1] record offsets; window w = [win_start[w], win_start[w+1])
   int win_base, n_windows;   // this launch = windows [win_base, win_base + n_windows) (one pass)
+  int32_t* win_counter;      // this pass's "next window" counter (zero at launch)
   const float* x;
   float* y;
   const float* addend;
@@ -69,7 +70,7 @@ __device__ __forceinline__ void stream_epilogue(const StreamParams& p, int row, 
 
 // the last piece of a hub row: add the row's pieces in slot order (same order as the single-pass kernel) and finish it
 template <int G, int VPL>
-__device__ __noinline__ void stream_finish_hub(const StreamParams& p, int slot, int gl, float4 (&acc)[VPL]) {
+__device__ __forceinline__ void stream_finish_hub(const StreamParams& p, int slot, int gl, float4 (&acc)[VPL]) {
   constexpr int D = G * VPL * 4;
 #pragma unroll
   for (int t = 0; t < VPL; ++t) __stcg(reinterpret_cast<float4*>(p.partial + (size_t)slot * D + (size_t)(gl + t * G) * 4), acc[t]);
@@ -98,79 +99,116 @@ __device__ __noinline__ void stream_finish_hub(const StreamParams& p, int slot, 
   stream_epilogue<G, VPL>(p, __ldg(p.long_row + li), gl, tot);
 }
 
-// an end record: park the running sum for a later pass, or finish the row / hub piece.  Out of line: the record loop is
-// unrolled 8x and this body (stores, epilogue loads, the hub hand-over) would be replicated in every slot.
+// finishing a row or a hub piece (once per row per layer; parks are handled inline).  Out of line: the record loop is
+// unrolled 8x and this body (epilogue loads and stores, the hub hand-over) would be replicated in every slot -- the first
+// build of this kernel was > 64 KB of SASS and ran at a quarter of the single-pass kernel's speed out of the
+// instruction cache.  `p` is a __grid_constant__ kernel parameter, so passing it by reference costs no local copy.
 template <int G, int VPL>
-__device__ __forceinline__ void stream_end_record(const StreamParams& p, unsigned code, int gl, float4 (&acc)[VPL]) {
-  constexpr int D = G * VPL * 4;
+__device__ __noinline__ void stream_finish(const StreamParams& p, unsigned code, int gl, float4 a0, float4 a1) {
+  float4 acc[VPL];
+  acc[0] = a0;
+  if (VPL > 1) acc[VPL - 1] = a1;
   const int id = (int)(code & REC_ID_MASK);
-  const bool hub = (code & (1u << 29)) != 0u;
-  if ((code >> 30) == REC_PARK) {  // the row (or hub piece) continues in a later pass
-    float* dst = (hub ? p.partial + (size_t)id * D : p.carry + (size_t)id * (size_t)p.ld) + (size_t)gl * 4;
-#pragma unroll
-    for (int t = 0; t < VPL; ++t) st_cs_f4(dst + t * G * 4, acc[t]);
-  } else if (!hub) {
-    stream_epilogue<G, VPL>(p, id, gl, acc);
-  } else {
-    stream_finish_hub<G, VPL>(p, id, gl, acc);
-  }
+  if (!(code & (1u << 29))) stream_epilogue<G, VPL>(p, id, gl, acc);
+  else stream_finish_hub<G, VPL>(p, id, gl, acc);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// Persistent grid; lane groups take windows from a per-pass counter (a warp's groups finish their windows at different
+// times -- a window holds whole segments, so one long segment makes it several times the nominal size -- and a static
+// assignment left the other groups of the warp idle).  While a block of records is being folded in, the next block is
+// already staged in registers, and the rows it will need from DRAM rather than from the L2-resident source block -- the
+// carried sums of segments that continue a row, the addend rows of segments that finish one -- are prefetched into L2, so
+// that a batch of eight gathers is never held up by one DRAM round trip.
 template <int G, int VPL>
-__global__ void __launch_bounds__(256, (VPL == 1) ? B200REC_STREAM_BLOCKS : 2) spmm_stream_kernel(const StreamParams p) {
+__global__ void __launch_bounds__(256, (VPL == 1) ? B200REC_STREAM_BLOCKS : 2) spmm_stream_kernel(const __grid_constant__ StreamParams p) {
   constexpr int D = G * VPL * 4;
   constexpr int U = 8;                      // rows in flight per lane
   constexpr int EB = (G >= 16) ? G : 16;    // records staged per group per block
   constexpr int EPL = EB / G;
   constexpr int CVS = (G == 32) ? EB : EB + 1;
+  constexpr int LINES = (D * 4 + 127) / 128;  // 128-byte lines per row
   __shared__ int2 s_rec[(256 / G) * CVS];
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
-  const int group = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G);
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   int2* my = s_rec + (threadIdx.x / G) * CVS;
-  int r0 = 0, r1 = 0;
-  if (group < p.n_windows) {
-    r0 = __ldg(p.win_start + p.win_base + group);
-    r1 = __ldg(p.win_start + p.win_base + group + 1);
-  }
-  int len = r1 - r0, maxlen = len;
-  if (G < 32) {
-#pragma unroll
-    for (int o = G; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-  }
-  // the record stream is static: the first block is fetched while the previous pass drains (PDL)
+  const size_t gl4 = (size_t)gl * 4;
+  const unsigned ld = (unsigned)p.ld;
+  const float* xb = p.x + gl4;
+  float* cb = p.carry + gl4;
+  float* pb = p.partial + gl4;
+  int w_pos = 0, w_end = 0;   // records of the current window not staged yet
+  bool more = true;           // the counter has not run out
   int2 nxt[EPL];
+  int nxt_cnt = 0;
+
+  auto take_window = [&]() {  // next window of this pass (possibly empty); group-uniform
+    int w = 0;
+    if (gl == 0) w = atomicAdd(p.win_counter, 1);
+    w = __shfl_sync(gmask, w, 0, G);
+    if (w < p.n_windows) {
+      w_pos = __ldg(p.win_start + p.win_base + w);
+      w_end = __ldg(p.win_start + p.win_base + w + 1);
+    } else {
+      more = false;
+      w_pos = w_end = 0;
+    }
+  };
+  auto stage_next = [&]() {   // records [w_pos, w_pos + nxt_cnt) -> registers; DRAM-side rows they name -> L2
+    nxt_cnt = min(EB, w_end - w_pos);
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) {
-    const int k = e * G + gl;
-    nxt[e] = (k < len) ? __ldcs(p.rec + r0 + k) : make_int2(0, 0);
-  }
+    for (int e = 0; e < EPL; ++e) {
+      const int k = e * G + gl;
+      nxt[e] = (k < nxt_cnt) ? __ldcs(p.rec + w_pos + k) : make_int2(0, 0);  // padding: a gather of row 0, never folded in
+    }
+    w_pos += nxt_cnt;
+  };
+  auto prefetch_staged = [&]() {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const unsigned code = (unsigned)nxt[e].x;
+      const unsigned type = code >> 30, id = code & REC_ID_MASK;
+      if (type == REC_CARRY) {
+        const float* r = (code & (1u << 29)) ? p.partial + (size_t)id * D : p.carry + (size_t)(id * ld);
+#pragma unroll
+        for (int q = 0; q < LINES; ++q) prefetch_l2(r + q * 32);
+      } else if (type == REC_FINISH && p.addend && !(code & (1u << 29))) {
+        const float* r = p.addend + (size_t)(id * ld);
+#pragma unroll
+        for (int q = 0; q < LINES; ++q) prefetch_l2(r + q * 32);
+      }
+    }
+  };
+
+  // the record stream, the windows and the counter are static / owned by this launch: fetched while the previous pass drains
+  take_window();
+  stage_next();
   pdl_trigger();
   pdl_wait();
+  prefetch_staged();  // carried sums are the previous pass's output
   float4 acc[VPL];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const size_t gl4 = (size_t)gl * 4;
-  const unsigned ld = (unsigned)p.ld;
 
-  for (int base = 0; base < maxlen; base += EB) {
+  for (;;) {
+    const int cnt = nxt_cnt;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) my[e * G + gl] = nxt[e];
-    // next block's records are requested before this block's gathers: two registers per staged record
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      const int k = base + EB + e * G + gl;
-      nxt[e] = (k < len) ? __ldcs(p.rec + r0 + k) : make_int2(0, 0);  // padding: a gather of row 0 with weight 0
-    }
-    const int cnt = min(EB, max(len - base, 0));
+    if (w_pos >= w_end && more) take_window();
+    stage_next();
+    prefetch_staged();
     int cntmax = cnt;
+    bool any_more = more || nxt_cnt > 0;
     if (G < 32) {
 #pragma unroll
       for (int o = G; o < 32; o <<= 1) cntmax = max(cntmax, __shfl_xor_sync(0xffffffffu, cntmax, o));
     }
+    any_more = __any_sync(0xffffffffu, any_more);
     __syncwarp();
-#pragma unroll
-    for (int j0 = 0; j0 < EB; j0 += U) {
+#pragma unroll 1
+    for (int j0 = 0; j0 < EB; j0 += U) {  // not unrolled: code size (see stream_finish)
       if (j0 >= cntmax) break;  // warp-uniform
       float4 xv[U][VPL];
 #pragma unroll
@@ -178,11 +216,10 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? B200REC_STREAM_BLOCKS : 2) s
         const unsigned code = (unsigned)my[j0 + u].x;  // broadcast LDS
         const unsigned type = code >> 30, id = code & REC_ID_MASK;
         if (type <= REC_CARRY) {
-          const float* r;
-          if (type == REC_GATHER) r = p.x + (size_t)(id * ld);
-          else r = (code & (1u << 29)) ? p.partial + (size_t)id * D : p.carry + (size_t)(id * ld);
+          const float* r = xb + (size_t)(id * ld);
+          if (type == REC_CARRY) r = (code & (1u << 29)) ? pb + (size_t)id * D : cb + (size_t)(id * ld);
 #pragma unroll
-          for (int t = 0; t < VPL; ++t) xv[u][t] = ldc_f4(r + gl4 + t * G * 4);
+          for (int t = 0; t < VPL; ++t) xv[u][t] = ldc_f4(r + t * G * 4);
         }
       }
 #pragma unroll
@@ -201,13 +238,21 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? B200REC_STREAM_BLOCKS : 2) s
             acc[t].w = fmaf(w, xv[u][t].w, acc[t].w);
           }
         } else {
-          stream_end_record<G, VPL>(p, code, gl, acc);
+          if (type == REC_PARK) {  // the row (or hub piece) continues in a later pass: park the running sum
+            const unsigned id = code & REC_ID_MASK;
+            float* dst = (code & (1u << 29)) ? pb + (size_t)id * D : cb + (size_t)(id * ld);
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) st_cs_f4(dst + t * G * 4, acc[t]);
+          } else {
+            stream_finish<G, VPL>(p, code, gl, acc[0], acc[VPL - 1]);
+          }
 #pragma unroll
           for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
     __syncwarp();  // slots are rewritten by the next block
+    if (!any_more) break;
   }
 }
 
@@ -260,11 +305,17 @@ __global__ void stream_windows_kernel(const int32_t* rec_off, int item_lo, int i
 template <int G, int VPL>
 static int launch_stream(const b200rec_csr* a, StreamParams p, cudaStream_t st) {
   const int groups_per_block = 256 / G;
+  int dev = 0, sms = 148;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int resident = sms * ((VPL == 1) ? B200REC_STREAM_BLOCKS : 2);  // persistent grid: one wave
+  B2_CUDA(cudaMemsetAsync(a->win_counter, 0, sizeof(int32_t) * (size_t)a->n_passes, st));
   for (int pass = 0; pass < a->n_passes; ++pass) {
     p.win_base = a->pass_win_ptr[pass];
     p.n_windows = a->pass_win_ptr[pass + 1] - a->pass_win_ptr[pass];
+    p.win_counter = a->win_counter + pass;
     if (p.n_windows <= 0) continue;
-    B2_LAUNCH_PDL(spmm_stream_kernel<G, VPL>, ceil_div(p.n_windows, groups_per_block), 256, 0, st, p);
+    B2_LAUNCH_PDL(spmm_stream_kernel<G, VPL>, min(resident, ceil_div(p.n_windows, groups_per_block)), 256, 0, st, p);
   }
   return 0;
 }
@@ -329,7 +380,7 @@ extern "C" int b200rec_spmm_f32_blocked(const b200rec_csr* a, const float* x, in
                                         const float* addend, float* out, float out_scale, float* carry, void* stream) {
   B2_REQUIRE(a && x && carry, "null operand");
   B2_REQUIRE(y || out, "no output");
-  B2_REQUIRE(a->n_passes >= 1 && a->records && a->win_start && a->pass_win_ptr,
+  B2_REQUIRE(a->n_passes >= 1 && a->records && a->win_start && a->pass_win_ptr && a->win_counter,
              "operand has no record stream (b200rec_plan_build with col_bounds + b200rec_stream_build)");
   B2_REQUIRE(a->n_long == 0 || (a->partial && a->long_row && a->long_slot0 && a->long_nslot && a->slot_long && a->long_cnt),
              "long-row plan missing");

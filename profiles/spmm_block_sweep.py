@@ -20,7 +20,7 @@ iters = int(arg(5, "5"))
 g = synth.generate_named(wl, device="cuda", heldout=False)
 rows = torch.repeat_interleave(torch.arange(g.n_users, device="cuda"), g.train_indptr[1:] - g.train_indptr[:-1])
 n = g.n_users + g.n_items
-os.environ["B200REC_BLOCK_MB"], os.environ["B200REC_BLOCK_MAX_D"] = "0", "256"
+os.environ["B200REC_BLOCK_MB"] = "0"
 op = graph.build_norm_adj(g.n_users, g.n_items, rows, g.train_items, "cuda")
 print("%s: n=%d nnz=%d items=%d long=%d chunk=%d" % (wl, n, op.nnz, op.n_items, op.n_long, op.chunk), flush=True)
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731

@@ -104,7 +104,7 @@ def _check_plan(op, rp, cols, chunk, bounds, row_order=False):
                 c = cols[start[k]:end[k]]
                 assert c.size == 0 or (c.min() >= bounds[b] and c.max() < bounds[b + 1])
             if row_order:
-                assert (np.diff(start[pp[b]:pp[b + 1]]) > 0).all()          # CSR order = rows ascending inside a pass
+                assert (np.diff(start[pp[b]:pp[b + 1]]) >= 0).all()         # CSR order = rows ascending inside a pass
             else:
                 assert (np.diff((end - start)[pp[b]:pp[b + 1]]) <= 0).all()   # longest first inside a pass
 
