@@ -329,6 +329,11 @@ int b200rec_rank_metrics(const int32_t* rec_ids, int32_t n_rows, int32_t k, int6
 int b200rec_hit_matrix(const int32_t* rec_ids, int32_t n_rows, int32_t k, int64_t user0,
                        const int32_t* eval_ptr, const int32_t* eval_idx, float* hit, void* stream);
 
+/* Global top-m of n candidate values (the flattened-matrix torch.topk of DOSE's similarity mining, model.py:503-560):
+ * out_idx int32 [m] = positions of the m largest values, largest first (ties: lower position first), out_vals [m]
+ * optional.  Setup-time call (once per epoch): allocates scratch, synchronises `stream`. */
+int b200rec_topk_global(const float* vals, int64_t n, int32_t m, int32_t* out_idx, float* out_vals, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Peer memory for the row-partitioned multi-GPU propagation (new: the reference has no multi-device code).
  * b200rec_peer_alloc: cudaMalloc + zero + CUDA IPC handle (HOST, 64 bytes) that the other ranks of the node open with

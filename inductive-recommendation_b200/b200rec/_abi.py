@@ -83,6 +83,7 @@ PROTOTYPES = {
     "b200rec_peer_free": (C.c_int, [_P]),
     "b200rec_peer_signal": (C.c_int, [_P, _I32, _I32, _P, _I64, _P]),
     "b200rec_peer_wait": (C.c_int, [_P, _I32, _P, _I64, _P]),
+    "b200rec_topk_global": (C.c_int, [_P, _I64, _I32, _P, _P, _P]),
     "b200rec_rank_metrics": (C.c_int, [_P, _I32, _I32, _I64, _P, _P, _P, _I32, _P, _P]),
     "b200rec_hit_matrix": (C.c_int, [_P, _I32, _I32, _I64, _P, _P, _P, _P]),
 }

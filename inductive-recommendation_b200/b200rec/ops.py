@@ -257,6 +257,18 @@ def score_topk(rep_users, users, rep_items, k, excl_a=None, excl_b=None, banned=
     return ids, sc
 
 
+def topk_global(vals, m):
+    """(positions int64 [m], values [m]) of the m largest entries of a 1-D fp32 tensor, largest first, ties by position"""
+    vals = vals.contiguous()
+    _abi.require_cuda(vals)
+    assert vals.dtype == torch.float32 and vals.dim() == 1 and 0 < m <= vals.numel()
+    idx = torch.empty(m, dtype=torch.int32, device=vals.device)
+    out = torch.empty(m, dtype=torch.float32, device=vals.device)
+    with torch.cuda.device(vals.device):
+        check(_lib().b200rec_topk_global(ptr(vals), vals.numel(), m, ptr(idx), ptr(out), stream_ptr()), "topk_global")
+    return idx.long(), out
+
+
 def rank_metrics(rec_ids, user0, eval_ptr, eval_idx, topks):
     """(precision, recall, ndcg) sums per cut-off and the number of users with eval items: float64 [3*len(topks)+1] on
     device.  topks ascending, each <= rec_ids.shape[1]."""

@@ -363,3 +363,44 @@ extern "C" int b200rec_plan_build(const int32_t* rowptr, const int32_t* colidx, 
   if (n_blocks <= 1) { pass_ptr[0] = 0; pass_ptr[1] = n_items; }  // one launch; rows >= order_split are merely scheduled last
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------- global top-m
+// The global cut of DOSE's similarity mining (model.py:503-560: the flattened U x I cosine matrix goes through
+// torch.topk(aug_num)): the m largest of n candidate values with their positions, largest first.  A descending radix sort
+// on order-preserving keys (setup-time: once per epoch; n = U x 128 candidates from the per-row pass).
+namespace b200rec {
+__global__ void topk_keys_kernel(const float* __restrict__ vals, int64_t n, uint32_t* keys, int32_t* idx) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t b = __float_as_uint(vals[i]);
+  keys[i] = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // unsigned order == float order (NaN sorts above +inf)
+  idx[i] = (int32_t)i;
+}
+__global__ void topk_take_kernel(const int32_t* sorted_idx, const float* vals, int m, int32_t* out_idx, float* out_vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int j = sorted_idx[i];
+  out_idx[i] = j;
+  if (out_vals) out_vals[i] = vals[j];
+}
+}  // namespace b200rec
+
+extern "C" int b200rec_topk_global(const float* vals, int64_t n, int32_t m, int32_t* out_idx, float* out_vals, void* stream) {
+  B2_REQUIRE(vals && out_idx && n > 0 && n < (1ll << 31) && m > 0 && m <= n, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch sc;
+  uint32_t *k0 = nullptr, *k1 = nullptr;
+  int32_t *i0 = nullptr, *i1 = nullptr;
+  B2_CUDA(sc.get(&k0, n)); B2_CUDA(sc.get(&k1, n)); B2_CUDA(sc.get(&i0, n)); B2_CUDA(sc.get(&i1, n));
+  topk_keys_kernel<<<ceil_div(n, 256), 256, 0, st>>>(vals, n, k0, i0);
+  B2_LAUNCHED();
+  size_t tb = 0;
+  B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, k0, k1, i0, i1, (int)n, 0, 32, st));
+  uint8_t* tmp = nullptr;
+  B2_CUDA(sc.get(&tmp, tb));
+  B2_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, k0, k1, i0, i1, (int)n, 0, 32, st));  // stable: ties keep position order
+  topk_take_kernel<<<ceil_div(m, 256), 256, 0, st>>>(i1, vals, m, out_idx, out_vals);
+  B2_LAUNCHED();
+  B2_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -364,3 +364,93 @@ class IMF(IGCN):
 
     def get_rep(self):
         return self._cached_rep(self.layer0)
+
+
+class DOSE_aug(IGCN):
+    """IGCN + a contrast between its representation and the one propagated on a graph EDITED by similarity mining
+    (reference model.py:367-613, trainer DOSEaugTrainer trainer.py:255-303): `cal_cos_sim` picks the `aug_num`
+    (user, item) pairs with the LOWEST cosine similarity (the item vectors are negated before the top-k, :507) and
+    `generate_aug_graph` adds them to the train graph (utils.py:71-89: set union, so every entry stays 1).  bpr_forward
+    returns the reference's 5-tuple; the contrastive term is InfoNCE (temperature 0.1: `taugh` is never passed on) between
+    the batch users' rows of the two representations, each built from its OWN edge-dropout draw of the feature matrix
+    (get_def_rep and get_aug_rep both call dropout_sp_mat, :472, :487).
+
+    Mining runs on the evaluation kernels (b200rec.mining.lowest_cosine_pairs: per-row top-128 on L2-normalised rows +
+    b200rec_topk_global) instead of a dense U x I sklearn matrix on the host.  Reference defects, kept or stated:
+      * the second half of the mined pairs is mapped to (user, item) with the wrong offset (:537-540); config key
+        `mining_offsets`: 'reference' (default, same pairs as the reference) | 'fixed';
+      * `DOSE_aug.update_aug_adj` calls `self.generate_drop_graph`, which the class does not define (:571-575), so the
+        reference raises AttributeError at the end of the first epoch; here it re-mines and rebuilds the augmented
+        graph (what the commented-out line in DOSEaugTrainer, trainer.py:301, intended).
+    `cal_cos_sim` returns an int64 [m, 2] device tensor (`.tolist()` gives the reference's list of [user, item])."""
+    edit = 'add'
+
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.taugh = model_config.get('taugh', 0.2)
+        self.aug_num = int(model_config['aug_num'])
+        self.times = model_config.get('times', 0.1)
+        self.temperature = 0.1
+        self.mining_offsets = model_config.get('mining_offsets', 'reference')
+        self.mining_precision = model_config.get('mining_precision', 0)
+        self.aug_version = 0
+        self.norm_aug_adj = self._edited_graph(model_config['dataset'])
+
+    _train_pairs_dev = SGL._train_pairs_dev
+
+    def get_def_rep(self):
+        return self.get_rep()
+
+    def get_aug_rep(self, norm_aug_adj):
+        return ops.propagate(norm_aug_adj, self.layer0(), self.n_layers)
+
+    def cal_cos_sim(self):
+        from b200rec import mining
+        with torch.no_grad():
+            rep = self.get_def_rep()
+            return mining.lowest_cosine_pairs(rep[:self.n_users], rep[self.n_users:], self.aug_num,
+                                              reference_offsets=self.mining_offsets == 'reference',
+                                              precision=self.mining_precision)
+
+    cal_cos_sim_v2 = cal_cos_sim
+
+    def _edited_graph(self, dataset, aug_idx=None):
+        """train graph with the mined pairs added ('add': utils.py:71-89) or removed ('drop': utils.py:126-141), as a
+        normalised adjacency with degrees recomputed on the edited graph (model.py:411-422)"""
+        pairs = self.cal_cos_sim() if aug_idx is None else torch.as_tensor(np.asarray(aug_idx), dtype=torch.int64)
+        pairs = pairs.to(self.device).reshape(-1, 2)
+        users, items = self._train_pairs_dev(dataset)
+        n_items = dataset.n_items
+        train_keys = users * n_items + items
+        mined_keys = pairs[:, 0] * n_items + pairs[:, 1]
+        if self.edit == 'add':
+            keys = torch.unique(torch.cat([train_keys, mined_keys]))
+        else:
+            keys = train_keys[~torch.isin(train_keys, mined_keys)]
+        return b2graph.build_norm_adj(dataset.n_users, dataset.n_items, torch.div(keys, n_items, rounding_mode='floor'),
+                                      keys % n_items, device=self.device, d=self.embedding_size)
+
+    def generate_aug_graph(self, dataset, aug_idx=None):
+        return self._edited_graph(dataset, aug_idx)
+
+    def cal_loss(self, users_r, aug_users_r):
+        return ops.infonce(users_r, aug_users_r, self.temperature)
+
+    def bpr_forward(self, users, pos_items, neg_items):
+        users_r, pos_items_r, neg_items_r, l2_norm_sq = super().bpr_forward(users, pos_items, neg_items)
+        aug_users_r = ops.gather_rows(self.get_aug_rep(self.norm_aug_adj), users)
+        return users_r, pos_items_r, neg_items_r, l2_norm_sq, self.cal_loss(users_r, aug_users_r)
+
+    def update_aug_adj(self):
+        self.norm_aug_adj = self._edited_graph(self.config['dataset'])
+        self.aug_version += 1
+
+
+class DOSE_drop3(DOSE_aug):
+    """The same model with the mined pairs REMOVED from the train graph where they are train edges (reference
+    model.py:2544-2863, `generate_drop_graph` -> utils.generate_drop_daj_mat3; trainer DOSEdropTrainer trainer.py:304-353)."""
+    edit = 'drop'
+
+    def generate_drop_graph(self, dataset, aug_idx=None):
+        return self._edited_graph(dataset, aug_idx)
+

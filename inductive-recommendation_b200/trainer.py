@@ -460,3 +460,40 @@ class SGLTrainer(BPRTrainer):
 
 class HALFTrainer(SGLTrainer):
     """one augmented view against the full graph (reference trainer.py:460-486)"""
+
+
+class DOSEaugTrainer(IGCNTrainer):
+    """IGCNTrainer + contrastive_reg * InfoNCE between the model's two views (reference trainer.py:255-303): the loop of
+    trainer.py:269-293, then feat_mat_anneal() and update_aug_adj() (re-mine, rebuild the edited graph) at the epoch end.
+    Runs through the library's autograd Functions (propagation, inductive layer, row gathers, InfoNCE are libb200rec
+    kernels with hand-written backwards); the CUDA-graphed engine does not carry this model's two dropout draws per step."""
+
+    def __init__(self, trainer_config):
+        super().__init__(trainer_config)
+        self.contrastive_reg = trainer_config['contrastive_reg']
+        self.fused = False
+
+    def _loss(self, inputs, aux_inputs):
+        users, pos_items, neg_items = inputs[:, 0].contiguous(), inputs[:, 1].contiguous(), inputs[:, 2].contiguous()
+        users_r, pos_items_r, neg_items_r, l2_norm_sq, contrastive_loss = self.model.bpr_forward(users, pos_items, neg_items)
+        pos_scores = torch.sum(users_r * pos_items_r, dim=1)
+        neg_scores = torch.sum(users_r * neg_items_r, dim=1)
+        bpr_loss = F.softplus(neg_scores - pos_scores).mean()
+        m = self.model
+        a_users, a_pos, a_neg = aux_inputs[:, 0].contiguous(), aux_inputs[:, 1].contiguous(), aux_inputs[:, 2].contiguous()
+        tu = len(m.user_map)
+        e_u = ops.gather_rows(m.embedding.weight, a_users)
+        e_p = ops.gather_rows(m.embedding.weight, a_pos, tu)
+        e_n = ops.gather_rows(m.embedding.weight, a_neg, tu)
+        aux_loss = F.softplus(torch.sum(e_u * e_n * m.w[None, :], dim=1) - torch.sum(e_u * e_p * m.w[None, :], dim=1)).mean()
+        return bpr_loss + self.l2_reg * l2_norm_sq.mean() + self.aux_reg * aux_loss + self.contrastive_reg * contrastive_loss.mean()
+
+    def train_one_epoch(self):
+        loss = super().train_one_epoch()  # the autograd loop + feat_mat_anneal()
+        self.model.update_aug_adj()
+        return loss
+
+
+class DOSEdropTrainer(DOSEaugTrainer):
+    """reference trainer.py:304-353 (the same loop; the model's update_aug_adj rebuilds the dropped graph)"""
+

@@ -387,9 +387,97 @@ def run_baseline_case(tag, shape, out_dir, n_rows_kept=2048, n_users_kept=1024, 
     print("   recall@20 test", out["metric_Recall_test"][-1], "ndcg@20", out["metric_NDCG_test"][-1], "loss", out["loss"])
 
 
+def run_dose_case(tag, graph, model_name, trainer_name, out_dir, aug_num=2000, seed=2021, batch=256):
+    """DOSE_aug (model.py:367-613) / DOSE_drop3 (:2544-2863) with DOSEaugTrainer / DOSEdropTrainer (trainer.py:255-353):
+    IGCN + a second propagation on a graph edited by similarity mining (cal_cos_sim: the aug_num (user, item) pairs with
+    the LOWEST cosine similarity are added to / removed from the train graph) + InfoNCE between the two views' user rows.
+    Recorded: the mined pairs, the edited adjacency, one training step (two dropout draws: one per view) and the
+    eval-mode representation."""
+    tmp = tempfile.mkdtemp()
+    synth.write_processed(graph, tmp)
+    ds = quiet(ref_dataset.get_dataset, {"name": "ProcessedDataset", "path": tmp, "device": CPU})
+    ref_utils.set_seed(seed)
+    mcfg = {"name": model_name, "embedding_size": 64, "n_layers": 3, "dropout": 0.3, "feature_ratio": 1, "aug_num": aug_num}
+    tcfg = {"name": trainer_name, "optimizer": "Adam", "lr": 1e-3, "l2_reg": 0., "contrastive_reg": 1e-1, "aux_reg": 0.001}
+    model = quiet(ref_model.get_model, dict(mcfg, device=CPU), ds)       # mines with the initial weights (eval of __init__: training mode!)
+    tr = quiet(ref_trainer.get_trainer, dict(tcfg, device=CPU, dataloader_num_workers=0, topks=TOPKS, n_epochs=1,
+                                             batch_size=batch, test_batch_size=128), ds, model)
+    out = {"n_users": ds.n_users, "n_items": ds.n_items, "aug_num": aug_num}
+    for split in ("train", "val", "test"):
+        out[split + "_indptr"] = getattr(graph, split + "_indptr").numpy()
+        out[split + "_items"] = getattr(graph, split + "_items").numpy()
+    out["emb0"] = model.embedding.weight.detach().numpy().copy()
+    out["w0"] = model.w.detach().numpy().copy()
+    out["adj_idx"], out["adj_val"] = coo_of(model.norm_adj)
+    # mining on a known representation: eval mode (no dropout), so that the test can reproduce the input exactly
+    model.eval()
+    with torch.no_grad():
+        rep = model.get_def_rep().numpy().copy()
+    out["rep_eval"] = rep
+    with torch.no_grad():
+        pairs = np.array(quiet(model.cal_cos_sim), dtype=np.int64)          # [aug_num, 2] in the reference's order
+    out["mined_pairs"] = pairs
+    # cosine values the selection saw (sklearn float32) at the mined pairs and the two cut values, for tie-aware checks
+    from sklearn.metrics.pairwise import cosine_similarity
+    cos = cosine_similarity(rep[:ds.n_users], -rep[ds.n_users:]).astype(np.float32).reshape(-1)
+    half = cos.shape[0] // 2
+    k = aug_num // 2
+    out["cut_first"] = np.float32(np.sort(cos[:half])[-k])
+    out["cut_second"] = np.float32(np.sort(cos[half:])[-k])
+    # the edited graph built from THOSE pairs (generate_aug_graph / generate_drop_graph re-run the mining: same input, same pairs)
+    with torch.no_grad():
+        edited = model.generate_aug_graph(ds) if model_name == "DOSE_aug" else model.generate_drop_graph(ds)
+    model.norm_aug_adj = edited
+    out["aug_idx"], out["aug_val"] = coo_of(edited)
+    # ---- one training step on a recorded batch, with the two recorded dropout draws ----
+    model.train()
+    ref_utils.set_seed(seed + 1)
+    rows = [ds[0] for _ in range(batch)]
+    b = torch.tensor(np.stack(rows)[:, 0, :], dtype=torch.int64)
+    aux_ds = tr.aux_dataloader.dataset
+    ref_utils.set_seed(seed + 3)
+    ab = torch.tensor(np.stack([aux_ds[0] for _ in range(batch)])[:, 0, :], dtype=torch.int64)
+    out["batch"], out["aux_batch"] = b.numpy().copy(), ab.numpy().copy()
+    nnz = model.feat_mat._nnz()
+    torch.manual_seed(seed + 2)
+    keeps = [torch.floor((1 - model.dropout) + torch.rand(nnz)).type(torch.bool) for _ in range(2)]  # def view, then aug view
+    out["drop_keep_def"], out["drop_keep_aug"] = np.packbits(keeps[0].numpy()), np.packbits(keeps[1].numpy())
+    out["drop_nnz"], out["dropout"] = nnz, model.dropout
+    torch.manual_seed(seed + 2)
+    F = torch.nn.functional
+    users, pos, neg = b[:, 0], b[:, 1], b[:, 2]
+    ur, pr, nr, l2, con = model.bpr_forward(users, pos, neg)
+    bpr = F.softplus((ur * nr).sum(1) - (ur * pr).sum(1)).mean()
+    au, ap, an = ab[:, 0], ab[:, 1], ab[:, 2]
+    tu = len(model.user_map)
+    e_u, e_p, e_n = model.embedding(au), model.embedding(ap + tu), model.embedding(an + tu)
+    aux = F.softplus((e_u * e_n * model.w[None, :]).sum(1) - (e_u * e_p * model.w[None, :]).sum(1)).mean()
+    loss = bpr + tcfg["l2_reg"] * l2.mean() + tcfg["aux_reg"] * aux + tcfg["contrastive_reg"] * con.mean()   # trainer.py:290-291
+    out["users_r"] = ur.detach().numpy().copy()
+    out["bpr_loss"], out["aux_loss"], out["contrastive_loss"], out["loss"] = float(bpr), float(aux), float(con), float(loss)
+    tr.opt.zero_grad()
+    loss.backward()
+    out["grad_emb"] = model.embedding.weight.grad.numpy().copy()
+    out["grad_w"] = model.w.grad.numpy().copy()
+    tr.opt.step()
+    out["emb1"] = model.embedding.weight.detach().numpy().copy()
+    out["w1"] = model.w.detach().numpy().copy()
+    out["lr"], out["l2_reg"], out["aux_reg"], out["contrastive_reg"] = tcfg["lr"], tcfg["l2_reg"], tcfg["aux_reg"], tcfg["contrastive_reg"]
+    out["n_layers"] = 3
+    path = os.path.join(out_dir, tag + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "loss", out["loss"], "con", out["contrastive_loss"],
+          "edited nnz", out["aug_val"].shape[0], "vs", out["adj_val"].shape[0])
+
+
 def main():
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--only-dose" in sys.argv:
+        g = synth.generate(300, 500, 6000, seed=7)
+        run_dose_case("dose_aug_tiny", g, "DOSE_aug", "DOSEaugTrainer", out_dir)
+        run_dose_case("dose_drop3_tiny", g, "DOSE_drop3", "DOSEdropTrainer", out_dir)
+        return
     if "--only-config" in sys.argv:  # the reference's config lists (positions + hyper-parameters), device = "DEV"
         import importlib.util
         import json

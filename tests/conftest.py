@@ -61,6 +61,10 @@ MODEL_CFG = {
     "imf_tiny": {"name": "IMF", "embedding_size": 64, "n_layers": 0, "dropout": 0.3, "feature_ratio": 1.0},
     "sgl_tiny": {"name": "SGL", "embedding_size": 64, "n_layers": 3, "aug_rate": 0.8},
     "half_tiny": {"name": "HALF", "embedding_size": 64, "n_layers": 3, "aug_rate": 0.8},
+    "dose_aug_tiny": {"name": "DOSE_aug", "embedding_size": 64, "n_layers": 3, "dropout": 0.3, "feature_ratio": 1,
+                      "aug_num": 2000},
+    "dose_drop3_tiny": {"name": "DOSE_drop3", "embedding_size": 64, "n_layers": 3, "dropout": 0.3, "feature_ratio": 1,
+                        "aug_num": 2000},
 }
 
 

@@ -11,10 +11,13 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_multi_gpu_parity():
-    n = 2
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_multi_gpu_parity(n):
+    """DimShard, RowPartition (NCCL block exchange) and PeerRowPartition (exchange fused into the kernels over NVLink peer
+    memory) on n ranks: fused steps equal the reference fixtures, row partitions are bit-identical to one GPU"""
+    if torch.cuda.device_count() < n:
+        pytest.skip("needs >= %d GPUs" % n)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
-           "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "dist_gpu_check.py")]
+           "127.0.0.1", "--master-port", str(29611 + n), os.path.join(HERE, "dist_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST_GPU_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
