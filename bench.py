@@ -14,7 +14,7 @@ batches: every step copies a pinned int64 [B,3] batch host->device and reads the
 `--impl reference` times the oracle port (oracle/ref_port.py: the reference's algorithm restated on torch-CPU with
 an MKL CSR SpMM, all host threads) on the same graph (the generator is device-independent); the reference itself is
 pure Python + DGL and cannot be installed or shipped to the GPU box (no DGL wheel, /root/reference is not present
-there).  On c4 one CPU step is tens of seconds, so a reference "step" is a bounded sample of it (see cpu_port_sample).
+there).  On c4 one CPU step is ~8-30 s, so a reference "step" is a bounded sample of it (see CpuPort).
 """
 import argparse
 import json
@@ -403,8 +403,9 @@ def run_own(args, rank, world):
                         "peak_source": peak_src, "bytes_min": bytes_min, "launch_ms": spmm_ms,
                         "launches_per_layer": launches_per_layer, "launch_ms_l2_warm": spmm_ms_warm,
                         "effective_gather_gbs": bytes_gather / (spmm_ms * 1e-3) / 1e9,
-                        "effective_gather_note": "nnz*D*4 gathered bytes / t: the rate the rows come out of L2 at (the bound "
-                                                 "that actually binds: ~10 TB/s L2 fabric, see DESIGN 4.1)"}
+                        "effective_gather_note": "nnz*D*4 gathered bytes / t; a pure random gather of whole rows (no index stream, "
+                                                 "no FMA) reaches 17.5 TB/s from a table that fits L2 and 7.5 TB/s from a 1.5 GB one "
+                                                 "(profiles/r02_l2_gather_ceiling.txt, DESIGN 4.1)"}
             line.update({"metric": "bpr_epochs_per_sec", "value": value, "unit": "epochs/s", "ms_per_step": ms_per_step,
                          "ms_per_step_l2_warm": t_warm, "epochs_per_sec_l2_warm": 1e3 / (t_warm * steps_per_epoch),
                          "e2e": {"value": e2e_value, "unit": "epochs/s", "h2d_bytes_per_step": BATCH * 3 * 8,
