@@ -62,7 +62,9 @@ typedef struct {
   int32_t n_cols;            /* rows of the gathered table */
   int32_t nnz;
   const int32_t* rowptr;     /* [n_rows+1] */
-  const int32_t* colidx;     /* [nnz] ascending inside a row */
+  const int32_t* colidx;     /* [nnz] ascending inside a row; with col_hint != 0 bit 31 marks a "hot" source row */
+  int32_t col_hint;          /* 0: plain ids.  1 / 2: hot rows are gathered L2::evict_last (kept in the persisting set-aside,
+                                b200rec_l2_persist), the others with the default policy (1) or L2::evict_first (2) */
   const float* vals;         /* [nnz] per-edge value, or NULL (all ones) */
   const float* nbr_scale;    /* [n_cols] multiplies each gathered row, or NULL */
   const float* row_scale;    /* [n_rows] multiplies the finished row sum, or NULL */
@@ -120,6 +122,11 @@ int b200rec_plan_build(const int32_t* rowptr, const int32_t* colidx, int32_t n_r
                        int32_t* item_start, int32_t* item_end, int32_t* item_dst, int32_t* item_row,
                        int32_t* long_row, int32_t* long_slot0, int32_t* long_nslot, int32_t* slot_long,
                        int32_t* pass_ptr /*HOST out*/, void* stream);
+
+/* Carve `bytes` of L2 out for persisting (evict_last) lines on the current device (cudaLimitPersistingL2CacheSize, capped at
+ * the device maximum; 0 gives it back).  Without a set-aside the evict_last hints of a col_hint operand do nothing.
+ * *granted_out (HOST, optional) = the size in effect.  Device-wide setting; call once at setup. */
+int b200rec_l2_persist(int64_t bytes, int64_t* granted_out /*HOST*/);
 
 /* Symmetric-normalised adjacency values (model.py:89-98 LightGCN.generate_graph; utils.py:42-50).
  * deg[r] = max(1, sum of multiplicities in row r); dinv = deg^-1/2 (fp32, correctly rounded);

@@ -21,7 +21,7 @@ class CsrStruct(C.Structure):
     """mirror of `b200rec_csr` (include/b200rec.h)"""
     _fields_ = [
         ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int32),
-        ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("vals", C.c_void_p),
+        ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("col_hint", C.c_int32), ("vals", C.c_void_p),
         ("nbr_scale", C.c_void_p), ("row_scale", C.c_void_p), ("eid", C.c_void_p),
         ("n_items", C.c_int32),
         ("item_start", C.c_void_p), ("item_end", C.c_void_p), ("item_dst", C.c_void_p), ("item_row", C.c_void_p),
@@ -46,6 +46,7 @@ PROTOTYPES = {
     "b200rec_adj_build": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "b200rec_plan_build": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200rec_stream_build": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "b200rec_l2_persist": (C.c_int, [_I64, _P]),
     "b200rec_adj_normalize": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P]),
     "b200rec_spmm_f32": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P]),
     "b200rec_spmm_f32_ex": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P, _P, _P]),

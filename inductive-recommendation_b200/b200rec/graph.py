@@ -84,6 +84,7 @@ class CsrOperand:
         # a column-blocked operand (col_bounds) is executed from its record stream: its plan is built in row order
         self.row_order = int(col_bounds is not None) if row_order is None else int(row_order)
         self.records = self.win_start = self.pass_win_ptr = self.win_counter = None
+        self.col_hint, self.colidx_enc, self.hot_rows = 0, None, 0
         self._build_plan(max_d)
         if self.col_bounds is not None and self.vals is not None and self.row_order:
             import os
@@ -152,7 +153,9 @@ class CsrOperand:
             s = _abi.CsrStruct()
             s.n_rows, s.n_cols, s.nnz = self.n_rows, self.n_cols, self.nnz
             p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
-            s.rowptr, s.vals, s.colidx = p(self.rowptr), p(self.vals), p(self.colidx)
+            s.rowptr, s.vals = p(self.rowptr), p(self.vals)
+            s.colidx = p(self.colidx_enc if self.col_hint else self.colidx)
+            s.col_hint = self.col_hint
             s.nbr_scale, s.row_scale, s.eid = p(self.nbr_scale), p(self.row_scale), p(self.eid)
             s.n_items = self.n_items
             s.item_start, s.item_end, s.item_dst = p(self.item_start), p(self.item_end), p(self.item_dst)
@@ -195,6 +198,43 @@ class CsrOperand:
             bop.drop_items()
             self._blocked[key] = bop
         return self._blocked[key], sweep
+
+    def hinted_for(self, d):
+        """twin of this operand whose gathers carry L2 residency hints, for a gathered table [n_cols, d] larger than L2 (or
+        None): the highest-degree source rows of each side -- as many as fit the persisting L2 set-aside -- are flagged
+        hot (bit 31 of a private colidx copy) and gathered L2::evict_last; B200REC_HOT_MB sizes the hot set (0 = off),
+        B200REC_HOT_COLD = 'first' loads the other rows L2::evict_first.  Same plan, same sums, same bits."""
+        import os
+        hot_mb = float(os.environ.get("B200REC_HOT_MB", "0"))
+        if hot_mb <= 0 or self.vals is None or self.nbr_scale is not None or self.eid is not None or self.n_rows != self.n_cols \
+                or getattr(self, "_row_sliced", False):
+            return None
+        l2 = torch.cuda.get_device_properties(self.device).L2_cache_size
+        if self.n_cols * d * 4 <= l2:
+            return None
+        key = ("hint", d, hot_mb, os.environ.get("B200REC_HOT_COLD", "normal"))
+        if key not in self._blocked:
+            granted = C.c_int64(0)
+            with torch.cuda.device(self.device):
+                _abi.check(_abi.load().b200rec_l2_persist(int(hot_mb * (1 << 20)), C.byref(granted)), "l2_persist")
+            k = int(min(hot_mb * (1 << 20), granted.value) // (d * 4))
+            deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
+            hot = torch.zeros(self.n_cols, dtype=torch.bool, device=self.device)
+            split = self.phase_split if 0 < self.phase_split < self.n_cols else 0
+            for lo, hi in ([(0, self.n_cols)] if not split else [(0, split), (split, self.n_cols)]):
+                kk = min(k, hi - lo)
+                if kk > 0:
+                    hot[lo + torch.topk(deg[lo:hi], kk).indices] = True
+            o = object.__new__(CsrOperand)
+            o.__dict__.update(self.__dict__)
+            o._struct, o._blocked, o._carry = None, {}, {}
+            enc = self.colidx.clone()
+            enc[hot[self.colidx.long()]] |= -2 ** 31
+            o.colidx_enc, o.hot_rows = enc, int(hot.sum())
+            o.col_hint = 2 if key[3] == "first" else 1
+            o.persist_bytes = granted.value
+            self._blocked[key] = o
+        return self._blocked[key]
 
     def carry(self, ld):
         if ld not in self._carry:

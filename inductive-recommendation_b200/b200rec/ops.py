@@ -27,10 +27,13 @@ def spmm(op, x, keep_bits=None, post_scale=1.0, y=None, addend=None, out=None, o
     assert op.partial is None or d <= op.max_d
     if keep_bits is None and dst_flags is None and src_flags is None and op.row_scale is None:
         blk = op.blocked_for(d)
-        if blk is not None:  # table larger than L2
+        if blk is not None:  # table larger than L2, opt-in column blocking
             spmm_blocked(blk[0], x, blk[1], op.carry(d), post_scale=post_scale, y=y, addend=addend, out=out,
                          out_scale=out_scale)
             return
+        hinted = op.hinted_for(d)
+        if hinted is not None:  # table larger than L2: hot source rows kept in the persisting L2 set-aside
+            op = hinted
     if dst_flags is None and src_flags is None:
         check(_lib().b200rec_spmm_f32(C.byref(op.struct()), ptr(x), d, ptr(keep_bits), post_scale, ptr(y), ptr(addend),
                                       ptr(out), out_scale, stream_ptr()), "spmm_f32")

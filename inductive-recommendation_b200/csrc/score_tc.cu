@@ -207,6 +207,14 @@ __device__ __forceinline__ bool row_has(const int32_t* __restrict__ ptr, const i
 // at the cursor.  Total work per row is O(E) for the whole sweep.  (Measured alternatives: deferring the test to the
 // re-score kernel with a K+E cut tripled the candidate volume, 8 -> 20 ms on the C2 sweep; a hash-bitmap prefilter left
 // the heavy rows at 13 ms.)
+#ifndef B200REC_TC_ACC_STAGES
+#define B200REC_TC_ACC_STAGES 4
+#endif
+constexpr int TC_ACC = B200REC_TC_ACC_STAGES;  // accumulator stages in TMEM (x 128 columns; 4 = all 512): the MMA warp runs up
+                                               // to TC_ACC - 1 tiles ahead of the drain warps, hiding the commit -> drain ->
+                                               // release -> issue hand-over latency (2 stages in round 1: tensor pipe 40 %)
+static_assert(TC_ACC == 2 || TC_ACC == 4, "TMEM allocations are powers of two columns");
+constexpr int TC_ACC_SHIFT = (TC_ACC == 4) ? 2 : 1;
 constexpr int TC_QCAP = 64;       // records per ring (power of two); 16 rings: (quadrant, column half, row half)
 constexpr int TC_RINGS = 16;
 constexpr int TC_CONSUMERS = 8;    // consumer warp (quadrant, row half) owns 16 rows and their two rings
@@ -248,8 +256,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* afull = tempty + 2;
+  uint64_t* tempty = tfull + TC_ACC;
+  uint64_t* afull = tempty + TC_ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -278,13 +286,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
   if (threadIdx.x < TC_RINGS) { s_tail[threadIdx.x] = 0; s_head[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
+    for (int s = 0; s < TC_ACC; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
     mbar_init(afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_ACC * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -309,8 +317,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
       constexpr uint32_t idesc = umma_idesc_bf16(TC_M, BN);
       mbar_wait(afull, 0);
       for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % STAGES, as = t & 1;
-        mbar_wait(tempty + as, ((t >> 1) & 1) ^ 1);
+        const int s = t % STAGES, as = t & (TC_ACC - 1);
+        mbar_wait(tempty + as, ((t >> TC_ACC_SHIFT) & 1) ^ 1);
         mbar_wait(full + s, (t / STAGES) & 1);
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
@@ -341,11 +349,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
     int tail = 0;
     const float cu = s_cu[row];
     for (int t = 0; t < n_tiles; ++t) {
-      const int as = t & 1;
+      const int as = t & (TC_ACC - 1);
       // hit test "U_i >= cutL": approx_i >= cutL - c_u * (largest norm in this tile).  cutL is refreshed once per tile
       // (the consumer may have raised it); the tile's norm is one broadcast load
       const float cut = active ? s_cut[row] - cu * __uint_as_float(__ldg(p.tile_vmax_bits + t)) : INFINITY;
-      mbar_wait(tfull + as, (t >> 1) & 1);
+      mbar_wait(tfull + as, (t >> TC_ACC_SHIFT) & 1);
       tc_fence_after();
       const int i0 = t * BN;
       // this warp's half of the tile: all its columns go to registers with ONE wait, and the accumulator stage is handed
@@ -618,7 +626,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_ACC * BN));
   }
 }
 

@@ -48,7 +48,27 @@ struct SpmmParams {
   int n_peer;
   float* peer_y[8];
   float* peer_out[8];
+  int cold_evict_first;  // HINT variant: rows not flagged hot are loaded L2::evict_first (else with the default policy)
 };
+
+// L2 residency control for tables larger than L2 (HINT variant).  The column ids then carry a "hot" flag in bit 31
+// (b200rec.graph: the highest-degree source rows of each side, as many as fit the persisting set-aside): hot rows are
+// gathered with an L2::evict_last policy, which the hardware honours inside the set-aside carved out by
+// cudaLimitPersistingL2CacheSize (b200rec_l2_persist) -- without a set-aside the hint is a no-op, which is what round 1
+// measured.  Coherent loads (no .nc): the gathered table is the previous kernel's output.
+__device__ __forceinline__ uint64_t make_policy(int kind) {  // 0 evict_normal, 1 evict_first, 2 evict_last
+  uint64_t p;
+  if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldc_f4_policy(const float* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+  return v;
+}
 
 template <int G, int VPL>
 __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int gl, float4 (&acc)[VPL]) {
@@ -83,7 +103,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int g
 //  * edges that contribute nothing (past the row end, dropped by the edge-dropout mask, or whose source row is
 //    flagged all-zero) are squeezed out with a ballot/popc compaction before the gather loop; the slack of the last
 //    sub-block is padded with (first column of the row, weight 0), so the loop body carries no predicates or selects.
-template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID, bool HAS_SRCF>
+template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID, bool HAS_SRCF, bool HINT>
 __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(const SpmmParams p) {
   constexpr int D = G * VPL * 4;
   constexpr int U = 8;                    // neighbour rows in flight per lane
@@ -131,7 +151,9 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
 #pragma unroll
     for (int o = G; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
   }
-  const int cfirst = live ? __ldg(p.colidx + start) : 0;  // padding target: a row this sum reads anyway
+  const int cfirst = live ? __ldg(p.colidx + start) : 0;  // padding target: a row this sum reads anyway (HINT: flag bit kept)
+  uint64_t pol_hot = 0, pol_cold = 0;
+  if (HINT) { pol_hot = make_policy(2); pol_cold = make_policy(p.cold_evict_first ? 1 : 0); }
   float4 acc[VPL];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -186,9 +208,16 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
       for (int u = 0; u < U; ++u) {
         const int2 cv = my_cv[j0 + u];  // broadcast LDS.64
         vv[u] = __int_as_float(cv.y);
-        const float* r = xg + (size_t)((unsigned)cv.x * (unsigned)D);
+        if (HINT) {
+          const float* r = xg + (size_t)(((unsigned)cv.x & 0x7fffffffu) * (unsigned)D);
+          const uint64_t pol = (cv.x < 0) ? pol_hot : pol_cold;
 #pragma unroll
-        for (int t = 0; t < VPL; ++t) xv[u][t] = ldc_f4(r + t * G * 4);
+          for (int t = 0; t < VPL; ++t) xv[u][t] = ldc_f4_policy(r + t * G * 4, pol);
+        } else {
+          const float* r = xg + (size_t)((unsigned)cv.x * (unsigned)D);
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) xv[u][t] = ldc_f4(r + t * G * 4);
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -266,9 +295,16 @@ static int launch_spmm(const b200rec_csr* a, const SpmmParams& p, cudaStream_t s
     const int grid = ceil_div(p.live_items ? min(max_live, a->n_items) : a->n_items, items_per_block);
     const bool hv = p.vals != nullptr, hn = p.nbr_scale != nullptr, hm = p.keep_bits != nullptr, he = p.eid != nullptr && hm;
     const bool hs = p.src_flags != nullptr;
+    if (a->col_hint) {  // hot-row residency hints: plain valued operand only
+      if (hv && !hn && !hm && !hs) {
+        B2_LAUNCH_PDL(spmm_items_kernel<G, VPL, true, false, false, false, false, true>, grid, tpb, 0, st, p);
+        return 0;
+      }
+      return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "b200rec_spmm_f32", "col_hint operands take no masks or scales");
+    }
 #define B2_SPMM_CASE(V, N, M, E, S)                                                      \
   if (hv == V && hn == N && hm == M && he == E && hs == S) {                             \
-    B2_LAUNCH_PDL(spmm_items_kernel<G, VPL, V, N, M, E, S>, grid, tpb, 0, st, p);       \
+    B2_LAUNCH_PDL(spmm_items_kernel<G, VPL, V, N, M, E, S, false>, grid, tpb, 0, st, p); \
   } else
     B2_SPMM_CASE(true, false, false, false, false)   // normalised adjacency
     B2_SPMM_CASE(true, false, false, false, true)    // normalised adjacency, sparse source (first backward hop)
@@ -310,6 +346,7 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
     p.peer_out[q] = (q < n_peer && peer_out) ? peer_out[q] : nullptr;
   }
   p.x = x; p.y = y; p.addend = addend; p.out = out; p.out_scale = out_scale; p.post_scale = post_scale;
+  p.cold_evict_first = (a->col_hint == 2);
   p.partial = a->partial; p.slot_long = a->slot_long; p.long_row = a->long_row; p.long_slot0 = a->long_slot0;
   p.long_nslot = a->long_nslot; p.long_cnt = a->long_cnt;
   switch (d) {
@@ -372,6 +409,19 @@ __global__ void adj_vals_kernel(const int32_t* rowptr, const int32_t* colidx, co
 }  // namespace b200rec
 
 using namespace b200rec;
+
+extern "C" int b200rec_l2_persist(int64_t bytes, int64_t* granted_out) {
+  int dev = 0, max_persist = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  size_t want = bytes < 0 ? 0 : (size_t)bytes;
+  if (want > (size_t)max_persist) want = (size_t)max_persist;
+  B2_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+  size_t got = 0;
+  B2_CUDA(cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize));
+  if (granted_out) *granted_out = (int64_t)got;
+  return 0;
+}
 
 extern "C" int b200rec_adj_normalize(const int32_t* rowptr, const int32_t* colidx, const float* mult, int32_t n_rows,
                                      float* dinv, float* vals, void* stream) {
