@@ -229,3 +229,34 @@ def test_blocking_policy_and_dispatch(monkeypatch):
     monkeypatch.setenv("B200REC_BLOCK_MB", "0")
     ops.propagate_fwd(a, x, 3, bufs, m0)
     assert torch.equal(m0, m1)
+
+
+def test_l2_residency_hints_are_bit_identical(monkeypatch):
+    """a table larger than L2 with the top-degree source rows flagged hot (bit 31 of a private colidx copy, evict_last into
+    the persisting set-aside): same plan, same sums, same bits as the plain operand"""
+    import ctypes as C
+    from b200rec import _abi
+    rng = np.random.default_rng(9)
+    nu, ni, e = 200_000, 140_000, 2_000_000
+    users = torch.from_numpy(rng.integers(0, nu, e))
+    items = torch.from_numpy((rng.pareto(1.2, e) * 50).astype(np.int64) % ni)     # skewed item popularity
+    a = graph.build_norm_adj(nu, ni, users, items, device=DEV)
+    x = torch.randn(nu + ni, 128, device=DEV)
+    assert x.numel() * 4 > torch.cuda.get_device_properties(0).L2_cache_size
+    monkeypatch.setenv("B200REC_HOT_MB", "0")
+    assert a.hinted_for(128) is None
+    y0, acc0 = torch.empty_like(x), torch.ones_like(x)
+    ops.spmm(a, x, y=y0, addend=acc0, out=acc0)
+    try:
+        for cold in ("normal", "first"):
+            monkeypatch.setenv("B200REC_HOT_MB", "24")
+            monkeypatch.setenv("B200REC_HOT_COLD", cold)
+            h = a.hinted_for(128)
+            assert h is not None and h.col_hint == (2 if cold == "first" else 1) and 0 < h.hot_rows <= 2 * (24 << 20) // 512
+            assert h.persist_bytes >= 16 << 20 and bool((h.colidx_enc < 0).any())
+            y1, acc1 = torch.empty_like(x), torch.ones_like(x)
+            ops.spmm(a, x, y=y1, addend=acc1, out=acc1)
+            assert torch.equal(y0, y1) and torch.equal(acc0, acc1)
+            assert a.hinted_for(64) is None          # 87 MB table: fits L2, left alone
+    finally:
+        _abi.check(_abi.load().b200rec_l2_persist(0, C.c_void_p(0)), "l2_persist(0)")
