@@ -313,3 +313,42 @@ def test_degenerate_graph_rows_and_k_larger_than_catalogue():
     assert sorted(rec[1, :6].tolist()) == [0, 2, 3, 5, 6, 8]            # user 1's train items 1, 4, 7 are masked
     _, metrics, _ = tr.eval("test")
     assert 0.0 <= metrics["Recall"][20] <= 1.0
+
+
+def test_arbitrary_banned_items_and_nonfinite_guard(golden):
+    """trainer.eval(banned_items=<any index array>) (trainer.py:166-167) == dense scores with those columns at -inf;
+    a contiguous range takes the in-kernel path, anything else scores against the compacted item table.  A diverged model
+    (NaN in the representation) raises instead of reporting all-zero metrics."""
+    g = golden("lightgcn_tiny")
+    ds, m = golden_model(g, "lightgcn_tiny")
+    tr = _trainer(g, "lightgcn_tiny", ds, m)
+    rng = np.random.default_rng(4)
+    banned = np.unique(rng.choice(ds.n_items, size=ds.n_items // 3, replace=False))
+    assert banned.max() - banned.min() + 1 != banned.size
+    rec = _np(tr.recommend_all("test", banned_items=banned))
+    m.eval()
+    with torch.no_grad():
+        sc = _np(m.predict(torch.arange(ds.n_users, device=DEV))).astype(np.float64)
+    for which in ("train", "val"):
+        ptr, idx = (a.cpu().numpy() for a in ds.csr(which))
+        for u in range(ds.n_users):
+            sc[u, idx[ptr[u]:ptr[u + 1]]] = -np.inf
+    sc[:, banned] = -np.inf
+    order = np.argsort(-sc, axis=1, kind="stable")[:, :20]
+    vals = np.take_along_axis(sc, order, axis=1)
+    sep = np.ones_like(order, dtype=bool)
+    d = np.abs(np.diff(vals, axis=1)) > 1e-6
+    sep[:, 1:] &= d
+    sep[:, :-1] &= d
+    assert sep.mean() > 0.99 and np.array_equal(rec[sep], order[sep])
+    assert not np.isin(rec, banned).any()
+    # same metrics through eval(), and the contiguous special case agrees with the general path
+    lo, hi = 100, 260
+    r1 = _np(tr.recommend_all("test", banned_items=np.arange(lo, hi)))
+    r2 = _np(tr.recommend_all("test", banned_items=np.concatenate([np.arange(lo, hi), [lo]])[::-1]))   # duplicates, unordered
+    assert np.array_equal(r1, r2)
+    with torch.no_grad():
+        m.embedding.weight[3, 5] = float("nan")
+    m._rep_cache = None
+    with pytest.raises(FloatingPointError):
+        tr.eval("val")
