@@ -279,8 +279,11 @@ def run_own(args, rank, world):
         elif args.parallelism == "peer":
             partition = PeerRowPartition(m.norm_adj, rank, world, d)
         else:
-            shard_model_dims(m, DimShard(rank, world))
+            shard = DimShard(rank, world)
+            shard_model_dims(m, shard)
             d = m.embedding_size
+            if big and not args.no_hybrid:  # replicas of the column-shard group split the rows instead of repeating work
+                partition = shard.row_partition(m.norm_adj, d)
     trainer_name = {"igcn": "IGCNTrainer", "sgl": "SGLTrainer", "half": "HALFTrainer"}.get(args.model, "BPRTrainer")
     tr = T.get_trainer({"name": trainer_name, "contrastive_reg": 0.1, "optimizer": "Adam", "lr": LR,
                         "l2_reg": 0.0 if args.model == "igcn" else L2_REG, "aux_reg": 0.01, "device": dev,
@@ -475,7 +478,11 @@ def run_own(args, rank, world):
                           "parallelism": "single GPU" if world == 1 else (
                               ("row-partitioned graph x%d, exchange fused into the SpMM / Adam epilogues (NVLink peer stores) "
                                "+ signal/wait hand-shake" % world) if args.parallelism == "peer" else
-                              "row-partitioned graph x%d, per-layer NCCL block exchange" % world if partition is not None else
+                              "row-partitioned graph x%d, per-layer NCCL block exchange" % world if args.parallelism == "row" else
+                              ("embedding dimension sharded x%d (%d columns per GPU) x rows partitioned x%d among the GPUs that hold "
+                               "the same columns (finished rows pushed over NVLink inside the SpMM / Adam epilogues), one [B,3] "
+                               "all-reduce per step; evaluation user-sharded x%d" % (m._dim_shard.world, d, m._dim_shard.n_replicas, world))
+                              if partition is not None else
                               "embedding dimension sharded x%d (%d columns per GPU) x %d replicas, one [B,3] all-reduce per "
                               "step; evaluation user-sharded x%d" % (m._dim_shard.world, d, world // m._dim_shard.world, world))}}
         out.update(line)
@@ -496,6 +503,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-hybrid", action="store_true", help="multi-GPU: column shards only (narrow shards / identical replicas)")
     ap.add_argument("--model", default="lightgcn", choices=["lightgcn", "igcn", "mf", "sgl", "half"],
                     help="lightgcn is the headline; igcn = inductive template-feature layer + propagation (config.py:18-23)")
     ap.add_argument("--parallelism", default="dim", choices=["dim", "row", "peer"],

@@ -42,22 +42,45 @@ class DimShard:
         if self._configured:
             return self
         if self.min_cols is None:
-            small = n_rows is not None and n_rows * d * 4 <= 64 * 1024 * 1024
-            self.min_cols = 32 if small else 16
+            # 32 columns (128-byte rows) is the narrowest shard worth having on either kind of table: L2-resident ones
+            # gain nothing below it (C2: 42 us at 32 columns, 40 at 16), HBM-streamed ones gather 64-byte rows at 6.5 TB/s
+            # against 8.8 TB/s for 128-byte rows (C4, round 2) -- there the remaining factor goes to the rows
+            # (row_partition), for L2-resident tables to identical replicas
+            self.min_cols = 32
         p = 1
         while p * 2 <= self.world_size and d % (p * 2) == 0 and d // (p * 2) >= self.min_cols:
             p *= 2
         self.world = p
         self.rank = self.world_rank % p
         self.replica = self.world_rank // p
+        self.n_replicas = self.world_size // p
         self.group = self.world_group
+        self.peer_group = None  # the ranks that hold the SAME columns in the other replicas (hybrid row partition)
         if p != self.world_size:
             for rep in range(self.world_size // p):  # every rank creates every group, in the same order
                 g = dist.new_group(list(range(rep * p, (rep + 1) * p)))
                 if rep == self.replica:
                     self.group = g
+            for col in range(p):
+                g = dist.new_group(list(range(col, self.world_size, p)))
+                if col == self.rank:
+                    self.peer_group = g
         self._configured = True
         return self
+
+    def row_partition(self, adj, d, kind="peer"):
+        """Hybrid layout for tables that stream from HBM: the world is (world // P') replicas of a P'-way column shard;
+        instead of running identical replicas, the replicas that hold the same columns split the ROWS among them
+        (PeerRowPartition over `peer_group`: finished rows are pushed into the peers' tables over NVLink inside the SpMM /
+        Adam epilogues).  Why: the gather rate falls with the row width -- on C4 a 16-column shard (64-byte rows) gathers at
+        6.5 TB/s, a 32-column one at 8.8 -- so 8 GPUs as 4 column shards x 2 row halves move the same bytes per GPU faster
+        than 8 column shards, and the index scan per GPU halves.  Returns None when there is one replica."""
+        if getattr(self, "n_replicas", 1) <= 1:
+            return None
+        cls = PeerRowPartition if kind == "peer" else RowPartition
+        if cls is PeerRowPartition:
+            return PeerRowPartition(adj, self.replica, self.n_replicas, d, group=self.peer_group)
+        return RowPartition(adj, self.replica, self.n_replicas, group=self.peer_group)
 
     def cols(self, d):
         assert d % self.world == 0, "embedding_size must be divisible by the shard count"
@@ -163,9 +186,10 @@ class RowPartition:
             return
         works = []
         for p in range(self.world):
+            src = dist.get_global_rank(self.group, p) if self.group is not None else p  # partition rank -> world rank
             for lo, hi in self.blocks[p]:
                 if hi > lo:
-                    works.append(dist.broadcast(buf[lo:hi], src=p, group=self.group, async_op=True))
+                    works.append(dist.broadcast(buf[lo:hi], src=src, group=self.group, async_op=True))
         for w in works:
             w.wait()
 

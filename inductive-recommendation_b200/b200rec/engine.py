@@ -45,7 +45,7 @@ class BprEngine:
         self.shard = dim_shard if dim_shard is not None else getattr(model, '_dim_shard', None)
         if self.shard is not None and self.shard.world == 1:
             self.shard = None
-        assert not (self.shard is not None and partition is not None), 'choose one decomposition'
+        # both at once = the hybrid layout (DimShard.row_partition): column shards x row-partitioned replicas
         dev = model.device
         self.dev = dev
         D = model.embedding_size

@@ -145,6 +145,42 @@ def main():
                 assert abs(eng.last_loss() - float(g["loss"])) < 2e-6
                 np.testing.assert_allclose(m.embedding.weight.data.cpu().numpy(), g["emb1"], rtol=1e-5, atol=5e-6)
                 log('peer', name, 'engine step ok, graph =', use_graph)
+    # ---- hybrid: column shards x row-partitioned replicas (bench.py's layout on 8 GPUs: 4 x 32 columns x 2 row halves) ----
+    if world >= 4 and world % 2 == 0 and os.environ.get("B200REC_SKIP_PEER", "0") != "1":
+        for name in ("lightgcn_d128", "lightgcn_tiny"):
+            g = load_golden(name)
+            ds, m = golden_model(g, name, device=dev)
+            d_full = m.embedding_size
+            shard = DimShard(rank, world, min_cols=d_full // (world // 2))
+            shard_model_dims(m, shard)
+            assert shard.world == world // 2 and shard.n_replicas == 2 and m.embedding_size == d_full // shard.world
+            part = shard.row_partition(m.norm_adj, m.embedding_size)
+            assert part is not None and part.world == 2 and part.rank == rank // shard.world
+            log('hybrid', name, 'tables mapped')
+            tr = trainer_for(g, name, ds, m, partition=part)
+            rec = tr.recommend_all("test").cpu().numpy()
+            ref_ids, ref_val = g["topk_ids_test"], g["topk_val_test"]
+            sep = np.ones_like(ref_ids, dtype=bool)
+            dd = np.abs(np.diff(ref_val, axis=1)) > 1e-6
+            sep[:, 1:] &= dd
+            sep[:, :-1] &= dd
+            assert np.array_equal(rec[sep], ref_ids[sep]), name
+            m.train()
+            eng = tr._engine()
+            engines.append(eng)
+            lo, hi = shard.cols(d_full)
+            for use_graph in (False, True):
+                with torch.no_grad():
+                    m.embedding.weight.data.copy_(torch.from_numpy(g["emb0"][:, lo:hi]).to(dev))
+                    eng.m.zero_(); eng.v.zero_(); eng.adam_step.zero_(); eng.loss_accum.zero_()
+                torch.cuda.synchronize(); dist.barrier()
+                eng.use_graph = use_graph
+                eng.step(host_batch=torch.from_numpy(g["batch"]).pin_memory())
+                torch.cuda.synchronize()
+                assert abs(eng.last_loss() - float(g["loss"])) < 2e-6, (name, eng.last_loss(), float(g["loss"]))
+                full = shard.gather_cols(m.embedding.weight.data).cpu().numpy()
+                np.testing.assert_allclose(full, g["emb1"], rtol=1e-5, atol=5e-6, err_msg=name)
+                log('hybrid', name, 'engine step ok, graph =', use_graph)
     dist.barrier()
     for e in engines:
         e.close()

@@ -43,13 +43,12 @@ def test_dim_shard_ranges():
     s = DimShard(5, 8, min_cols=8)
     s.configure(64)
     assert (s.world, s.rank) == (8, 5)
-    # default narrowest shard by table residency: 32 columns for an L2-resident table, 16 for one that streams from HBM
+    # default narrowest shard: 32 columns (128-byte rows) for either kind of table; what is left of the world becomes
+    # replicas -- identical ones for an L2-resident table, row-partitioned ones (row_partition) for one that streams from HBM
     small = DimShard(1, 2).configure(64, n_rows=69716)             # C2: 17.8 MB table
-    assert (small.min_cols, small.world, small.rank) == (32, 2, 1)
-    big = DimShard(3, 8).configure(128, n_rows=3_000_000)          # C4: 1.5 GB table -> 8 x 16 columns
-    assert (big.min_cols, big.world, big.rank) == (16, 8, 3)
-    legacy = DimShard(0, 2).configure(64)                          # no size given: the HBM rule
-    assert legacy.min_cols == 16
+    assert (small.min_cols, small.world, small.rank, small.n_replicas) == (32, 2, 1, 1)
+    big = DimShard(3, 4).configure(128, n_rows=3_000_000)          # C4 on 4 GPUs: 4 x 32 columns, no replicas
+    assert (big.min_cols, big.world, big.rank, big.n_replicas) == (32, 4, 3, 1) and big.row_partition(None, 32) is None
 
 
 def _worker(rank, world, port, out):
@@ -128,6 +127,26 @@ def _worker_replicas(rank, world, port, out):
     a, b = s.user_range(10)
     assert (a, b) == (min(10, rank * 3), min(10, rank * 3 + 3))
     assert torch.equal(s.gather_user_rows(ids[a:b].contiguous(), 10), ids)
+    # hybrid layout: the ranks that hold the same columns in the two replicas ({0,2} and {1,3}) split the rows
+    assert s.n_replicas == 2 and s.peer_group is not None
+    t = torch.tensor([float(rank)])
+    dist.all_reduce(t, group=s.peer_group)
+    assert float(t) == float(2 * (rank % 2) + 2)           # {0,2} -> 2, {1,3} -> 4
+
+    class _Adj:  # only what RowPartition reads
+        rowptr = torch.tensor([0, 1, 1, 9, 10, 12, 12, 20], dtype=torch.int32)
+        n_rows, phase_split = 7, 3
+
+        def row_slice(self, ranges):
+            return ranges
+    part = s.row_partition(_Adj(), 4, kind="row")          # NCCL/gloo block exchange among the peers
+    assert part.world == 2 and part.rank == rank // 2
+    table = torch.arange(7 * 4, dtype=torch.float32).reshape(7, 4) + 100 * (rank % 2)   # each column shard its own values
+    mine = torch.full_like(table, -1.0)
+    for lo2, hi2 in part.my_blocks:
+        mine[lo2:hi2] = table[lo2:hi2]
+    part.exchange(mine)
+    assert torch.equal(mine, table)
     out.put(rank)
     dist.destroy_process_group()
 
