@@ -105,7 +105,7 @@ class BprEngine:
             L = model.n_layers
             # compacted work list of the last forward layer (only the sampled rows are needed): built beside the first layers
             self.live = None
-            if partition is None and self.shard is None and self.kind == 'LightGCN' and L >= 2 \
+            if partition is None and self.kind == 'LightGCN' and L >= 2 \
                     and os.environ.get('B200REC_NO_LIVE_LIST', '0') != '1':
                 op = self.adj_sparse
                 n_hub_items = int((op.item_dst[:op.n_items] < 0).sum())
