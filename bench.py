@@ -245,6 +245,50 @@ def _fingerprint(graph):
 
 
 # ---------------------------------------------------------------------------------------------------- own arm
+def small_shape_leg(dev, steps=20, warmup=5):
+    """C2 (Yelp2018-shaped, L2-resident tables) beside the headline: the same step and the full-rank evaluation on the shape
+    round 1 was quoted on, L2 flushed between timed steps, evaluation at the near-initial embeddings these few steps leave
+    (the state in which round 1's global candidate band was slowest)."""
+    import dataset as D
+    import model as M
+    import trainer as T
+    from b200rec import synth
+    _, _, _, d, n_layers = synth.SHAPES["c2"]
+    graph = synth.generate_named("c2", seed=0, device=dev)
+    ds = D.get_dataset({"name": "SyntheticDataset", "device": dev, "graph": graph})
+    torch.manual_seed(2021)
+    m = M.get_model({"name": "LightGCN", "embedding_size": d, "n_layers": n_layers, "device": dev}, ds)
+    tr = T.get_trainer({"name": "BPRTrainer", "optimizer": "Adam", "lr": LR, "l2_reg": L2_REG, "device": dev, "n_epochs": 1,
+                        "batch_size": BATCH, "dataloader_num_workers": 0, "test_batch_size": 512, "topks": TOPKS}, ds, m)
+    m.train()
+    eng = tr._engine()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        eng.step()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush_buf.fill_(1)
+        a.record()
+        eng.step()
+        b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    m.eval()
+    tr.eval("test")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        _, metrics, _ = tr.eval("test")
+    torch.cuda.synchronize()
+    eval_s = (time.perf_counter() - t0) / 3
+    out = {"workload": "c2: " + WORKLOAD_DOC["c2"], "ms_per_step": ms, "epochs_per_s": 1e3 / (ms * tr.steps_per_epoch()),
+           "kernels_per_step": eng.kernels_per_step(), "eval_users_per_s_e2e": ds.n_users / eval_s, "eval_ms": 1e3 * eval_s,
+           "trained_steps": eng.steps_done, "recall@20": float(metrics["Recall"][20]),
+           "l2": "flushed between timed steps (write of 256 MiB)"}
+    eng.close()
+    return out
+
+
 def run_own(args, rank, world):
     import dataset as D
     import model as M
@@ -456,6 +500,10 @@ def run_own(args, rank, world):
                              "gpu_launches": None, "roofline": eval_info["score_roofline"]})
 
     # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload on the host cores ----
+    small = None
+    if rank == 0 and world == 1 and big and not args.no_small:
+        small = small_shape_leg(dev)
+        _log("small-shape leg (c2): %.3f ms/step, evaluation %.2f ms" % (small["ms_per_step"], small["eval_ms"]))
     _log("GPU legs done")
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "lightgcn":
@@ -486,7 +534,7 @@ def run_own(args, rank, world):
                               "embedding dimension sharded x%d (%d columns per GPU) x %d replicas, one [B,3] all-reduce per "
                               "step; evaluation user-sharded x%d" % (m._dim_shard.world, d, world // m._dim_shard.world, world))}}
         out.update(line)
-        out.update({"cpu_baseline": cpu_baseline, "eval": eval_info, "clocks": clocks.summary()})
+        out.update({"cpu_baseline": cpu_baseline, "eval": eval_info, "small_shape": small, "clocks": clocks.summary()})
         print(json.dumps(out), flush=True)
     if world > 1:
         eng.close()
@@ -503,6 +551,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the C2 leg reported beside the headline at N=1")
     ap.add_argument("--no-hybrid", action="store_true", help="multi-GPU: column shards only (narrow shards / identical replicas)")
     ap.add_argument("--model", default="lightgcn", choices=["lightgcn", "igcn", "mf", "sgl", "half"],
                     help="lightgcn is the headline; igcn = inductive template-feature layer + propagation (config.py:18-23)")

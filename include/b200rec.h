@@ -244,25 +244,28 @@ int b200rec_bpr_fwd_bwd_sharded(const float* rep, int32_t d, const int64_t* batc
                                 float loss_scale, float* g_rep, float* g_w, float* loss_out, float* block_scratch,
                                 float* dots /*[B,3]*/, int32_t phase, float loss_weight, void* stream);
 /* Ordered (deterministic, aggregated) form of the scatter.  Batches repeat ids (popular items), and one atomic per sample
- * sums a row's contributions in arrival order.  b200rec_bpr_group_rows sorts the 3B (row, slot) pairs of a batch once
- * (slot = 3 * sample + {0 user, 1 pos, 2 neg}; one block, 3B <= 8192): order int32 [3B] = slots grouped by row, ascending
- * inside a group; seg_start int32 [3B+1] = first position of every group (+ end); *n_seg = number of distinct rows.
+ * sums a row's contributions in arrival order.  b200rec_bpr_group_rows ranks the 3B (row, slot) pairs of a batch once
+ * (slot = 3 * sample + {0 user, 1 pos, 2 neg}; 3B <= 12288, rows < 2^31): order int32 [3B] = the slots in (row, slot)
+ * order, bit 31 set on every position that continues the row of the position before it (so a clear bit 31 marks the
+ * first slot of a distinct row).
  * b200rec_bpr_fwd_bwd_ordered is b200rec_bpr_fwd_bwd (phase 0) / _sharded (phase 1, 2) whose gradient rows are formed by
  * ONE lane group per distinct row, adding that row's contributions in slot order and storing the row once
  * (accumulate = 0: overwrite, g_rep must be zero elsewhere; 1: add to the row) -- no atomics, run-to-run identical bits.
- * coef: float [B] scratch.  b200rec_bpr_l2_emb0_ordered likewise for the layer-0 regulariser (adds to g_emb0).
- * b200rec_clear_rows zeroes the rows a batch touches (so g_rep can stay all-zero between steps without a full memset). */
-int b200rec_bpr_group_rows(const int64_t* batch, int32_t n_batch, int64_t item_offset, int32_t* order,
-                           int32_t* seg_start, int32_t* n_seg, void* stream);
+ * coef: float [B] scratch.  emb0 (optional) folds LightGCN's layer-0 regulariser into the same launch's loss:
+ * *loss_out += l2_emb0 * mean(||e_u||^2 + ||e_p||^2 + ||e_n||^2) over the layer-0 rows (model.py:114-117).
+ * b200rec_bpr_l2_emb0_ordered adds that term's gradient to g_emb0, one lane group per distinct row (loss_out NULL when
+ * the loss was folded in as above; clear_table, optional: the same rows of that [rows, D] table are zeroed in the same
+ * launch -- G after the backward chain has consumed it).  b200rec_clear_rows zeroes the rows a batch touches on its own
+ * (so g_rep can stay all-zero between steps without a full memset). */
+int b200rec_bpr_group_rows(const int64_t* batch, int32_t n_batch, int64_t item_offset, int32_t* order, void* stream);
 int b200rec_bpr_fwd_bwd_ordered(const float* rep, int32_t d, const int64_t* batch, int32_t n_batch,
                                 int64_t item_offset, float l2_reg, int32_t reg_mode, const float* w,
                                 float loss_scale, float* g_rep, float* g_w, float* loss_out, float* block_scratch,
                                 float* dots, int32_t phase, float loss_weight, float* coef, const int32_t* order,
-                                const int32_t* seg_start, const int32_t* n_seg, int32_t accumulate, void* stream);
+                                int32_t accumulate, const float* emb0, float l2_emb0, void* stream);
 int b200rec_bpr_l2_emb0_ordered(const float* emb0, int32_t d, const int64_t* batch, int32_t n_batch,
                                 int64_t item_offset, float l2_reg, float* g_emb0, float* loss_out,
-                                float* block_scratch, const int32_t* order, const int32_t* seg_start,
-                                const int32_t* n_seg, void* stream);
+                                float* block_scratch, const int32_t* order, float* clear_table, void* stream);
 int b200rec_clear_rows(const int64_t* batch, int32_t n_batch, int64_t item_offset, float* table, int32_t d, void* stream);
 /* LightGCN's layer-0 regulariser (model.py:114-117): g_emb0 += l2_reg * d(mean ||e_u||^2+||e_p||^2+||e_n||^2)/de,
  * *loss_out += l2_reg * mean(l2). */

@@ -62,10 +62,10 @@ PROTOTYPES = {
     "b200rec_bpr_scratch_floats": (C.c_int64, [_I32, _I32]),
     "b200rec_bpr_fwd_bwd": (C.c_int, [_P, _I32, _P, _I32, _I64, _F, _I32, _P, _F, _P, _P, _P, _P, _P]),
     "b200rec_bpr_fwd_bwd_sharded": (C.c_int, [_P, _I32, _P, _I32, _I64, _F, _I32, _P, _F, _P, _P, _P, _P, _P, _I32, _F, _P]),
-    "b200rec_bpr_group_rows": (C.c_int, [_P, _I32, _I64, _P, _P, _P, _P]),
+    "b200rec_bpr_group_rows": (C.c_int, [_P, _I32, _I64, _P, _P]),
     "b200rec_bpr_fwd_bwd_ordered": (C.c_int, [_P, _I32, _P, _I32, _I64, _F, _I32, _P, _F, _P, _P, _P, _P, _P, _I32, _F, _P, _P,
-                                              _P, _P, _I32, _P]),
-    "b200rec_bpr_l2_emb0_ordered": (C.c_int, [_P, _I32, _P, _I32, _I64, _F, _P, _P, _P, _P, _P, _P, _P]),
+                                              _I32, _P, _F, _P]),
+    "b200rec_bpr_l2_emb0_ordered": (C.c_int, [_P, _I32, _P, _I32, _I64, _F, _P, _P, _P, _P, _P, _P]),
     "b200rec_clear_rows": (C.c_int, [_P, _I32, _I64, _P, _I32, _P]),
     "b200rec_bpr_l2_emb0": (C.c_int, [_P, _I32, _P, _I32, _I64, _F, _P, _P, _P, _P]),
     "b200rec_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),

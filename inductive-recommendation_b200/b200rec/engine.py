@@ -207,20 +207,20 @@ class BprEngine:
             src = dst
 
     def _bpr(self, rep, batch, item_offset, l2_reg, reg_mode, g_rep, w=None, g_w=None, loss_scale=1.0, grouping=None,
-             accumulate=False):
-        """grouping: the batch's (order, seg_start, n_seg, coef) from ops.bpr_group_rows -> deterministic aggregated
+             accumulate=False, emb0=None, l2_emb0=0.0):
+        """grouping: the batch's (order, coef) from ops.bpr_group_rows -> deterministic aggregated
         scatter (g_rep rows are STORED unless accumulate); None -> one 128-bit red per sample and role"""
         if grouping is not None:
             if self.shard is None:
                 ops.bpr_fwd_bwd_ordered(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, grouping,
-                                        w=w, g_w=g_w, loss_scale=loss_scale, accumulate=accumulate)
+                                        w=w, g_w=g_w, loss_scale=loss_scale, accumulate=accumulate, emb0=emb0, l2_emb0=l2_emb0)
                 return
             ops.bpr_fwd_bwd_ordered(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, grouping,
                                     dots=self.dots, phase=1, w=w, g_w=g_w, loss_scale=loss_scale)
             self.shard.all_reduce_sum(self.dots)
             ops.bpr_fwd_bwd_ordered(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, grouping,
                                     dots=self.dots, phase=2, loss_weight=1.0 if self.shard.rank == 0 else 0.0, w=w, g_w=g_w,
-                                    loss_scale=loss_scale, accumulate=accumulate)
+                                    loss_scale=loss_scale, accumulate=accumulate, emb0=emb0, l2_emb0=l2_emb0)
             return
         if self.shard is None:
             ops.bpr_fwd_bwd(rep, batch, item_offset, l2_reg, reg_mode, g_rep, self.loss, self.scratch, w=w, g_w=g_w,
@@ -261,7 +261,7 @@ class BprEngine:
                 ops.bpr_sample(self.user_ptr, self.user_items, self.dataset.n_users, self.dataset.n_items, self.seed,
                                self.sample_step, B, out=self.batch)
             if grp is not None:
-                ops.bpr_group_rows(self.batch, nu, grp)
+                ops.bpr_group_rows(self.batch, nu, grp)  # full-grid rank sort, a few microseconds beside the first layers
             if self.kind != 'MF':
                 # the step reads rep only at the <= 3B sampled rows, and G is non-zero only there: the last forward layer
                 # and the first backward hop are restricted to them (bit-identical on the rows that matter)
@@ -271,8 +271,11 @@ class BprEngine:
                     ops.live_items(self.adj_sparse, self.row_flags, self.live[0], self.live[1])
             if forked and not lazy_clear:
                 self.g_rep.zero_()  # needed only by the BPR kernel: cleared beside the first forward layers
+            if forked:
+                self.loss.zero_()  # off the critical path too
         join = (lambda: main.wait_stream(side)) if forked else None
-        self.loss.zero_()
+        if not forked:
+            self.loss.zero_()
         if self.kind == 'MF':
             self.grad.zero_()
             self._bpr(self.table, self.batch, nu, self.l2_reg, 1, self.grad, grouping=grp)
@@ -281,14 +284,17 @@ class BprEngine:
             if not forked and not lazy_clear:
                 self.g_rep.zero_()
             self._propagate_fwd(self.table, join)
-            self._bpr(self.rep, self.batch, nu, 0.0, 0, self.g_rep, grouping=grp)
+            fold = grp is not None and self.l2_reg != 0.0  # layer-0 L2: loss inside the BPR launch, gradient + row clear in one
+            self._bpr(self.rep, self.batch, nu, 0.0, 0, self.g_rep, grouping=grp, emb0=self.table if fold else None,
+                      l2_emb0=self.l2_reg if fold else 0.0)
             self._propagate_bwd(self.grad)
-            if lazy_clear:
-                ops.clear_rows(self.batch, nu, self.g_rep)
-            if self.l2_reg != 0.0:
-                if grp is not None:
-                    ops.bpr_l2_emb0_ordered(self.table, self.batch, nu, self.l2_reg, self.grad, self.loss, self.scratch, grp)
-                else:
+            if fold:
+                ops.bpr_l2_emb0_ordered(self.table, self.batch, nu, self.l2_reg, self.grad, None, None, grp,
+                                        clear_table=self.g_rep if lazy_clear else None)
+            else:
+                if lazy_clear:
+                    ops.clear_rows(self.batch, nu, self.g_rep)
+                if self.l2_reg != 0.0:
                     ops.bpr_l2_emb0(self.table, self.batch, nu, self.l2_reg, self.grad, self.loss, self.scratch)
             self._adam(self.table, self.grad, self.m, self.v)
         elif self.kind in ('SGL', 'HALF'):

@@ -137,40 +137,43 @@ def bpr_fwd_bwd_sharded(rep, batch, item_offset, l2_reg, reg_mode, g_rep, loss_o
           "bpr_fwd_bwd_sharded")
 
 
-GROUP_CAP = 8192  # slots (3 * batch) the single-block grouping sort holds
+GROUP_CAP = 12288  # slots (3 * batch) the grouping holds in shared memory (csrc/bpr.cu)
+GROUP_CONT = 0x80000000  # order bit 31: the position continues the row of the position before it
 
 
 def bpr_grouping(batch_size, device):
-    """buffers of bpr_group_rows for a [B,3] batch: (order int32 [3B], seg_start int32 [3B+1], n_seg int32 [1], coef f32 [B])"""
-    i32 = dict(dtype=torch.int32, device=device)
-    return (torch.zeros(3 * batch_size, **i32), torch.zeros(3 * batch_size + 1, **i32), torch.zeros(1, **i32),
+    """buffers of bpr_group_rows for a [B,3] batch: (order int32 [3B], coef f32 [B])"""
+    return (torch.zeros(3 * batch_size, dtype=torch.int32, device=device),
             torch.zeros(batch_size, dtype=torch.float32, device=device))
 
 
 def bpr_group_rows(batch, item_offset, grouping):
-    """sort the 3B (row, slot) pairs of a batch once: the ordered scatter sums a row's contributions in slot order"""
+    """rank the 3B (row, slot) pairs of a batch once: the ordered scatter sums a row's contributions in slot order"""
     _abi.require_cuda(batch, *grouping)
-    check(_lib().b200rec_bpr_group_rows(ptr(batch), batch.shape[0], item_offset, ptr(grouping[0]), ptr(grouping[1]),
-                                        ptr(grouping[2]), stream_ptr()), "bpr_group_rows")
+    check(_lib().b200rec_bpr_group_rows(ptr(batch), batch.shape[0], item_offset, ptr(grouping[0]), stream_ptr()),
+          "bpr_group_rows")
 
 
 def bpr_fwd_bwd_ordered(rep, batch, item_offset, l2_reg, reg_mode, g_rep, loss_out, scratch, grouping, dots=None, phase=0,
-                        loss_weight=1.0, w=None, g_w=None, loss_scale=1.0, accumulate=False):
-    """bpr_fwd_bwd / bpr_fwd_bwd_sharded with the deterministic, aggregated scatter (one store per distinct row)"""
-    _abi.require_cuda(rep, batch, g_rep, loss_out, scratch, dots, w, g_w)
-    order, seg_start, n_seg, coef = grouping
+                        loss_weight=1.0, w=None, g_w=None, loss_scale=1.0, accumulate=False, emb0=None, l2_emb0=0.0):
+    """bpr_fwd_bwd / bpr_fwd_bwd_sharded with the deterministic, aggregated scatter (one store per distinct row);
+    emb0 / l2_emb0: LightGCN's layer-0 regulariser folded into the loss of the same launch"""
+    _abi.require_cuda(rep, batch, g_rep, loss_out, scratch, dots, w, g_w, emb0)
+    order, coef = grouping
     check(_lib().b200rec_bpr_fwd_bwd_ordered(ptr(rep), rep.shape[1], ptr(batch), batch.shape[0], item_offset, l2_reg,
                                              reg_mode, ptr(w), loss_scale, ptr(g_rep), ptr(g_w), ptr(loss_out),
                                              ptr(scratch), ptr(dots), phase, loss_weight, ptr(coef), ptr(order),
-                                             ptr(seg_start), ptr(n_seg), 1 if accumulate else 0, stream_ptr()),
+                                             1 if accumulate else 0, ptr(emb0), l2_emb0, stream_ptr()),
           "bpr_fwd_bwd_ordered")
 
 
-def bpr_l2_emb0_ordered(emb0, batch, item_offset, l2_reg, g_emb0, loss_out, scratch, grouping):
-    _abi.require_cuda(emb0, batch, g_emb0, loss_out, scratch)
+def bpr_l2_emb0_ordered(emb0, batch, item_offset, l2_reg, g_emb0, loss_out, scratch, grouping, clear_table=None):
+    """gradient of the layer-0 regulariser, one lane group per distinct row (+ its loss term unless loss_out is None: then
+    bpr_fwd_bwd_ordered(emb0=...) has added it); clear_table: rows of that table zeroed in the same launch"""
+    _abi.require_cuda(emb0, batch, g_emb0, loss_out, scratch, clear_table)
     check(_lib().b200rec_bpr_l2_emb0_ordered(ptr(emb0), emb0.shape[1], ptr(batch), batch.shape[0], item_offset, l2_reg,
-                                             ptr(g_emb0), ptr(loss_out), ptr(scratch), ptr(grouping[0]), ptr(grouping[1]),
-                                             ptr(grouping[2]), stream_ptr()), "bpr_l2_emb0_ordered")
+                                             ptr(g_emb0), ptr(loss_out), ptr(scratch), ptr(grouping[0]), ptr(clear_table),
+                                             stream_ptr()), "bpr_l2_emb0_ordered")
 
 
 def clear_rows(batch, item_offset, table):

@@ -156,7 +156,11 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* rep, const 
                                                         float* __restrict__ g_rep, float* __restrict__ g_w,
                                                         float* __restrict__ loss_out, float* scratch,
                                                         float* __restrict__ dots, int dots_mode, float loss_weight,
-                                                        float* __restrict__ coef_out) {
+                                                        float* __restrict__ coef_out, const float* __restrict__ emb0,
+                                                        float l2_emb0) {
+  // emb0 != NULL: LightGCN's layer-0 regulariser (model.py:114-117) is folded into this launch's loss -- l2_emb0 * mean of
+  // ||e_u||^2 + ||e_p||^2 + ||e_n||^2 over the layer-0 rows; its gradient is formed per distinct row by
+  // bpr_grad_rows_kernel<L2ROWS> after the backward chain.
   // coef_out != NULL (ordered mode): the per-sample score derivative is stored and NO gradient row is scattered here;
   // bpr_grad_rows_kernel then forms every touched row's gradient once, in sample order (deterministic, no atomics).
   // dots_mode 0: everything in one launch.  Embedding-dimension sharding (each rank holds D/P columns) splits it:
@@ -213,6 +217,20 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* rep, const 
   float loss = softplus_t(x);
   if (reg_mode == 1) loss += l2_reg * l2;
   loss *= loss_weight;
+  if (emb0) {  // every rank adds its own columns' share of the layer-0 term
+    float l0 = 0.f;
+    if (active) {
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) {
+        const int c = (gl + t * G) * 4;
+        const float4 a = ldc_f4(emb0 + (size_t)ru * D + c), b = ldc_f4(emb0 + (size_t)rp * D + c), e = ldc_f4(emb0 + (size_t)rn * D + c);
+        l0 += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w +
+              e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+      }
+    }
+    l0 = group_sum<G>(l0);
+    loss += l2_emb0 * l0;
+  }
   const float coef = loss_scale * inv_b * sigmoid_t(x);
   const float rc = (reg_mode == 1) ? 2.f * l2_reg * loss_scale * inv_b : 0.f;
   if (coef_out && active && gl == 0) coef_out[smp] = coef;
@@ -280,79 +298,48 @@ __global__ void __launch_bounds__(256) bpr_fused_kernel(const float* rep, const 
 
 // ---------------------------------------------------------------------------------------------- ordered scatter
 // Duplicate ids inside a batch are the rule (popular items; a user drawn twice), and a red.global.add per sample sums
-// them in arrival order -- different bits from run to run.  Instead the 3B (row, slot) pairs of the batch are sorted once
-// (one block, bitonic sort in shared memory, beside the forward layers on the side stream) and every DISTINCT row gets its
+// them in arrival order -- different bits from run to run.  Instead the 3B (row, slot) pairs of the batch are ranked once
+// (bpr_group_rows_kernel, beside the forward layers on the side stream) and every DISTINCT row gets its
 // gradient from one lane group that adds the contributions of its slots in slot order and issues one plain store: the
 // aggregation north_star asks of the scatter (one write per distinct row instead of one atomic per sample), with a
 // fixed summation order on top.
-constexpr int GROUP_CAP = 8192;  // slots (3 * batch) the single-block sort holds: batches up to 2730 samples
-__global__ void __launch_bounds__(1024, 1) bpr_group_rows_kernel(const int64_t* __restrict__ batch, int n_slots, int64_t item_offset,
-                                                                 int32_t* __restrict__ order, int32_t* __restrict__ seg_start,
-                                                                 int32_t* __restrict__ n_seg) {
-  extern __shared__ unsigned long long s_key[];  // [GROUP_CAP] (row << 13) | slot
-  __shared__ int s_warp[32];
-  for (int i = threadIdx.x; i < GROUP_CAP; i += 1024) {
-    unsigned long long k = ~0ull;
-    if (i < n_slots) {
-      const int64_t r = batch[i] + ((i % 3) ? item_offset : 0);
-      k = ((unsigned long long)r << 13) | (unsigned)i;
-    }
-    s_key[i] = k;
-  }
+constexpr int GROUP_CAP = 12288;    // slots (3 * batch) the grouping holds in 48 KB of shared memory: batches up to 4096
+constexpr int GROUP_EPW = 4;        // slots ranked per warp
+constexpr unsigned GROUP_CONT = 0x80000000u;  // order[k] bit 31: position k continues the row of position k - 1
+// Rank sort over the whole grid instead of a sort in one block: the position of slot e in (row, slot) order is the number
+// of slots with a smaller (row, slot) -- every warp counts that for GROUP_EPW slots against all 3B rows held in shared
+// memory (37.7 M compares at B = 2048, a few microseconds of the whole GPU, no serial stage) and stores
+// order[position] = e, with bit 31 set when an earlier slot names the same row.  Rows are compared as int32: the tables
+// of this library have < 2^31 rows (int32 column indices in b200rec_csr).
+__global__ void __launch_bounds__(256) bpr_group_rows_kernel(const int64_t* __restrict__ batch, int n_slots, int64_t item_offset,
+                                                             int32_t* __restrict__ order) {
+  extern __shared__ int32_t s_row[];  // [n_slots rounded up to 32]
+  const int n_pad = (n_slots + 31) & ~31;
+  for (int i = threadIdx.x; i < n_pad; i += 256)
+    s_row[i] = i < n_slots ? (int32_t)(batch[i] + ((i % 3) ? item_offset : 0)) : 0x7fffffff;
   __syncthreads();
-  for (int size = 2; size <= GROUP_CAP; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < GROUP_CAP / 2; t += 1024) {
-        const int lo = 2 * t - (t & (stride - 1));   // index of the lower element of pair t
-        const int hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const unsigned long long a = s_key[lo], b = s_key[hi];
-        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
-      }
-      __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int e0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GROUP_EPW;
+  if (e0 >= n_slots) return;
+  int re[GROUP_EPW], lt[GROUP_EPW], eqb[GROUP_EPW];
+#pragma unroll
+  for (int j = 0; j < GROUP_EPW; ++j) {
+    re[j] = e0 + j < n_slots ? s_row[e0 + j] : 0x7fffffff;
+    lt[j] = eqb[j] = 0;
+  }
+#pragma unroll 4
+  for (int f = lane; f < n_pad; f += 32) {
+    const int rf = s_row[f];
+#pragma unroll
+    for (int j = 0; j < GROUP_EPW; ++j) {
+      lt[j] += rf < re[j];
+      eqb[j] += (rf == re[j]) & (f < e0 + j);
     }
   }
-  // segment heads: 8 consecutive sorted slots per thread, block-wide exclusive scan of the head counts
-  const int base = threadIdx.x * 8;
-  int heads = 0;
-  unsigned flags = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int i = base + j;
-    const bool h = i < n_slots && (i == 0 || (s_key[i] >> 13) != (s_key[i - 1] >> 13));
-    if (h) { flags |= 1u << j; ++heads; }
-  }
-  int incl = heads;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((int)(threadIdx.x & 31) >= o) incl += v;
-  }
-  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    int w = s_warp[threadIdx.x];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, w, o);
-      if ((int)threadIdx.x >= o) w += v;
-    }
-    s_warp[threadIdx.x] = w;  // inclusive over warps
-  }
-  __syncthreads();
-  int pos = incl - heads + ((threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int i = base + j;
-    if (i < n_slots) {
-      order[i] = (int32_t)(s_key[i] & 8191ull);
-      if ((flags >> j) & 1u) seg_start[pos++] = i;
-    }
-  }
-  if (threadIdx.x == 1023) {
-    const int total = s_warp[31];
-    *n_seg = total;
-    seg_start[total] = n_slots;
+  for (int j = 0; j < GROUP_EPW; ++j) {
+    const int l = __reduce_add_sync(0xffffffffu, lt[j]), q = __reduce_add_sync(0xffffffffu, eqb[j]);
+    if (lane == j && e0 + j < n_slots) order[l + q] = (int32_t)((unsigned)(e0 + j) | (q ? GROUP_CONT : 0u));
   }
 }
 
@@ -364,15 +351,16 @@ __global__ void __launch_bounds__(1024, 1) bpr_group_rows_kernel(const int64_t* 
 template <int G, int VPL, bool HAS_W, bool L2ROWS, bool ACCUM>
 __global__ void __launch_bounds__(256) bpr_grad_rows_kernel(const float* rep, const int64_t* __restrict__ batch, int64_t item_offset,
                                                             const float* __restrict__ coef, const float* __restrict__ w,
-                                                            float rc, const int32_t* __restrict__ order,
-                                                            const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_seg,
-                                                            float* __restrict__ g_out) {
+                                                            float rc, const int32_t* __restrict__ order, int n_slots,
+                                                            float* __restrict__ g_out, float* __restrict__ clear_table) {
   constexpr int D = G * VPL * 4;
-  const int seg = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G), gl = threadIdx.x & (G - 1);
+  int k = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G);
+  const int gl = threadIdx.x & (G - 1);
   pdl_trigger();
   pdl_wait();
-  if (seg >= *n_seg) return;
-  const int b = seg_start[seg], e = seg_start[seg + 1];
+  if (k >= n_slots) return;
+  unsigned o = (unsigned)order[k];
+  if (o & GROUP_CONT) return;  // one lane group per distinct row: the one at the row's first position
   float4 acc[VPL], wv[VPL];
 #pragma unroll
   for (int t = 0; t < VPL; ++t) {
@@ -381,8 +369,8 @@ __global__ void __launch_bounds__(256) bpr_grad_rows_kernel(const float* rep, co
     if constexpr (HAS_W) wv[t] = ldg_f4(w + (gl + t * G) * 4);
   }
   int64_t row = 0;
-  for (int k = b; k < e; ++k) {
-    const int slot = order[k];
+  for (bool more = true; more; more = ++k < n_slots && ((o = (unsigned)order[k]) & GROUP_CONT)) {
+    const int slot = (int)(o & ~GROUP_CONT);
     const int smp = slot / 3, role = slot - 3 * smp;
     const int64_t ru = batch[3 * (size_t)smp];
     const int64_t rp = batch[3 * (size_t)smp + 1] + item_offset;
@@ -419,6 +407,7 @@ __global__ void __launch_bounds__(256) bpr_grad_rows_kernel(const float* rep, co
   }
 #pragma unroll
   for (int t = 0; t < VPL; ++t) {
+    if (clear_table) st_f4(clear_table + (size_t)row * D + (gl + t * G) * 4, make_float4(0.f, 0.f, 0.f, 0.f));  // G back to all-zero
     float* dst = g_out + (size_t)row * D + (gl + t * G) * 4;
     if (ACCUM) {
       const float4 old = ld_f4(dst);
@@ -554,15 +543,15 @@ template <int G, int VPL>
 static int launch_bpr(const float* rep, const int64_t* batch, int nb, int64_t off, float l2_reg, int reg_mode,
                       const float* w, float loss_scale, float* g_rep, float* g_w, float* loss_out, float* scratch,
                       float* dots, int dots_mode, float loss_weight, cudaStream_t st, float* coef = nullptr,
-                      const int32_t* order = nullptr, const int32_t* seg_start = nullptr, const int32_t* n_seg = nullptr,
-                      bool accumulate = false) {
+                      const int32_t* order = nullptr,
+                      bool accumulate = false, const float* emb0 = nullptr, float l2_emb0 = 0.f) {
   const int grid = ceil_div(nb, 256 / G);
-  if (w) B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, true>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight, coef);
-  else B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, false>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight, coef);
+  if (w) B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, true>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight, coef, emb0, l2_emb0);
+  else B2_LAUNCH_PDL(bpr_fused_kernel<G, VPL, false>, grid, 256, 0, st, rep, batch, nb, off, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, scratch, dots, dots_mode, loss_weight, coef, emb0, l2_emb0);
   if (coef && dots_mode != 1) {  // ordered mode: one lane group per distinct row
     const float rc = (reg_mode == 1) ? 2.f * l2_reg * loss_scale / (float)nb : 0.f;
     const int grid2 = ceil_div(3 * nb, 256 / G);
-#define B2_GRAD_ROWS(W, A) B2_LAUNCH_PDL(bpr_grad_rows_kernel<G, VPL, W, false, A>, grid2, 256, 0, st, rep, batch, off, (const float*)coef, w, rc, order, seg_start, n_seg, g_rep)
+#define B2_GRAD_ROWS(W, A) B2_LAUNCH_PDL(bpr_grad_rows_kernel<G, VPL, W, false, A>, grid2, 256, 0, st, rep, batch, off, (const float*)coef, w, rc, order, 3 * nb, g_rep, (float*)nullptr)
     if (w) { if (accumulate) B2_GRAD_ROWS(true, true); else B2_GRAD_ROWS(true, false); }
     else { if (accumulate) B2_GRAD_ROWS(false, true); else B2_GRAD_ROWS(false, false); }
 #undef B2_GRAD_ROWS
@@ -652,13 +641,13 @@ extern "C" int b200rec_bpr_fwd_bwd_sharded(const float* rep, int32_t d, const in
 }
 
 extern "C" int b200rec_bpr_group_rows(const int64_t* batch, int32_t n_batch, int64_t item_offset, int32_t* order,
-                                      int32_t* seg_start, int32_t* n_seg, void* stream) {
-  B2_REQUIRE(batch && order && seg_start && n_seg && n_batch > 0, "bad argument");
+                                      void* stream) {
+  B2_REQUIRE(batch && order && n_batch > 0, "bad argument");
   if (3 * (int64_t)n_batch > GROUP_CAP)
-    return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", __func__, "batch too large for the single-block grouping (3 * n_batch <= 8192)");
-  const size_t smem = (size_t)GROUP_CAP * sizeof(unsigned long long);
-  B2_CUDA(cudaFuncSetAttribute(bpr_group_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  bpr_group_rows_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(batch, 3 * n_batch, item_offset, order, seg_start, n_seg);
+    return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", __func__, "batch too large for the grouping (3 * n_batch <= 12288)");
+  const int n_slots = 3 * n_batch;
+  const size_t smem = (size_t)((n_slots + 31) & ~31) * sizeof(int32_t);  // <= 48 KB: no opt-in needed
+  bpr_group_rows_kernel<<<ceil_div(n_slots, 8 * GROUP_EPW), 256, smem, (cudaStream_t)stream>>>(batch, n_slots, item_offset, order);
   B2_LAUNCHED();
   return 0;
 }
@@ -667,27 +656,29 @@ extern "C" int b200rec_bpr_fwd_bwd_ordered(const float* rep, int32_t d, const in
                                            int64_t item_offset, float l2_reg, int32_t reg_mode, const float* w,
                                            float loss_scale, float* g_rep, float* g_w, float* loss_out,
                                            float* block_scratch, float* dots, int32_t phase, float loss_weight,
-                                           float* coef, const int32_t* order, const int32_t* seg_start,
-                                           const int32_t* n_seg, int32_t accumulate, void* stream) {
+                                           float* coef, const int32_t* order, int32_t accumulate, const float* emb0, float l2_emb0,
+                                           void* stream) {
   B2_REQUIRE(rep && batch && block_scratch && n_batch > 0, "bad argument");
   B2_REQUIRE(phase >= 0 && phase <= 2, "phase must be 0 (one GPU), 1 (partial dots) or 2 (gradients from reduced dots)");
   B2_REQUIRE(phase == 0 || dots, "dots required when the dimension is sharded");
-  B2_REQUIRE(phase == 1 || (g_rep && loss_out && coef && order && seg_start && n_seg), "null output / grouping");
+  B2_REQUIRE(phase == 1 || (g_rep && loss_out && coef && order), "null output / grouping");
   B2_REQUIRE(reg_mode == 0 || reg_mode == 1, "reg_mode must be 0 or 1");
   B2_REQUIRE(!w || g_w || phase == 1, "g_w required with w");
-  B2_DISPATCH_D(d, { int rc = launch_bpr<G, VPL>(rep, batch, n_batch, item_offset, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, block_scratch, dots, phase, loss_weight, (cudaStream_t)stream, phase == 1 ? nullptr : coef, order, seg_start, n_seg, accumulate != 0); if (rc) return rc; });
+  B2_DISPATCH_D(d, { int rc = launch_bpr<G, VPL>(rep, batch, n_batch, item_offset, l2_reg, reg_mode, w, loss_scale, g_rep, g_w, loss_out, block_scratch, dots, phase, loss_weight, (cudaStream_t)stream, phase == 1 ? nullptr : coef, order, accumulate != 0, phase == 1 ? nullptr : emb0, l2_emb0); if (rc) return rc; });
   return 0;
 }
 
 extern "C" int b200rec_bpr_l2_emb0_ordered(const float* emb0, int32_t d, const int64_t* batch, int32_t n_batch,
                                            int64_t item_offset, float l2_reg, float* g_emb0, float* loss_out,
-                                           float* block_scratch, const int32_t* order, const int32_t* seg_start,
-                                           const int32_t* n_seg, void* stream) {
-  B2_REQUIRE(emb0 && batch && g_emb0 && loss_out && block_scratch && order && seg_start && n_seg && n_batch > 0, "bad argument");
+                                           float* block_scratch, const int32_t* order, float* clear_table,
+                                           void* stream) {
+  B2_REQUIRE(emb0 && batch && g_emb0 && order && n_batch > 0, "bad argument");
+  B2_REQUIRE(!loss_out || block_scratch, "block_scratch required with loss_out");
   const float rc = 2.f * l2_reg / (float)n_batch;
   B2_DISPATCH_D(d, {
-    B2_LAUNCH_PDL(bpr_l2_emb0_kernel<G, VPL>, ceil_div(n_batch, 256 / G), 256, 0, (cudaStream_t)stream, emb0, batch, n_batch, item_offset, l2_reg, (float*)nullptr, loss_out, block_scratch);
-    B2_LAUNCH_PDL(bpr_grad_rows_kernel<G, VPL, false, true, true>, ceil_div(3 * n_batch, 256 / G), 256, 0, (cudaStream_t)stream, emb0, batch, item_offset, (const float*)nullptr, (const float*)nullptr, rc, order, seg_start, n_seg, g_emb0);
+    if (loss_out)  // NULL: the loss term was folded into b200rec_bpr_fwd_bwd_ordered (emb0 / l2_emb0)
+      B2_LAUNCH_PDL(bpr_l2_emb0_kernel<G, VPL>, ceil_div(n_batch, 256 / G), 256, 0, (cudaStream_t)stream, emb0, batch, n_batch, item_offset, l2_reg, (float*)nullptr, loss_out, block_scratch);
+    B2_LAUNCH_PDL(bpr_grad_rows_kernel<G, VPL, false, true, true>, ceil_div(3 * n_batch, 256 / G), 256, 0, (cudaStream_t)stream, emb0, batch, item_offset, (const float*)nullptr, (const float*)nullptr, rc, order, 3 * n_batch, g_emb0, clear_table);
   });
   return 0;
 }

@@ -331,12 +331,13 @@ def test_bpr_ordered_scatter_is_deterministic_and_matches_atomic(d):
     grp = ops.bpr_grouping(b, DEV)
     ops.bpr_group_rows(batch, nu, grp)
     rows = np.concatenate([batch_np[:, :1], batch_np[:, 1:] + nu], 1).reshape(-1)
-    order, seg, nseg = grp[0].cpu().numpy(), grp[1].cpu().numpy(), int(grp[2])
-    assert nseg == np.unique(rows).size and seg[nseg] == 3 * b
-    for j in range(nseg):
-        sl = order[seg[j]:seg[j + 1]]
-        assert (np.diff(sl) > 0).all() and np.unique(rows[sl]).size == 1
-    assert (np.diff(rows[order[seg[:nseg]]]) > 0).all()
+    # order = the slots in (row, slot) order (exactly numpy's stable argsort of the rows); bit 31 marks a continued row
+    raw = grp[0].cpu().numpy().view(np.uint32)
+    order, cont = (raw & 0x7fffffff).astype(np.int64), (raw >> 31).astype(bool)
+    expect = np.argsort(rows, kind="stable")
+    assert np.array_equal(order, expect)
+    assert np.array_equal(cont, np.concatenate([[False], rows[expect][1:] == rows[expect][:-1]]))
+    assert int((~cont).sum()) == np.unique(rows).size
     outs = []
     for _ in range(3):
         g = torch.zeros_like(rep)
@@ -371,10 +372,29 @@ def test_bpr_ordered_scatter_is_deterministic_and_matches_atomic(d):
     ops.bpr_l2_emb0(rep, batch, nu, 1e-2, e1, loss_a, scratch)
     ops.bpr_l2_emb0_ordered(rep, batch, nu, 1e-2, e2, loss_o, scratch, grp)
     torch.testing.assert_close(e1, e2, rtol=2e-5, atol=2e-6)
+    # folded form the LightGCN step uses: the loss term rides the BPR launch, gradient + row clear are one launch
+    loss_sep, loss_fold = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    g_sep, g_fold = torch.zeros_like(rep), torch.zeros_like(rep)
+    ops.bpr_fwd_bwd_ordered(rep, batch, nu, 0.0, 0, g_sep, loss_sep, scratch, grp)
+    e3 = base.clone()
+    ops.bpr_l2_emb0_ordered(base, batch, nu, 1e-2, e3, loss_sep, scratch, grp)
+    ops.bpr_fwd_bwd_ordered(rep, batch, nu, 0.0, 0, g_fold, loss_fold, scratch, grp, emb0=base, l2_emb0=1e-2)
+    e4 = base.clone()
+    ops.bpr_l2_emb0_ordered(base, batch, nu, 1e-2, e4, None, None, grp, clear_table=g_fold)
+    assert torch.equal(e3, e4)
+    assert not bool(g_fold.any())                                   # every row the batch touched is zero again
+    torch.testing.assert_close(loss_fold, loss_sep, rtol=1e-5, atol=1e-7)
     ops.clear_rows(batch, nu, e2)
     touched = torch.zeros(nu + ni, dtype=torch.bool, device=DEV)
     touched[torch.from_numpy(rows).to(DEV)] = True
     assert bool((e2[touched] == 0).all()) and torch.equal(e2[~touched], base[~touched])
     from b200rec import _abi
     with pytest.raises(_abi.B200RecError):
-        ops.bpr_group_rows(torch.zeros((3000, 3), dtype=torch.int64, device=DEV), nu, ops.bpr_grouping(3000, DEV))
+        ops.bpr_group_rows(torch.zeros((4097, 3), dtype=torch.int64, device=DEV), nu, ops.bpr_grouping(4097, DEV))
+    # a batch of the largest supported size, with a ragged tail (3B not a multiple of the warp's slots), still ranks exactly
+    for bb in (4096, 1, 333):
+        bt = torch.from_numpy(np.stack([rng.integers(0, nu, bb), rng.integers(0, 7, bb), rng.integers(0, ni, bb)], 1)).to(DEV)
+        g2 = ops.bpr_grouping(bb, DEV)
+        ops.bpr_group_rows(bt, nu, g2)
+        r2 = (bt.cpu().numpy() + np.array([0, nu, nu])).reshape(-1)
+        assert np.array_equal(g2[0].cpu().numpy().view(np.uint32) & 0x7fffffff, np.argsort(r2, kind="stable"))
