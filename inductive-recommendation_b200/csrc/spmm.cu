@@ -70,6 +70,16 @@ __device__ __forceinline__ float4 ldc_f4_policy(const float* ptr, uint64_t pol) 
   return v;
 }
 
+#ifndef B200REC_SPMM_MINB
+#define B200REC_SPMM_MINB 4      // resident 256-thread blocks per SM the D <= 128 kernels are compiled for (register cap)
+#endif
+#ifndef B200REC_SPMM_EBMUL
+#define B200REC_SPMM_EBMUL 1     // edges staged per group and block = max(G, 16) * this (unfiltered variants)
+#endif
+#ifndef B200REC_SPMM_PREFETCH
+#define B200REC_SPMM_PREFETCH 0  // 1: the next block's (column, value) pairs are loaded under the current block's gathers
+#endif
+
 template <int G, int VPL>
 __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int gl, float4 (&acc)[VPL]) {
   constexpr int D = G * VPL * 4;
@@ -104,7 +114,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int g
 //    flagged all-zero) are squeezed out with a ballot/popc compaction before the gather loop; the slack of the last
 //    sub-block is padded with (first column of the row, weight 0), so the loop body carries no predicates or selects.
 template <int G, int VPL, bool HAS_VALS, bool HAS_NBR, bool HAS_MASK, bool HAS_EID, bool HAS_SRCF, bool HINT>
-__global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(256, (VPL == 1) ? B200REC_SPMM_MINB : 2) spmm_items_kernel(const SpmmParams p) {
   constexpr int D = G * VPL * 4;
   constexpr int U = 8;                    // neighbour rows in flight per lane
   constexpr int GPW = 32 / G;             // groups per warp
@@ -113,7 +123,7 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   // their index / flag loads are independent and pipeline, and the survivors of the wider window fill the U-deep gather
   // batches (a 16-edge window with ~30 % survivors issues 5 real loads and 3 pads per L2 round trip).
   constexpr int SCAN = !COMPACT ? 1 : (G >= 4 ? B200REC_SPMM_SCAN : 2);  // G = 2: 128 groups per block, shared-memory budget
-  constexpr int EB = ((G >= 16) ? G : 16) * SCAN;
+  constexpr int EB = ((G >= 16) ? G : 16) * SCAN * (COMPACT ? 1 : B200REC_SPMM_EBMUL);
   constexpr int EPL = EB / G;             // edges loaded per lane per block
   constexpr int CVS = (G == 32) ? EB : EB + 1;  // slot stride per group: +1 keeps the groups' broadcast reads off one bank
   __shared__ int2 s_cv[(256 / G) * CVS];
@@ -159,6 +169,21 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
   for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* xg = p.x + (size_t)gl * 4;
 
+  int c_nx[EPL];
+  float v_nx[EPL];
+  if (!COMPACT && B200REC_SPMM_PREFETCH) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int k = start + e * G + gl;
+      c_nx[e] = cfirst;
+      v_nx[e] = 0.f;
+      if (k < end) {
+        c_nx[e] = ld_stream_i32(p.colidx + k);
+        v_nx[e] = HAS_VALS ? ld_stream_f32(p.vals + k) : 1.f;
+        if (HAS_NBR) v_nx[e] *= p.nbr_scale[c_nx[e]];
+      }
+    }
+  }
   for (int base = 0; base < maxlen; base += EB) {
     int cnt = 0;  // contributing edges of this group in this block of EB; cntmax: warp-uniform loop bound
     if (COMPACT) {
@@ -166,30 +191,48 @@ __global__ void __launch_bounds__(256, (VPL == 1) ? 4 : 2) spmm_items_kernel(con
       for (int e = 0; e < EPL; ++e) my_cv[e * G + gl] = make_int2(cfirst, 0);  // pad
       __syncwarp();
     }
+    if (!COMPACT && B200REC_SPMM_PREFETCH) {
+      // software pipeline: the (column, value) pairs of this block were loaded while the previous block's rows were being
+      // gathered; park them and start the loads of the next block before this block's gathers
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      const int k = start + base + e * G + gl;
-      int c = cfirst;
-      float v = 0.f;
-      bool valid = k < end;
-      if (valid) {
-        c = ld_stream_i32(p.colidx + k);
-        v = HAS_VALS ? ld_stream_f32(p.vals + k) : 1.f;
-        if (HAS_MASK) {
-          const int eidx = HAS_EID ? ld_stream_i32(p.eid + k) : k;
-          valid = ((*(p.keep_bits + (eidx >> 5)) >> (eidx & 31)) & 1u) != 0u;
+      for (int e = 0; e < EPL; ++e) my_cv[e * G + gl] = make_int2(c_nx[e], __float_as_int(v_nx[e]));
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = start + base + EB + e * G + gl;
+        c_nx[e] = cfirst;
+        v_nx[e] = 0.f;
+        if (k < end) {
+          c_nx[e] = ld_stream_i32(p.colidx + k);
+          v_nx[e] = HAS_VALS ? ld_stream_f32(p.vals + k) : 1.f;
+          if (HAS_NBR) v_nx[e] *= p.nbr_scale[c_nx[e]];
         }
-        if (HAS_SRCF) valid = valid && (ldc_u8(p.src_flags + c) != 0);
-        if (HAS_NBR && valid) v *= p.nbr_scale[c];
       }
-      if (COMPACT) {
-        const unsigned bal = __ballot_sync(0xffffffffu, valid);
-        const unsigned gm = (G == 32) ? bal : ((bal >> (lane & ~(G - 1))) & ((1u << (G & 31)) - 1u));
-        const int rank = cnt + __popc(gm & ((1u << gl) - 1u));
-        if (valid) my_cv[rank] = make_int2(c, __float_as_int(v));
-        cnt += __popc(gm);
-      } else {
-        my_cv[e * G + gl] = valid ? make_int2(c, __float_as_int(v)) : make_int2(cfirst, 0);
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = start + base + e * G + gl;
+        int c = cfirst;
+        float v = 0.f;
+        bool valid = k < end;
+        if (valid) {
+          c = ld_stream_i32(p.colidx + k);
+          v = HAS_VALS ? ld_stream_f32(p.vals + k) : 1.f;
+          if (HAS_MASK) {
+            const int eidx = HAS_EID ? ld_stream_i32(p.eid + k) : k;
+            valid = ((*(p.keep_bits + (eidx >> 5)) >> (eidx & 31)) & 1u) != 0u;
+          }
+          if (HAS_SRCF) valid = valid && (ldc_u8(p.src_flags + c) != 0);
+          if (HAS_NBR && valid) v *= p.nbr_scale[c];
+        }
+        if (COMPACT) {
+          const unsigned bal = __ballot_sync(0xffffffffu, valid);
+          const unsigned gm = (G == 32) ? bal : ((bal >> (lane & ~(G - 1))) & ((1u << (G & 31)) - 1u));
+          const int rank = cnt + __popc(gm & ((1u << gl) - 1u));
+          if (valid) my_cv[rank] = make_int2(c, __float_as_int(v));
+          cnt += __popc(gm);
+        } else {
+          my_cv[e * G + gl] = valid ? make_int2(c, __float_as_int(v)) : make_int2(cfirst, 0);
+        }
       }
     }
     if (!COMPACT) cnt = min(EB, max(end - start - base, 0));
