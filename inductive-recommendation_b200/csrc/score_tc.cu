@@ -92,6 +92,17 @@ __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+// ring flags in shared memory: acquire loads are plain LDS (ordering only), a release store is one MEMBAR.ALL.CTA + STS --
+// the rings used to bracket every poll with __threadfence_block() (MEMBAR.SC.CTA, ~100 cycles each, five per pass of a
+// consumer warp), which cost more than the records' own processing
+__device__ __forceinline__ int lds_acquire(const volatile int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<const int*>(p))) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_release(volatile int* p, int v) {
+  asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(const_cast<int*>(p))), "r"(v) : "memory");
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -160,8 +171,21 @@ struct TcParams {
   Cand* cand;                // [b, TC_CAP]
   int* cand_cnt;             // [b]
   int* overflow;             // [b]
+#ifdef B200REC_TC_PROF
+  unsigned long long* prof;  // [16] clock / event counters summed over the grid (debug build only)
+#endif
 };
+#ifdef B200REC_TC_PROF
+#define TCPROF_ADD(i, v) atomicAdd(p.prof + (i), (unsigned long long)(v))
+#define TCPROF_CLK() clock64()
+#else
+#define TCPROF_ADD(i, v) ((void)0)
+#define TCPROF_CLK() 0ll
+#endif
 
+// order-preserving float <-> int map (for redux.sync, which has no float form)
+__device__ __forceinline__ int float_to_ord(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+__device__ __forceinline__ float ord_to_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 __device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) { return a.s > b.s || (a.s == b.s && a.id < b.id); }
 __device__ __forceinline__ void warp_sort_desc(Cand* c, int np, int lane) {
   for (int k = 2; k <= np; k <<= 1) {
@@ -227,7 +251,8 @@ struct __align__(16) HitRec {
   float v[8];
   int base;   // item id of v[0]
   int row;    // row inside the CTA tile
-  int pad[2];
+  float vmax; // largest item norm of the record's tile (the consumer's eps_t = c_u * vmax without a global load)
+  int pad;
 };
 
 template <int D, int BN, int STAGES>
@@ -318,8 +343,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
       mbar_wait(afull, 0);
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t % STAGES, as = t & (TC_ACC - 1);
+        const long long m0 = TCPROF_CLK();
         mbar_wait(tempty + as, ((t >> TC_ACC_SHIFT) & 1) ^ 1);
+        const long long m1 = TCPROF_CLK();
         mbar_wait(full + s, (t / STAGES) & 1);
+        TCPROF_ADD(0, m1 - m0);                 // MMA warp waiting for a free accumulator stage
+        TCPROF_ADD(1, TCPROF_CLK() - m1);       // ... for an item tile
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
 #pragma unroll
@@ -352,8 +381,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
       const int as = t & (TC_ACC - 1);
       // hit test "U_i >= cutL": approx_i >= cutL - c_u * (largest norm in this tile).  cutL is refreshed once per tile
       // (the consumer may have raised it); the tile's norm is one broadcast load
-      const float cut = active ? s_cut[row] - cu * __uint_as_float(__ldg(p.tile_vmax_bits + t)) : INFINITY;
+      const float tvmax = __uint_as_float(__ldg(p.tile_vmax_bits + t));
+      const float cut = active ? s_cut[row] - cu * tvmax : INFINITY;
+      const long long d0 = TCPROF_CLK();
       mbar_wait(tfull + as, (t >> TC_ACC_SHIFT) & 1);
+      if (lane == 0) TCPROF_ADD(2, TCPROF_CLK() - d0);  // drain warp waiting for the MMA
       tc_fence_after();
       const int i0 = t * BN;
       // this warp's half of the tile: all its columns go to registers with ONE wait, and the accumulator stage is handed
@@ -393,11 +425,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
         }
         const int total = __shfl_sync(0xffffffffu, pre, 15, 16);
         pre -= mine_n;
+        if (lane == 0) TCPROF_ADD(5, 1);
+        TCPROF_ADD(6, mine_n);
         if (__all_sync(0xffffffffu, total <= TC_QCAP)) {
           unsigned spins = 0;
+          const long long r0 = TCPROF_CLK();
           while (__any_sync(0xffffffffu, tail + total - s_head[ring] > TC_QCAP)) {
             if (++spins > 200000000u) __trap();
           }
+          if (lane == 0) TCPROF_ADD(3, TCPROF_CLK() - r0);  // drain warp waiting for ring room
           int k2 = tail + pre;
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
@@ -410,14 +446,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
                 *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
                 r->base = i0 + half * 64 + cc * 32 + g * 8;
                 r->row = row;
+                r->vmax = tvmax;
                 ++k2;
               }
             }
           }
           tail += total;
-          __threadfence_block();
-          __syncwarp();
-          if ((lane & 15) == 0) s_tail[ring] = tail;  // publish (one lane per half)
+          __syncwarp();  // orders the lanes' record stores before the publishing lane's release
+          if ((lane & 15) == 0) sts_release(s_tail + ring, tail);  // publish (one lane per half)
         } else {
           // more records than the ring holds (the first tiles, before the rows have a cut): group by group
 #pragma unroll
@@ -431,28 +467,29 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
               const unsigned bal = (bal_all >> (lh * 16)) & 0xffffu;  // this row half's lanes
               const int n = __popc(bal);
               unsigned spins = 0;
+              const long long r0 = TCPROF_CLK();
               while (__any_sync(0xffffffffu, tail + n - s_head[ring] > TC_QCAP)) {
                 if (++spins > 200000000u) __trap();
               }
+              if (lane == 0) TCPROF_ADD(4, TCPROF_CLK() - r0);  // ... in the group-by-group (flood) path
               if (mine) {
                 HitRec* r = q + ((tail + __popc(bal & ((1u << (lane & 15)) - 1u))) & (TC_QCAP - 1));
                 *reinterpret_cast<uint4*>(&r->v[0]) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
                 *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
                 r->base = i0 + half * 64 + cc * 32 + g * 8;
                 r->row = row;
+                r->vmax = tvmax;
               }
               tail += n;
-              __threadfence_block();
               __syncwarp();
-              if ((lane & 15) == 0) s_tail[ring] = tail;  // publish
+              if ((lane & 15) == 0) sts_release(s_tail + ring, tail);  // publish
             }
           }
         }
       }
     }
-    __threadfence_block();
     __syncwarp();
-    if ((lane & 15) == 0) s_done[ring] = 1;
+    if ((lane & 15) == 0) sts_release(s_done + ring, 1);
   } else {
     // ===== consumer warps: warp 10 + 2q + h owns rows 32q + 16h .. +15 and their two rings (one per column half) =====
     const int cw = warp - 10;
@@ -461,6 +498,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
     Cand* my_sort = sort_area + (size_t)cw * TC_CAP;
     int head2[2] = {0, 0};
 
+    long long c_loop = 0, c_refine = 0, c_iters = 0, c_passes = 0, c_nref = 0, c_app = 0;
+    const long long c_begin = TCPROF_CLK();
     auto refine_row = [&](int row) {
       // warp-cooperative: lower bound of the K'-th best approximate score by value bisection, then keep the band above
       // (bound - margin) with a ballot compaction (see the exactness argument at the top of the file)
@@ -478,11 +517,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
         mx = fmaxf(mx, c.s);
         mn = fminf(mn, c.s);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      }
+      mx = ord_to_float(__reduce_max_sync(0xffffffffu, float_to_ord(mx)));  // one REDUX each instead of five shuffles
+      mn = ord_to_float(__reduce_min_sync(0xffffffffu, float_to_ord(mn)));
       __syncwarp();
       float lo = (rcut > -INFINITY) ? rcut : mn;  // #(entries with L >= lo) >= K' always holds
       lo = fminf(lo, mx);
@@ -492,8 +528,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
         if (!(pv > lo && pv < hi)) break;
         int c = 0;
         for (int t = lane; t < rc; t += 32) c += (my_sort[t].s >= pv) ? 1 : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        c = __reduce_add_sync(0xffffffffu, c);
         if (c >= kk) { lo = pv; if (c <= kk + kk / 2 + 8) break; } else { hi = pv; }
       }
       const float ncut = lo;  // lower bound of the K'-th largest L: the new cutL
@@ -521,31 +556,33 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
       for (int hf = 0; hf < 2; ++hf) {
         const int ring = (quad * 2 + hf) * 2 + rh;
         HitRec* q = queues + ring * TC_QCAP;
-        const int done = s_done[ring];      // read BEFORE the tail: done => the tail read below is final
-        __threadfence_block();
-        const int tl_all = s_tail[ring];
-        __threadfence_block();              // acquire: the records below were written before the tail was published
+        const int done = lds_acquire(s_done + ring);    // read BEFORE the tail: done => the tail read below is final
+        const int tl_all = lds_acquire(s_tail + ring);  // acquire: the records below were written before this tail
         int head = head2[hf];
         // at most 16 records per ring per pass: a pass appends <= 2 * 16 * 8 = 256 values to one row (all records may
         // belong to the same row, e.g. a tile with a single live user), and the refinement check below runs before a list
         // that was under its threshold (<= 3/4 TC_CAP) can reach TC_CAP
         const int tl = min(tl_all, head + 16);
         const bool any = head < tl;
+        const long long l0 = TCPROF_CLK();
+        if (any) ++c_passes;
         while (head < tl) {
+          ++c_iters;
           const int nrec = min(4, tl - head);
           const int ri = lane >> 3, j = lane & 7;   // 8 lanes per record, lane j <-> item base + j
           const unsigned gmask = 0xffu << (ri * 8);
-          float sc = -INFINITY;
+          float sc = -INFINITY, tvmax = 0.f;
           int row = 0, base = 0;
           if (ri < nrec) {
             const HitRec* r = q + ((head + ri) & (TC_QCAP - 1));
             sc = r->v[j];
             row = r->row;
             base = r->base;
+            tvmax = r->vmax;
           }
           const int item = base + j;
           // records carry approx; the list keeps L = approx - eps_t, the test is U = approx + eps_t >= cutL
-          const float eps_t = (ri < nrec) ? s_cu[row] * __uint_as_float(__ldg(p.tile_vmax_bits + base / BN)) : 0.f;
+          const float eps_t = s_cu[row] * tvmax;
           bool pass = ri < nrec && sc + eps_t >= s_cut[row] && item < p.n_items && !(item >= p.banned_lo && item < p.banned_hi);
           // merge test against the row's sorted exclusion lists (group-cooperative, warp-uniform control flow)
 #pragma unroll
@@ -580,6 +617,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
             }
           }
           if (pass) {
+            ++c_app;
             const int pos = atomicAdd(&s_cnt[row], 1);
             if (pos < TC_CAP) p.cand[(size_t)(u0 + row) * TC_CAP + pos] = Cand{sc - eps_t, item};
             else p.overflow[u0 + row] = 1;
@@ -587,32 +625,44 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
           head += nrec;
         }
         __syncwarp();
+        c_loop += TCPROF_CLK() - l0;
         if (any) {
           head2[hf] = head;
-          __threadfence_block();
-          if (lane == 0) s_head[ring] = head;  // free the slots
+          if (lane == 0) sts_release(s_head + ring, head);  // free the slots (the __syncwarp above ordered the lanes' reads)
           progressed = true;
         }
         if (!(done && head == tl_all)) all_done = false;
       }
       if (progressed) {
-        // rows whose list grew long: tighten their cut
-        __threadfence_block();  // list entries written by the lanes above are visible to the whole warp (same SM)
+        // rows whose list grew long: tighten their cut (the list entries were written by other lanes of this warp: the
+        // __syncwarp after the record loop ordered them)
         const int row = row_base + (lane & 15);
         const int kk = s_kk[row];
         const bool need = lane < 16 && (u0 + row) < p.n_users && s_cnt[row] >= max(TC_REFINE_AT, min(2 * kk, 3 * TC_CAP / 4));
         unsigned needm = __ballot_sync(0xffffffffu, need);
+        const long long f0 = TCPROF_CLK();
         while (needm) {
           const int r = __ffs(needm) - 1;
           needm &= needm - 1;
           refine_row(row_base + r);
+          ++c_nref;
         }
+        c_refine += TCPROF_CLK() - f0;
         idle = 0;
       } else {
         if (all_done) break;
         if (++idle > 400000000u) __trap();
       }
     }
+    if (lane == 0) {
+      TCPROF_ADD(7, TCPROF_CLK() - c_begin);  // consumer warp: total, record loop, refinement
+      TCPROF_ADD(8, c_loop);
+      TCPROF_ADD(9, c_refine);
+      TCPROF_ADD(10, c_iters);
+      TCPROF_ADD(11, c_passes);
+      TCPROF_ADD(12, c_nref);
+    }
+    TCPROF_ADD(13, c_app);
     // final: lower-bound pass for every row, publish counts
     __threadfence_block();
     for (int r = 0; r < 16; ++r) {
@@ -779,8 +829,27 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
   const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + TC_RINGS * TC_QCAP * sizeof(HitRec) +
                       TC_CONSUMERS * TC_CAP * sizeof(Cand) + 14 * TC_M * 4 + 1024;
   B2_CUDA(cudaFuncSetAttribute(score_tc2_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifdef B200REC_TC_PROF
+  static unsigned long long* prof_d = nullptr;
+  if (!prof_d) B2_CUDA(cudaMalloc(&prof_d, 16 * sizeof(unsigned long long)));
+  B2_CUDA(cudaMemsetAsync(prof_d, 0, 16 * sizeof(unsigned long long), st));
+  p.prof = prof_d;
+#endif
   score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), TC2_THREADS, smem, st>>>(mu, mi, p);
   B2_LAUNCHED();
+#ifdef B200REC_TC_PROF
+  {
+    unsigned long long h[16];
+    B2_CUDA(cudaStreamSynchronize(st));
+    B2_CUDA(cudaMemcpy(h, prof_d, sizeof(h), cudaMemcpyDeviceToHost));
+    const double ctas = (double)ceil_div(nb, TC_M), tiles = (double)ceil_div(ni, BN);
+    fprintf(stderr, "[tc prof] ctas %.0f tiles %.0f | per CTA (cycles): mma wait acc %.0f, wait tile %.0f | per drain warp: wait mma %.0f, "
+            "wait ring %.0f, flood wait %.0f | per consumer warp: total %.0f, record loop %.0f, refine %.0f, iterations %.0f, passes %.0f, "
+            "refines %.0f | per CTA: record batches %.0f, records %.0f, appended %.0f\n", ctas, tiles, h[0] / ctas, h[1] / ctas,
+            h[2] / ctas / 8, h[3] / ctas / 8, h[4] / ctas / 8, h[7] / ctas / 8, h[8] / ctas / 8, h[9] / ctas / 8, h[10] / ctas / 8,
+            h[11] / ctas / 8, h[12] / ctas / 8, h[5] / ctas, h[6] / ctas, h[13] / ctas);
+  }
+#endif
   const size_t rsmem = 4 * TC_CAP * sizeof(Cand);
   tc_rescore_kernel<D><<<ceil_div(nb, 4), 128, rsmem, st>>>(rep_users, users, nb, rep_items, cand, cnt, k, out_ids, out_scores, p);
   B2_LAUNCHED();

@@ -32,7 +32,35 @@ def _lists_to_csr(lists):
     return ptr, idx
 
 
+class _TrackedList(list):
+    """Outer list of a split (`train_data` / `val_data` / `test_data`) that counts its in-place edits, so the cached
+    device CSR of the split is dropped after `dataset.test_data[u] = []` (the reference's inductive_eval,
+    trainer.py:219-227) at O(1) per lookup instead of a pass over all rows.  Behaves like the list it wraps."""
+    version = 0  # class-level default: unpickling (DataLoader workers) refills the list before any __init__ runs
+
+
+def _counting(name):
+    base = getattr(list, name)
+
+    def method(self, *args, **kwargs):
+        self.version += 1
+        return base(self, *args, **kwargs)
+    method.__name__ = name
+    return method
+
+
+for _name in ('__setitem__', '__delitem__', '__iadd__', '__imul__', 'append', 'extend', 'insert', 'pop', 'remove', 'clear',
+              'reverse', 'sort'):
+    setattr(_TrackedList, _name, _counting(_name))
+_SPLIT_ATTRS = ('train_data', 'val_data', 'test_data')
+
+
 class BasicDataset(Dataset):
+    def __setattr__(self, name, value):
+        if name in _SPLIT_ATTRS and type(value) is list:
+            value = _TrackedList(value)  # (a shallow copy: the row lists are shared)
+        object.__setattr__(self, name, value)
+
     def __init__(self, dataset_config):
         self.config = dataset_config
         self.name = dataset_config['name']
@@ -77,10 +105,10 @@ class BasicDataset(Dataset):
         lists = getattr(self, split + '_data')
         key = (split, str(device))
         hit = self._csr_cache.get(key)
-        # valid while it is the same outer list AND the same row objects of the same lengths: the reference's
-        # inductive_eval idiom `dataset.test_data[u] = []` (trainer.py:219-227) mutates the outer list in place, which
-        # identity of the outer list alone would miss.  (Editing the items INSIDE a row list in place is not detected:
-        # call invalidate_csr(split) after such an edit.)
+        # valid while it is the same outer list and that list has not been edited: the reference's inductive_eval idiom
+        # `dataset.test_data[u] = []` (trainer.py:219-227) mutates the outer list in place, which identity alone would
+        # miss -- the split attributes are _TrackedList (edit counter, O(1)); a foreign list type falls back to a pass
+        # over its rows.  (Editing the items INSIDE a row list in place is not detected: call invalidate_csr(split).)
         if hit is not None and hit[0] is lists and hit[2] == self._rows_fingerprint(lists):
             return hit[1]
         ptr, idx = _lists_to_csr(lists)
@@ -98,6 +126,8 @@ class BasicDataset(Dataset):
     def _rows_fingerprint(lists):
         if hasattr(lists, 'ptr'):  # CSR-backed lazy lists are immutable
             return None
+        if isinstance(lists, _TrackedList):
+            return ('version', lists.version)
         return hash(tuple(map(id, lists))) ^ hash(tuple(map(len, lists)))
 
     def invalidate_csr(self, split=None):

@@ -27,3 +27,14 @@ for i in range(3):
     tr.eval("test")
     torch.cuda.synchronize()
     print("eval %d: %.2f ms  (%.2f M users/s)" % (i, (time.perf_counter() - t0) * 1e3, ds.n_users / (time.perf_counter() - t0) / 1e6))
+if os.environ.get("PROFILE", "0") == "1":  # host-side cost of one evaluation (cumulative, python level)
+    import cProfile
+    import pstats
+    m._rep_cache = None
+    torch.cuda.synchronize()
+    pr = cProfile.Profile()
+    pr.enable()
+    tr.eval("test")
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(45)

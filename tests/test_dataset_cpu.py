@@ -133,3 +133,23 @@ def test_csr_cache_follows_in_place_row_edits():
     ds.test_data[u].append(int(idx0.max()))      # an edit INSIDE a row needs the explicit invalidation
     ds.invalidate_csr("test")
     assert int(ds.csr("test")[0][-1]) == int(ptr0[-1]) + 1
+
+
+def test_split_lists_count_their_edits_and_survive_pickling():
+    """the split attributes are list subclasses with an edit counter (the CSR cache check is O(1), not a pass over all
+    rows -- 3 ms per evaluation on a Yelp-sized dataset); DataLoader workers pickle the dataset"""
+    import pickle
+    import dataset as D
+    from b200rec import synth
+    ds = D.get_dataset({"name": "SyntheticDataset", "device": "cpu", "graph": synth.generate(40, 50, 400, seed=2)})
+    assert isinstance(ds.test_data, list) and type(ds.test_data).__name__ == "_TrackedList"
+    v0 = ds.test_data.version
+    ds.test_data[1] = []
+    ds.test_data.append([3])
+    assert ds.test_data.version == v0 + 2
+    plain = ds.test_data.copy()                      # the reference keeps `test_data.copy()` and assigns it back
+    assert type(plain) is list
+    ds.test_data = plain
+    assert type(ds.test_data).__name__ == "_TrackedList" and ds.test_data == plain
+    again = pickle.loads(pickle.dumps(ds.test_data))
+    assert again == plain and type(again).__name__ == "_TrackedList"
