@@ -8,6 +8,8 @@ On the C1-C3 shapes one SpMM layer is ~10 us of memory work, so per-kernel launc
 loop; the graph removes it.  The Adam moments are the tensors inside the trainer's torch.optim.Adam state, so
 optimiser state_dicts stay interchangeable with the eager path.
 """
+import os
+
 import torch
 
 from . import ops
@@ -60,7 +62,6 @@ class BprEngine:
         self.scratch = ops.bpr_scratch(batch_size, D, dev)
         self.dots = torch.zeros((batch_size, 3), **f32)  # per-sample (pos, neg, l2) partials when the dimension is sharded
         # ordered scatter (b200rec_bpr_group_rows): one store per distinct row, contributions summed in slot order
-        import os
         self.ordered = 3 * batch_size <= ops.GROUP_CAP and os.environ.get('B200REC_ATOMIC_SCATTER', '0') != '1'
         self.grouping = ops.bpr_grouping(batch_size, dev) if self.ordered else None
         self.aux_grouping = None
@@ -98,7 +99,6 @@ class BprEngine:
             # The two masked layers (last forward layer on the sampled rows, first backward hop from the sampled rows) can be
             # given their own hub-row chunk (B200REC_SPARSE_CHUNK).  Measured on C2 (ms/step): same plan 0.377, chunk 128
             # 0.387, 64 0.404, 32 0.435, 1024 0.494 -- the auto chunk is the optimum for them too, so the default is off.
-            import os
             sc = int(os.environ.get('B200REC_SPARSE_CHUNK', '0'))
             self.adj_sparse = model.norm_adj.replan(sc) if (partition is None and sc > 0 and sc != model.norm_adj.chunk) \
                 else model.norm_adj
@@ -140,10 +140,11 @@ class BprEngine:
                 if aux_dataset is not None:
                     self.aux_ptr, self.aux_items = aux_dataset.csr('train', device=dev)
                     self.aux_grouping = ops.bpr_grouping(batch_size, dev) if self.ordered else None
-        import os
         self.use_graph = use_graph and os.environ.get('B200REC_NO_GRAPH', '0') != '1'
         self._adj_ref = getattr(model, 'norm_adj', None)  # the step (and its captured graph) is built on THIS operand
         self._side_stream = torch.cuda.Stream(device=dev)
+        fork_env = os.environ.get('B200REC_FORK', 'auto')  # auto: fork the batch prelude only when the tables fit L2
+        self.fork = (self.table.numel() * 4 <= 96 * 2 ** 20) if fork_env == 'auto' else fork_env == '1'
         self._graphs = {}
         self._kernels = {}
         self.steps_done = 0
@@ -248,7 +249,14 @@ class BprEngine:
         m, B = self.model, self.B
         nu = m.n_users
         main = torch.cuda.current_stream()
-        forked = self.kind == 'LightGCN' and self.partition is None and m.n_layers >= 2
+        # the batch's small kernels (sampler, row grouping, row marks, live work list) are needed by the last forward layer
+        # only: `prelude` = they are issued ahead of the layers and the last layer runs on the compacted work list;
+        # `forked` = they run on a side stream beside the first layers instead of in front of them.  Forking pays on the
+        # L2-resident shapes (C2, same box: 0.386 ms/step forked, 0.403 serial) and not on the large ones, where ~60 us of
+        # prelude is nothing and the forked graph measured WORSE with host batches (C4, same box: 76.2 ms device-sampled,
+        # 90.5 ms with a host batch copied in before the graph; serial 75.6 / 75.7).  self.fork: tables fit L2.
+        prelude = self.kind == 'LightGCN' and self.partition is None and m.n_layers >= 2
+        forked = prelude and self.fork
         side = self._side_stream if forked else main
         grp = self.grouping
         # g_rep is all-zero between steps: with the ordered scatter the BPR kernel STORES the touched rows and they are
@@ -267,13 +275,13 @@ class BprEngine:
                 # and the first backward hop are restricted to them (bit-identical on the rows that matter)
                 self.row_flags.zero_()
                 ops.mark_rows(self.batch, nu, self.row_flags)
-                if forked and self.live is not None:
+                if prelude and self.live is not None:
                     ops.live_items(self.adj_sparse, self.row_flags, self.live[0], self.live[1])
             if forked and not lazy_clear:
                 self.g_rep.zero_()  # needed only by the BPR kernel: cleared beside the first forward layers
             if forked:
                 self.loss.zero_()  # off the critical path too
-        join = (lambda: main.wait_stream(side)) if forked else None
+        join = (lambda: main.wait_stream(side)) if forked else ((lambda: None) if prelude else None)
         if not forked:
             self.loss.zero_()
         if self.kind == 'MF':

@@ -81,6 +81,30 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand in tensor memory (row m of the 128 x K tile in lane m, two bf16 per 32-bit column, element 2c in the low half:
+// the memory image of a K-major bf16 row): the user tile is the same for every item tile of the sweep, and an SS-form
+// 128 x 128 x 16 UMMA reads 8 KB of shared memory per 64 cycles -- all 128 B/clk an SM has, which the record rings and
+// candidate lists also need.  With A in TMEM the tensor core reads 4 KB (B only) per instruction.
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -102,6 +126,14 @@ __device__ __forceinline__ int lds_acquire(const volatile int* p) {
 }
 __device__ __forceinline__ void sts_release(volatile int* p, int v) {
   asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(const_cast<int*>(p))), "r"(v) : "memory");
+}
+// The compiler does not know that tcgen05.ld is asynchronous: tie the destination registers to a point after
+// tcgen05.wait::ld so no use of them can be scheduled above the wait (no instruction is emitted)
+__device__ __forceinline__ void tc_regs_fence(uint32_t (&r)[32]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+  asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+               "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
@@ -167,6 +199,7 @@ struct TcParams {
   const int32_t *excl_ptr_a, *excl_idx_a, *excl_ptr_b, *excl_idx_b;
   int banned_lo, banned_hi;
   const float* unorm;        // [b]
+  const __nv_bfloat16* ub;   // [b, D] the users' rows in bf16 (tc_prep_kernel)
   const unsigned* tile_vmax_bits; // [n_tiles] largest item norm of each BN-item tile (float bits)
   Cand* cand;                // [b, TC_CAP]
   int* cand_cnt;             // [b]
@@ -232,12 +265,12 @@ __device__ __forceinline__ bool row_has(const int32_t* __restrict__ ptr, const i
 // re-score kernel with a K+E cut tripled the candidate volume, 8 -> 20 ms on the C2 sweep; a hash-bitmap prefilter left
 // the heavy rows at 13 ms.)
 #ifndef B200REC_TC_ACC_STAGES
-#define B200REC_TC_ACC_STAGES 4
+#define B200REC_TC_ACC_STAGES 2
 #endif
 constexpr int TC_ACC = B200REC_TC_ACC_STAGES;  // accumulator stages in TMEM (x 128 columns; 4 = all 512): the MMA warp runs up
                                                // to TC_ACC - 1 tiles ahead of the drain warps, hiding the commit -> drain ->
                                                // release -> issue hand-over latency (2 stages in round 1: tensor pipe 40 %)
-static_assert(TC_ACC == 2 || TC_ACC == 4, "TMEM allocations are powers of two columns");
+static_assert(TC_ACC == 2, "512 TMEM columns: TC_ACC x 128 accumulator columns + D / 2 columns of the user tile");
 constexpr int TC_ACC_SHIFT = (TC_ACC == 4) ? 2 : 1;
 constexpr int TC_QCAP = 64;       // records per ring (power of two); 16 rings: (quadrant, column half, row half)
 constexpr int TC_RINGS = 16;
@@ -256,15 +289,16 @@ struct __align__(16) HitRec {
 };
 
 template <int D, int BN, int STAGES>
-__global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_constant__ CUtensorMap tm_users,
-                                                                            const __grid_constant__ CUtensorMap tm_items,
+__global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_constant__ CUtensorMap tm_items,
                                                                             const TcParams p) {
   constexpr int KB = D / 64;
-  constexpr uint32_t A_BYTES = TC_M * D * 2, B_STAGE_BYTES = BN * D * 2;
+  constexpr uint32_t B_STAGE_BYTES = BN * D * 2;
+  constexpr uint32_t TMEM_A_COL = TC_ACC * BN;   // the user tile sits behind the accumulator stages
+  constexpr uint32_t TMEM_COLS = 512;            // power of two >= TC_ACC * BN + D / 2
+  static_assert(TC_ACC * BN + D / 2 <= 512, "TMEM budget");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + A_BYTES;
+  uint8_t* sB = smem;
   HitRec* queues = reinterpret_cast<HitRec*>(sB + (size_t)STAGES * B_STAGE_BYTES);      // [TC_RINGS][TC_QCAP]
   Cand* sort_area = reinterpret_cast<Cand*>(queues + TC_RINGS * TC_QCAP);                 // [TC_CONSUMERS][TC_CAP]
   float* s_cut = reinterpret_cast<float*>(sort_area + TC_CONSUMERS * TC_CAP);                        // [128]
@@ -312,12 +346,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int s = 0; s < TC_ACC; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
-    mbar_init(afull, 1);
+    mbar_init(afull, 4);  // the four drain warps that store the user tile into TMEM
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_ACC * BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -327,8 +361,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      mbar_expect_tx(afull, A_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + (size_t)kb * TC_M * 128, &tm_users, kb * 64, u0, afull);
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t % STAGES;
         mbar_wait(empty + s, ((t / STAGES) & 1) ^ 1);
@@ -341,33 +373,42 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
     if (lane == 0) {  // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc_bf16(TC_M, BN);
       mbar_wait(afull, 0);
+      tc_fence_after();
+      long long w_acc = 0, w_tile = 0;
+      const long long mm0 = TCPROF_CLK();
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t % STAGES, as = t & (TC_ACC - 1);
         const long long m0 = TCPROF_CLK();
         mbar_wait(tempty + as, ((t >> TC_ACC_SHIFT) & 1) ^ 1);
         const long long m1 = TCPROF_CLK();
         mbar_wait(full + s, (t / STAGES) & 1);
-        TCPROF_ADD(0, m1 - m0);                 // MMA warp waiting for a free accumulator stage
-        TCPROF_ADD(1, TCPROF_CLK() - m1);       // ... for an item tile
+        w_acc += m1 - m0;                       // MMA warp waiting for a free accumulator stage
+        w_tile += TCPROF_CLK() - m1;            // ... for an item tile
         tc_fence_after();
-        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
+        const uint32_t b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_desc_sw128(a0 + kb * TC_M * 128 + k * 32);
             const uint64_t bd = umma_desc_sw128(b0 + kb * BN * 128 + k * 32);
-            tc_mma_bf16(tmem_base + as * BN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            // K-step (kb, k) = elements 64 kb + 16 k .. + 15 of every row = 8 TMEM columns
+            tc_mma_bf16_ts(tmem_base + as * BN, tmem_base + TMEM_A_COL + (uint32_t)(kb * 32 + k * 8), bd, idesc, (kb | k) ? 1u : 0u);
           }
         }
         tc_commit(empty + s);
         tc_commit(tfull + as);
       }
+      TCPROF_ADD(0, w_acc);
+      TCPROF_ADD(1, w_tile);
+      TCPROF_ADD(14, TCPROF_CLK() - mm0);       // MMA warp: whole sweep
     }
   } else if (warp < 10) {
     // ===== drain warps: TMEM -> group maxima -> hit records.  Two warps per TMEM lane quadrant (a warp may only touch
-    // lanes 32 * (warp % 4) ..), each taking half of a tile's columns: two drain warps per scheduler hide each other's
-    // tcgen05.ld / FMNMX latency.
+    // lanes 32 * (warp % 4) ..), each taking half of a tile's columns in two 32-column chunks.  The chunks are software-
+    // pipelined: while one chunk's maxima / records are formed, the tcgen05.ld of the next chunk (the other half of this
+    // tile, or the first half of the next tile) is in flight -- TMEM reads are the unit this kernel is bound by (64 B/clk
+    // per SM: 1 024 cycles per 128 x 128 fp32 tile), and a drain warp that loads, waits, then computes leaves it idle a
+    // third of the time (measured 1.5 k cycles per tile at D = 128 before this).
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int lh = lane >> 4;                          // row half: lanes 0-15 feed one consumer, 16-31 the other
@@ -377,117 +418,121 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
     HitRec* q = queues + ring * TC_QCAP;
     int tail = 0;
     const float cu = s_cu[row];
-    for (int t = 0; t < n_tiles; ++t) {
-      const int as = t & (TC_ACC - 1);
-      // hit test "U_i >= cutL": approx_i >= cutL - c_u * (largest norm in this tile).  cutL is refreshed once per tile
-      // (the consumer may have raised it); the tile's norm is one broadcast load
+    static_assert(BN == 128, "drain layout: two 32-column chunks per warp");
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64);
+
+    // one 32-column chunk: group-of-8 maxima against the row's cut ("U_i >= cutL": approx_i >= cutL - c_u * largest norm in
+    // the tile; cutL is re-read per chunk, the consumer may have raised it), hit groups pushed as ONE batch -- per-lane
+    // record count -> prefix inside the 16-lane row half -> one wait for room, one publish.  A lane's records stay
+    // consecutive and ascending in item id (what the consumer's forward-only exclusion cursor relies on); a batch holds at
+    // most 16 lanes x 4 groups = TC_QCAP records, so it always fits an empty ring.
+    long long d_wait_mma = 0, d_wait_ring = 0, d_batches = 0, d_records = 0;
+    auto process = [&](const uint32_t (&v)[32], int t, int cc) {
       const float tvmax = __uint_as_float(__ldg(p.tile_vmax_bits + t));
       const float cut = active ? s_cut[row] - cu * tvmax : INFINITY;
+      unsigned hit4 = 0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        // eight values in four instructions (FMNMX3, sm_100)
+        const float a = fmax3(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]), __uint_as_float(v[g * 8 + 2]));
+        const float b = fmax3(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+        const float c2 = fmax3(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]), a);
+        if (fmaxf(b, c2) >= cut) hit4 |= 1u << g;
+      }
+      if (!__any_sync(0xffffffffu, hit4 != 0)) return;
+      const int mine_n = __popc(hit4);
+      int pre = mine_n;  // prefix sum inside each 16-lane row half (each half has its own ring; `tail` is per half)
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const int t2 = __shfl_up_sync(0xffffffffu, pre, o, 16);
+        if ((lane & 15) >= o) pre += t2;
+      }
+      const int total = __shfl_sync(0xffffffffu, pre, 15, 16);
+      pre -= mine_n;
+      static_assert(16 * 4 <= TC_QCAP, "a chunk's batch must fit the ring");
+      ++d_batches;
+      d_records += mine_n;
+      unsigned spins = 0;
+      const long long r0 = TCPROF_CLK();
+      while (__any_sync(0xffffffffu, tail + total - s_head[ring] > TC_QCAP)) {
+        if (++spins > 200000000u) __trap();
+      }
+      d_wait_ring += TCPROF_CLK() - r0;  // drain warp waiting for ring room
+      int k2 = tail + pre;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if ((hit4 >> g) & 1u) {
+          HitRec* r = q + (k2 & (TC_QCAP - 1));
+          *reinterpret_cast<uint4*>(&r->v[0]) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+          *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+          r->base = t * BN + half * 64 + cc * 32 + g * 8;
+          r->row = row;
+          r->vmax = tvmax;
+          ++k2;
+        }
+      }
+      tail += total;
+      __syncwarp();  // orders the lanes' record stores before the publishing lane's release
+      if ((lane & 15) == 0) sts_release(s_tail + ring, tail);  // publish (one lane per half)
+    };
+
+    uint32_t va[32], vb[32];
+    if (half == 0) {
+      // the user tile -> TMEM, once per CTA: this lane's row (zeros past the last user), 32 columns (64 bf16) per store
+      const uint4* src = reinterpret_cast<const uint4*>(p.ub + (size_t)(u0 + row) * D);
+#pragma unroll
+      for (int c = 0; c < D / 64; ++c) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 w = active ? __ldg(src + c * 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+          va[j * 4 + 0] = w.x; va[j * 4 + 1] = w.y; va[j * 4 + 2] = w.z; va[j * 4 + 3] = w.w;
+        }
+        tc_st32(tmem_base + ((uint32_t)(quad * 32) << 16) + TMEM_A_COL + (uint32_t)(c * 32), va);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(afull);
+    }
+    {
       const long long d0 = TCPROF_CLK();
-      mbar_wait(tfull + as, (t >> TC_ACC_SHIFT) & 1);
-      if (lane == 0) TCPROF_ADD(2, TCPROF_CLK() - d0);  // drain warp waiting for the MMA
+      mbar_wait(tfull + 0, 0);
+      d_wait_mma += TCPROF_CLK() - d0;
       tc_fence_after();
-      const int i0 = t * BN;
-      // this warp's half of the tile: all its columns go to registers with ONE wait, and the accumulator stage is handed
-      // back to the MMA warp before any of the (slow, ring-dependent) hit handling below
-      static_assert(BN == 128, "drain layout: two 32-column chunks per warp");
-      uint32_t vv[2][32];
-      const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * 64);
-      tc_ld32_nowait(tcol, vv[0]);
-      tc_ld32_nowait(tcol + 32, vv[1]);
+      tc_ld32_nowait(tlane, va);
       tc_wait_ld();
+      tc_regs_fence(va);
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      const int as = t & (TC_ACC - 1);
+      tc_ld32_nowait(tlane + (uint32_t)(as * BN + 32), vb);  // second chunk of this tile: in flight under the first's work
+      process(va, t, 0);
+      tc_wait_ld();
+      tc_regs_fence(vb);
+      // this warp has read all its columns of the tile: hand the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + as);
-      // group-of-8 maxima against the row's cut: bit cc*4+g <-> columns half*64 + cc*32 + g*8 .. +7
-      unsigned hit8 = 0;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t* v = vv[cc];
-          // eight values in four instructions (FMNMX3, sm_100)
-          const float a = fmax3(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]), __uint_as_float(v[g * 8 + 2]));
-          const float b = fmax3(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-          const float c2 = fmax3(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]), a);
-          if (fmaxf(b, c2) >= cut) hit8 |= 1u << (cc * 4 + g);
-        }
+      if (t + 1 < n_tiles) {
+        const int an = (t + 1) & (TC_ACC - 1);
+        const long long d0 = TCPROF_CLK();
+        mbar_wait(tfull + an, ((t + 1) >> TC_ACC_SHIFT) & 1);
+        d_wait_mma += TCPROF_CLK() - d0;  // drain warp waiting for the MMA
+        tc_fence_after();
+        tc_ld32_nowait(tlane + (uint32_t)(an * BN), va);     // first chunk of the next tile: under the second chunk's work
       }
-      if (__any_sync(0xffffffffu, hit8 != 0)) {
-        // one batch per tile: per-lane record count -> warp prefix -> one wait for room, one fence, one publish.  A lane's
-        // records stay consecutive and ascending in item id (what the consumer's forward-only exclusion cursor relies on).
-        const int mine_n = __popc(hit8);
-        int pre = mine_n;  // prefix sum inside each 16-lane row half (each half has its own ring; `tail` is per half)
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-          const int t2 = __shfl_up_sync(0xffffffffu, pre, o, 16);
-          if ((lane & 15) >= o) pre += t2;
-        }
-        const int total = __shfl_sync(0xffffffffu, pre, 15, 16);
-        pre -= mine_n;
-        if (lane == 0) TCPROF_ADD(5, 1);
-        TCPROF_ADD(6, mine_n);
-        if (__all_sync(0xffffffffu, total <= TC_QCAP)) {
-          unsigned spins = 0;
-          const long long r0 = TCPROF_CLK();
-          while (__any_sync(0xffffffffu, tail + total - s_head[ring] > TC_QCAP)) {
-            if (++spins > 200000000u) __trap();
-          }
-          if (lane == 0) TCPROF_ADD(3, TCPROF_CLK() - r0);  // drain warp waiting for ring room
-          int k2 = tail + pre;
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if ((hit8 >> (cc * 4 + g)) & 1u) {
-                const uint32_t* v = vv[cc];
-                HitRec* r = q + (k2 & (TC_QCAP - 1));
-                *reinterpret_cast<uint4*>(&r->v[0]) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
-                *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
-                r->base = i0 + half * 64 + cc * 32 + g * 8;
-                r->row = row;
-                r->vmax = tvmax;
-                ++k2;
-              }
-            }
-          }
-          tail += total;
-          __syncwarp();  // orders the lanes' record stores before the publishing lane's release
-          if ((lane & 15) == 0) sts_release(s_tail + ring, tail);  // publish (one lane per half)
-        } else {
-          // more records than the ring holds (the first tiles, before the rows have a cut): group by group
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t* v = vv[cc];
-              const bool mine = (hit8 >> (cc * 4 + g)) & 1u;
-              const unsigned bal_all = __ballot_sync(0xffffffffu, mine);
-              if (bal_all == 0) continue;
-              const unsigned bal = (bal_all >> (lh * 16)) & 0xffffu;  // this row half's lanes
-              const int n = __popc(bal);
-              unsigned spins = 0;
-              const long long r0 = TCPROF_CLK();
-              while (__any_sync(0xffffffffu, tail + n - s_head[ring] > TC_QCAP)) {
-                if (++spins > 200000000u) __trap();
-              }
-              if (lane == 0) TCPROF_ADD(4, TCPROF_CLK() - r0);  // ... in the group-by-group (flood) path
-              if (mine) {
-                HitRec* r = q + ((tail + __popc(bal & ((1u << (lane & 15)) - 1u))) & (TC_QCAP - 1));
-                *reinterpret_cast<uint4*>(&r->v[0]) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
-                *reinterpret_cast<uint4*>(&r->v[4]) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
-                r->base = i0 + half * 64 + cc * 32 + g * 8;
-                r->row = row;
-                r->vmax = tvmax;
-              }
-              tail += n;
-              __syncwarp();
-              if ((lane & 15) == 0) sts_release(s_tail + ring, tail);  // publish
-            }
-          }
-        }
+      process(vb, t, 1);
+      if (t + 1 < n_tiles) {
+        tc_wait_ld();
+        tc_regs_fence(va);
       }
     }
+    if (lane == 0) {
+      TCPROF_ADD(2, d_wait_mma);
+      TCPROF_ADD(3, d_wait_ring);
+      TCPROF_ADD(5, d_batches);
+    }
+    TCPROF_ADD(6, d_records);
     __syncwarp();
     if ((lane & 15) == 0) sts_release(s_done + ring, 1);
   } else {
@@ -676,7 +721,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) score_tc2_kernel(const __grid_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_ACC * BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
@@ -816,17 +861,15 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
   B2_LAUNCHED();
   tc_prep_kernel<D><<<ceil_div((long long)ni * G, 256), 256, 0, st>>>(rep_items, nullptr, ni, ib, vnorm, vmax, BN);
   B2_LAUNCHED();
-  CUtensorMap mu, mi;
-  int rc = make_map(&mu, ub, nb, D, TC_M);
-  if (rc) return rc;
-  rc = make_map(&mi, ib, ni, D, BN);
+  CUtensorMap mi;
+  int rc = make_map(&mi, ib, ni, D, BN);
   if (rc) return rc;
   TcParams p;
   p.users = users; p.n_users = nb; p.n_items = ni; p.k = k;
   p.excl_ptr_a = ea_ptr; p.excl_idx_a = ea_idx; p.excl_ptr_b = eb_ptr; p.excl_idx_b = eb_idx;
-  p.banned_lo = blo; p.banned_hi = bhi; p.unorm = unorm; p.tile_vmax_bits = vmax; p.cand = cand; p.cand_cnt = cnt; p.overflow = ovf;
+  p.banned_lo = blo; p.banned_hi = bhi; p.unorm = unorm; p.ub = ub; p.tile_vmax_bits = vmax; p.cand = cand; p.cand_cnt = cnt; p.overflow = ovf;
   B2_CUDA(cudaMemsetAsync(ovf, 0, (size_t)nb * sizeof(int), st));
-  const size_t smem = 1024 + (size_t)TC_M * D * 2 + (size_t)STAGES * BN * D * 2 + TC_RINGS * TC_QCAP * sizeof(HitRec) +
+  const size_t smem = 1024 + (size_t)STAGES * BN * D * 2 + TC_RINGS * TC_QCAP * sizeof(HitRec) +
                       TC_CONSUMERS * TC_CAP * sizeof(Cand) + 14 * TC_M * 4 + 1024;
   B2_CUDA(cudaFuncSetAttribute(score_tc2_kernel<D, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #ifdef B200REC_TC_PROF
@@ -835,7 +878,7 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
   B2_CUDA(cudaMemsetAsync(prof_d, 0, 16 * sizeof(unsigned long long), st));
   p.prof = prof_d;
 #endif
-  score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), TC2_THREADS, smem, st>>>(mu, mi, p);
+  score_tc2_kernel<D, BN, STAGES><<<ceil_div(nb, TC_M), TC2_THREADS, smem, st>>>(mi, p);
   B2_LAUNCHED();
 #ifdef B200REC_TC_PROF
   {
@@ -843,10 +886,10 @@ static int tc_launch(const float* rep_users, const int64_t* users, int nb, const
     B2_CUDA(cudaStreamSynchronize(st));
     B2_CUDA(cudaMemcpy(h, prof_d, sizeof(h), cudaMemcpyDeviceToHost));
     const double ctas = (double)ceil_div(nb, TC_M), tiles = (double)ceil_div(ni, BN);
-    fprintf(stderr, "[tc prof] ctas %.0f tiles %.0f | per CTA (cycles): mma wait acc %.0f, wait tile %.0f | per drain warp: wait mma %.0f, "
-            "wait ring %.0f, flood wait %.0f | per consumer warp: total %.0f, record loop %.0f, refine %.0f, iterations %.0f, passes %.0f, "
-            "refines %.0f | per CTA: record batches %.0f, records %.0f, appended %.0f\n", ctas, tiles, h[0] / ctas, h[1] / ctas,
-            h[2] / ctas / 8, h[3] / ctas / 8, h[4] / ctas / 8, h[7] / ctas / 8, h[8] / ctas / 8, h[9] / ctas / 8, h[10] / ctas / 8,
+    fprintf(stderr, "[tc prof] ctas %.0f tiles %.0f | per CTA (cycles): mma sweep %.0f, wait acc %.0f, wait tile %.0f | per drain warp: wait mma %.0f, "
+            "wait ring %.0f | per consumer warp: total %.0f, record loop %.0f, refine %.0f, iterations %.0f, passes %.0f, "
+            "refines %.0f | per CTA: record batches %.0f, records %.0f, appended %.0f\n", ctas, tiles, h[14] / ctas, h[0] / ctas, h[1] / ctas,
+            h[2] / ctas / 8, h[3] / ctas / 8, h[7] / ctas / 8, h[8] / ctas / 8, h[9] / ctas / 8, h[10] / ctas / 8,
             h[11] / ctas / 8, h[12] / ctas / 8, h[5] / ctas, h[6] / ctas, h[13] / ctas);
   }
 #endif
@@ -864,7 +907,7 @@ int b200rec_score_topk_tc(const float* rep_users, const int64_t* users, int nb, 
     return tc_launch<64, 128, 3>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
                                  out_scores, out_overflow, workspace, st);
   if (d == 128)
-    return tc_launch<128, 128, 2>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
+    return tc_launch<128, 128, 3>(rep_users, users, nb, rep_items, ni, ea_ptr, ea_idx, eb_ptr, eb_idx, blo, bhi, k, out_ids,
                                   out_scores, out_overflow, workspace, st);
   return fail(B200REC_ERR_UNSUPPORTED, "%s: %s", "score_topk_tc", "tensor-core scoring supports embedding size 64 / 128");
 }

@@ -454,3 +454,82 @@ class DOSE_drop3(DOSE_aug):
     def generate_drop_graph(self, dataset, aug_idx=None):
         return self._edited_graph(dataset, aug_idx)
 
+
+
+class DOSE_drop2(DOSE_aug):
+    """IGCN contrasted with its propagation on a RANDOM edge subset of the train graph (reference model.py:1673-1962,
+    used by the reference's Gowalla config): `generate_drop_graph` keeps int(E * aug_rate) train pairs drawn without
+    replacement (utils.generate_drop_daj_mat, utils.py:91-103 -- random.sample there, a seeded device permutation here),
+    degrees recomputed on the subset; `update_aug_adj` redraws it after every epoch (trainer.py:350-351).  No mining:
+    `aug_num` is read like the reference does but only `cal_cos_sim` (never called by the trainer) uses it."""
+    edit = 'random'
+
+    def __init__(self, model_config):
+        self.aug_rate = model_config.get('aug_rate', 0.2)
+        self._aug_gen = None
+        super().__init__(model_config)
+
+    def _edited_graph(self, dataset, aug_idx=None):
+        if self._aug_gen is None:
+            self._aug_gen = torch.Generator(device=self.device)
+            self._aug_gen.manual_seed(int(self.config.get('aug_seed', 2021)))
+        return SGL.generate_drop_graph(self, dataset, keep_index=aug_idx)
+
+    def generate_drop_graph(self, dataset, keep_index=None):
+        return self._edited_graph(dataset, keep_index)
+
+
+class DOSE_aug_drop2(DOSE_aug):
+    """IGCN contrasted with its propagation on the train graph PLUS the `aug_num` most similar (user, item) pairs among the
+    low-degree nodes (reference model.py:3182-3430): `cal_cos_sim` ranks users and items by train degree, leaves out the
+    top `aug_ratio` fraction of each, and takes the flat top-k of the cosine matrix of what remains (:3290-3324).
+    The reference builds two graphs from two separate minings -- `norm_aug_adj` (utils.generate_aug_daj_mat) and
+    `norm_drop_adj` (utils.generate_drop_daj_mat2) -- and contrasts with the second one (:3391-3404).
+    Reference defects, stated: `generate_drop_graph` calls generate_drop_daj_mat2 without its `aug_rate` argument
+    (model.py:3241 vs utils.py:105), so the reference class raises TypeError when constructed; the function itself
+    discards its `random.sample` (utils.py:110), i.e. it returns the same union graph as generate_aug_daj_mat.  Here both
+    graphs are that union, each from its own mining pass like the reference's constructor."""
+    edit = 'add'
+
+    def __init__(self, model_config):
+        self.aug_ratio = model_config.get('aug_ratio', 0.2)
+        self._core = None
+        super().__init__(model_config)
+        self.norm_drop_adj = self._edited_graph(model_config['dataset'])
+
+    def _core_nodes(self, dataset):
+        if self._core is None:
+            import utils as _utils
+            ranked_users, ranked_items = _utils.graph_rank_nodes(dataset, 'degree')
+            cu = ranked_users[int(self.n_users * self.aug_ratio):]
+            ci = ranked_items[int(self.n_items * self.aug_ratio):]
+            self._core = (torch.from_numpy(np.ascontiguousarray(cu)).to(self.device),
+                          torch.from_numpy(np.ascontiguousarray(ci)).to(self.device))
+        return self._core
+
+    def cal_cos_sim(self, dataset=None):
+        from b200rec import mining
+        core_users, core_items = self._core_nodes(self.config['dataset'] if dataset is None else dataset)
+        with torch.no_grad():
+            rep = self.get_def_rep()
+            u, i, _ = mining.pair_topk_global(rep[core_users].contiguous(), rep[self.n_users + core_items].contiguous(),
+                                              self.aug_num, precision=self.mining_precision)
+        return torch.stack([core_users[u], core_items[i]], dim=1)
+
+    cal_cos_sim_v2 = cal_cos_sim
+
+    def generate_drop_graph(self, dataset, aug_idx=None):
+        return self._edited_graph(dataset, aug_idx)
+
+    def get_drop_rep(self, norm_drop_adj):
+        return self.get_aug_rep(norm_drop_adj)
+
+    def bpr_forward(self, users, pos_items, neg_items):
+        users_r, pos_items_r, neg_items_r, l2_norm_sq = IGCN.bpr_forward(self, users, pos_items, neg_items)
+        aug_users_r = ops.gather_rows(self.get_drop_rep(self.norm_drop_adj), users)
+        return users_r, pos_items_r, neg_items_r, l2_norm_sq, self.cal_loss(users_r, aug_users_r)
+
+    def update_aug_adj(self):  # not defined by the reference class (DOSEdropTrainer would raise): both graphs are re-mined
+        self.norm_aug_adj = self._edited_graph(self.config['dataset'])
+        self.norm_drop_adj = self._edited_graph(self.config['dataset'])
+        self.aug_version += 1

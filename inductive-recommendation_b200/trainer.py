@@ -7,8 +7,9 @@ save_path / opt / dataloader / test_user_loader; BPRTrainer (:403-429); IGCNTrai
 reference's (config.py); optional extras: 'fused' (default True: CUDA-graphed libb200rec step with on-device
 sampling), 'sampler' ('device' | 'host': draw triples on device, or iterate the DataLoader like the reference),
 'seed', 'eval_precision' (0 exact fp32, 1 tcgen05 bf16 candidates + exact re-score).
-SGLTrainer (:432-459) and HALFTrainer (:460-486) ride on the same engine.
-Out of scope: DOSE*/IDCF/BCE/ML trainers.
+SGLTrainer (:432-459) and HALFTrainer (:460-486) ride on the same engine; DOSEaugTrainer (:255-303) and
+DOSEdropTrainer (:304-353) drive the DOSE_* models through the library's autograd Functions.
+Out of scope: DOSEtest/IDCF/BCE/ML trainers.
 
 What changes underneath: one training step is a replayed CUDA graph (b200rec.engine.BprEngine); evaluation computes
 the representation once, then runs the fused score + mask + top-K kernel over large user chunks and a hit-matrix

@@ -124,3 +124,79 @@ def test_epoch_runs_and_remines(golden, name):
     _, metrics, _ = tr.eval("val")
     assert 0.0 <= metrics["Recall"][20] <= 1.0 and nnz0 > 0
     assert MODEL_CFG[name]["aug_num"] == 2000
+
+
+def _small_dataset():
+    import dataset as D
+    from b200rec import synth
+    return D.get_dataset({"name": "SyntheticDataset", "device": DEV, "graph": synth.generate(300, 400, 9000, seed=7)})
+
+
+def _dose_cfg(name, **kw):
+    return dict({"name": name, "embedding_size": 64, "n_layers": 2, "device": DEV, "dropout": 0.3, "feature_ratio": 1.0,
+                 "aug_num": 500}, **kw)
+
+
+def test_dose_drop2_random_subgraph_and_epoch():
+    """DOSE_drop2 (reference model.py:1673-1962): the contrast graph holds exactly int(E * aug_rate) train pairs
+    (utils.py:91-103), every one a train edge, degrees recomputed on the subset; update_aug_adj redraws it"""
+    import model as M
+    import trainer as T
+    ds = _small_dataset()
+    m = M.get_model(_dose_cfg("DOSE_drop2", aug_rate=0.25), ds)
+    users, items = ds.train_pairs()
+    n_keep = int(len(users) * 0.25)
+    a = m.norm_aug_adj
+    assert a.nnz == 2 * n_keep
+    rp, ci = _np(a.rowptr).astype(np.int64), _np(a.colidx).astype(np.int64)
+    rows = np.repeat(np.arange(ds.n_users + ds.n_items), np.diff(rp))
+    upper = rows < ds.n_users
+    kept = set(zip(rows[upper].tolist(), (ci[upper] - ds.n_users).tolist()))
+    assert len(kept) == n_keep and kept <= set(zip(users.tolist(), items.tolist()))
+    deg = np.maximum(np.diff(rp), 1).astype(np.float64)
+    np.testing.assert_allclose(_np(a.vals), (deg[rows] ** -0.5 * deg[ci] ** -0.5).astype(np.float32), rtol=1e-6)
+    tr = T.get_trainer({"name": "DOSEdropTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 0.0, "aux_reg": 0.001,
+                        "contrastive_reg": 0.1, "device": DEV, "n_epochs": 1, "batch_size": 512, "dataloader_num_workers": 0,
+                        "test_batch_size": 128, "topks": TOPKS}, ds, m)
+    first = _np(a.colidx).copy()
+    m.train()
+    assert np.isfinite(tr.train_one_epoch()) and m.aug_version == 1
+    assert m.norm_aug_adj.nnz == 2 * n_keep and not np.array_equal(_np(m.norm_aug_adj.colidx), first)
+
+
+def test_dose_aug_drop2_mines_the_most_similar_low_degree_pairs():
+    """DOSE_aug_drop2.cal_cos_sim (reference model.py:3290-3324): flat top-k of the cosine matrix of the users x items that
+    remain after the aug_ratio highest-degree ones are left out, mapped back to global ids -- against a dense float64
+    restatement; both graphs are the train graph plus those pairs"""
+    import model as M
+    import trainer as T
+    import utils as U
+    ds = _small_dataset()
+    m = M.get_model(_dose_cfg("DOSE_aug_drop2", aug_ratio=0.2), ds)
+    m.eval()
+    pairs = _np(m.cal_cos_sim())
+    assert pairs.shape == (500, 2)
+    ru, ri = U.graph_rank_nodes(ds, "degree")
+    cu, ci = ru[int(ds.n_users * 0.2):], ri[int(ds.n_items * 0.2):]
+    assert set(pairs[:, 0].tolist()) <= set(cu.tolist()) and set(pairs[:, 1].tolist()) <= set(ci.tolist())
+    with torch.no_grad():
+        rep = m.get_def_rep().double()
+    un = torch.nn.functional.normalize(rep[torch.from_numpy(cu.copy()).to(DEV)], dim=1)
+    vn = torch.nn.functional.normalize(rep[ds.n_users + torch.from_numpy(ci.copy()).to(DEV)], dim=1)
+    cos = _np(un @ vn.T)
+    cut = np.sort(cos.reshape(-1))[-500]
+    pos_u = {int(u): k for k, u in enumerate(cu)}
+    pos_i = {int(i): k for k, i in enumerate(ci)}
+    got = np.array([cos[pos_u[int(u)], pos_i[int(i)]] for u, i in pairs])
+    assert (got >= cut - 1e-6).all() and (np.diff(got) <= 1e-6).all()           # the top-k, best first
+    clear = np.argwhere(cos > cut + 1e-6)
+    assert {(int(cu[a]), int(ci[b])) for a, b in clear} <= {(int(u), int(i)) for u, i in pairs}
+    users, items = ds.train_pairs()
+    n_union = len(set(zip(users.tolist(), items.tolist())) | {(int(u), int(i)) for u, i in pairs})
+    assert m.generate_aug_graph(ds, pairs).nnz == m.generate_drop_graph(ds, pairs).nnz == 2 * n_union
+    assert m.norm_aug_adj.nnz > m.norm_adj.nnz     # (the constructor mined with its own dropout draw, like the reference)
+    tr = T.get_trainer({"name": "DOSEdropTrainer", "optimizer": "Adam", "lr": 1e-3, "l2_reg": 0.0, "aux_reg": 0.001,
+                        "contrastive_reg": 0.1, "device": DEV, "n_epochs": 1, "batch_size": 512, "dataloader_num_workers": 0,
+                        "test_batch_size": 128, "topks": TOPKS}, ds, m)
+    m.train()
+    assert np.isfinite(tr.train_one_epoch()) and m.aug_version == 1 and m.norm_drop_adj.nnz > m.norm_adj.nnz
