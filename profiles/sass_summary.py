@@ -9,7 +9,7 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(REPO, "inductive-recommendation_b200", "b200rec", "libb200rec.so")
-KEY = ["UTCHMMA", "UTCBAR", "UTMALDG", "LDTM", "SYNCS", "LDG", "LDG.E.128", "STG", "LDS", "STS", "REDG", "ATOMG", "FFMA", "FMNMX3",
+KEY = ["UTCHMMA", "UTCBAR", "UTMALDG", "LDTM", "STTM", "SYNCS", "REDUX", "LDG", "LDG.E.128", "STG", "LDS", "STS", "REDG", "ATOMG", "FFMA", "FMNMX3",
        "SHFL", "BAR", "LDL", "STL", "CCTL"]
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 kern, rows = None, []
@@ -42,7 +42,7 @@ flush()
 rows = [r for r in rows if not r[0].startswith("cub::") and "EmptyKernel" not in r[0]]
 rows.sort(key=lambda r: -r[1])
 print("# libb200rec.so -- SASS opcode counts per kernel (cuobjdump -sass, sm_100a).  size = bytes of SASS.")
-print("# tcgen05.mma -> UTCHMMA, tcgen05.commit -> UTCBAR, TMA tile load -> UTMALDG, tcgen05.ld -> LDTM, mbarrier -> SYNCS")
+print("# tcgen05.mma -> UTCHMMA, tcgen05.commit -> UTCBAR, TMA tile load -> UTMALDG, tcgen05.ld -> LDTM, tcgen05.st -> STTM, mbarrier -> SYNCS, redux.sync -> REDUX")
 print("%-78s %7s " % ("kernel", "size") + " ".join("%9s" % k for k in KEY))
 for name, sz, h in rows:
     print("%-78s %7d " % (name[:78], sz) + " ".join("%9d" % h.get(k, 0) for k in KEY))
