@@ -209,6 +209,16 @@ int b200rec_spmm_f32_live(const b200rec_csr* a, const float* x, int32_t d, float
  * flags [n_rows] must be zeroed by the caller first.  Feeds needed_rows / nonzero_rows of the propagation calls. */
 int b200rec_mark_rows(const int64_t* batch /*[B,3]*/, int32_t n_batch, int64_t item_offset, uint8_t* flags, void* stream);
 
+/* Byte mask of the rows WITHIN ONE HOP of a batch (new; no reference counterpart -- the reference propagates every row in
+ * every layer, model.py:100-110): the sampled rows and every train item of a sampled user (user_ptr / user_items = the
+ * sampler's CSR by user).  Only flags[user], flags[item_offset + item] entries are written (set to 1): the caller zeroes
+ * the ITEM half before the call and keeps the USER half all-ones (a superset is always valid; the users within a hop of
+ * the sampled items are ~98 % of the users of the C4 graph).  A BPR step reads the propagated table only at the sampled
+ * rows, so layer L-1 of the forward pass is needed only inside this mask (dst_flags) and after the first backward hop the
+ * gradient is non-zero only inside it (dst_flags of hop 1, src_flags of hop 2); rows computed are bit-identical. */
+int b200rec_mark_reach(const int64_t* batch /*[B,3]*/, int32_t n_batch, int64_t item_offset, const int32_t* user_ptr,
+                       const int32_t* user_items, uint8_t* flags, void* stream);
+
 /* Row gather / scatter-add used by the autograd-compatible bpr_forward (model.py:118-119 rep[idx,:] and its
  * index_put_(accumulate) backward).  idx int64 [n]; offset is added to every index (n_users for items). */
 int b200rec_gather_rows(const float* table, int32_t d, const int64_t* idx, int64_t offset, int32_t n,

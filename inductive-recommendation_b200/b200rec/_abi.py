@@ -57,6 +57,7 @@ PROTOTYPES = {
     "b200rec_propagate_bwd": (C.c_int, [_CSRP, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "b200rec_bpr_sample": (C.c_int, [_P, _P, _I32, _I32, _U64, _P, _I32, _P, _P]),
     "b200rec_mark_rows": (C.c_int, [_P, _I32, _I64, _P, _P]),
+    "b200rec_mark_reach": (C.c_int, [_P, _I32, _I64, _P, _P, _P, _P]),
     "b200rec_gather_rows": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _P, _P]),
     "b200rec_scatter_add_rows": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _P]),
     "b200rec_bpr_scratch_floats": (C.c_int64, [_I32, _I32]),

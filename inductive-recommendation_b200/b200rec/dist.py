@@ -193,8 +193,10 @@ class RowPartition:
         for w in works:
             w.wait()
 
-    def propagate_fwd(self, adj, x0, n_layers, bufs, mean_out, needed_rows=None):
-        """same contract as ops.propagate_fwd; x0 must be complete on every rank, mean_out is complete on return"""
+    def propagate_fwd(self, adj, x0, n_layers, bufs, mean_out, needed_rows=None, reach_rows=None):
+        """same contract as ops.propagate_fwd; x0 must be complete on every rank, mean_out is complete on return.
+        reach_rows: optional byte mask of the rows within one hop of needed_rows (ops.mark_reach) -- layer L-1 is computed
+        only there"""
         from . import ops
         if n_layers == 0:
             mean_out.copy_(x0)
@@ -205,13 +207,14 @@ class RowPartition:
             last = k == n_layers - 1
             y = None if last else bufs[k & 1]
             ops.spmm(self.local_op, src, y=y, addend=x0 if k == 0 else mean_out, out=mean_out,
-                     out_scale=inv if last else 1.0, dst_flags=needed_rows if last else None)
+                     out_scale=inv if last else 1.0,
+                     dst_flags=needed_rows if last else (reach_rows if k == n_layers - 2 else None))
             if not last:
                 self.exchange(y)
                 src = y
         self.exchange(mean_out)
 
-    def propagate_bwd(self, adj, g, n_layers, bufs, dx0, nonzero_rows=None):
+    def propagate_bwd(self, adj, g, n_layers, bufs, dx0, nonzero_rows=None, reach_rows=None):
         """dx0 rows of this rank's blocks are valid on return (each rank updates only the parameters it owns)"""
         from . import ops
         if n_layers == 0:
@@ -223,7 +226,8 @@ class RowPartition:
             last = k == n_layers
             dst = dx0 if last else bufs[(k - 1) & 1]
             ops.spmm(self.local_op, src, addend=g, out=dst, out_scale=inv if last else 1.0,
-                     src_flags=nonzero_rows if k == 1 else None)
+                     src_flags=nonzero_rows if k == 1 else (reach_rows if k == 2 else None),
+                     dst_flags=reach_rows if (k == 1 and not last) else None)
             if not last:
                 self.exchange(dst)
                 src = dst
@@ -327,7 +331,7 @@ class PeerRowPartition(RowPartition):
                                                 ptr(addend), ptr(out), out_scale, ptr(dst_flags), ptr(src_flags),
                                                 self.n_others, py, po, stream_ptr()), "spmm_f32_peer")
 
-    def propagate_fwd(self, adj, x0, n_layers, bufs, mean_out, needed_rows=None):
+    def propagate_fwd(self, adj, x0, n_layers, bufs, mean_out, needed_rows=None, reach_rows=None):
         assert mean_out is self.rep and x0.shape[1] == self.d
         if n_layers == 0:
             mean_out.copy_(x0)
@@ -339,11 +343,12 @@ class PeerRowPartition(RowPartition):
             last = k == n_layers - 1
             y = None if last else bufs[k & 1]
             self._spmm(src, y=y, addend=x0 if k == 0 else mean_out, out=mean_out, out_scale=inv if last else 1.0,
-                       dst_flags=needed_rows if last else None, push_y=not last, push_out=last)
+                       dst_flags=needed_rows if last else (reach_rows if k == n_layers - 2 else None), push_y=not last,
+                       push_out=last)
             self.handshake()
             src = y
 
-    def propagate_bwd(self, adj, g, n_layers, bufs, dx0, nonzero_rows=None):
+    def propagate_bwd(self, adj, g, n_layers, bufs, dx0, nonzero_rows=None, reach_rows=None):
         if n_layers == 0:
             dx0.copy_(g)
             return
@@ -353,8 +358,9 @@ class PeerRowPartition(RowPartition):
         for k in range(1, n_layers + 1):
             last = k == n_layers
             dst = dx0 if last else bufs[(k - 1) & 1]
-            self._spmm(src, addend=g, out=dst, out_scale=inv if last else 1.0, src_flags=nonzero_rows if k == 1 else None,
-                       push_out=not last)
+            self._spmm(src, addend=g, out=dst, out_scale=inv if last else 1.0,
+                       src_flags=nonzero_rows if k == 1 else (reach_rows if k == 2 else None),
+                       dst_flags=reach_rows if (k == 1 and not last) else None, push_out=not last)
             if not last:
                 self.handshake()
                 src = dst

@@ -103,6 +103,13 @@ class BprEngine:
             self.adj_sparse = model.norm_adj.replan(sc) if (partition is None and sc > 0 and sc != model.norm_adj.chunk) \
                 else model.norm_adj
             L = model.n_layers
+            # rows within one hop of the batch (ops.mark_reach): forward layer L-1 is needed only there, and after the first
+            # backward hop the gradient is non-zero only there.  The user half stays all-ones (see _reach_gain).
+            self.reach = None
+            reach_env = os.environ.get('B200REC_REACH', 'auto')
+            if self.kind in ('LightGCN', 'IGCN') and L >= 2 and reach_env != '0' \
+                    and (reach_env == '1' or self._reach_gain() >= 0.25):
+                self.reach = torch.ones(n, dtype=torch.uint8, device=dev)
             # compacted work list of the last forward layer (only the sampled rows are needed): built beside the first layers
             self.live = None
             if partition is None and self.kind == 'LightGCN' and L >= 2 \
@@ -149,6 +156,16 @@ class BprEngine:
         self._kernels = {}
         self.steps_done = 0
 
+    def _reach_gain(self):
+        """Share of the item-side edges that lies OUTSIDE one hop of an average batch: an item of degree d is missed by B
+        uniformly drawn users with probability (1 - d/U)^B, so the share is sum_i d_i (1 - d_i/U)^B / E.  C4 (2 M users,
+        batch 2048): 0.58 -- the two restricted layers skip that share of one side's gathers; C1-C3: < 0.05 (a batch's
+        users reach nearly every item that carries edges), where the extra mask costs more than it saves."""
+        m = self.model
+        deg = torch.bincount(self.user_items.long(), minlength=m.n_items).double()
+        miss = torch.exp(self.B * torch.log1p(-(deg / m.n_users).clamp(max=1.0 - 1e-12)))
+        return float((deg * miss).sum() / deg.sum().clamp(min=1.0))
+
     # ------------------------------------------------------------------------------------------------ one step
     def _propagate_fwd(self, x0, join=None, adj=None, flags=None, rep=None):
         """L x SpMM + layer mean into self.rep.  Only the LAST layer needs the batch (it is restricted to the sampled
@@ -158,12 +175,13 @@ class BprEngine:
         L = m.n_layers
         own = adj is None  # the model's full graph; otherwise an augmented view (SGL / HALF)
         adj = m.norm_adj if own else adj
+        reach = self.reach if (own and flags is None) else None  # the batch's one-hop mask goes with the batch's row mask
         flags = self.row_flags if flags is None else flags
         rep = self.rep if rep is None else rep
         if self.partition is not None:
             if join:
                 join()
-            self.partition.propagate_fwd(adj, x0, L, self.bufs, rep, needed_rows=flags)
+            self.partition.propagate_fwd(adj, x0, L, self.bufs, rep, needed_rows=flags, reach_rows=reach)
             return
         if L == 0:
             if join:
@@ -174,7 +192,8 @@ class BprEngine:
         src = x0
         for k in range(L):  # the layer loop of b200rec_propagate_fwd, opened up for the join and the sparse plan
             last = k == L - 1
-            if last and join:
+            near = reach is not None and k == L - 2  # layer L-1 feeds the last layer only: needed within one hop of the batch
+            if join and (near or (last and (reach is None or L < 2))):
                 join()
             y = None if last else self.bufs[k & 1]
             if last and own and join is not None and self.live is not None and flags is self.row_flags:
@@ -182,17 +201,18 @@ class BprEngine:
                               out=rep, out_scale=inv)
             else:
                 ops.spmm(self.adj_sparse if (last and own) else adj, src, y=y, addend=x0 if k == 0 else rep, out=rep,
-                         out_scale=inv if last else 1.0, dst_flags=flags if last else None)
+                         out_scale=inv if last else 1.0, dst_flags=flags if last else (reach if near else None))
             src = y
 
     def _propagate_bwd(self, out, adj=None, flags=None, g=None):
         m = self.model
         own = adj is None
         adj = m.norm_adj if own else adj
+        reach = self.reach if (own and flags is None) else None
         flags = self.row_flags if flags is None else flags
         g = self.g_rep if g is None else g
         if self.partition is not None:
-            self.partition.propagate_bwd(adj, g, m.n_layers, self.bufs, out)
+            self.partition.propagate_bwd(adj, g, m.n_layers, self.bufs, out, nonzero_rows=flags, reach_rows=reach)
             return
         L = m.n_layers
         if L == 0:
@@ -203,8 +223,11 @@ class BprEngine:
         for k in range(1, L + 1):  # H_k = G + A H_{k-1}; the first hop reads only the <= 3B non-zero rows of G
             last = k == L
             dst = out if last else self.bufs[(k - 1) & 1]
+            # H_1 is zero outside one hop of the batch: those rows are neither computed (unless H_1 is the result) nor
+            # gathered by the second hop
             ops.spmm(self.adj_sparse if (k == 1 and own) else adj, src, addend=g, out=dst, out_scale=inv if last else 1.0,
-                     src_flags=flags if k == 1 else None)
+                     src_flags=flags if k == 1 else (reach if k == 2 else None),
+                     dst_flags=reach if (k == 1 and not last) else None)
             src = dst
 
     def _bpr(self, rep, batch, item_offset, l2_reg, reg_mode, g_rep, w=None, g_w=None, loss_scale=1.0, grouping=None,
@@ -275,6 +298,9 @@ class BprEngine:
                 # and the first backward hop are restricted to them (bit-identical on the rows that matter)
                 self.row_flags.zero_()
                 ops.mark_rows(self.batch, nu, self.row_flags)
+                if self.reach is not None:
+                    self.reach[nu:].zero_()
+                    ops.mark_reach(self.batch, nu, self.user_ptr, self.user_items, self.reach)
                 if prelude and self.live is not None:
                     ops.live_items(self.adj_sparse, self.row_flags, self.live[0], self.live[1])
             if forked and not lazy_clear:

@@ -115,6 +115,14 @@ def mark_rows(batch, item_offset, flags):
     check(_lib().b200rec_mark_rows(ptr(batch), batch.shape[0], item_offset, ptr(flags), stream_ptr()), "mark_rows")
 
 
+def mark_reach(batch, item_offset, user_ptr, user_items, flags):
+    """flags (uint8 [n_rows]; item half zeroed by the caller, user half kept all-ones) <- 1 at the sampled rows and at
+    every train item of a sampled user: the rows within one hop of the batch"""
+    _abi.require_cuda(batch, user_ptr, user_items, flags)
+    check(_lib().b200rec_mark_reach(ptr(batch), batch.shape[0], item_offset, ptr(user_ptr), ptr(user_items), ptr(flags),
+                                    stream_ptr()), "mark_reach")
+
+
 def bpr_scratch(batch_size, d, device):
     n = int(_lib().b200rec_bpr_scratch_floats(batch_size, d))
     return torch.zeros(n, dtype=torch.float32, device=device)

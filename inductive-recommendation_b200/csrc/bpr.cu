@@ -86,6 +86,22 @@ __global__ void mark_rows_kernel(const int64_t* __restrict__ batch, int n_batch,
   flags[r] = 1;
 }
 
+// Rows within one hop of a batch: the sampled rows themselves and every item a sampled user interacted with (one warp per
+// sample walks the user's sorted train row).  The user half of `flags` is not written here: the caller keeps it all-ones
+// (the users within a hop of the sampled items are nearly all users of a power-law graph, and a superset is always valid).
+__global__ void mark_reach_kernel(const int64_t* __restrict__ batch, int n_batch, int64_t item_offset,
+                                  const int32_t* __restrict__ user_ptr, const int32_t* __restrict__ user_items,
+                                  uint8_t* __restrict__ flags) {
+  const int s = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (s >= n_batch) return;
+  const int64_t u = batch[3 * s];
+  if (lane == 0) flags[u] = 1;
+  if (lane == 1) flags[item_offset + batch[3 * s + 1]] = 1;
+  if (lane == 2) flags[item_offset + batch[3 * s + 2]] = 1;
+  const int lo = __ldg(user_ptr + u), hi = __ldg(user_ptr + u + 1);
+  for (int k = lo + lane; k < hi; k += 32) flags[item_offset + __ldg(user_items + k)] = 1;
+}
+
 // ---------------------------------------------------------------------------------------------- gather / scatter
 template <int G, int VPL>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
@@ -585,6 +601,15 @@ extern "C" int b200rec_bpr_sample(const int32_t* user_ptr, const int32_t* user_i
 extern "C" int b200rec_mark_rows(const int64_t* batch, int32_t n_batch, int64_t item_offset, uint8_t* flags, void* stream) {
   B2_REQUIRE(batch && flags && n_batch > 0, "bad argument");
   mark_rows_kernel<<<ceil_div(3 * n_batch, 256), 256, 0, (cudaStream_t)stream>>>(batch, n_batch, item_offset, flags);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200rec_mark_reach(const int64_t* batch, int32_t n_batch, int64_t item_offset, const int32_t* user_ptr,
+                                  const int32_t* user_items, uint8_t* flags, void* stream) {
+  B2_REQUIRE(batch && flags && user_ptr && user_items && n_batch > 0, "bad argument");
+  mark_reach_kernel<<<ceil_div(32 * n_batch, 256), 256, 0, (cudaStream_t)stream>>>(batch, n_batch, item_offset, user_ptr,
+                                                                                    user_items, flags);
   B2_LAUNCHED();
   return 0;
 }

@@ -199,6 +199,56 @@ def test_c3_igcn_step_and_topk_against_port():
     assert ops is not None
 
 
+@pytest.mark.parametrize("kind", ["LightGCN", "LightGCN4", "IGCN"])
+def test_one_hop_restricted_layers_change_no_bit(kind, monkeypatch):
+    """B200REC_REACH=1: forward layer L-1 is computed only within one hop of the batch (ops.mark_reach), the first
+    backward hop only writes those rows and the second only gathers them.  With a batch of 64 on the C1 graph most item
+    rows lie outside the mask (the restriction really skips work); loss, gradient and the weights after three device-
+    sampled steps must equal the unrestricted engine's bit for bit -- and the port's to the usual bars (LightGCN)."""
+    from oracle import ref_port as rp
+    L = 4 if kind == "LightGCN4" else 3
+    mcfg = {"name": "IGCN", "embedding_size": 64, "n_layers": L, "dropout": 0.3, "feature_ratio": 1.0} if kind == "IGCN" \
+        else {"name": "LightGCN", "embedding_size": 64, "n_layers": L}
+    tcfg = {"name": "IGCNTrainer", "l2_reg": 0.0, "aux_reg": 0.01, "batch_size": 64} if kind == "IGCN" \
+        else {"name": "BPRTrainer", "l2_reg": 1e-4, "batch_size": 64}
+    out = {}
+    for reach in ("0", "1"):
+        monkeypatch.setenv("B200REC_REACH", reach)
+        g, ds, m, tr = _build("c1", mcfg, tcfg)
+        emb0 = _np(m.embedding.weight).copy()
+        m.train()
+        eng = tr._engine()
+        assert (eng.reach is not None) == (reach == "1")
+        losses = []
+        for _ in range(3):
+            eng.step()
+            losses.append(eng.last_loss())
+        if reach == "1":
+            share = float(eng.reach[ds.n_users:].float().mean())
+            assert 0.0 < share < 0.5, share                      # the mask is sparse on the item side, all-ones on the users
+            assert bool(eng.reach[:ds.n_users].all())
+            b = eng.batch
+            assert bool(eng.reach[b[:, 1] + ds.n_users].all()) and bool(eng.reach[b[:, 2] + ds.n_users].all())
+        out[reach] = (losses, m.embedding.weight.grad.clone(), m.embedding.weight.detach().clone(), eng.batch.clone())
+        if reach == "1" and kind == "LightGCN":
+            # the restricted engine against the CPU port on the first batch (a fresh engine: same seed, same first draw)
+            g2, ds2, m2, tr2 = _build("c1", mcfg, tcfg)
+            m2.train()
+            e2 = tr2._engine()
+            e2.step()
+            users, items = ds2.train_pairs()
+            port = rp.LightGCNPort(ds2.n_users, ds2.n_items, users, items, emb0, L)
+            opt = torch.optim.Adam(port.parameters(), lr=1e-3)
+            ref_loss = rp.train_step(port.train(), opt, e2.batch.cpu(), 1e-4)
+            assert abs(e2.last_loss() - ref_loss) < 2e-6
+            np.testing.assert_allclose(_np(m2.embedding.weight.grad), port.embedding.weight.grad.numpy(), rtol=1e-4, atol=1e-9)
+            np.testing.assert_allclose(_np(m2.embedding.weight), port.embedding.weight.detach().numpy(), rtol=1e-5, atol=5e-6)
+    assert out["0"][0] == out["1"][0]
+    assert torch.equal(out["0"][3], out["1"][3])
+    assert torch.equal(out["0"][1], out["1"][1])
+    assert torch.equal(out["0"][2], out["1"][2])
+
+
 # ------------------------------------------------------------------------------------------- C5
 def test_c5_sweep_slice_tensor_core_equals_exact():
     """BASELINE config 5: 2M users x 1M items, D=128, top-20 with the real train CSR (100M entries) masked -- the tcgen05
