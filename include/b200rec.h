@@ -152,6 +152,17 @@ int b200rec_spmm_f32(const b200rec_csr* a /*HOST struct of device pointers*/, co
 int b200rec_spmm_f32_ex(const b200rec_csr* a, const float* x, int32_t d, const uint32_t* keep_bits, float post_scale,
                         float* y, const float* addend, float* out, float out_scale,
                         const uint8_t* dst_flags, const uint8_t* src_flags, void* stream);
+/* Same (no dropout mask), plus a byte mask of the rows where the fused `out` / `addend` matter to the caller -- a training
+ * step reads the layer sum only at the <= 3B sampled rows, and its gradient G (the addend of every backward hop) is zero
+ * outside them:
+ *   out_mode 1: `out` is written (and `addend` read) only at rows with a non-zero out_rows flag; `y` is written everywhere
+ *               (forward layers 1 .. L-1: saves 2 x N x D x 4 bytes per layer);
+ *   out_mode 2: `addend` is known to be zero outside the flagged rows and is not read there; `out` is written everywhere
+ *               (backward hops: saves N x D x 4 bytes per hop).
+ * Bit-identical to b200rec_spmm_f32_ex wherever something is written. */
+int b200rec_spmm_f32_sel(const b200rec_csr* a, const float* x, int32_t d, float post_scale, float* y, const float* addend,
+                         float* out, float out_scale, const uint8_t* dst_flags, const uint8_t* src_flags,
+                         const uint8_t* out_rows, int32_t out_mode, void* stream);
 
 /* Record stream of a column-blocked plan (items sorted by pass, row_order = 1).  window: records per window (>= 32; 128).
  * Call with records == NULL for *n_records_out / *n_windows_out (HOST), allocate records [n_records] x 8 B and win_start
@@ -367,7 +378,8 @@ int b200rec_spmm_f32_peer(const b200rec_csr* a, const float* x, int32_t d, const
                           float* y, const float* addend, float* out, float out_scale,
                           const uint8_t* dst_flags, const uint8_t* src_flags, int32_t n_peers,
                           float* const* peer_y /*HOST [n_peers] device pointers, or NULL*/,
-                          float* const* peer_out /*HOST [n_peers], or NULL*/, void* stream);
+                          float* const* peer_out /*HOST [n_peers], or NULL*/,
+                          const uint8_t* out_rows /*or NULL*/, int32_t out_mode /*as b200rec_spmm_f32_sel*/, void* stream);
 /* b200rec_adam_step on a row block whose updated parameters are also stored into the peers' tables. */
 int b200rec_adam_step_peer(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                            double lr, double beta1, double beta2, double eps, const int64_t* step,

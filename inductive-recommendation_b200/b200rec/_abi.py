@@ -50,6 +50,7 @@ PROTOTYPES = {
     "b200rec_adj_normalize": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P]),
     "b200rec_spmm_f32": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P]),
     "b200rec_spmm_f32_ex": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P, _P, _P]),
+    "b200rec_spmm_f32_sel": (C.c_int, [_CSRP, _P, _I32, _F, _P, _P, _P, _F, _P, _P, _P, _I32, _P]),
     "b200rec_spmm_f32_blocked": (C.c_int, [_CSRP, _P, _I32, _I32, _F, _P, _P, _P, _F, _P, _P]),
     "b200rec_live_items": (C.c_int, [_CSRP, _P, _P, _P, _P]),
     "b200rec_spmm_f32_live": (C.c_int, [_CSRP, _P, _I32, _F, _P, _P, _P, _F, _P, _P, _I32, _P]),
@@ -77,7 +78,7 @@ PROTOTYPES = {
     "b200rec_score_dense_f32": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P]),
     "b200rec_score_topk_workspace": (C.c_int64, [_I32, _I32, _I32, _I32, _I32]),
     "b200rec_score_topk": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
-    "b200rec_spmm_f32_peer": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P, _P, _I32, _P, _P, _P]),
+    "b200rec_spmm_f32_peer": (C.c_int, [_CSRP, _P, _I32, _P, _F, _P, _P, _P, _F, _P, _P, _I32, _P, _P, _P, _I32, _P]),
     "b200rec_adam_step_peer": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _P, _I32, _P, _P]),
     "b200rec_peer_alloc": (C.c_int, [_I64, _P, _P]),
     "b200rec_peer_open": (C.c_int, [_P, _P]),

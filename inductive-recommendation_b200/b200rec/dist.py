@@ -206,9 +206,11 @@ class RowPartition:
         for k in range(n_layers):
             last = k == n_layers - 1
             y = None if last else bufs[k & 1]
+            # the caller reads mean_out only at needed_rows: the running layer sum is kept only there (out_mode 1)
             ops.spmm(self.local_op, src, y=y, addend=x0 if k == 0 else mean_out, out=mean_out,
                      out_scale=inv if last else 1.0,
-                     dst_flags=needed_rows if last else (reach_rows if k == n_layers - 2 else None))
+                     dst_flags=needed_rows if last else (reach_rows if k == n_layers - 2 else None),
+                     out_rows=None if last else needed_rows, out_mode=1)
             if not last:
                 self.exchange(y)
                 src = y
@@ -227,7 +229,7 @@ class RowPartition:
             dst = dx0 if last else bufs[(k - 1) & 1]
             ops.spmm(self.local_op, src, addend=g, out=dst, out_scale=inv if last else 1.0,
                      src_flags=nonzero_rows if k == 1 else (reach_rows if k == 2 else None),
-                     dst_flags=reach_rows if (k == 1 and not last) else None)
+                     dst_flags=reach_rows if (k == 1 and not last) else None, out_rows=nonzero_rows, out_mode=2)
             if not last:
                 self.exchange(dst)
                 src = dst
@@ -321,7 +323,7 @@ class PeerRowPartition(RowPartition):
         self.handshake()  # the rows were pushed by the kernel that produced them
 
     def _spmm(self, src, y=None, addend=None, out=None, out_scale=1.0, dst_flags=None, src_flags=None, push_y=False,
-              push_out=False):
+              push_out=False, out_rows=None, out_mode=0):
         from . import _abi
         from ._abi import check, ptr, stream_ptr
         C = self._C
@@ -329,7 +331,8 @@ class PeerRowPartition(RowPartition):
         po = self._others(self._name_of(out)) if push_out else None
         check(_abi.load().b200rec_spmm_f32_peer(C.byref(self.local_op.struct()), ptr(src), src.shape[1], None, 1.0, ptr(y),
                                                 ptr(addend), ptr(out), out_scale, ptr(dst_flags), ptr(src_flags),
-                                                self.n_others, py, po, stream_ptr()), "spmm_f32_peer")
+                                                self.n_others, py, po, ptr(out_rows), out_mode if out_rows is not None else 0,
+                                                stream_ptr()), "spmm_f32_peer")
 
     def propagate_fwd(self, adj, x0, n_layers, bufs, mean_out, needed_rows=None, reach_rows=None):
         assert mean_out is self.rep and x0.shape[1] == self.d
@@ -344,7 +347,7 @@ class PeerRowPartition(RowPartition):
             y = None if last else bufs[k & 1]
             self._spmm(src, y=y, addend=x0 if k == 0 else mean_out, out=mean_out, out_scale=inv if last else 1.0,
                        dst_flags=needed_rows if last else (reach_rows if k == n_layers - 2 else None), push_y=not last,
-                       push_out=last)
+                       push_out=last, out_rows=None if last else needed_rows, out_mode=1)
             self.handshake()
             src = y
 
@@ -360,7 +363,8 @@ class PeerRowPartition(RowPartition):
             dst = dx0 if last else bufs[(k - 1) & 1]
             self._spmm(src, addend=g, out=dst, out_scale=inv if last else 1.0,
                        src_flags=nonzero_rows if k == 1 else (reach_rows if k == 2 else None),
-                       dst_flags=reach_rows if (k == 1 and not last) else None, push_out=not last)
+                       dst_flags=reach_rows if (k == 1 and not last) else None, push_out=not last,
+                       out_rows=nonzero_rows, out_mode=2)
             if not last:
                 self.handshake()
                 src = dst

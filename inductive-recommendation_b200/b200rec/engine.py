@@ -147,6 +147,9 @@ class BprEngine:
                 if aux_dataset is not None:
                     self.aux_ptr, self.aux_items = aux_dataset.csr('train', device=dev)
                     self.aux_grouping = ops.bpr_grouping(batch_size, dev) if self.ordered else None
+        # out / addend traffic of the layers limited to the sampled rows (b200rec_spmm_f32_sel); B200REC_SEL=0 turns it off
+        self.sel = os.environ.get('B200REC_SEL', '1') != '0'
+        self._batch_early = True
         self.use_graph = use_graph and os.environ.get('B200REC_NO_GRAPH', '0') != '1'
         self._adj_ref = getattr(model, 'norm_adj', None)  # the step (and its captured graph) is built on THIS operand
         self._side_stream = torch.cuda.Stream(device=dev)
@@ -200,8 +203,12 @@ class BprEngine:
                 ops.spmm_live(self.adj_sparse, src, self.live[0], self.live[1], self.live[2], addend=x0 if k == 0 else rep,
                               out=rep, out_scale=inv)
             else:
+                # the step reads rep only at the flagged rows: the running layer sum is kept only there (when the batch is
+                # known before the first layer, i.e. the prelude is not forked onto the side stream)
+                keep = flags if (self.sel and not last and (join is None or self._batch_early)) else None
                 ops.spmm(self.adj_sparse if (last and own) else adj, src, y=y, addend=x0 if k == 0 else rep, out=rep,
-                         out_scale=inv if last else 1.0, dst_flags=flags if last else (reach if near else None))
+                         out_scale=inv if last else 1.0, dst_flags=flags if last else (reach if near else None),
+                         out_rows=keep, out_mode=1)
             src = y
 
     def _propagate_bwd(self, out, adj=None, flags=None, g=None):
@@ -227,7 +234,8 @@ class BprEngine:
             # gathered by the second hop
             ops.spmm(self.adj_sparse if (k == 1 and own) else adj, src, addend=g, out=dst, out_scale=inv if last else 1.0,
                      src_flags=flags if k == 1 else (reach if k == 2 else None),
-                     dst_flags=reach if (k == 1 and not last) else None)
+                     dst_flags=reach if (k == 1 and not last) else None,
+                     out_rows=flags if self.sel else None, out_mode=2)  # G is zero outside the flagged rows: not read there
             src = dst
 
     def _bpr(self, rep, batch, item_offset, l2_reg, reg_mode, g_rep, w=None, g_w=None, loss_scale=1.0, grouping=None,
@@ -280,6 +288,7 @@ class BprEngine:
         # 90.5 ms with a host batch copied in before the graph; serial 75.6 / 75.7).  self.fork: tables fit L2.
         prelude = self.kind == 'LightGCN' and self.partition is None and m.n_layers >= 2
         forked = prelude and self.fork
+        self._batch_early = not forked
         side = self._side_stream if forked else main
         grp = self.grouping
         # g_rep is all-zero between steps: with the ordered scatter the BPR kernel STORES the touched rows and they are

@@ -20,8 +20,16 @@ def _lib():
 
 # ------------------------------------------------------------------------------------------------ raw calls
 def spmm(op, x, keep_bits=None, post_scale=1.0, y=None, addend=None, out=None, out_scale=1.0, dst_flags=None,
-         src_flags=None):
-    _abi.require_cuda(x, keep_bits, y, addend, out, dst_flags, src_flags)
+         src_flags=None, out_rows=None, out_mode=0):
+    """out_rows / out_mode: byte mask of the rows where out / addend matter (1: out written only there; 2: addend zero
+    elsewhere, not read) -- include/b200rec.h b200rec_spmm_f32_sel"""
+    _abi.require_cuda(x, keep_bits, y, addend, out, dst_flags, src_flags, out_rows)
+    if out_rows is not None:
+        assert keep_bits is None and out_mode in (1, 2) and x.dtype == torch.float32 and x.shape[0] >= op.n_cols
+        check(_lib().b200rec_spmm_f32_sel(C.byref(op.struct()), ptr(x), x.shape[1], post_scale, ptr(y), ptr(addend), ptr(out),
+                                          out_scale, ptr(dst_flags), ptr(src_flags), ptr(out_rows), out_mode, stream_ptr()),
+              "spmm_f32_sel")
+        return
     d = x.shape[1]
     assert x.dtype == torch.float32 and x.shape[0] >= op.n_cols
     assert op.partial is None or d <= op.max_d

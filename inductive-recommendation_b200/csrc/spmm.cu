@@ -25,6 +25,8 @@ struct SpmmParams {
   const uint32_t* keep_bits;
   const uint8_t* dst_flags;  // optional: only rows with a non-zero flag are computed (others left untouched)
   const uint8_t* src_flags;  // optional: gathered rows with a zero flag are known to be all-zero and are skipped
+  const uint8_t* out_rows;   // optional: the rows where `out` / `addend` matter (out_mode)
+  int out_mode;              // 1: out is written (addend read) only at flagged rows; 2: addend is zero outside them (not read)
   const int32_t* live_items; // optional: compacted list of the work items to run (b200rec_live_items), instead of all of them
   const int32_t* live_count; // device scalar: entries in live_items
   const int32_t* item_start;
@@ -85,6 +87,10 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int g
   constexpr int D = G * VPL * 4;
   float sc = p.post_scale;
   if (p.row_scale) sc *= p.row_scale[row];
+  // a training step reads the layer sum only at the sampled rows, and its gradient G is zero outside them: the 2 x N x D
+  // (forward) / N x D (backward) bytes of out / addend traffic per layer shrink to those rows
+  const bool sel = !p.out_rows || ldc_u8(p.out_rows + row) != 0;
+  const bool wr_out = sel || p.out_mode != 1, rd_add = sel || p.out_mode != 2;
 #pragma unroll
   for (int t = 0; t < VPL; ++t) {
     const size_t off = (size_t)row * D + (size_t)(gl + t * G) * 4;
@@ -94,9 +100,9 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int row, int g
       for (int q = 0; q < p.n_peer; ++q)
         if (p.peer_y[q]) st_f4(p.peer_y[q] + off, s);  // NVLink store into the peer's table, overlapped with the gathers
     }
-    if (p.out) {
+    if (p.out && wr_out) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.addend) a = ld_f4(p.addend + off);
+      if (p.addend && rd_add) a = ld_f4(p.addend + off);
       const float os = p.out_scale;
       const float4 o4 = make_float4((a.x + s.x) * os, (a.y + s.y) * os, (a.z + s.z) * os, (a.w + s.w) * os);
       st_f4(p.out + off, o4);
@@ -367,8 +373,10 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
                          float* y, const float* addend, float* out, float out_scale, const uint8_t* dst_flags,
                          const uint8_t* src_flags, cudaStream_t st, int n_peer = 0, float* const* peer_y = nullptr,
                          float* const* peer_out = nullptr, const int32_t* live_items = nullptr,
-                         const int32_t* live_count = nullptr, int max_live = 0) {
+                         const int32_t* live_count = nullptr, int max_live = 0, const uint8_t* out_rows = nullptr,
+                         int out_mode = 0) {
   B2_REQUIRE(a && x, "null operand");
+  B2_REQUIRE(!out_rows || out_mode == 1 || out_mode == 2, "out_rows needs out_mode 1 or 2");
   B2_REQUIRE(y || out, "no output");
   B2_REQUIRE(a->n_items == 0 || (a->item_start && a->item_end && a->item_dst && a->colidx), "csr plan missing");
   B2_REQUIRE(a->n_long == 0 || (a->partial && a->long_row && a->long_slot0 && a->long_nslot && a->slot_long && a->long_cnt),
@@ -380,6 +388,7 @@ static int spmm_dispatch(const b200rec_csr* a, const float* x, int d, const uint
   p.colidx = a->colidx; p.vals = a->vals; p.nbr_scale = a->nbr_scale; p.row_scale = a->row_scale; p.eid = a->eid;
   p.keep_bits = keep_bits; p.dst_flags = dst_flags; p.src_flags = src_flags;
   p.live_items = live_items; p.live_count = live_count;
+  p.out_rows = out_rows; p.out_mode = out_rows ? out_mode : 0;
   B2_REQUIRE(!live_items || (live_count && max_live > 0), "live_items needs live_count and max_live");
   p.item_start = a->item_start; p.item_end = a->item_end; p.item_dst = a->item_dst; p.item_row = a->item_row;
   p.n_items = a->n_items;
@@ -491,14 +500,21 @@ extern "C" int b200rec_spmm_f32_ex(const b200rec_csr* a, const float* x, int32_t
                        (cudaStream_t)stream);
 }
 
+extern "C" int b200rec_spmm_f32_sel(const b200rec_csr* a, const float* x, int32_t d, float post_scale, float* y,
+                                    const float* addend, float* out, float out_scale, const uint8_t* dst_flags,
+                                    const uint8_t* src_flags, const uint8_t* out_rows, int32_t out_mode, void* stream) {
+  return spmm_dispatch(a, x, d, nullptr, post_scale, y, addend, out, out_scale, dst_flags, src_flags, (cudaStream_t)stream,
+                       0, nullptr, nullptr, nullptr, nullptr, 0, out_rows, out_mode);
+}
+
 extern "C" int b200rec_spmm_f32_peer(const b200rec_csr* a, const float* x, int32_t d, const uint32_t* keep_bits,
                                      float post_scale, float* y, const float* addend, float* out, float out_scale,
                                      const uint8_t* dst_flags, const uint8_t* src_flags, int32_t n_peers,
                                      float* const* peer_y /*HOST [n_peers] or NULL*/, float* const* peer_out /*HOST or NULL*/,
-                                     void* stream) {
+                                     const uint8_t* out_rows, int32_t out_mode, void* stream) {
   B2_REQUIRE(n_peers >= 0 && n_peers <= 8, "at most 8 peers");
   return spmm_dispatch(a, x, d, keep_bits, post_scale, y, addend, out, out_scale, dst_flags, src_flags, (cudaStream_t)stream,
-                       n_peers, peer_y, peer_out);
+                       n_peers, peer_y, peer_out, nullptr, nullptr, 0, out_rows, out_mode);
 }
 
 extern "C" int b200rec_live_items(const b200rec_csr* a, const uint8_t* row_flags, int32_t* live_items, int32_t* live_count,

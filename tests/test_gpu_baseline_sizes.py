@@ -202,7 +202,8 @@ def test_c3_igcn_step_and_topk_against_port():
 @pytest.mark.parametrize("kind", ["LightGCN", "LightGCN4", "IGCN"])
 def test_one_hop_restricted_layers_change_no_bit(kind, monkeypatch):
     """B200REC_REACH=1: forward layer L-1 is computed only within one hop of the batch (ops.mark_reach), the first
-    backward hop only writes those rows and the second only gathers them.  With a batch of 64 on the C1 graph most item
+    backward hop only writes those rows and the second only gathers them; B200REC_SEL=1 (the default): the running layer
+    sum is kept only at the sampled rows and G is read only there.  With a batch of 64 on the C1 graph most item
     rows lie outside the mask (the restriction really skips work); loss, gradient and the weights after three device-
     sampled steps must equal the unrestricted engine's bit for bit -- and the port's to the usual bars (LightGCN)."""
     from oracle import ref_port as rp
@@ -214,6 +215,7 @@ def test_one_hop_restricted_layers_change_no_bit(kind, monkeypatch):
     out = {}
     for reach in ("0", "1"):
         monkeypatch.setenv("B200REC_REACH", reach)
+        monkeypatch.setenv("B200REC_SEL", reach)  # and the out / addend traffic limited to the sampled rows (spmm_f32_sel)
         g, ds, m, tr = _build("c1", mcfg, tcfg)
         emb0 = _np(m.embedding.weight).copy()
         m.train()

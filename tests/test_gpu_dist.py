@@ -11,12 +11,15 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("n", [2, 4, 8])
-def test_multi_gpu_parity(n):
+@pytest.mark.parametrize("n,reach", [(2, "auto"), (2, "1"), (4, "1"), (8, "1")])
+def test_multi_gpu_parity(n, reach):
     """DimShard, RowPartition (NCCL block exchange) and PeerRowPartition (exchange fused into the kernels over NVLink peer
-    memory) on n ranks: fused steps equal the reference fixtures, row partitions are bit-identical to one GPU"""
+    memory) on n ranks: fused steps equal the reference fixtures, row partitions are bit-identical to one GPU.
+    reach = "1": the engines also restrict layer L-1 / backward hops 1-2 to the batch's one-hop mask (B200REC_REACH, which
+    the C4 bench turns on by itself) -- same fixtures, same bars."""
     if torch.cuda.device_count() < n:
         pytest.skip("needs >= %d GPUs" % n)
+    os.environ["B200REC_REACH"] = reach
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
            "127.0.0.1", "--master-port", str(29611 + n), os.path.join(HERE, "dist_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
