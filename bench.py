@@ -236,7 +236,7 @@ def run_reference(args, rank):
             "train": {"epochs_per_s": value, "ms_per_step": 1e3 * s_per_step},
             "eval": {"users_per_s_e2e": eval_rate, "sample": "first %d users, test split, K=%d, 512-user batches, re-propagation "
                      "per batch like trainer.py:150-170" % (eval_n, max(TOPKS))}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def _fingerprint(graph):
@@ -535,11 +535,32 @@ def run_own(args, rank, world):
                               "step; evaluation user-sharded x%d" % (m._dim_shard.world, d, world // m._dim_shard.world, world))}}
         out.update(line)
         out.update({"cpu_baseline": cpu_baseline, "eval": eval_info, "small_shape": small, "clocks": clocks.summary()})
-        print(json.dumps(out), flush=True)
+        _emit(out)
     if world > 1:
         eng.close()
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries ONE JSON line: everything else written to descriptor 1 -- NCCL prints its version banner there from
+    native code -- is sent to stderr, and the line goes out through a private duplicate of the original descriptor"""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -561,6 +582,7 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
