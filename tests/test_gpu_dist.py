@@ -19,8 +19,7 @@ def test_multi_gpu_parity(n, reach):
     the C4 bench turns on by itself) -- same fixtures, same bars."""
     if torch.cuda.device_count() < n:
         pytest.skip("needs >= %d GPUs" % n)
-    os.environ["B200REC_REACH"] = reach
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
            "127.0.0.1", "--master-port", str(29611 + n), os.path.join(HERE, "dist_gpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, B200REC_REACH=reach))
     assert out.returncode == 0 and "DIST_GPU_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
