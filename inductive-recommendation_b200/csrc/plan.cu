@@ -124,6 +124,7 @@ struct PlanIn {
   const int32_t* rowptr;
   const int32_t* colidx;
   int n_rows, chunk, order_split, n_blocks, row_order;
+  int col_sort;           // single-pass plans: full hub chunks ordered by first source column (see walk_row)
   const int32_t* bounds;  // device [n_blocks + 1]
 };
 
@@ -166,7 +167,15 @@ __device__ __forceinline__ void walk_row(const PlanIn& in, int r, int& n_items, 
         item_start[k] = vs; item_end[k] = ve;
         item_dst[k] = is_long ? (int32_t)~idcode : (int32_t)idcode;
         item_row[k] = r;
-        item_key[k] = (order_hi << 32) | (in.row_order ? 0u : (uint32_t)(0x7fffffff - (ve - vs)));
+        // phase, then longest first; FULL chunks of hub rows (all the same length) are then ordered by their first source
+        // column instead of row by row (B200REC_PLAN_COLSORT, default on): the chunks in flight at one time cover one
+        // window of source rows across many hub rows -- the dense hub rows of a power-law graph share most of it -- so that
+        // window is fetched from DRAM once instead of once per hub row.  Chunk boundaries and the slot-ordered sum are
+        // untouched: the same bits.
+        const uint64_t len_key = in.row_order ? 0u : (uint32_t)(0x7fffffff - (ve - vs));
+        const uint64_t col_key = (in.col_sort && is_long && (ve - vs) == in.chunk) ? (uint32_t)__ldg(in.colidx + vs) : 0u;
+        // (column-blocked plans keep the pass number in the high word: an empty row is an item of pass 0)
+        item_key[k] = (in.n_blocks <= 1) ? ((order_hi << 63) | (len_key << 32) | col_key) : len_key;
       }
       ++ni;
       continue;
@@ -307,6 +316,10 @@ extern "C" int b200rec_plan_build(const int32_t* rowptr, const int32_t* colidx, 
   PlanIn in;
   in.rowptr = rowptr; in.colidx = colidx; in.n_rows = n_rows; in.chunk = chunk; in.order_split = order_split;
   in.n_blocks = n_blocks; in.bounds = nullptr; in.row_order = row_order;
+  {
+    const char* e = getenv("B200REC_PLAN_COLSORT");
+    in.col_sort = (e && atoi(e) == 0) ? 0 : 1;
+  }
   if (n_blocks > 1) {
     for (int b = 0; b < n_blocks; ++b) B2_REQUIRE(col_bounds[b] <= col_bounds[b + 1], "col_bounds must ascend");
     int32_t* dbounds = nullptr;
