@@ -171,6 +171,42 @@ def test_record_stream_structure():
         assert ws[pw[b]] == item_first[op.pass_ptr[b]] and ws[pw[b + 1]] == item_first[op.pass_ptr[b + 1]]
 
 
+@pytest.mark.parametrize("d", [16, 64, 128])
+def test_column_ordered_hub_chunks_same_plan_same_bits(d, monkeypatch):
+    """B200REC_PLAN_COLSORT=1 (the default for graphs of >= 16 M entries): the full chunks of hub rows are scheduled by their
+    first source column instead of row by row.  Same work items (the plan's invariants hold), full chunks in column order,
+    and the product equals the row-ordered plan's and the C oracle's bit for bit."""
+    rng = np.random.default_rng(100 + d)
+    n, chunk = 1200, 64
+    rp, cols = _random_csr(rng, n, n, hubs=12)
+    vals = rng.standard_normal(cols.size).astype(np.float32)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(DEV)  # noqa: E731
+    ops_ = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("B200REC_PLAN_COLSORT", flag)
+        ops_[flag] = graph.CsrOperand(t(rp), t(cols), n, vals=t(vals), chunk=chunk, phase_split=500)
+        _check_plan(ops_[flag], rp, cols, chunk, None)
+    a, b = ops_["0"], ops_["1"]
+    key = lambda o: sorted(zip(*(v[:o.n_items].cpu().tolist() for v in (o.item_start, o.item_end, o.item_dst, o.item_row))))  # noqa: E731
+    assert key(a) == key(b)                                       # the same work items, in another order
+    start, end, row = (v[:b.n_items].cpu().numpy() for v in (b.item_start, b.item_end, b.item_row))
+    assert not np.array_equal(start, a.item_start[:a.n_items].cpu().numpy())
+    for ph in (row < 500, row >= 500):                            # inside a phase: full chunks first, by first column
+        full = ph & (end - start == chunk) & np.isin(row, np.nonzero(np.diff(rp) > chunk)[0])
+        first_col = cols[start[full]]
+        assert full.sum() > 10 and (np.diff(first_col) >= 0).all()
+        assert (np.diff((end - start)[ph]) <= 0).all()
+    xd = t(x)
+    ya, yb = torch.empty_like(xd), torch.empty_like(xd)
+    for _ in range(2):                                            # twice: the hub counters are reused
+        ops.spmm(a, xd, y=ya)
+        ops.spmm(b, xd, y=yb)
+    torch.cuda.synchronize()
+    assert torch.equal(ya, yb)
+    assert np.array_equal(yb.cpu().numpy(), oc.spmm_csr(rp, cols, vals, x, chunk=chunk))
+
+
 @pytest.mark.parametrize("d,sweep", [(16, 16), (64, 64), (128, 64), (128, 32), (256, 256)])
 def test_blocked_spmm_bit_identical_to_single_pass_and_oracle(d, sweep):
     rng = np.random.default_rng(d + sweep)
