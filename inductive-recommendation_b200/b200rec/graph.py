@@ -16,23 +16,26 @@ import torch
 
 from . import _abi
 
-CHUNK_MAX = 256   # with the plan's column-sorted hub chunks (plan.cu) 256 beats 512 / 1024 on C4 too: 64.2 / 64.4 / 65.6 ms per step
+CHUNK_MAX = 1024
+COLSORT_NNZ = 1 << 24   # b200rec_plan_build orders the hub chunks of graphs at least this large by source column (plan.cu)
 
 
 def auto_chunk(nnz, d=None):
     """Rows longer than `chunk` are split into chunk-sized work items (deterministic ordered reduce by the lane group that
     parks the row's last chunk).  One lane group walks its item serially, about 8 neighbour rows per memory round trip, so
     the longest item is a critical path (ncu, C2 shape with 1024-edge items: SMs 54 % active); every extra chunk costs a
-    partial-row round trip through L2.  Measured sweet spot: a few items per resident lane group, within [64, 256]: the
-    full chunks of all hub rows are scheduled by their first source column (b200rec_plan_build), and the shorter a chunk,
-    the narrower the window of source rows the chunks in flight share (C4 step: 128 / 256 / 512 / 1024 edges = 66.2 /
-    64.2 / 64.4 / 65.6 ms; 256 WITHOUT the column order 70.8)."""
+    partial-row round trip through L2.  Measured sweet spot: a few items per resident lane group, within [64, 1024]
+    (C3: 512 edges 0.963 ms/step, 256 0.977).  Graphs of >= 16 M entries: the full chunks of all hub rows are scheduled by
+    their first source column (b200rec_plan_build), and the shorter a chunk, the narrower the window of source rows the
+    chunks in flight share -- C4 step: 128 / 256 / 512 / 1024 edges = 66.2 / 64.2 / 64.4 / 65.6 ms (256 WITHOUT the column
+    order 70.8) -- so the chunk is capped at 256 there."""
     import os
     if os.environ.get("B200REC_CHUNK"):
         return int(os.environ["B200REC_CHUNK"])
     target = max(1, nnz // (148 * 32 * 4))
+    cap = 256 if nnz >= COLSORT_NNZ else CHUNK_MAX
     c = 64
-    while c < target and c < CHUNK_MAX:
+    while c < target and c < cap:
         c *= 2
     return c
 
