@@ -164,10 +164,9 @@ class BprEngine:
         uniformly drawn users with probability (1 - d/U)^B, so the share is sum_i d_i (1 - d_i/U)^B / E.  C4 (2 M users,
         batch 2048): 0.58 -- the two restricted layers skip that share of one side's gathers; C1-C3: < 0.05 (a batch's
         users reach nearly every item that carries edges), where the extra mask costs more than it saves."""
+        from .graph import reach_gain
         m = self.model
-        deg = torch.bincount(self.user_items.long(), minlength=m.n_items).double()
-        miss = torch.exp(self.B * torch.log1p(-(deg / m.n_users).clamp(max=1.0 - 1e-12)))
-        return float((deg * miss).sum() / deg.sum().clamp(min=1.0))
+        return reach_gain(torch.bincount(self.user_items.long(), minlength=m.n_items), m.n_users, self.B)
 
     # ------------------------------------------------------------------------------------------------ one step
     def _propagate_fwd(self, x0, join=None, adj=None, flags=None, rep=None):

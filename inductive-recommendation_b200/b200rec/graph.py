@@ -40,6 +40,15 @@ def auto_chunk(nnz, d=None):
     return c
 
 
+def reach_gain(item_deg, n_users, batch):
+    """Share of the item-side edges that lies OUTSIDE one hop of an average BPR batch (engine: whether the one-hop mask of
+    ops.mark_reach pays).  An item of degree d is missed by `batch` uniformly drawn users with probability (1 - d/U)^batch,
+    so the share is sum_i d_i (1 - d_i/U)^batch / sum_i d_i.  item_deg: integer tensor [n_items] (any device)."""
+    deg = item_deg.double()
+    miss = torch.exp(batch * torch.log1p(-(deg / float(n_users)).clamp(max=1.0 - 1e-12)))
+    return float((deg * miss).sum() / deg.sum().clamp(min=1.0))
+
+
 def blocking_policy(n_cols, d):
     """(sweep width, source rows per block) for a gathered table [n_cols, d] fp32, or None when the table is left to the
     cache as it is -- the default.

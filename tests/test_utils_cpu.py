@@ -75,3 +75,29 @@ def test_config_lists_equal_the_reference():
         assert ours == triples, name
     syn = config.get_synthetic_config("DEV", "c4")
     assert [m["name"] for _, m, _ in syn] == ["MF", "LightGCN", "IGCN", "IMF"] and syn[1][1]["embedding_size"] == 128
+
+
+def test_reach_gain_and_auto_chunk():
+    """host-side choices of the training engine / work plan: the expected share of item-side edges outside one hop of a
+    batch (closed form against a Monte-Carlo draw of batches), and the hub-chunk rule (256-edge cap with the column-ordered
+    plan of graphs >= 16 M entries, the nnz-scaled rule below)"""
+    import torch
+    from b200rec import graph
+    rng = np.random.default_rng(3)
+    n_users, n_items, batch = 5000, 800, 64
+    p = np.arange(1, n_items + 1, dtype=np.float64) ** -0.9
+    p /= p.sum()
+    rows = [np.unique(rng.choice(n_items, size=int(k), p=p)) for k in rng.integers(1, 40, size=n_users)]
+    deg = np.bincount(np.concatenate(rows), minlength=n_items)
+    closed = graph.reach_gain(torch.from_numpy(deg), n_users, batch)
+    mc = []
+    for _ in range(200):
+        hit = np.zeros(n_items, dtype=bool)
+        for u in rng.integers(0, n_users, size=batch):
+            hit[rows[u]] = True
+        mc.append(deg[~hit].sum() / deg.sum())
+    assert 0.0 < closed < 1.0 and abs(closed - float(np.mean(mc))) < 0.02
+    assert graph.reach_gain(torch.from_numpy(deg), n_users, 100000) < 1e-3       # a huge batch reaches everything
+    assert graph.reach_gain(torch.zeros(4, dtype=torch.int64), 10, 8) == 0.0    # no edges: nothing to skip
+    assert graph.auto_chunk(2 * 1561406) == 256 and graph.auto_chunk(2 * 2984108) == 512   # C2, C3
+    assert graph.auto_chunk(200_000_000) == 256 and graph.auto_chunk(graph.COLSORT_NNZ - 1) == 1024
