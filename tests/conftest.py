@@ -16,6 +16,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _cuda_context():
+    """create the CUDA context once, before the first test, and retry a box that is not ready yet (a freshly leased GPU
+    has answered the very first call of a session with a transient error once); a CPU-only session does nothing"""
+    import time
+    import torch
+    if torch.cuda.is_available():
+        for attempt in range(3):
+            try:
+                torch.zeros(1, device="cuda")
+                torch.cuda.synchronize()
+                break
+            except RuntimeError:
+                if attempt == 2:
+                    raise
+                time.sleep(3.0)
+    yield
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
 
